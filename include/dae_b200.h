@@ -1,0 +1,136 @@
+/* dae_b200.h -- C ABI of the B200-native DAE hot path (libdae_b200.so).
+ *
+ * Drop-in boundary for the denoising-autoencoder path of hojinYang/spotify_recSys_challenge_2018.
+ * The reference has no FFI: its boundary is the Python protocol between the runners and the TF1
+ * graph objects of models/DAEs.py (`sess.run(fetches, feed_dict)`).  Each entry point below names
+ * the reference call it replaces (file:line relative to the reference root).  All `const T*`
+ * inputs of the model-level calls are HOST pointers in exactly the layout the reference's readers
+ * produce (utils/data_reader.py): `pos` = int64 [nnz,2] (row-in-batch, item id), `val` = float32
+ * [nnz].  No torch types appear anywhere in this ABI.
+ *
+ * Every function returns 0 on success, non-zero on error; dae_last_error() describes the last
+ * error of the calling thread.  There is no CPU fallback: creation fails if no sm_100 device is
+ * present.
+ */
+#ifndef DAE_B200_H
+#define DAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAE_B200_ABI_VERSION 1
+
+typedef struct dae_model dae_model; /* opaque: parameters, Adam state, workspaces, stream */
+
+typedef struct dae_config {
+    int32_t n_input;     /* conf.n_input  = tracks + artists            (DAEs.py:18)            */
+    int32_t n_tracks;    /* conf.n_tracks: ranking uses [:, :n_tracks]  (main_train.py:86)       */
+    int32_t n_hidden;    /* conf.hidden   (multiple of 64, <= 256)      (DAEs.py:19)            */
+    int32_t max_batch;   /* conf.batch    (train: <= 256 per GPU)       (DAEs.py:17)            */
+    int32_t tied;        /* 1 = DAE_tied (DAEs.py:13), 0 = DAE (DAEs.py:114)                     */
+    float lr;            /* conf.lr                                      (DAEs.py:20, :102)      */
+    float reg_lambda;    /* conf.reg_lambda                              (DAEs.py:21, :100)      */
+    uint64_t seed;       /* Philox key of the dropout masks and of dae_model_init_xavier          */
+    int32_t device;      /* CUDA device ordinal                                                    */
+    int32_t trainable;   /* 0: inference only (no Adam state / gradient buffers; DAE_title's frozen DAE, DAEs.py:164-171) */
+    void* stream;        /* cudaStream_t to run on, or NULL to create a private stream            */
+} dae_config;
+
+int32_t dae_abi_version(void);
+const char* dae_last_error(void);
+
+/* DAE_tied(conf) / DAE(conf) + model.fit() + sess.run(init_op)      DAEs.py:14,84-105,115; main_train.py:171-173 */
+int32_t dae_model_create(const dae_config* cfg, dae_model** out);
+void dae_model_destroy(dae_model* m);
+
+/* tf.contrib.layers.xavier_initializer / zeros_initializer           DAEs.py:54-59, :121-128 */
+int32_t dae_model_init_xavier(dae_model* m, uint64_t seed);
+
+/* pickle.load -> tf.constant initialisers / save_model: the four arrays of d_params, host fp32:
+ * W_enc [n_input,n_hidden], W_dec [n_input,n_hidden] (ignored/aliased when tied), b_enc [n_hidden],
+ * b_dec [n_input].                                                    DAEs.py:107-111, :129-138 */
+int32_t dae_model_set_params(dae_model* m, const float* W_enc, const float* W_dec, const float* b_enc,
+                             const float* b_dec);
+int32_t dae_model_get_params(dae_model* m, float* W_enc, float* W_dec, float* b_enc, float* b_dec);
+/* Adam moments + step counter (not saved by the reference; exposed for exact resume and tests) */
+int32_t dae_model_get_adam_state(dae_model* m, float* m_W_enc, float* v_W_enc, float* m_W_dec, float* v_W_dec,
+                                 int64_t* step);
+
+/* sess.run([model.optimizer, model.cost], feed_dict={x_positions, x_ones, y_positions, y_ones,
+ * keep_prob, input_keep_prob}) -> cost.  Synchronous, host buffers in, host scalar out.
+ *                                                                     main_train.py:204-213 */
+int32_t dae_model_train_step(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                             const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch,
+                             float keep_prob, float input_keep_prob, float* cost_out);
+
+/* sess.run(model.y_pred, {x_positions, x_ones, keep_prob: 1, input_keep_prob: 1}) -> [batch, n_cols]
+ * fp32 host matrix, n_cols = n_input or n_tracks (the runner slices [:, :n_tracks] anyway).
+ *                                                                     main_train.py:66-68, :86 */
+int32_t dae_model_predict(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
+                          int32_t n_cols, float* y_pred_out);
+
+/* y_pred + np.argsort + seed removal + [:k] fused on the device: met.single_eval /
+ * cand_generate.  seed_ptr [batch+1] / seed_idx: CSR of the seed track ids to exclude (host).
+ * out_idx [batch,k] int32 (-1 padded), out_score [batch,k] fp32 (may be NULL).
+ *                                                   metrics.py:58-68; main_challenge.py:26-36,80-90 */
+int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
+                            const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t* out_idx,
+                            float* out_score);
+
+/* ---- device-resident / asynchronous variants (bench `value`, data-parallel training) ---------- */
+
+/* Copy one batch (host COO) into device staging slot 0 or 1 (async on the model's stream). */
+int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                              const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch);
+/* Forward + backward from a staged slot; gradients stay in device buffers; no host sync.
+ * global_batch / row_offset: the loss is a mean over the GLOBAL batch (DAEs.py:100) and dropout is
+ * keyed by the global row, so N ranks x B_local == one rank x (N*B_local). */
+int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
+                                  int32_t global_batch, int32_t row_offset);
+/* Dense TF1 Adam on every variable from the gradient buffers, then step += 1.   DAEs.py:102 */
+int32_t dae_model_apply_adam(dae_model* m);
+/* backward_staged + apply_adam (single GPU). */
+int32_t dae_model_train_step_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob);
+/* Synchronise the stream, check the device-side error flag, return the last step's cost. */
+int32_t dae_model_sync_cost(dae_model* m, float* cost_out);
+
+/* Named device buffers (pointer, element count, element size) for collectives issued by the host
+ * layer (torch.distributed / NCCL all-reduce of the gradients) and for parity tests.  Names:
+ * "g_dec" "g_enc" "g_b_enc" "g_b_dec" "touched" "cost" "W_enc" "W_dec" "W_dec_bf16" "b_enc" "b_dec"
+ * "h" "h_d" "dzT" "dh_partial" "da" "x_row_ptr" "x_row_len" "x_col" "x_val" "x_rowsum"
+ * "y_row_ptr" "y_row_len" "y_col" "ybits" "scores". */
+int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size);
+/* number of kernels launched by this model since creation (bench.py `gpu_launches`) */
+int64_t dae_model_launch_count(dae_model* m);
+
+/* ---- kernel-level entry points on caller-owned DEVICE memory (parity tests, other hosts) ------- */
+
+/* met.single_eval ranking on an existing score matrix.              metrics.py:58-68 */
+int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t batch, int32_t n_tracks, int32_t k,
+                        const int32_t* seed_ptr_dev, const int32_t* seed_idx_dev, int32_t idx_base,
+                        int32_t* out_idx_dev, float* out_score_dev, void* stream);
+/* ApplyAdam on one variable.                                         DAEs.py:102 [TF1] */
+int32_t dae_adam_device(float* w_dev, float* m_dev, float* v_dev, const float* g_dev, uint16_t* w_bf16_dev,
+                        int64_t n, float lr, float beta1_power, float beta2_power, float reg_lambda, void* stream);
+/* tf.sparse_tensor_to_dense semantics kept sparse: COO -> per-row unique sorted columns, last value wins.
+ * row_ptr_dev [batch+1] raw offsets, row_len_dev [batch], col_dev/val_dev [nnz].     DAEs.py:33-38 */
+int32_t dae_coo_to_csr_device(const int64_t* pos_dev, const float* val_dev, int64_t nnz, int32_t batch,
+                              int32_t n_input, int32_t* row_ptr_dev, int32_t* row_len_dev, int32_t* col_dev,
+                              float* val_out_dev, void* stream);
+/* The three tensor-core contractions on caller-owned bf16 operands (descriptor / layout tests):
+ *   op 0: out[b, item] = sigmoid(W[item,:].h_d[b,:] + bias[item])          (decode, DAEs.py:75)
+ *   op 1: out[item, :] = sum_b dzT[item,b] h_dT[:,b]                        (dW_dec)
+ *   op 2: out[split, b, :] = partial sums of sum_item dzT[item,b] W[item,:] (dh, split-K)
+ * lbo/sbo: MN-major descriptor strides for op 2 (0 = defaults). */
+int32_t dae_dh_nsplit(int32_t n_items); /* number of split-K partials op 2 writes */
+int32_t dae_gemm_test_device(int32_t op, const uint16_t* a_dev, const uint16_t* b_dev, const float* bias_dev,
+                             float* out_dev, int32_t n_items, int32_t n_hidden, int32_t batch, int32_t bpad,
+                             int32_t lbo, int32_t sbo, int32_t* nsplit_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAE_B200_H */

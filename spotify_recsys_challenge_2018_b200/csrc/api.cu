@@ -1,0 +1,622 @@
+// C-ABI of libdae_b200.so (include/dae_b200.h): the model object (parameters, TF1-Adam state,
+// workspaces, staging) and the orchestration of one train / predict / recommend step.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dae_b200.h"
+#include "kernels.h"
+#include "philox.cuh"
+
+using namespace dae;
+
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;   // [TF1] AdamOptimizer defaults (DAEs.py:102)
+constexpr int kSqBlocks = 256;
+
+struct Slot {
+    long long *x_pos = nullptr, *y_pos = nullptr;   // device
+    float *x_val = nullptr, *y_val = nullptr;
+    long long *hx_pos = nullptr, *hy_pos = nullptr; // pinned host mirrors
+    float *hx_val = nullptr, *hy_val = nullptr;
+    int nnz_x = 0, nnz_y = 0, batch = 0;
+    cudaEvent_t h2d_done = nullptr;                 // the pinned mirror may be overwritten after this
+};
+
+struct dae_model {
+    dae_config cfg{};
+    int N = 0, T = 0, H = 0, Bmax = 0, rows_alloc = 0, max_nnz = 0;
+    bool tied = false, trainable = true, own_stream = false;
+    cudaStream_t st = nullptr;
+    float *W_enc = nullptr, *W_dec = nullptr, *b_enc = nullptr, *b_dec = nullptr;
+    __nv_bfloat16* W_dec_bf16 = nullptr;
+    float *mW_enc = nullptr, *vW_enc = nullptr, *mW_dec = nullptr, *vW_dec = nullptr;
+    float *mb_enc = nullptr, *vb_enc = nullptr, *mb_dec = nullptr, *vb_dec = nullptr;
+    float b1_pow = kBeta1, b2_pow = kBeta2;
+    long long step = 0;
+    float *g_dec = nullptr, *g_enc = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
+    unsigned char* touched = nullptr;
+    Slot slots[2];
+    CsrWork xw{}, yw{};
+    int* err = nullptr;
+    int* err_host = nullptr;
+    uint32_t* ybits = nullptr;
+    int ywords = 8;
+    float *rowsum = nullptr, *h = nullptr, *da = nullptr, *dh_partial = nullptr;
+    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr;
+    int nsplit = 0;
+    float *loss_partial = nullptr, *sq_partial = nullptr, *cost = nullptr, *cost_host = nullptr;
+    int n_loss_partial = 0;
+    float* scores = nullptr;
+    size_t scores_elems = 0;
+    int *topk_idx = nullptr, *seed_ptr = nullptr, *seed_idx = nullptr;
+    float* topk_score = nullptr;
+    size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
+    int last_batch = 0, last_bpad = 0;
+    long long launches = 0;
+    std::vector<void*> dev_allocs, host_allocs;
+};
+
+template <typename T>
+static int dalloc(dae_model* m, T** p, size_t n, bool zero = true) {
+    CK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T) + 16));
+    m->dev_allocs.push_back(*p);
+    if (zero) CK(cudaMemsetAsync(*p, 0, n * sizeof(T), m->st));
+    return 0;
+}
+template <typename T>
+static int halloc(dae_model* m, T** p, size_t n) {
+    CK(cudaMallocHost(reinterpret_cast<void**>(p), n * sizeof(T)));
+    m->host_allocs.push_back(*p);
+    return 0;
+}
+#define TRY(x) do { if (int rc_ = (x)) return rc_; } while (0)
+
+static int alloc_csr(dae_model* m, CsrWork* w, int B, int max_nnz) {
+    TRY(dalloc(m, &w->cnt, B));
+    TRY(dalloc(m, &w->row_ptr, B + 1));
+    TRY(dalloc(m, &w->cursor, B));
+    TRY(dalloc(m, &w->keys, max_nnz));
+    TRY(dalloc(m, &w->row_len, B));
+    TRY(dalloc(m, &w->col, max_nnz));
+    TRY(dalloc(m, &w->val, max_nnz));
+    return 0;
+}
+
+extern "C" int32_t dae_abi_version(void) { return DAE_B200_ABI_VERSION; }
+extern "C" const char* dae_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
+    if (!cfg || !out) return fail("null argument");
+    *out = nullptr;
+    if (cfg->n_hidden <= 0 || cfg->n_hidden % 64 != 0 || cfg->n_hidden > 256)
+        return fail("n_hidden must be a multiple of 64 in [64,256], got %d", cfg->n_hidden);
+    if (cfg->n_input <= 0 || cfg->n_tracks <= 0 || cfg->n_tracks > cfg->n_input)
+        return fail("need 0 < n_tracks <= n_input (got %d, %d)", cfg->n_tracks, cfg->n_input);
+    if (cfg->max_batch <= 0) return fail("max_batch must be positive");
+    if (cfg->trainable && cfg->max_batch > kMaxBpad)
+        return fail("training batch per GPU is limited to %d rows (one tensor-core batch tile); got %d", kMaxBpad,
+                    cfg->max_batch);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: libdae_b200 has no CPU fallback");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    dae_model* m = new dae_model();
+    m->cfg = *cfg;
+    m->N = cfg->n_input; m->T = cfg->n_tracks; m->H = cfg->n_hidden; m->Bmax = cfg->max_batch;
+    m->tied = cfg->tied != 0; m->trainable = cfg->trainable != 0;
+    if (cfg->stream) { m->st = reinterpret_cast<cudaStream_t>(cfg->stream); }
+    else { CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)); m->own_stream = true; }
+    m->rows_alloc = m->Bmax <= kMaxBpad ? round_up(m->Bmax, 64) : round_up(m->Bmax, kMaxBpad);
+    m->max_nnz = m->Bmax * 1024;
+    const size_t NH = (size_t)m->N * m->H;
+    const int N = m->N, H = m->H;
+
+    TRY(dalloc(m, &m->W_enc, NH));
+    TRY(dalloc(m, &m->b_enc, H));
+    TRY(dalloc(m, &m->b_dec, N));
+    if (m->tied) m->W_dec = m->W_enc; else TRY(dalloc(m, &m->W_dec, NH));
+    TRY(dalloc(m, &m->W_dec_bf16, NH));
+    if (m->trainable) {
+        TRY(dalloc(m, &m->mW_enc, NH)); TRY(dalloc(m, &m->vW_enc, NH));
+        if (m->tied) { m->mW_dec = m->mW_enc; m->vW_dec = m->vW_enc; }
+        else { TRY(dalloc(m, &m->mW_dec, NH)); TRY(dalloc(m, &m->vW_dec, NH)); }
+        TRY(dalloc(m, &m->mb_enc, H)); TRY(dalloc(m, &m->vb_enc, H));
+        TRY(dalloc(m, &m->mb_dec, N)); TRY(dalloc(m, &m->vb_dec, N));
+        TRY(dalloc(m, &m->g_dec, NH));
+        if (m->tied) m->g_enc = m->g_dec; else { TRY(dalloc(m, &m->g_enc, NH)); TRY(dalloc(m, &m->touched, N)); }
+        TRY(dalloc(m, &m->g_b_enc, H)); TRY(dalloc(m, &m->g_b_dec, N));
+        TRY(alloc_csr(m, &m->yw, m->Bmax, m->max_nnz));
+        TRY(dalloc(m, &m->ybits, (size_t)N * m->ywords));
+        TRY(dalloc(m, &m->da, (size_t)m->Bmax * H));
+        TRY(dalloc(m, &m->dzT, (size_t)N * kMaxBpad));
+        m->nsplit = dh_nsplit(N);
+        TRY(dalloc(m, &m->dh_partial, (size_t)m->nsplit * kMaxBpad * H));
+        m->n_loss_partial = 148 * 2;
+        TRY(dalloc(m, &m->loss_partial, m->n_loss_partial));
+        TRY(dalloc(m, &m->sq_partial, 4 * kSqBlocks));
+    }
+    TRY(alloc_csr(m, &m->xw, m->Bmax, m->max_nnz));
+    TRY(dalloc(m, &m->err, 1));
+    TRY(halloc(m, &m->err_host, 1));
+    TRY(dalloc(m, &m->rowsum, m->Bmax));
+    TRY(dalloc(m, &m->h, (size_t)m->Bmax * H));
+    TRY(dalloc(m, &m->h_d, (size_t)m->rows_alloc * H));
+    TRY(dalloc(m, &m->h_dT, (size_t)m->rows_alloc * H));
+    TRY(dalloc(m, &m->cost, 1));
+    TRY(halloc(m, &m->cost_host, 1));
+    for (int s = 0; s < 2; ++s) {
+        Slot& sl = m->slots[s];
+        CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+        TRY(dalloc(m, &sl.x_pos, (size_t)m->max_nnz * 2)); TRY(dalloc(m, &sl.x_val, m->max_nnz));
+        TRY(halloc(m, &sl.hx_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hx_val, m->max_nnz));
+        if (m->trainable) {
+            TRY(dalloc(m, &sl.y_pos, (size_t)m->max_nnz * 2)); TRY(dalloc(m, &sl.y_val, m->max_nnz));
+            TRY(halloc(m, &sl.hy_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hy_val, m->max_nnz));
+        }
+    }
+    CK(cudaStreamSynchronize(m->st));
+    *out = m;
+    return 0;
+}
+
+extern "C" void dae_model_destroy(dae_model* m) {
+    if (!m) return;
+    cudaStreamSynchronize(m->st);
+    for (void* p : m->dev_allocs) cudaFree(p);
+    for (void* p : m->host_allocs) cudaFreeHost(p);
+    if (m->scores) cudaFree(m->scores);
+    if (m->topk_idx) cudaFree(m->topk_idx);
+    if (m->topk_score) cudaFree(m->topk_score);
+    if (m->seed_ptr) cudaFree(m->seed_ptr);
+    if (m->seed_idx) cudaFree(m->seed_idx);
+    for (int s = 0; s < 2; ++s) if (m->slots[s].h2d_done) cudaEventDestroy(m->slots[s].h2d_done);
+    if (m->own_stream) cudaStreamDestroy(m->st);
+    delete m;
+}
+
+static void refresh_shadow(dae_model* m) {
+    launch_cast_bf16(m->W_dec, m->W_dec_bf16, (long long)m->N * m->H, m->st);
+    m->launches += 1;
+}
+
+extern "C" int32_t dae_model_init_xavier(dae_model* m, uint64_t seed) {
+    if (!m) return fail("null model");
+    const float lim = sqrtf(6.0f / (float)(m->N + m->H));
+    const long long NH = (long long)m->N * m->H;
+    launch_xavier_init(m->W_enc, NH, lim, seed, kStreamInit, m->st);
+    if (!m->tied) launch_xavier_init(m->W_dec, NH, lim, seed, kStreamInit + 1, m->st);
+    CK(cudaMemsetAsync(m->b_enc, 0, sizeof(float) * m->H, m->st));
+    CK(cudaMemsetAsync(m->b_dec, 0, sizeof(float) * m->N, m->st));
+    m->launches += m->tied ? 1 : 2;
+    refresh_shadow(m);
+    CK(cudaStreamSynchronize(m->st));
+    return 0;
+}
+
+extern "C" int32_t dae_model_set_params(dae_model* m, const float* W_enc, const float* W_dec, const float* b_enc,
+                                        const float* b_dec) {
+    if (!m || !W_enc || !b_enc || !b_dec) return fail("null argument");
+    const size_t NH = (size_t)m->N * m->H;
+    CK(cudaMemcpyAsync(m->W_enc, W_enc, NH * 4, cudaMemcpyHostToDevice, m->st));
+    if (!m->tied) {
+        if (!W_dec) return fail("W_dec required for the untied model");
+        CK(cudaMemcpyAsync(m->W_dec, W_dec, NH * 4, cudaMemcpyHostToDevice, m->st));
+    }
+    CK(cudaMemcpyAsync(m->b_enc, b_enc, (size_t)m->H * 4, cudaMemcpyHostToDevice, m->st));
+    CK(cudaMemcpyAsync(m->b_dec, b_dec, (size_t)m->N * 4, cudaMemcpyHostToDevice, m->st));
+    refresh_shadow(m);
+    CK(cudaStreamSynchronize(m->st));
+    return 0;
+}
+
+extern "C" int32_t dae_model_get_params(dae_model* m, float* W_enc, float* W_dec, float* b_enc, float* b_dec) {
+    if (!m) return fail("null model");
+    const size_t NH = (size_t)m->N * m->H;
+    if (W_enc) CK(cudaMemcpyAsync(W_enc, m->W_enc, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (W_dec) CK(cudaMemcpyAsync(W_dec, m->W_dec, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (b_enc) CK(cudaMemcpyAsync(b_enc, m->b_enc, (size_t)m->H * 4, cudaMemcpyDeviceToHost, m->st));
+    if (b_dec) CK(cudaMemcpyAsync(b_dec, m->b_dec, (size_t)m->N * 4, cudaMemcpyDeviceToHost, m->st));
+    CK(cudaStreamSynchronize(m->st));
+    return 0;
+}
+
+extern "C" int32_t dae_model_get_adam_state(dae_model* m, float* m_W_enc, float* v_W_enc, float* m_W_dec,
+                                            float* v_W_dec, int64_t* step) {
+    if (!m || !m->trainable) return fail("model is not trainable");
+    const size_t NH = (size_t)m->N * m->H;
+    if (m_W_enc) CK(cudaMemcpyAsync(m_W_enc, m->mW_enc, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (v_W_enc) CK(cudaMemcpyAsync(v_W_enc, m->vW_enc, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (m_W_dec) CK(cudaMemcpyAsync(m_W_dec, m->mW_dec, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (v_W_dec) CK(cudaMemcpyAsync(v_W_dec, m->vW_dec, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (step) *step = m->step;
+    CK(cudaStreamSynchronize(m->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// staging
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val,
+                                         int64_t nnz_x, const int64_t* y_pos, const float* y_val, int64_t nnz_y,
+                                         int32_t batch) {
+    if (!m) return fail("null model");
+    if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
+    if (batch <= 0 || batch > m->Bmax) return fail("batch %d outside (0, %d]", batch, m->Bmax);
+    if (nnz_x < 0 || nnz_x > m->max_nnz || nnz_y < 0 || nnz_y > m->max_nnz)
+        return fail("nnz (%lld, %lld) exceeds the staging capacity %d", (long long)nnz_x, (long long)nnz_y, m->max_nnz);
+    if ((nnz_x > 0 && (!x_pos || !x_val)) || (nnz_y > 0 && (!y_pos || !y_val))) return fail("null COO pointer");
+    if (nnz_y > 0 && !m->trainable) return fail("y given to an inference-only model");
+    Slot& s = m->slots[slot];
+    CK(cudaEventSynchronize(s.h2d_done));   // previous H2D out of this slot's pinned mirror has finished
+    s.nnz_x = (int)nnz_x; s.nnz_y = (int)nnz_y; s.batch = batch;
+    if (nnz_x > 0) {
+        memcpy(s.hx_pos, x_pos, (size_t)nnz_x * 16);
+        memcpy(s.hx_val, x_val, (size_t)nnz_x * 4);
+        CK(cudaMemcpyAsync(s.x_pos, s.hx_pos, (size_t)nnz_x * 16, cudaMemcpyHostToDevice, m->st));
+        CK(cudaMemcpyAsync(s.x_val, s.hx_val, (size_t)nnz_x * 4, cudaMemcpyHostToDevice, m->st));
+    }
+    if (nnz_y > 0) {
+        memcpy(s.hy_pos, y_pos, (size_t)nnz_y * 16);
+        memcpy(s.hy_val, y_val, (size_t)nnz_y * 4);
+        CK(cudaMemcpyAsync(s.y_pos, s.hy_pos, (size_t)nnz_y * 16, cudaMemcpyHostToDevice, m->st));
+        CK(cudaMemcpyAsync(s.y_val, s.hy_val, (size_t)nnz_y * 4, cudaMemcpyHostToDevice, m->st));
+    }
+    CK(cudaEventRecord(s.h2d_done, m->st));
+    return 0;
+}
+
+static int check_device_flag(dae_model* m) {
+    CK(cudaMemcpyAsync(m->err_host, m->err, sizeof(int), cudaMemcpyDeviceToHost, m->st));
+    CK(cudaStreamSynchronize(m->st));
+    CK(cudaGetLastError());
+    const int e = *m->err_host;
+    if (e != 0) {
+        cudaMemsetAsync(m->err, 0, sizeof(int), m->st);
+        return fail("invalid sparse batch:%s%s%s", (e & kErrIndexRange) ? " index out of range" : "",
+                    (e & kErrRowTooLong) ? " row longer than 2048 entries" : "",
+                    (e & kErrYNotBinary) ? " y values must be 0 or 1" : "");
+    }
+    return 0;
+}
+
+// encode forward from a staged slot (shared by train / predict / recommend)
+static void run_encode(dae_model* m, const Slot& s, int rows_pad, float kp, float kp_in, int row_offset) {
+    launch_coo_to_csr(s.x_pos, s.x_val, s.nnz_x, s.batch, m->N, m->xw, m->err, m->st);
+    m->launches += s.nnz_x > 0 ? 4 : 2;
+    EncodeArgs e{};
+    e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = m->xw; e.rowsum = m->rowsum; e.h = m->h; e.h_d = m->h_d;
+    e.h_dT = m->h_dT; e.B = s.batch; e.bpad = rows_pad; e.H = m->H; e.kp = kp; e.kp_in = kp_in;
+    e.seed = m->cfg.seed; e.step = (unsigned long long)m->step; e.row_offset = row_offset;
+    launch_encode_fwd(e, m->st);
+    m->launches += 1;
+}
+
+extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
+                                             int32_t global_batch, int32_t row_offset) {
+    if (!m || !m->trainable) return fail("model is not trainable");
+    if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
+    const Slot& s = m->slots[slot];
+    if (s.batch <= 0) return fail("slot %d holds no batch", slot);
+    if (!(keep_prob > 0.f) || !(input_keep_prob > 0.f)) return fail("keep probabilities must be > 0");
+    const int B = s.batch, bpad = round_up(B, 64), H = m->H, N = m->N;
+    if (bpad > kMaxBpad) return fail("training batch %d exceeds %d", B, kMaxBpad);
+    const int gb = global_batch > 0 ? global_batch : B;
+    m->last_batch = B; m->last_bpad = bpad;
+
+    run_encode(m, s, bpad, keep_prob, input_keep_prob, row_offset);
+    launch_coo_to_csr(s.y_pos, s.y_val, s.nnz_y, B, N, m->yw, m->err, m->st);
+    launch_ybits_set(m->yw, B, m->ybits, m->ywords, 1, m->err, m->st);
+    m->launches += (s.nnz_y > 0 ? 4 : 2) + 1;
+
+    DecodeArgs d{};
+    d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
+    d.ybits = m->ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.db_dec = m->g_b_dec;
+    d.loss_partial = m->loss_partial; d.inv_batch = 1.0f / (float)gb;
+    const int ngrid = decode_grid(N, 1);
+    launch_decode_train(d, m->st);
+
+    DwArgs w{}; w.dzT = m->dzT; w.h_dT = m->h_dT; w.g = m->g_dec; w.N = N; w.H = H; w.bpad = bpad;
+    launch_dw(w, m->st);
+
+    DhArgs q{}; q.dzT = m->dzT; q.W = m->W_dec_bf16; q.partial = m->dh_partial; q.N = N; q.H = H; q.bpad = bpad;
+    q.nsplit = m->nsplit;
+    launch_dh(q, m->st);
+
+    EncodeBwdArgs eb{};
+    eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.x = m->xw; eb.da = m->da;
+    eb.g_enc = m->g_enc; eb.touched = m->touched; eb.db_enc = m->g_b_enc; eb.B = B; eb.bpad = bpad; eb.H = H;
+    eb.kp = keep_prob; eb.seed = m->cfg.seed; eb.step = (unsigned long long)m->step; eb.row_offset = row_offset;
+    launch_encode_bwd(eb, m->st);
+    launch_ybits_set(m->yw, B, m->ybits, m->ywords, 0, m->err, m->st);
+    m->launches += 3 + 2 + 1;
+
+    int n_sq = 0;
+    const float lam = m->cfg.reg_lambda;
+    if (lam != 0.f && row_offset == 0) {                    // l2 term once per global batch (DAEs.py:79-82, :147-150)
+        const long long NH = (long long)N * H;
+        launch_sumsq(m->W_enc, NH, m->sq_partial, kSqBlocks, m->st);
+        launch_sumsq(m->b_dec, N, m->sq_partial + kSqBlocks, kSqBlocks, m->st);
+        launch_sumsq(m->b_enc, H, m->sq_partial + 2 * kSqBlocks, kSqBlocks, m->st);
+        n_sq = 3 * kSqBlocks;
+        if (!m->tied) { launch_sumsq(m->W_dec, NH, m->sq_partial + 3 * kSqBlocks, kSqBlocks, m->st); n_sq = 4 * kSqBlocks; }
+        m->launches += m->tied ? 3 : 4;
+    }
+    launch_reduce_loss2(m->loss_partial, ngrid, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost, m->st);
+    m->launches += 1;
+    return 0;
+}
+
+extern "C" int32_t dae_model_apply_adam(dae_model* m) {
+    if (!m || !m->trainable) return fail("model is not trainable");
+    const float alpha = m->cfg.lr * sqrtf(1.0f - m->b2_pow) / (1.0f - m->b1_pow);   // [TF1] ApplyAdam, fp32
+    AdamArgs a{};
+    a.alpha = alpha; a.one_minus_b1 = 1.0f - kBeta1; a.one_minus_b2 = 1.0f - kBeta2; a.eps = kAdamEps;
+    a.lambda = m->cfg.reg_lambda;
+    const long long NH = (long long)m->N * m->H;
+    // decoder (or the tied matrix): dense gradient, refreshes the bf16 operand shadow
+    a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.w_bf16 = m->W_dec_bf16;
+    a.row_touched = nullptr; a.n = NH; a.row_len = m->H;
+    launch_adam(a, m->st);
+    m->launches += 1;
+    if (!m->tied) {   // encoder: gradient rows exist only where the batch touched them; all rows still update
+        a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = m->g_enc; a.w_bf16 = nullptr;
+        a.row_touched = m->touched;
+        launch_adam(a, m->st);
+        launch_clear_flagged(m->N, m->H, m->g_enc, m->touched, m->st);
+        m->launches += 2;
+    }
+    a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
+    a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = m->H;
+    launch_adam(a, m->st);
+    a.w = m->b_dec; a.m = m->mb_dec; a.v = m->vb_dec; a.g = m->g_b_dec; a.n = m->N;
+    launch_adam(a, m->st);
+    m->launches += 2 + (m->N % 4 ? 1 : 0);
+    m->b1_pow *= kBeta1;
+    m->b2_pow *= kBeta2;
+    m->step += 1;
+    return 0;
+}
+
+extern "C" int32_t dae_model_train_step_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob) {
+    TRY(dae_model_backward_staged(m, slot, keep_prob, input_keep_prob, 0, 0));
+    return dae_model_apply_adam(m);
+}
+
+extern "C" int32_t dae_model_sync_cost(dae_model* m, float* cost_out) {
+    if (!m) return fail("null model");
+    if (m->trainable) CK(cudaMemcpyAsync(m->cost_host, m->cost, sizeof(float), cudaMemcpyDeviceToHost, m->st));
+    TRY(check_device_flag(m));
+    if (cost_out) *cost_out = m->trainable ? *m->cost_host : 0.f;
+    return 0;
+}
+
+extern "C" int32_t dae_model_train_step(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                        const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch,
+                                        float keep_prob, float input_keep_prob, float* cost_out) {
+    TRY(dae_model_stage_batch(m, 0, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch));
+    TRY(dae_model_train_step_staged(m, 0, keep_prob, input_keep_prob));
+    return dae_model_sync_cost(m, cost_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// inference
+// ------------------------------------------------------------------------------------------
+static int ensure_scores(dae_model* m, size_t elems) {
+    if (m->scores_elems >= elems) return 0;
+    if (m->scores) { CK(cudaStreamSynchronize(m->st)); CK(cudaFree(m->scores)); m->scores = nullptr; }
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->scores), elems * sizeof(float)));
+    m->scores_elems = elems;
+    return 0;
+}
+
+static int run_predict(dae_model* m, const Slot& s, int n_cols, float* out_dev, long long ld) {
+    const int B = s.batch;
+    int bpad, nbt;
+    if (B <= kMaxBpad) { bpad = round_up(B, 64); nbt = 1; }
+    else { bpad = kMaxBpad; nbt = (B + kMaxBpad - 1) / kMaxBpad; }
+    run_encode(m, s, bpad * nbt, 1.0f, 1.0f, 0);          // keep_prob = input_keep_prob = 1 (main_train.py:68)
+    DecodeArgs d{};
+    d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
+    d.n_batch_tiles = nbt; d.out = out_dev; d.ld_out = ld; d.n_out = n_cols;
+    launch_decode_predict(d, m->st);
+    m->launches += 1;
+    return 0;
+}
+
+extern "C" int32_t dae_model_predict(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                     int32_t batch, int32_t n_cols, float* y_pred_out) {
+    if (!m || !y_pred_out) return fail("null argument");
+    if (n_cols <= 0 || n_cols > m->N) return fail("n_cols must be in (0, n_input]");
+    TRY(dae_model_stage_batch(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch));
+    TRY(ensure_scores(m, (size_t)batch * n_cols));
+    TRY(run_predict(m, m->slots[0], n_cols, m->scores, n_cols));
+    CK(cudaMemcpyAsync(y_pred_out, m->scores, (size_t)batch * n_cols * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+    return check_device_flag(m);
+}
+
+template <typename T>
+static int ensure_buf(T** p, size_t* have, size_t need, cudaStream_t st) {
+    if (*have >= need) return 0;
+    if (*p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(*p)); *p = nullptr; }
+    CK(cudaMalloc(reinterpret_cast<void**>(p), need * sizeof(T)));
+    *have = need;
+    return 0;
+}
+
+extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                       int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
+                                       int32_t* out_idx, float* out_score) {
+    if (!m || !out_idx) return fail("null argument");
+    if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
+    TRY(dae_model_stage_batch(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch));
+    const int T = m->T;
+    TRY(ensure_scores(m, (size_t)batch * T));
+    size_t tk = m->topk_elems;
+    TRY(ensure_buf(&m->topk_idx, &tk, (size_t)batch * k, m->st));
+    tk = m->topk_elems;
+    TRY(ensure_buf(&m->topk_score, &tk, (size_t)batch * k, m->st));
+    m->topk_elems = tk;
+    const int* sp = nullptr; const int* si = nullptr;
+    if (seed_ptr) {
+        const int nseed = seed_ptr[batch];
+        TRY(ensure_buf(&m->seed_ptr, &m->seed_ptr_elems, (size_t)batch + 1, m->st));
+        TRY(ensure_buf(&m->seed_idx, &m->seed_idx_elems, (size_t)(nseed > 0 ? nseed : 1), m->st));
+        CK(cudaMemcpyAsync(m->seed_ptr, seed_ptr, ((size_t)batch + 1) * 4, cudaMemcpyHostToDevice, m->st));
+        if (nseed > 0) CK(cudaMemcpyAsync(m->seed_idx, seed_idx, (size_t)nseed * 4, cudaMemcpyHostToDevice, m->st));
+        sp = m->seed_ptr; si = m->seed_idx;
+    }
+    TRY(run_predict(m, m->slots[0], T, m->scores, T));
+    TopkArgs a{};
+    a.scores = m->scores; a.ld = T; a.B = batch; a.T = T; a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.idx_base = 0;
+    a.out_idx = m->topk_idx; a.out_score = m->topk_score;
+    launch_topk(a, m->st);
+    m->launches += 1;
+    CK(cudaMemcpyAsync(out_idx, m->topk_idx, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
+    if (out_score) CK(cudaMemcpyAsync(out_score, m->topk_score, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
+    return check_device_flag(m);
+}
+
+// ------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t* n_elem,
+                                    int32_t* elem_size) {
+    if (!m || !name || !dev_ptr) return fail("null argument");
+    const int64_t NH = (int64_t)m->N * m->H;
+    struct E { const char* n; void* p; int64_t c; int32_t s; };
+    const E table[] = {
+        {"g_dec", m->g_dec, NH, 4}, {"g_enc", m->g_enc, NH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
+        {"g_b_dec", m->g_b_dec, m->N, 4}, {"touched", m->touched, m->N, 1}, {"cost", m->cost, 1, 4},
+        {"W_enc", m->W_enc, NH, 4}, {"W_dec", m->W_dec, NH, 4}, {"W_dec_bf16", m->W_dec_bf16, NH, 2},
+        {"b_enc", m->b_enc, m->H, 4}, {"b_dec", m->b_dec, m->N, 4},
+        {"h", m->h, (int64_t)m->Bmax * m->H, 4}, {"h_d", m->h_d, (int64_t)m->rows_alloc * m->H, 2},
+        {"h_dT", m->h_dT, (int64_t)m->rows_alloc * m->H, 2},
+        {"dzT", m->dzT, (int64_t)m->N * kMaxBpad, 2},
+        {"dh_partial", m->dh_partial, (int64_t)m->nsplit * kMaxBpad * m->H, 4}, {"da", m->da, (int64_t)m->Bmax * m->H, 4},
+        {"x_row_ptr", m->xw.row_ptr, m->Bmax + 1, 4}, {"x_row_len", m->xw.row_len, m->Bmax, 4},
+        {"x_col", m->xw.col, m->max_nnz, 4}, {"x_val", m->xw.val, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
+        {"y_row_ptr", m->yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", m->yw.row_len, m->Bmax, 4},
+        {"y_col", m->yw.col, m->max_nnz, 4}, {"ybits", m->ybits, (int64_t)m->N * m->ywords, 4},
+        {"scores", m->scores, (int64_t)m->scores_elems, 4},
+        {"mW_dec", m->mW_dec, NH, 4}, {"vW_dec", m->vW_dec, NH, 4}, {"mW_enc", m->mW_enc, NH, 4}, {"vW_enc", m->vW_enc, NH, 4},
+    };
+    for (const E& e : table) {
+        if (strcmp(e.n, name) == 0) {
+            if (!e.p) return fail("buffer '%s' is not allocated for this model", name);
+            *dev_ptr = e.p;
+            if (n_elem) *n_elem = e.c;
+            if (elem_size) *elem_size = e.s;
+            return 0;
+        }
+    }
+    return fail("unknown buffer '%s'", name);
+}
+
+extern "C" int64_t dae_model_launch_count(dae_model* m) { return m ? m->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// kernel-level entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t batch, int32_t n_tracks, int32_t k,
+                                   const int32_t* seed_ptr_dev, const int32_t* seed_idx_dev, int32_t idx_base,
+                                   int32_t* out_idx_dev, float* out_score_dev, void* stream) {
+    if (!scores_dev || !out_idx_dev || !out_score_dev) return fail("null argument");
+    if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
+    TopkArgs a{};
+    a.scores = scores_dev; a.ld = ld; a.B = batch; a.T = n_tracks; a.k = k; a.seed_ptr = seed_ptr_dev;
+    a.seed_idx = seed_idx_dev; a.idx_base = idx_base; a.out_idx = out_idx_dev; a.out_score = out_score_dev;
+    launch_topk(a, reinterpret_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t dae_adam_device(float* w_dev, float* m_dev, float* v_dev, const float* g_dev, uint16_t* w_bf16_dev,
+                                   int64_t n, float lr, float beta1_power, float beta2_power, float reg_lambda,
+                                   void* stream) {
+    AdamArgs a{};
+    a.w = w_dev; a.m = m_dev; a.v = v_dev; a.g = g_dev; a.w_bf16 = reinterpret_cast<__nv_bfloat16*>(w_bf16_dev);
+    a.n = n; a.row_len = 1;
+    a.alpha = lr * sqrtf(1.0f - beta2_power) / (1.0f - beta1_power);
+    a.one_minus_b1 = 1.0f - kBeta1; a.one_minus_b2 = 1.0f - kBeta2; a.eps = kAdamEps; a.lambda = reg_lambda;
+    launch_adam(a, reinterpret_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t dae_coo_to_csr_device(const int64_t* pos_dev, const float* val_dev, int64_t nnz, int32_t batch,
+                                         int32_t n_input, int32_t* row_ptr_dev, int32_t* row_len_dev, int32_t* col_dev,
+                                         float* val_out_dev, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CsrWork w{};
+    int* scratch = nullptr;
+    unsigned long long* keys = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&scratch), sizeof(int) * (2 * (size_t)batch + 1)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&keys), sizeof(unsigned long long) * (size_t)(nnz > 0 ? nnz : 1)));
+    CK(cudaMemsetAsync(scratch, 0, sizeof(int) * (2 * (size_t)batch + 1), st));
+    w.cnt = scratch; w.cursor = scratch + batch; int* err = scratch + 2 * batch;
+    w.row_ptr = row_ptr_dev; w.keys = keys; w.row_len = row_len_dev; w.col = col_dev; w.val = val_out_dev;
+    launch_coo_to_csr(reinterpret_cast<const long long*>(pos_dev), val_dev, (int)nnz, batch, n_input, w, err, st);
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(scratch); cudaFree(keys);
+    CK(cudaGetLastError());
+    if (herr) return fail("invalid sparse batch (flag %d)", herr);
+    return 0;
+}
+
+extern "C" int32_t dae_dh_nsplit(int32_t n_items) { return dh_nsplit(n_items); }
+
+extern "C" int32_t dae_gemm_test_device(int32_t op, const uint16_t* a_dev, const uint16_t* b_dev,
+                                        const float* bias_dev, float* out_dev, int32_t n_items, int32_t n_hidden,
+                                        int32_t batch, int32_t bpad, int32_t lbo, int32_t sbo, int32_t* nsplit_out,
+                                        void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n_hidden % 64 || n_hidden > 256 || bpad % 64 || bpad > 256) return fail("bad shape");
+    const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(a_dev);
+    const __nv_bfloat16* Bm = reinterpret_cast<const __nv_bfloat16*>(b_dev);
+    if (op == 0) {
+        DecodeArgs d{};
+        d.W = A; d.h_d = Bm; d.bias = bias_dev; d.N = n_items; d.H = n_hidden; d.batch = batch; d.bpad = bpad;
+        d.n_batch_tiles = (batch + bpad - 1) / bpad; d.out = out_dev; d.ld_out = n_items; d.n_out = n_items;
+        launch_decode_predict(d, st);
+    } else if (op == 1) {
+        DwArgs w{}; w.dzT = A; w.h_dT = Bm; w.g = out_dev; w.N = n_items; w.H = n_hidden; w.bpad = bpad;
+        launch_dw(w, st);
+    } else if (op == 2) {
+        DhArgs q{}; q.dzT = A; q.W = Bm; q.partial = out_dev; q.N = n_items; q.H = n_hidden; q.bpad = bpad;
+        q.nsplit = dh_nsplit(n_items); q.lbo = lbo; q.sbo = sbo;
+        if (nsplit_out) *nsplit_out = q.nsplit;
+        launch_dh(q, st);
+    } else {
+        return fail("unknown op %d", op);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}

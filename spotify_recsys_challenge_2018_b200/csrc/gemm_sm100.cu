@@ -1,0 +1,559 @@
+// Tensor-core kernels of the DAE step for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+//   G1  k_itemtile<TRAIN|PREDICT>   Z[item, b] = W_dec[item,:] . h_d[b,:]      (DAEs.py:75 / :143)
+//         TRAIN   epilogue: +b_dec, sigmoid, weighted BCE (DAEs.py:98-99), d cost/dz (bf16, item-major),
+//                           db_dec = sum_b dz, per-CTA loss partial.  The [B,N] score matrix is never written.
+//         PREDICT epilogue: +b_dec, sigmoid (, title mix DAEs.py:180) -> y_pred[b, item] fp32
+//   G2  k_itemtile<DW>              dW_dec[item, :] = sum_b dz[item,b] h_d[b,:]  (autodiff of DAEs.py:75)
+//   G3  k_dh                        dh_d[b,:] = sum_item dz[item,b] W_dec[item,:]  (split-K over items,
+//                                   both operands MN-major straight from their item-major layouts)
+//
+// Shape of every kernel: persistent, 1 CTA / SM, 192 threads =
+//   warp 0  TMA producer (one elected lane)      -> smem ring, mbarrier full/empty
+//   warp 1  TMEM allocator + MMA issuer (one lane) -> 2 x 256-column fp32 accumulators, tcgen05.commit
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, lane == item row (G1/G2) or batch row (G3)
+// The small operand (h_d, 128 KB at B=256,H=256) stays resident in shared memory for the CTA's
+// lifetime; only the catalogue-sized operand streams through the ring, so W / dz are read from
+// HBM exactly once per kernel.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace dae {
+
+// ------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = []() -> PFN_tmapEncodeTiled {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess || p == nullptr) {
+            fprintf(stderr, "dae_b200: cuTensorMapEncodeTiled not available from the driver\n");
+            abort();
+        }
+        return reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }();
+    return fn;
+}
+
+// Row-major bf16 matrix [outer, inner]; box = [box_outer rows, 64 elements (128 B)], SWIZZLE_128B,
+// out-of-bounds elements read as zero.
+static CUtensorMap make_map_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {64, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = tmap_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "dae_b200: cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu box=%u\n", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, box_outer);
+        abort();
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// G1 / G2: item-tile kernels
+// ------------------------------------------------------------------------------------------
+enum { MODE_TRAIN = 0, MODE_PREDICT = 1, MODE_DW = 2 };
+
+constexpr int kStages = 6;
+constexpr int kABytes = kTileItems * 128;           // one K-chunk of the streamed operand: 128 rows x 128 B
+constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the resident operand: <=256 rows x 128 B
+constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
+constexpr int kSmemA = kStages * kABytes;           // 98304
+constexpr int kSmemBars = 256;
+constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + 1024;  // + alignment slack
+
+struct ItemTileDev {
+    int n_items;      // valid rows of the streamed operand
+    int tiles;        // ceil(n_items / 128)
+    int kchunks;      // K / 64
+    int n_cols;       // UMMA N: rows of the resident operand (bpad for G1, H for G2)
+    int batch;        // valid batch rows (G1)
+    int b_rows_box;   // rows per resident-operand box
+    const float* bias;
+    const uint32_t* ybits;
+    int ywords;
+    __nv_bfloat16* dzT;
+    int ld_dz;
+    float* db_dec;
+    float* loss_partial;
+    float inv_batch;
+    float* out;
+    long long ld_out;
+    int n_out;
+    const float* mix_wp;
+    const float* mix_wt;
+    const float* title_score;
+    float* g;         // G2 output [n_items, n_cols]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 1)
+k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ItemTileDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+    uint8_t* sB = smem;
+    uint8_t* sA = smem + kSmemB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemB + kSmemA);
+    uint64_t* full = bars;                 // [kStages]
+    uint64_t* empty = bars + kStages;      // [kStages]
+    uint64_t* bfull = bars + 2 * kStages;  // [1]
+    uint64_t* tfull = bfull + 1;           // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [4]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bt = blockIdx.y;  // batch tile (PREDICT only; 0 otherwise)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(bfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const uint64_t pol_stream = policy_evict_first();
+            const uint64_t pol_keep = policy_evict_last();
+            mbar_expect_tx(bfull, static_cast<uint32_t>(p.kchunks * p.b_rows_box * 128));
+            for (int kc = 0; kc < p.kchunks; ++kc)
+                tma_load_2d_hint(sB + kc * kBChunkBytes, &tmB, bfull, kc * 64, bt * p.b_rows_box, pol_keep);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], kABytes);
+                    tma_load_2d_hint(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
+                                     pol_stream);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kTileItems, static_cast<uint32_t>(p.n_cols), 0, 0);
+            mbar_wait(bfull, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+                    const uint32_t b_addr = smem_u32(sB + kc * kBChunkBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t ad = umma_smem_desc(a_addr + ks * 32, 16, 1024);
+                        const uint64_t bd = umma_smem_desc(b_addr + ks * 32, 16, 1024);
+                        umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int row_in_tile = q * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        float loss_acc = 0.f;
+        const int nchunks = p.n_cols >> 5;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int item = tile * kTileItems + row_in_tile;
+            const bool item_ok = item < p.n_items;
+            float bz = 0.f;
+            uint32_t yw_next = 0;
+            const uint32_t* yrow = nullptr;
+            if (MODE != MODE_DW) {
+                if (item_ok) bz = __ldg(p.bias + item);
+            }
+            if (MODE == MODE_TRAIN) {
+                if (item_ok) {
+                    yrow = p.ybits + (size_t)item * p.ywords;
+                    yw_next = __ldg(yrow);
+                }
+            }
+            float db = 0.f;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                tmem_ld32(t_addr + c * 32, r);
+                tmem_ld_wait();
+                if (MODE == MODE_TRAIN) {
+                    uint32_t packed[16];
+                    const uint32_t w = yw_next;
+                    if (item_ok && c + 1 < nchunks) yw_next = __ldg(yrow + c + 1);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float dzv[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int b = c * 32 + j + u;
+                            const float z = __uint_as_float(r[j + u]) + bz;
+                            const float e = __expf(-z);
+                            const float pr = __fdividef(1.f, 1.f + e);
+                            const float omp = 1.f - pr;
+                            const bool yb = (w >> (j + u)) & 1u;
+                            const float den = (yb ? pr : omp) + kEpsLog;
+                            const float wgt = yb ? 1.f : kNegWeight;
+                            const float pq = pr * omp;
+                            float ratio = yb ? omp : pr;                   // pq/den when eps is below half an ulp of den
+                            if (den < 2e-3f) ratio = __fdividef(pq, den);  // exact form near saturation (p==1.0f -> 0)
+                            const bool live = item_ok && (b < p.batch);
+                            const float lterm = -wgt * __logf(den);
+                            loss_acc += live ? lterm : 0.f;
+                            float dz = (yb ? -ratio : kNegWeight * ratio) * p.inv_batch;
+                            dz = live ? dz : 0.f;
+                            db += dz;
+                            dzv[u] = dz;
+                        }
+                        packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
+                    }
+                    if (item_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(p.dzT + (size_t)item * p.ld_dz + c * 32);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                    }
+                } else if (MODE == MODE_PREDICT) {
+                    const bool col_ok = item < p.n_out;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int b = bt * p.b_rows_box + c * 32 + j;
+                        const float z = __uint_as_float(r[j]) + bz;
+                        float pr = __fdividef(1.f, 1.f + __expf(-z));
+                        if (b < p.batch && col_ok) {
+                            const size_t o = (size_t)b * p.ld_out + item;
+                            if (p.mix_wp != nullptr) {
+                                const float ts = p.title_score ? __ldg(p.title_score + o) : 0.f;
+                                pr = ts * __ldg(p.mix_wt + b) + pr * __ldg(p.mix_wp + b);
+                            }
+                            p.out[o] = pr;   // lanes = consecutive items -> 128 B per warp store
+                        }
+                    }
+                } else {  // MODE_DW
+                    if (item_ok) {
+                        float4* dst = reinterpret_cast<float4*>(p.g + (size_t)item * p.n_cols + c * 32);
+#pragma unroll
+                        for (int v = 0; v < 8; ++v)
+                            dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    }
+                }
+            }
+            if (MODE == MODE_TRAIN) {
+                if (item_ok) p.db_dec[item] = db;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (MODE == MODE_TRAIN) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+            if (lane == 0) loss_smem[q] = loss_acc;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (MODE == MODE_TRAIN) {
+        if (threadIdx.x == 0) p.loss_partial[blockIdx.x] = (loss_smem[0] + loss_smem[1]) + (loss_smem[2] + loss_smem[3]);
+    }
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+int decode_grid(int N, int n_batch_tiles) {
+    const int tiles = (N + kTileItems - 1) / kTileItems;
+    int gx = sm_count() / (n_batch_tiles > 0 ? n_batch_tiles : 1);
+    if (gx < 1) gx = 1;
+    return tiles < gx ? tiles : gx;
+}
+
+template <int MODE>
+static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, const ItemTileDev& p, dim3 grid,
+                            cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_itemtile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+        configured = true;
+    }
+    k_itemtile<MODE><<<grid, 192, kSmemItemTile, st>>>(tmA, tmB, p);
+}
+
+static ItemTileDev decode_dev(const DecodeArgs& a) {
+    ItemTileDev p{};
+    p.n_items = a.N;
+    p.tiles = (a.N + kTileItems - 1) / kTileItems;
+    p.kchunks = a.H / 64;
+    p.n_cols = a.bpad;
+    p.batch = a.batch;
+    p.b_rows_box = a.bpad;
+    p.bias = a.bias;
+    p.ybits = a.ybits;
+    p.ywords = a.ywords;
+    p.dzT = a.dzT;
+    p.ld_dz = a.bpad;
+    p.db_dec = a.db_dec;
+    p.loss_partial = a.loss_partial;
+    p.inv_batch = a.inv_batch;
+    p.out = a.out;
+    p.ld_out = a.ld_out;
+    p.n_out = a.n_out;
+    p.mix_wp = a.mix_wp;
+    p.mix_wt = a.mix_wt;
+    p.title_score = a.title_score;
+    return p;
+}
+
+void launch_decode_train(const DecodeArgs& a, cudaStream_t st) {
+    const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
+    const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, a.bpad, a.bpad);
+    ItemTileDev p = decode_dev(a);
+    launch_itemtile<MODE_TRAIN>(tmA, tmB, p, dim3(decode_grid(a.N, 1), 1, 1), st);
+}
+
+void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
+    const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
+    const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
+    const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
+    ItemTileDev p = decode_dev(a);
+    p.n_items = a.n_out < a.N ? a.n_out : a.N;       // only the columns that are kept (tracks) are scored
+    p.tiles = (p.n_items + kTileItems - 1) / kTileItems;
+    launch_itemtile<MODE_PREDICT>(tmA, tmB, p, dim3(decode_grid(p.n_items, nbt), nbt, 1), st);
+}
+
+void launch_dw(const DwArgs& a, cudaStream_t st) {
+    const CUtensorMap tmA = make_map_bf16(a.dzT, a.bpad, a.N, kTileItems);
+    const CUtensorMap tmB = make_map_bf16(a.h_dT, a.bpad, a.H, a.H);
+    ItemTileDev p{};
+    p.n_items = a.N;
+    p.tiles = (a.N + kTileItems - 1) / kTileItems;
+    p.kchunks = a.bpad / 64;
+    p.n_cols = a.H;
+    p.b_rows_box = a.H;
+    p.g = a.g;
+    launch_itemtile<MODE_DW>(tmA, tmB, p, dim3(decode_grid(a.N, 1), 1, 1), st);
+}
+
+// ------------------------------------------------------------------------------------------
+// G3: dh = dz . W_dec, contraction over the catalogue (split-K), MN-major operands
+// ------------------------------------------------------------------------------------------
+constexpr int kDhStages = 3;
+constexpr int kDhBox = 64 * 128;                       // [64 items x 64 elements] bf16 box = 8 KB
+constexpr int kDhStageBytes = 8 * kDhBox;              // up to 4 boxes of dz + 4 boxes of W = 64 KB
+constexpr int kSmemDh = kDhStages * kDhStageBytes + 256 + 1024;
+
+struct DhDev {
+    int kchunks_total;   // ceil(N / 64)
+    int mboxes;          // bpad / 64
+    int nboxes;          // H / 64
+    int H, bpad;
+    uint32_t lbo, sbo;
+    float* partial;      // [gridDim.x, bpad, H]
+};
+
+__global__ void __launch_bounds__(192, 1)
+k_dh(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW, const DhDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDhStages * kDhStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kDhStages;
+    uint64_t* tfull = bars + 2 * kDhStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // this CTA's slice of the contraction dimension (64-item chunks)
+    const int per = (p.kchunks_total + gridDim.x - 1) / gridDim.x;
+    const int kc0 = blockIdx.x * per;
+    const int kc1 = min(kc0 + per, p.kchunks_total);
+    const int nk = max(kc1 - kc0, 0);
+    const int halves = p.bpad > 128 ? 2 : 1;
+    const int m_rows = p.bpad > 128 ? 128 : p.bpad;   // UMMA M must be 128: bpad in {64} is handled as M=128 with zero rows
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDz);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kDhStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    (void)m_rows;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t bytes = static_cast<uint32_t>((p.mboxes + p.nboxes) * kDhBox);
+            for (int k = 0; k < nk; ++k) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_expect_tx(&full[stage], bytes);
+                uint8_t* sa = smem + stage * kDhStageBytes;
+                uint8_t* sb = sa + 4 * kDhBox;
+                const int item0 = (kc0 + k) * 64;
+                for (int m = 0; m < p.mboxes; ++m) tma_load_2d_hint(sa + m * kDhBox, &tmDz, &full[stage], m * 64, item0, pol);
+                for (int n = 0; n < p.nboxes; ++n) tma_load_2d_hint(sb + n * kDhBox, &tmW, &full[stage], n * 64, item0, pol);
+                if (++stage == kDhStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, static_cast<uint32_t>(p.H), 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < nk; ++k) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + stage * kDhStageBytes);
+                const uint32_t b_addr = a_addr + 4 * kDhBox;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {          // 16 items per UMMA
+                    const uint64_t bd = umma_smem_desc(b_addr + ks * 2048, p.lbo, p.sbo);
+                    for (int hf = 0; hf < halves; ++hf) {
+                        const uint64_t ad = umma_smem_desc(a_addr + hf * 2 * kDhBox + ks * 2048, p.lbo, p.sbo);
+                        umma_bf16(tmem_base + static_cast<uint32_t>(hf * 256), ad, bd, idesc, (k | ks) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == kDhStages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        float* out = p.partial + (size_t)blockIdx.x * p.bpad * p.H;
+        if (nk > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int hf = 0; hf < halves; ++hf) {
+            const int brow = hf * 128 + q * 32 + lane;
+            for (int c = 0; c < (p.H >> 5); ++c) {
+                uint32_t r[32];
+                if (nk > 0) {
+                    tmem_ld32(tmem_base + lane_addr + static_cast<uint32_t>(hf * 256 + c * 32), r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                if (brow < p.bpad) {
+                    float4* dst = reinterpret_cast<float4*>(out + (size_t)brow * p.H + c * 32);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                             __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int dh_nsplit(int N) {
+    const int chunks = (N + 63) / 64;
+    const int sms = sm_count();
+    return chunks < sms ? chunks : sms;
+}
+
+void launch_dh(const DhArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
+        configured = true;
+    }
+    const CUtensorMap tmDz = make_map_bf16(a.dzT, a.bpad, a.N, 64);
+    const CUtensorMap tmW = make_map_bf16(a.W, a.H, a.N, 64);
+    DhDev p{};
+    p.kchunks_total = (a.N + 63) / 64;
+    p.mboxes = a.bpad / 64;
+    p.nboxes = a.H / 64;
+    p.H = a.H;
+    p.bpad = a.bpad;
+    p.lbo = a.lbo > 0 ? (uint32_t)a.lbo : (uint32_t)kDhBox;   // next 64 elements along M/N: the next box
+    p.sbo = a.sbo > 0 ? (uint32_t)a.sbo : 1024u;              // next 8 items along K
+    p.partial = a.partial;
+    k_dh<<<a.nsplit, 192, kSmemDh, st>>>(tmDz, tmW, p);
+}
+
+}  // namespace dae

@@ -1,0 +1,178 @@
+// Optimizer and parameter utilities: dense TF1-form Adam (HBM-bound, the floor of the train step),
+// Xavier-uniform init, fp32 -> bf16 shadow cast, l2 / loss reductions.
+//
+// [TF1] tf.train.AdamOptimizer (models/DAEs.py:102, :198) == ApplyAdam functor:
+//     m   += (g - m) * (1 - beta1)
+//     v   += (g*g - v) * (1 - beta2)
+//     var -= (m * alpha) / (sqrt(v) + eps),   alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+// dense on every element of every trainable variable, every step (rows with g == 0 still move).
+// Every operation is an explicitly rounded fp32 op (no FMA contraction) so the update is bit-exact
+// against the NumPy oracle given the same gradient.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace dae {
+
+struct AdamConst {
+    float alpha, omb1, omb2, eps, lambda;
+};
+
+__device__ __forceinline__ void adam_one(float& w, float& m, float& v, float g, const AdamConst c) {
+    if (c.lambda != 0.f) g = __fadd_rn(g, __fmul_rn(c.lambda, w));          // d/dw of lambda * l2_loss(w)  (DAEs.py:100)
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), c.omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), c.omb2));
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(m, c.alpha), __fadd_rn(__fsqrt_rn(v), c.eps)));
+}
+
+// n4 float4 groups; row_len4 = row_len/4 (groups per row) when row_touched != nullptr
+__global__ void __launch_bounds__(256)
+k_adam_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v, const float4* __restrict__ g,
+            uint2* __restrict__ wb, const unsigned char* __restrict__ touched, long long n4, int row_len4,
+            const AdamConst c) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (touched == nullptr || touched[i / row_len4] != 0) gv = __ldcs(g + i);
+        float4 wv = __ldcs(w + i), mv = __ldcs(m + i), vv = __ldcs(v + i);
+        adam_one(wv.x, mv.x, vv.x, gv.x, c);
+        adam_one(wv.y, mv.y, vv.y, gv.y, c);
+        adam_one(wv.z, mv.z, vv.z, gv.z, c);
+        adam_one(wv.w, mv.w, vv.w, gv.w, c);
+        __stcs(w + i, wv);
+        __stcs(m + i, mv);
+        __stcs(v + i, vv);
+        if (wb != nullptr) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(wv.x, wv.y), hi = __floats2bfloat162_rn(wv.z, wv.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned int*>(&lo);
+            pk.y = *reinterpret_cast<unsigned int*>(&hi);
+            wb[i] = pk;      // default policy: the shadow is re-read by the next step's decode
+        }
+    }
+}
+
+__global__ void k_adam_scalar(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                              const float* __restrict__ g, __nv_bfloat16* __restrict__ wb,
+                              const unsigned char* __restrict__ touched, long long begin, long long n, int row_len,
+                              const AdamConst c) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gv = 0.f;
+        if (touched == nullptr || touched[i / row_len] != 0) gv = g[i];
+        float wv = w[i], mv = m[i], vv = v[i];
+        adam_one(wv, mv, vv, gv, c);
+        w[i] = wv; m[i] = mv; v[i] = vv;
+        if (wb != nullptr) wb[i] = __float2bfloat16(wv);
+    }
+}
+
+void launch_adam(const AdamArgs& a, cudaStream_t st) {
+    AdamConst c{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
+    const bool vec_ok = (a.row_len % 4 == 0 || a.row_touched == nullptr) &&
+                        ((reinterpret_cast<uintptr_t>(a.w) | reinterpret_cast<uintptr_t>(a.m) |
+                          reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.g)) % 16 == 0);
+    long long n4 = vec_ok ? a.n / 4 : 0;
+    if (n4 > 0) {
+        long long blocks = (n4 + 255) / 256;
+        const long long cap = 148LL * 16;
+        if (blocks > cap) blocks = cap;
+        k_adam_vec4<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(a.w), reinterpret_cast<float4*>(a.m),
+                                                 reinterpret_cast<float4*>(a.v), reinterpret_cast<const float4*>(a.g),
+                                                 reinterpret_cast<uint2*>(a.w_bf16), a.row_touched, n4,
+                                                 a.row_touched ? a.row_len / 4 : 1, c);
+    }
+    const long long done = n4 * 4;
+    if (done < a.n) {
+        long long blocks = (a.n - done + 255) / 256;
+        if (blocks > 1184) blocks = 1184;
+        k_adam_scalar<<<(int)blocks, 256, 0, st>>>(a.w, a.m, a.v, a.g, a.w_bf16, a.row_touched, done, a.n,
+                                                   a.row_len > 0 ? a.row_len : 1, c);
+    }
+}
+
+// tf.contrib.layers.xavier_initializer() [TF1]: U(-l, l), l = sqrt(6 / (fan_in + fan_out))   (DAEs.py:54-55)
+__global__ void k_xavier(float* __restrict__ w, long long n, float limit, unsigned long long seed, unsigned stream_id) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float u = philox_uniform24(seed, stream_id, 0ull, static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(i));
+        w[i] = (2.f * u - 1.f) * limit;
+    }
+}
+void launch_xavier_init(float* w, long long n, float limit, unsigned long long seed, unsigned stream_id,
+                        cudaStream_t st) {
+    k_xavier<<<1184, 256, 0, st>>>(w, n, limit, seed, stream_id);
+}
+
+__global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __float2bfloat16(src[i]);
+}
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {
+    k_cast_bf16<<<1184, 256, 0, st>>>(src, dst, n);
+}
+
+// sum of squares, one partial per block (tf.nn.l2_loss = sum(t^2)/2 [TF1], DAEs.py:79-82)
+__global__ void k_sumsq(const float* __restrict__ x, long long n, float* __restrict__ partial) {
+    __shared__ double s_red[8];
+    double acc = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = x[i];
+        acc += (double)v * (double)v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+        partial[blockIdx.x] = (float)t;
+    }
+}
+void launch_sumsq(const float* x, long long n, float* partial, int nblocks, cudaStream_t st) {
+    k_sumsq<<<nblocks, 256, 0, st>>>(x, n, partial);
+}
+
+// cost = inv_batch * sum(loss partials) + lambda * 0.5 * sum(sumsq partials)      (DAEs.py:100)
+__global__ void k_reduce_loss(const float* __restrict__ partial, int n, const float* __restrict__ sq, int n_sq,
+                              float lambda_half, float inv_batch, float* __restrict__ out) {
+    __shared__ double s_red[8];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i] * (double)inv_batch;
+    for (int i = threadIdx.x; i < n_sq; i += blockDim.x) acc += (double)sq[i] * (double)lambda_half;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+        out[0] = (float)t;
+    }
+}
+void launch_reduce_loss2(const float* partial, int n, const float* sumsq_partial, int n_sq, float lambda,
+                         float inv_batch, float* loss_out, cudaStream_t st) {
+    k_reduce_loss<<<1, 256, 0, st>>>(partial, n, sumsq_partial, n_sq, 0.5f * lambda, inv_batch, loss_out);
+}
+
+// zero every gradient row whose flag is set, and the flag (rows may have been touched by any rank)
+__global__ void k_clear_flagged(int N, int H, float* __restrict__ g_enc, unsigned char* __restrict__ touched) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < N; row += gridDim.x * warps_per_block) {
+        if (touched[row] != 0) {
+            for (int k = lane; k < H; k += 32) g_enc[(size_t)row * H + k] = 0.f;
+            __syncwarp();
+            if (lane == 0) touched[row] = 0;
+        }
+    }
+}
+void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, cudaStream_t st) {
+    k_clear_flagged<<<592, 256, 0, st>>>(N, H, g_enc, touched);
+}
+
+}  // namespace dae

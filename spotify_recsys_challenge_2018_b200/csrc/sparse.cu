@@ -1,0 +1,336 @@
+// Sparse side of the DAE step: the reader's COO batch -> de-duplicated CSR, the y bitmask, the
+// encode forward (gather) and the encode backward (sparse-row scatter-add).  HBM-bound integer /
+// gather work: coalesced row reads of the item-major weight matrix, no densification.
+//
+// Reference semantics restated here:
+//   tf.sparse_tensor_to_dense(validate_indices=False)  models/DAEs.py:33-38   (duplicates: last wins)
+//   dropout + reduce_sum + divide                      models/DAEs.py:40-42
+//   encoder: matmul + bias + sigmoid + dropout         models/DAEs.py:64-70
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace dae {
+
+// ------------------------------------------------------------------------------------------
+// COO [nnz,2] int64 (row-in-batch, item) -> per-row sorted unique columns, value of the LAST
+// occurrence (utils/data_reader.py:48-54 emits "track block then artist block", so rows are not
+// contiguous in the COO list: bucket by row first).
+// ------------------------------------------------------------------------------------------
+__global__ void k_coo_count(const long long* __restrict__ pos, int nnz, int B, int N, int* __restrict__ cnt,
+                            int* __restrict__ err) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const long long r = pos[2 * (size_t)e], c = pos[2 * (size_t)e + 1];
+    if (r < 0 || r >= B || c < 0 || c >= N) {
+        atomicOr(err, kErrIndexRange);
+        return;
+    }
+    atomicAdd(&cnt[r], 1);
+}
+
+__global__ void k_row_scan(const int* __restrict__ cnt, int B, int* __restrict__ row_ptr, int* __restrict__ cursor,
+                           int* __restrict__ err) {
+    // single block; B is a few hundred to a few thousand
+    __shared__ int s_part[1024];
+    const int t = threadIdx.x;
+    const int per = (B + blockDim.x - 1) / blockDim.x;
+    const int lo = min(t * per, B), hi = min(lo + per, B);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) {
+        const int c = cnt[i];
+        if (c > kMaxRowNnz) atomicOr(err, kErrRowTooLong);
+        sum += c;
+    }
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+        const int v = (t >= o) ? s_part[t - o] : 0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    int run = s_part[t] - sum;
+    for (int i = lo; i < hi; ++i) {
+        row_ptr[i] = run;
+        cursor[i] = run;
+        run += cnt[i];
+    }
+    if (t == blockDim.x - 1) row_ptr[B] = s_part[t];
+}
+
+__global__ void k_coo_fill(const long long* __restrict__ pos, int nnz, int B, int N, int* __restrict__ cursor,
+                           unsigned long long* __restrict__ keys) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const long long r = pos[2 * (size_t)e], c = pos[2 * (size_t)e + 1];
+    if (r < 0 || r >= B || c < 0 || c >= N) return;
+    const int slot = atomicAdd(&cursor[r], 1);
+    keys[slot] = (static_cast<unsigned long long>(c) << 32) | static_cast<unsigned int>(e);
+}
+
+// One CTA per row: bitonic sort of (col, entry) keys in shared memory, keep the last entry of each
+// column run (largest entry index == last occurrence), compact.
+__global__ void __launch_bounds__(256)
+k_row_sort_dedup(const int* __restrict__ row_ptr, const unsigned long long* __restrict__ keys,
+                 const float* __restrict__ val_in, int* __restrict__ row_len, int* __restrict__ col_out,
+                 float* __restrict__ val_out) {
+    __shared__ unsigned long long s_key[kMaxRowNnz];
+    __shared__ int s_scan[256];
+    const int r = blockIdx.x;
+    const int beg = row_ptr[r];
+    int n = row_ptr[r + 1] - beg;
+    if (n > kMaxRowNnz) n = kMaxRowNnz;   // flagged by k_row_scan
+    if (n == 0) {
+        if (threadIdx.x == 0) row_len[r] = 0;
+        return;
+    }
+    int npow = 1;
+    while (npow < n) npow <<= 1;
+    for (int i = threadIdx.x; i < npow; i += blockDim.x) s_key[i] = (i < n) ? keys[beg + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_key[i], b = s_key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_key[i] = b; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // keep flags + block scan (each thread owns a contiguous span so output stays column-sorted)
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int lo = min((int)threadIdx.x * per, n), hi = min(lo + per, n);
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) {
+        const bool keep = (i == n - 1) || ((s_key[i] >> 32) != (s_key[i + 1] >> 32));
+        mine += keep ? 1 : 0;
+    }
+    s_scan[threadIdx.x] = mine;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+        const int v = (threadIdx.x >= o) ? s_scan[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int w = s_scan[threadIdx.x] - mine;
+    for (int i = lo; i < hi; ++i) {
+        const bool keep = (i == n - 1) || ((s_key[i] >> 32) != (s_key[i + 1] >> 32));
+        if (keep) {
+            col_out[beg + w] = static_cast<int>(s_key[i] >> 32);
+            val_out[beg + w] = val_in[static_cast<unsigned int>(s_key[i] & 0xFFFFFFFFull)];
+            ++w;
+        }
+    }
+    if (threadIdx.x == blockDim.x - 1) row_len[r] = s_scan[threadIdx.x];
+}
+
+void launch_coo_to_csr(const long long* pos, const float* val, int nnz, int B, int N, CsrWork w, int* err,
+                       cudaStream_t st) {
+    cudaMemsetAsync(w.cnt, 0, sizeof(int) * B, st);
+    if (nnz > 0) k_coo_count<<<(nnz + 255) / 256, 256, 0, st>>>(pos, nnz, B, N, w.cnt, err);
+    k_row_scan<<<1, 1024, 0, st>>>(w.cnt, B, w.row_ptr, w.cursor, err);
+    if (nnz > 0) k_coo_fill<<<(nnz + 255) / 256, 256, 0, st>>>(pos, nnz, B, N, w.cursor, w.keys);
+    k_row_sort_dedup<<<B, 256, 0, st>>>(w.row_ptr, w.keys, val, w.row_len, w.col, w.val);
+}
+
+// y as an item-major bitmask: bit b of ybits[item*ywords + b/32] == y[b, item] (y in {0,1}; the
+// runner feeds ones, main_train.py:206).  set=1 writes the bits, set=0 clears the same words.
+__global__ void k_ybits(const int* __restrict__ row_ptr, const int* __restrict__ row_len, const int* __restrict__ col,
+                        const float* __restrict__ val, int B, uint32_t* __restrict__ ybits, int ywords, int set,
+                        int* __restrict__ err) {
+    const int r = blockIdx.x;
+    const int beg = row_ptr[r], n = row_len[r];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = col[beg + i];
+        uint32_t* wp = ybits + (size_t)c * ywords + (r >> 5);
+        if (set) {
+            const float v = val[beg + i];
+            if (v == 1.0f) atomicOr(wp, 1u << (r & 31));
+            else if (v != 0.0f) atomicOr(err, kErrYNotBinary);
+        } else {
+            *wp = 0u;
+        }
+    }
+}
+
+void launch_ybits_set(const CsrWork& y, int B, uint32_t* ybits, int ywords, int set, int* err, cudaStream_t st) {
+    k_ybits<<<B, 128, 0, st>>>(y.row_ptr, y.row_len, y.col, y.val, B, ybits, ywords, set, err);
+}
+
+// ------------------------------------------------------------------------------------------
+// encode forward: one CTA per playlist row, blockDim = H threads (H <= 256), thread k owns
+// hidden unit k; every gathered W_enc row is one fully coalesced H*4-byte read.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += s_red[i];   // fixed order: deterministic
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const int* __restrict__ row_ptr,
+             const int* __restrict__ row_len, const int* __restrict__ col, float* __restrict__ val,
+             float* __restrict__ rowsum, float* __restrict__ h, __nv_bfloat16* __restrict__ h_d,
+             __nv_bfloat16* __restrict__ h_dT, int B, int bpad, int H, float kp, float kp_in,
+             unsigned long long seed, unsigned long long step, int row_offset) {
+    __shared__ float s_x[kMaxRowNnz];
+    __shared__ int s_c[kMaxRowNnz];
+    __shared__ float s_red[8];
+    const int r = blockIdx.x;
+    const int k = threadIdx.x;
+    if (r >= B) {   // padding rows of the tensor-core operand
+        if (k < H) {
+            h_d[(size_t)r * H + k] = __float2bfloat16(0.f);
+            h_dT[(size_t)k * bpad + r] = __float2bfloat16(0.f);
+        }
+        return;
+    }
+    const int beg = row_ptr[r], n = row_len[r];
+    const uint32_t grow = static_cast<uint32_t>(r + row_offset);
+    // a3: x_d = x / kp_in * keep ; s = sum x_d
+    float part = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = col[beg + i];
+        const float v = val[beg + i];
+        const bool keep = philox_keep(seed, kStreamInput, step, grow, static_cast<uint32_t>(c), kp_in);
+        const float xd = keep ? __fdiv_rn(v, kp_in) : 0.f;
+        s_x[i] = xd;
+        s_c[i] = c;
+        part += xd;
+    }
+    const float s = block_sum(part, s_red);
+    const float inv = __fdiv_rn(1.f, s + kEpsLog);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float xn = __fdiv_rn(s_x[i], s + kEpsLog);
+        s_x[i] = xn;
+        val[beg + i] = xn;            // x_n is reused by the backward scatter
+    }
+    (void)inv;
+    if (threadIdx.x == 0) rowsum[r] = s;
+    __syncthreads();
+    if (k >= H) return;
+    // a4: a = sum_j x_n[j] * W_enc[col_j, k]   (4 independent accumulators -> 4 loads in flight)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const float x0 = s_x[i], x1 = s_x[i + 1], x2 = s_x[i + 2], x3 = s_x[i + 3];
+        const float w0 = x0 != 0.f ? __ldg(W + (size_t)s_c[i] * H + k) : 0.f;
+        const float w1 = x1 != 0.f ? __ldg(W + (size_t)s_c[i + 1] * H + k) : 0.f;
+        const float w2 = x2 != 0.f ? __ldg(W + (size_t)s_c[i + 2] * H + k) : 0.f;
+        const float w3 = x3 != 0.f ? __ldg(W + (size_t)s_c[i + 3] * H + k) : 0.f;
+        a0 = fmaf(x0, w0, a0);
+        a1 = fmaf(x1, w1, a1);
+        a2 = fmaf(x2, w2, a2);
+        a3 = fmaf(x3, w3, a3);
+    }
+    for (; i < n; ++i) {
+        const float x0 = s_x[i];
+        if (x0 != 0.f) a0 = fmaf(x0, __ldg(W + (size_t)s_c[i] * H + k), a0);
+    }
+    const float a = ((a0 + a1) + (a2 + a3)) + b_enc[k];
+    const float hv = __fdividef(1.f, 1.f + __expf(-a));
+    const bool keep = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(k), kp);
+    const float hd = keep ? __fdiv_rn(hv, kp) : 0.f;
+    h[(size_t)r * H + k] = hv;
+    const __nv_bfloat16 hb = __float2bfloat16(hd);
+    h_d[(size_t)r * H + k] = hb;
+    h_dT[(size_t)k * bpad + r] = hb;
+}
+
+void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st) {
+    const int threads = a.H <= 64 ? 64 : (a.H <= 128 ? 128 : 256);
+    k_encode_fwd<<<a.bpad, threads, 0, st>>>(a.W_enc, a.b_enc, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val, a.rowsum,
+                                             a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.kp, a.kp_in, a.seed, a.step,
+                                             a.row_offset);
+}
+
+// ------------------------------------------------------------------------------------------
+// encode backward: reduce the split-K partials of dh, da = dh * (keep/kp) * h(1-h), then the
+// sparse-row scatter-add dW_enc[col_j,:] += x_n[j] * da[row,:]  (coalesced fp32 reductions).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_encode_bwd(const float* __restrict__ dh_partial, int nsplit, const float* __restrict__ h,
+             const int* __restrict__ row_ptr, const int* __restrict__ row_len, const int* __restrict__ col,
+             const float* __restrict__ xn, float* __restrict__ da_out, float* __restrict__ g_enc,
+             unsigned char* __restrict__ touched, int B, int bpad, int H, float kp, unsigned long long seed,
+             unsigned long long step, int row_offset) {
+    const int r = blockIdx.x;
+    const int k = threadIdx.x;
+    if (k >= H) return;
+    float dh = 0.f;
+    const size_t stride = (size_t)bpad * H;
+    const float* p = dh_partial + (size_t)r * H + k;
+    int s = 0;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    for (; s + 4 <= nsplit; s += 4) {
+        d0 += p[(size_t)s * stride];
+        d1 += p[(size_t)(s + 1) * stride];
+        d2 += p[(size_t)(s + 2) * stride];
+        d3 += p[(size_t)(s + 3) * stride];
+    }
+    for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
+    dh = (d0 + d1) + (d2 + d3);
+    const float hv = h[(size_t)r * H + k];
+    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(r + row_offset),
+                                  static_cast<uint32_t>(k), kp);
+    const float da = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
+    da_out[(size_t)r * H + k] = da;
+    const int beg = row_ptr[r], n = row_len[r];
+    for (int i = 0; i < n; ++i) {
+        const float x = xn[beg + i];
+        if (x != 0.f) {
+            const int c = col[beg + i];
+            atomicAdd(g_enc + (size_t)c * H + k, x * da);
+            if (touched != nullptr && k == 0) touched[c] = 1;
+        }
+    }
+}
+
+__global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= H) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += x[(size_t)r * H + k];
+    out[k] = s;
+}
+
+void launch_encode_bwd(const EncodeBwdArgs& a, cudaStream_t st) {
+    const int threads = a.H <= 64 ? 64 : (a.H <= 128 ? 128 : 256);
+    k_encode_bwd<<<a.B, threads, 0, st>>>(a.dh_partial, a.nsplit, a.h, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val,
+                                          a.da, a.g_enc, a.touched, a.B, a.bpad, a.H, a.kp, a.seed, a.step,
+                                          a.row_offset);
+    k_colsum<<<(a.H + 63) / 64, 64, 0, st>>>(a.da, a.B, a.H, a.db_enc);
+}
+
+// zero the rows of g_enc that the step touched (and their flags) so the buffer is clean again
+__global__ void k_clear_touched(const int* __restrict__ row_ptr, const int* __restrict__ row_len,
+                                const int* __restrict__ col, int H, float* __restrict__ g_enc,
+                                unsigned char* __restrict__ touched) {
+    const int r = blockIdx.x;
+    const int beg = row_ptr[r], n = row_len[r];
+    for (int i = 0; i < n; ++i) {
+        const int c = col[beg + i];
+        for (int k = threadIdx.x; k < H; k += blockDim.x) g_enc[(size_t)c * H + k] = 0.f;
+        if (threadIdx.x == 0) touched[c] = 0;
+    }
+}
+
+void launch_clear_touched(const CsrWork& x, int B, int H, float* g_enc, unsigned char* touched, cudaStream_t st) {
+    k_clear_touched<<<B, 256, 0, st>>>(x.row_ptr, x.row_len, x.col, H, g_enc, touched);
+}
+
+}  // namespace dae

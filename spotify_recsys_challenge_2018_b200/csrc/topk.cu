@@ -1,0 +1,232 @@
+// Seed-masked top-K ranking (K6).
+//
+// Restates utils/metrics.py:58-68 (single_eval) and main_runner/main_challenge.py:26-36
+// (cand_generate): argsort(-scores[:T]) -> drop every seed id -> first K.  The reference's argsort
+// is unstable, so ties are undefined upstream; the canonical order here is (score desc, index asc).
+//
+// One CTA per playlist row.  Exact 3-pass radix select (12+12+8 bits of the order-preserving key)
+// finds the (K + #seeds)-th largest score, the survivors (<= 2048) are sorted in shared memory,
+// seeds are removed and the first K are written.  Nothing of size T is ever sorted.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "kernels.h"
+
+namespace dae {
+
+constexpr int kTopkThreads = 1024;
+constexpr int kCandMax = 2048;
+
+__device__ __forceinline__ uint32_t score_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // monotone: larger score -> larger key
+}
+__device__ __forceinline__ float key_score(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+}
+
+// histogram increment with warp aggregation (scores cluster in a few bins -> avoid same-address atomics)
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t digit, bool active) {
+    const uint32_t amask = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const uint32_t peers = __match_any_sync(amask, digit);
+    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], __popc(peers));
+}
+
+// Whole block: largest bin b with sum_{d>=b} hist[d] >= want.  Returns via smem: s_out[0]=b, s_out[1]=sum_{d>b}.
+__device__ void select_bin(const uint32_t* hist, int nbins, uint32_t want, uint32_t* s_warp, uint32_t* s_out) {
+    const int t = threadIdx.x;
+    const int per = nbins / kTopkThreads > 0 ? nbins / kTopkThreads : 1;
+    const int nthreads_used = nbins / per;
+    // thread t owns bins [hi - per + 1, hi] counted from the top
+    uint32_t mine = 0;
+    const int top = nbins - 1 - t * per;
+    if (t < nthreads_used)
+        for (int j = 0; j < per; ++j) mine += hist[top - j];
+    // inclusive scan over threads (thread 0 = highest bins)
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < (t >> 5); ++w) base += s_warp[w];
+    incl += base;
+    const uint32_t excl = incl - mine;
+    if (t < nthreads_used && excl < want && incl >= want) {
+        uint32_t run = excl;
+        for (int j = 0; j < per; ++j) {
+            const uint32_t h = hist[top - j];
+            if (run + h >= want) { s_out[0] = top - j; s_out[1] = run; break; }
+            run += h;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTopkThreads, 1)
+k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* __restrict__ seed_ptr,
+       const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score) {
+    __shared__ uint32_t s_hist[4096];
+    __shared__ unsigned long long s_cand[kCandMax];
+    __shared__ int s_seed[kCandMax];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_out[2];
+    __shared__ uint32_t s_cnt[2];
+    const int row = blockIdx.x;
+    const int t = threadIdx.x;
+    const float* x = scores + (size_t)row * ld;
+
+    int nseed = 0;
+    if (seed_ptr != nullptr) {
+        const int sb = seed_ptr[row];
+        nseed = min(seed_ptr[row + 1] - sb, kCandMax - K > 0 ? kCandMax - K : 0);
+        for (int i = t; i < nseed; i += kTopkThreads) s_seed[i] = seed_idx[sb + i] - idx_base;
+    }
+    uint32_t want = (uint32_t)min(K + nseed, T);
+    if (want > (uint32_t)kCandMax) want = kCandMax;
+    const uint32_t want0 = want;
+
+    // ---- pass 1..3: radix select of the want-th largest key -------------------------------
+    uint32_t prefix = 0;      // selected high bits so far
+    uint32_t above_total = 0; // elements strictly above the final threshold
+    const int shifts[3] = {20, 8, 0};
+    const int nbins[3] = {4096, 4096, 256};
+    const uint32_t masks[3] = {0xFFFu, 0xFFFu, 0xFFu};
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = t; i < nbins[pass]; i += kTopkThreads) s_hist[i] = 0;
+        __syncthreads();
+        const int sh = shifts[pass];
+        const int Tround = (T + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
+        for (int i = t; i < Tround; i += kTopkThreads) {
+            bool act = i < T;
+            uint32_t key = 0;
+            if (act) key = score_key(x[i]);
+            if (pass == 1) act = act && ((key >> 20) == prefix);
+            if (pass == 2) act = act && ((key >> 8) == prefix);
+            hist_add(s_hist, (key >> sh) & masks[pass], act);
+        }
+        __syncthreads();
+        select_bin(s_hist, nbins[pass], want, s_warp, s_out);
+        const uint32_t bin = s_out[0], above = s_out[1];
+        above_total += above;
+        want -= above;
+        prefix = (pass == 0) ? bin : ((prefix << (pass == 1 ? 12 : 8)) | bin);
+        __syncthreads();
+    }
+    const uint32_t thr = prefix;          // full 32-bit key of the want0-th largest element
+    const uint32_t need_eq = want;        // how many elements equal to thr are needed (>= 1)
+
+    // ---- collect: all keys > thr (any order) + the need_eq lowest-index keys == thr ---------
+    if (t == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+    __syncthreads();
+    const int Tround = (T + kTopkThreads - 1) / kTopkThreads * kTopkThreads;
+    uint32_t eq_seen = 0;                 // block-uniform running count of == thr elements
+    for (int i = t; i < Tround; i += kTopkThreads) {
+        uint32_t key = 0;
+        const bool in = i < T;
+        if (in) key = score_key(x[i]);
+        if (in && key > thr) {
+            const uint32_t slot = atomicAdd(&s_cnt[0], 1u);
+            if (slot < (uint32_t)kCandMax)
+                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)i);
+        }
+        if (eq_seen < need_eq) {          // ordered pick among ties: chunk-ordered block scan
+            const bool eq = in && key == thr;
+            const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+            const uint32_t wrank = __popc(bal & ((1u << (t & 31)) - 1u));
+            if ((t & 31) == 0) s_warp[t >> 5] = __popc(bal);
+            __syncthreads();
+            uint32_t base = 0, total = 0;
+            for (int w = 0; w < 32; ++w) {
+                const uint32_t c = s_warp[w];
+                if (w < (t >> 5)) base += c;
+                total += c;
+            }
+            const uint32_t rank = eq_seen + base + wrank;
+            if (eq && rank < need_eq) {
+                const uint32_t slot = (want0 - need_eq) + rank;   // ties go after the strictly-greater block
+                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)i);
+            }
+            eq_seen += total;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // slots [0, want0-need_eq) hold keys > thr (count == above_total == want0-need_eq), then the ties
+    (void)above_total;
+    const int ncand = (int)want0;
+    int npow = 1;
+    while (npow < ncand) npow <<= 1;
+    for (int i = ncand + t; i < npow; i += kTopkThreads) s_cand[i] = 0ull;
+    __syncthreads();
+    // ---- bitonic sort, descending on (key, ~idx) => score desc, index asc ----------------------
+    for (int k = 2; k <= npow; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < npow; i += kTopkThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_cand[i], b = s_cand[ixj];
+                    const bool desc = (i & k) == 0;
+                    if ((a < b) == desc) { s_cand[i] = b; s_cand[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- drop seeds, ordered compaction, first K --------------------------------------------------
+    // each thread owns 2 consecutive candidates (kCandMax / kTopkThreads)
+    uint32_t keepf[2] = {0, 0};
+    for (int u = 0; u < 2; ++u) {
+        const int i = t * 2 + u;
+        if (i < ncand) {
+            const int idx = (int)(0xFFFFFFFFu - (uint32_t)(s_cand[i] & 0xFFFFFFFFull));
+            bool is_seed = false;
+            for (int s = 0; s < nseed; ++s) is_seed |= (s_seed[s] == idx);
+            keepf[u] = is_seed ? 0u : 1u;
+        }
+    }
+    uint32_t mine = keepf[0] + keepf[1];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    __syncthreads();
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < (t >> 5)) base += c;
+        total += c;
+    }
+    uint32_t pos = base + incl - mine;
+    for (int u = 0; u < 2; ++u) {
+        if (keepf[u]) {
+            if (pos < (uint32_t)K) {
+                const unsigned long long c = s_cand[t * 2 + u];
+                out_idx[(size_t)row * K + pos] = (int)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull)) + idx_base;
+                out_score[(size_t)row * K + pos] = key_score((uint32_t)(c >> 32));
+            }
+            ++pos;
+        }
+    }
+    for (int i = (int)total + t; i < K; i += kTopkThreads) {   // fewer than K candidates: pad
+        out_idx[(size_t)row * K + i] = -1;
+        out_score[(size_t)row * K + i] = -CUDART_INF_F;
+    }
+}
+
+void launch_topk(const TopkArgs& a, cudaStream_t st) {
+    k_topk<<<a.B, kTopkThreads, 0, st>>>(a.scores, a.ld, a.T, a.k, a.seed_ptr, a.seed_idx, a.idx_base, a.out_idx,
+                                         a.out_score);
+}
+
+}  // namespace dae

@@ -1,0 +1,215 @@
+"""DAE_tied / DAE / DAE_title over libdae_b200.so -- host mirror of the reference's models/DAEs.py.
+
+Same class names, constructor signatures and `conf` fields as the reference
+(models/DAEs.py:13-21, :114-117, :153-156); `fit()` builds the device model instead of a TF graph;
+`sess.run([optimizer, cost], feed_dict)` becomes `train_step(...)`, `sess.run(y_pred, feed_dict)`
+becomes `predict(...)`, and `recommend(...)` fuses the ranking the runners do on the host
+(utils/metrics.py:58-68).  `save_model()` writes the reference's 4-array pickle (DAEs.py:107-111).
+
+No compute happens in Python and there is no CPU path: every method calls the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pickle
+
+import numpy as np
+
+from .. import _lib
+
+
+def _coo(positions, vals):
+    """Reader output -> contiguous int64 [nnz,2] + float32 [nnz].  The reference readers emit
+    float64 positions whenever a batch row is empty and Python lists for values."""
+    pos = np.ascontiguousarray(np.asarray(positions).reshape(-1, 2), dtype=np.int64)
+    val = np.ascontiguousarray(np.asarray(vals, dtype=np.float32).reshape(-1))
+    if pos.shape[0] != val.shape[0]:
+        raise ValueError("positions (%d) and values (%d) differ in length" % (pos.shape[0], val.shape[0]))
+    return pos, val
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class DAE_tied:
+    """Tied-weight DAE used by --pretrain (reference models/DAEs.py:13-111)."""
+
+    tied = True
+    trainable = True
+
+    def __init__(self, conf):
+        self.save_dir = conf.save                         # DAEs.py:15
+        self.n_batch = int(conf.batch)                    # DAEs.py:17
+        self.n_input = int(conf.n_input)                  # DAEs.py:18
+        self.n_hidden = int(conf.hidden)                  # DAEs.py:19
+        self.learning_rate = float(conf.lr)               # DAEs.py:20
+        self.reg_lambda = float(conf.reg_lambda)          # DAEs.py:21
+        self.n_tracks = int(getattr(conf, "n_tracks", self.n_input))
+        self.seed = int(getattr(conf, "seed", 0))
+        self.device = int(getattr(conf, "device", 0))
+        self.stream = getattr(conf, "stream", None)
+        self._h = None
+        self._lib = None
+
+    # ---- lifecycle ---------------------------------------------------------------
+    def _create(self):
+        lib = _lib.load()
+        cfg = _lib.DaeConfig(self.n_input, self.n_tracks, self.n_hidden, self.n_batch, int(self.tied),
+                             self.learning_rate, self.reg_lambda, self.seed, self.device, int(self.trainable),
+                             self.stream)
+        h = C.c_void_p()
+        _lib.check(lib.dae_model_create(C.byref(cfg), C.byref(h)))
+        self._h, self._lib = h, lib
+
+    def init_weight(self):
+        """Xavier-uniform W, zero biases (DAEs.py:53-61)."""
+        _lib.check(self._lib.dae_model_init_xavier(self._h, self.seed))
+
+    def fit(self):
+        """Build the model on the device and initialise it (DAEs.py:84-105 + sess.run(init_op))."""
+        self._create()
+        self.init_weight()
+        return self
+
+    def close(self):
+        if self._h is not None:
+            self._lib.dae_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ----------------------------------------------------------------
+    def set_params(self, params):
+        W_enc, W_dec, b_enc, b_dec = [np.ascontiguousarray(p, dtype=np.float32) for p in params]
+        if W_enc.shape != (self.n_input, self.n_hidden) or b_enc.shape != (self.n_hidden,) \
+                or b_dec.shape != (self.n_input,) or W_dec.shape != W_enc.shape:
+            raise ValueError("parameter shapes do not match the model")
+        _lib.check(self._lib.dae_model_set_params(self._h, _ptr(W_enc), _ptr(W_dec), _ptr(b_enc), _ptr(b_dec)))
+
+    def get_params(self):
+        """d_params order: [encoder_h, decoder_h (== encoder_h when tied), encoder_b, decoder_b] (DAEs.py:60-61)."""
+        W_enc = np.empty((self.n_input, self.n_hidden), np.float32)
+        b_enc = np.empty(self.n_hidden, np.float32)
+        b_dec = np.empty(self.n_input, np.float32)
+        if self.tied:
+            _lib.check(self._lib.dae_model_get_params(self._h, _ptr(W_enc), None, _ptr(b_enc), _ptr(b_dec)))
+            W_dec = W_enc
+        else:
+            W_dec = np.empty_like(W_enc)
+            _lib.check(self._lib.dae_model_get_params(self._h, _ptr(W_enc), _ptr(W_dec), _ptr(b_enc), _ptr(b_dec)))
+        return [W_enc, W_dec, b_enc, b_dec]
+
+    def save_model(self, sess=None):
+        """pickle.dump(sess.run(d_params)) (DAEs.py:107-111); `sess` accepted and ignored."""
+        with open(self.save_dir, "wb") as f:
+            pickle.dump(self.get_params(), f)
+
+    # ---- the hot path -----------------------------------------------------------------
+    def train_step(self, x_positions, x_vals, y_positions, y_vals, keep_prob, input_keep_prob):
+        """One `sess.run([optimizer, cost])` (main_train.py:204-213) -> cost (float)."""
+        xp, xv = _coo(x_positions, x_vals)
+        yp, yv = _coo(y_positions, y_vals)
+        cost = C.c_float()
+        _lib.check(self._lib.dae_model_train_step(self._h, _ptr(xp), _ptr(xv), xp.shape[0], _ptr(yp), _ptr(yv),
+                                                  yp.shape[0], self.n_batch, float(keep_prob),
+                                                  float(input_keep_prob), C.byref(cost)))
+        return float(cost.value)
+
+    def predict(self, x_positions, x_vals, tracks_only=False):
+        """`sess.run(y_pred, keep_prob=1, input_keep_prob=1)` (main_train.py:66-68) -> [batch, n_input]
+        (or [batch, n_tracks], the slice the runner keeps, main_train.py:86)."""
+        xp, xv = _coo(x_positions, x_vals)
+        n_cols = self.n_tracks if tracks_only else self.n_input
+        out = np.empty((self.n_batch, n_cols), np.float32)
+        _lib.check(self._lib.dae_model_predict(self._h, _ptr(xp), _ptr(xv), xp.shape[0], self.n_batch, n_cols,
+                                               _ptr(out)))
+        return out
+
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False):
+        """Top-k track ids per playlist with the seeds removed (metrics.py:58-68, main_challenge.py:26-36),
+        decode + ranking on the device.  `seeds`: list of per-row seed id lists.  -> int32 [batch, k]."""
+        xp, xv = _coo(x_positions, x_vals)
+        seed_ptr = np.zeros(self.n_batch + 1, np.int32)
+        lens = [len(s) for s in seeds]
+        seed_ptr[1:len(lens) + 1] = np.cumsum(lens)
+        seed_ptr[len(lens) + 1:] = seed_ptr[len(lens)]
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int64).reshape(-1) for s in seeds])
+                                    if lens and sum(lens) else np.zeros(0, np.int64))
+        flat = np.clip(flat, -1, 2 ** 31 - 1).astype(np.int32)
+        idx = np.empty((self.n_batch, k), np.int32)
+        sc = np.empty((self.n_batch, k), np.float32) if return_scores else None
+        _lib.check(self._lib.dae_model_recommend(self._h, _ptr(xp), _ptr(xv), xp.shape[0], self.n_batch,
+                                                 _ptr(seed_ptr), _ptr(flat), int(k), _ptr(idx), _ptr(sc)))
+        return (idx, sc) if return_scores else idx
+
+    # ---- staged / asynchronous surface (bench, data-parallel trainer) -------------------
+    def stage_batch(self, slot, x_positions, x_vals, y_positions, y_vals):
+        xp, xv = _coo(x_positions, x_vals)
+        yp, yv = _coo(y_positions, y_vals)
+        _lib.check(self._lib.dae_model_stage_batch(self._h, slot, _ptr(xp), _ptr(xv), xp.shape[0], _ptr(yp),
+                                                   _ptr(yv), yp.shape[0], self.n_batch))
+
+    def train_step_staged(self, slot, keep_prob, input_keep_prob):
+        _lib.check(self._lib.dae_model_train_step_staged(self._h, slot, float(keep_prob), float(input_keep_prob)))
+
+    def backward_staged(self, slot, keep_prob, input_keep_prob, global_batch=0, row_offset=0):
+        _lib.check(self._lib.dae_model_backward_staged(self._h, slot, float(keep_prob), float(input_keep_prob),
+                                                       int(global_batch), int(row_offset)))
+
+    def apply_adam(self):
+        _lib.check(self._lib.dae_model_apply_adam(self._h))
+
+    def sync_cost(self):
+        cost = C.c_float()
+        _lib.check(self._lib.dae_model_sync_cost(self._h, C.byref(cost)))
+        return float(cost.value)
+
+    def launch_count(self):
+        return int(self._lib.dae_model_launch_count(self._h))
+
+    def buffer(self, name):
+        """(device pointer, n_elem, elem_size) of a named internal buffer (include/dae_b200.h)."""
+        p = C.c_void_p(); n = C.c_int64(); s = C.c_int32()
+        _lib.check(self._lib.dae_model_buffer(self._h, name.encode(), C.byref(p), C.byref(n), C.byref(s)))
+        return p.value, n.value, s.value
+
+
+class DAE(DAE_tied):
+    """Untied DAE used by --dae, optionally initialised from a pickle (reference models/DAEs.py:114-150)."""
+
+    tied = False
+
+    def __init__(self, conf):
+        DAE_tied.__init__(self, conf)
+        self.initval_dir = conf.initval                   # DAEs.py:117
+
+    def init_weight(self):
+        # DAEs.py:120-135 ('NULL' may arrive joined under --dir, main.py:44)
+        if self.initval_dir == "NULL" or str(self.initval_dir).endswith("NULL"):
+            _lib.check(self._lib.dae_model_init_xavier(self._h, self.seed))
+        else:
+            with open(self.initval_dir, "rb") as f:
+                emb = pickle.load(f)
+            self.set_params(emb)
+
+
+class DAE_title(DAE):
+    """Frozen DAE whose scores are mixed with a title model's scores (reference models/DAEs.py:153-201).
+
+    The DAE weights come from conf.DAEval and are constants (DAEs.py:164-171): the device model is
+    created inference-only.  The mixing weights follow DAEs.py:159-162:
+        x_count = rowsum(x_dropout) * input_keep_prob ; w_t = u / (u + x_count + 1e-10) ; w_p = x_count / (...)
+    """
+
+    trainable = False
+
+    def __init__(self, conf, title_score=None):
+        DAE_tied.__init__(self, conf)
+        self.DAEval_dir = conf.DAEval                     # DAEs.py:156
+        self.initval_dir = conf.DAEval
+        self.title_score = title_score

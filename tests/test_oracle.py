@@ -1,0 +1,222 @@
+"""CPU tests: the oracle against its pins (golden vectors from the reference, known-answer cases,
+independent derivations).  No GPU, no /root/reference at run time."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dae_oracle as O
+from oracle import philox, ranking
+from oracle.tf1_graph_cpu import TF1GraphCPU
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---------------------------------------------------------------- Philox: Random123 known answers
+@pytest.mark.parametrize("ctr,key,out", [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+])
+def test_philox_kat(ctr, key, out):
+    r = philox.philox4x32_10(*ctr, *key)
+    assert tuple(int(x) for x in r) == out
+
+
+def test_keep_mask_rate_and_identity():
+    rows, cols = np.meshgrid(np.arange(200, dtype=np.uint32), np.arange(500, dtype=np.uint32), indexing="ij")
+    m = philox.keep_mask(7, philox.STREAM_INPUT, 3, rows, cols, 0.75)
+    assert abs(m.mean() - 0.75) < 0.01
+    assert philox.keep_mask(7, 0, 3, rows, cols, 1.0).all()
+    m2 = philox.keep_mask(7, philox.STREAM_INPUT, 4, rows, cols, 0.75)
+    assert (m != m2).any()
+
+
+# ---------------------------------------------------------------- a2: densify, last wins
+def test_densify_last_wins_and_csr_agree():
+    rng = np.random.default_rng(0)
+    B, N = 6, 15
+    pos = np.stack([rng.integers(0, B, 80), rng.integers(0, N, 80)], 1)
+    val = rng.integers(0, 3, 80).astype(np.float32)
+    dense = O.densify_last_wins(pos, val, B, N)
+    # hand check of one duplicate
+    pos2 = np.array([[0, 2], [0, 2], [1, 1]]); val2 = np.array([1.0, 0.0, 5.0], np.float32)
+    d2 = O.densify_last_wins(pos2, val2, 2, 3)
+    assert d2[0, 2] == 0.0 and d2[1, 1] == 5.0 and d2.sum() == 5.0
+    row_ptr, col, v = O.coo_to_csr_last_wins(pos, val, B, N)
+    rebuilt = np.zeros((B, N), np.float32)
+    rebuilt[O.csr_rows(row_ptr), col] = v
+    assert np.array_equal(rebuilt, dense)
+    for r in range(B):      # sorted unique columns per row
+        c = col[row_ptr[r]:row_ptr[r + 1]]
+        assert np.all(np.diff(c) > 0)
+
+
+def test_empty_rows_and_empty_batch():
+    row_ptr, col, v = O.coo_to_csr_last_wins(np.zeros((0, 2)), [], 4, 10)
+    assert row_ptr.tolist() == [0] * 5 and col.size == 0
+    # float64 positions as the reference emits for batches with an empty row
+    row_ptr, col, v = O.coo_to_csr_last_wins(np.array([[2.0, 3.0]]), [1.0], 4, 10)
+    assert row_ptr.tolist() == [0, 0, 0, 1, 1] and col.tolist() == [3]
+
+
+# ---------------------------------------------------------------- known-answer: tiny forward / loss (B=2,N=5,H=2)
+def test_known_answer_tiny_forward_loss():
+    W = np.array([[0.1, -0.2], [0.3, 0.4], [-0.5, 0.6], [0.7, -0.8], [0.9, 1.0]], np.float32)
+    b_enc = np.array([0.05, -0.05], np.float32)
+    b_dec = np.array([0.0, 0.1, -0.1, 0.2, -0.2], np.float32)
+    m = O.DAEOracle(5, 2, lr=0.01, tied=True, params=[W, W, b_enc, b_dec])
+    x_pos = np.array([[0, 0], [0, 2], [1, 4]]); x_val = [1, 1, 1]
+    f = m.forward(x_pos, x_val, 2)
+    # row 0: x_n = [.5, 0, .5, 0, 0]; row 1: [0,0,0,0,1]
+    a0 = 0.5 * W[0] + 0.5 * W[2] + b_enc
+    a1 = W[4] + b_enc
+    sig = lambda t: 1 / (1 + np.exp(-t))
+    h = np.stack([sig(a0), sig(a1)])
+    np.testing.assert_allclose(f["h"], h, rtol=1e-6)
+    p = sig(h @ W.T + b_dec)
+    np.testing.assert_allclose(f["p"], p, rtol=1e-5)
+    y = O.densify_last_wins(np.array([[0, 0], [0, 2], [0, 3], [1, 4], [1, 1]]), np.ones(5), 2, 5)
+    L = -(y * np.log(p + 1e-10) + 0.55 * (1 - y) * np.log(1 - p + 1e-10)).sum(1)
+    np.testing.assert_allclose(O.bce_rows(f["p"], y), L, rtol=1e-5)
+
+
+def test_sigmoid_saturation_fp32():
+    # sigma(17) == 1.0f, so log(1-p+eps) clamps at log(1e-10) and p(1-p) == 0
+    p = O.sigmoid32(np.array([17.0], np.float32))
+    assert p[0] == np.float32(1.0)
+    dz = O.bce_dz(p, np.zeros(1, np.float32), 1.0)
+    assert dz[0] == 0.0
+    L = O.bce_rows(p.reshape(1, 1), np.zeros((1, 1), np.float32))
+    np.testing.assert_allclose(L, 0.55 * 23.02585, rtol=1e-5)
+
+
+# ---------------------------------------------------------------- a7: closed-form backward vs autograd (fp64)
+@pytest.mark.parametrize("tied", [True, False])
+def test_backward_matches_autograd(tied):
+    rng = np.random.default_rng(1)
+    B, N, H = 4, 12, 3
+    m = O.DAEOracle(N, H, lr=0.01, tied=tied, seed=3)
+    m.b_enc[:] = rng.normal(0, 0.1, H); m.b_dec[:] = rng.normal(0, 0.1, N)
+    x_pos = np.stack([rng.integers(0, B, 14), rng.integers(0, N, 14)], 1); x_val = np.ones(14, np.float32)
+    y_pos = np.stack([rng.integers(0, B, 20), rng.integers(0, N, 20)], 1); y_val = np.ones(20, np.float32)
+    kp, kp_in = 0.8, 0.75
+    cost, g, f = m.loss_and_grads(x_pos, x_val, y_pos, y_val, B, kp, kp_in, seed=5, step=2)
+    # independent: torch autograd in float64 on the dense graph with the same masks
+    t = lambda a: torch.tensor(np.asarray(a, dtype=np.float64), requires_grad=True)
+    W_enc = t(m.W_enc); W_dec = W_enc if tied else t(m.W_dec); b_enc = t(m.b_enc); b_dec = t(m.b_dec)
+    x = torch.tensor(O.densify_last_wins(x_pos, x_val, B, N).astype(np.float64))
+    keep = np.zeros((B, N)); keep[O.csr_rows(f["row_ptr"]), f["col"]] = f["keep_in"]
+    x_d = x / kp_in * torch.tensor(keep)
+    x_n = x_d / (x_d.sum(1, keepdim=True) + 1e-10)
+    h = torch.sigmoid(x_n @ W_enc + b_enc)
+    h_d = h * torch.tensor(f["keep_h"].astype(np.float64)) / kp
+    p = torch.sigmoid(h_d @ W_dec.T + b_dec)
+    y = torch.tensor(f["y"].astype(np.float64))
+    L = -(y * torch.log(p + 1e-10) + 0.55 * (1 - y) * torch.log(1 - p + 1e-10)).sum(1)
+    c = L.mean()
+    c.backward()
+    assert abs(float(c) - cost) < 1e-4 * abs(cost)
+    gW = g["W_enc"] + g["W_dec"] if tied else g["W_enc"]
+    np.testing.assert_allclose(gW, W_enc.grad.numpy(), rtol=2e-3, atol=2e-6)
+    if not tied:
+        np.testing.assert_allclose(g["W_dec"], W_dec.grad.numpy(), rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(g["b_enc"], b_enc.grad.numpy(), rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(g["b_dec"], b_dec.grad.numpy(), rtol=2e-3, atol=2e-6)
+
+
+# ---------------------------------------------------------------- a8: TF1 Adam known answer
+def test_adam_tf1_first_steps():
+    a = O.AdamTF1(0.01)
+    w = np.array([1.0, -2.0], np.float32); g = np.array([0.5, -0.25], np.float32)
+    a.apply("w", w, g); a.finish_step()
+    # step 1: m = .1 g, v = .001 g^2, alpha = lr*sqrt(1-.999)/(1-.9); update = alpha*m/(sqrt(v)+eps) ~ lr*sign(g)
+    alpha = 0.01 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    exp = np.array([1.0, -2.0]) - alpha * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-8)
+    np.testing.assert_allclose(w, exp, rtol=1e-6)
+    np.testing.assert_allclose(w, [1.0 - 0.01, -2.0 + 0.01], rtol=1e-5)
+    # a zero gradient still moves the weight on the next step (dense Adam, m decays)
+    w0 = w.copy()
+    a.apply("w", w, np.zeros(2, np.float32)); a.finish_step()
+    assert np.all(w != w0)
+
+
+# ---------------------------------------------------------------- dense TF1 graph port == sparse oracle
+@pytest.mark.parametrize("tied", [True, False])
+def test_tf1_graph_port_matches_oracle(tied):
+    rng = np.random.default_rng(2)
+    B, N, H = 8, 60, 16
+    ref = O.DAEOracle(N, H, lr=0.01, tied=tied, seed=1)
+    port = TF1GraphCPU(N, H, lr=0.01, tied=tied, params=[p.copy() for p in ref.params()])
+    for step in range(3):
+        x_pos = np.stack([rng.integers(0, B, 40), rng.integers(0, N, 40)], 1); x_val = np.ones(40, np.float32)
+        y_pos = np.stack([rng.integers(0, B, 70), rng.integers(0, N, 70)], 1); y_val = np.ones(70, np.float32)
+        c_ref, g, f = ref.loss_and_grads(x_pos, x_val, y_pos, y_val, B, 0.8, 0.7, seed=9, step=step)
+        ref.apply_grads(g)
+        keep_dense = np.zeros((B, N), bool); keep_dense[O.csr_rows(f["row_ptr"]), f["col"]] = f["keep_in"]
+        c_port = port.train_step(x_pos, x_val, y_pos, y_val, B, 0.8, 0.7,
+                                 keep_in_dense=torch.tensor(keep_dense), keep_h=torch.tensor(f["keep_h"]))
+        assert abs(c_ref - c_port) < 1e-4 * abs(c_ref)
+    np.testing.assert_allclose(port.vars["W_enc"].numpy(), ref.W_enc, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(port.vars["b_dec"].numpy(), ref.b_dec, rtol=1e-4, atol=2e-5)
+    x_pos = np.stack([rng.integers(0, B, 30), rng.integers(0, N, 30)], 1)
+    np.testing.assert_allclose(port.predict(x_pos, np.ones(30), B), ref.predict(x_pos, np.ones(30), B),
+                               rtol=1e-4, atol=1e-6)
+
+
+def test_bf16_round_matches_torch():
+    x = np.random.default_rng(0).normal(0, 1, 10000).astype(np.float32)
+    x[:4] = [0.0, 1.0, -1.0000001, 3.3895314e38]
+    ours = O.bf16_round(x)
+    theirs = torch.tensor(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(ours, theirs)
+
+
+def test_b200_mode_close_to_fp32():
+    rng = np.random.default_rng(4)
+    B, N, H = 8, 200, 64
+    a = O.DAEOracle(N, H, lr=0.01, seed=1, mode="fp32")
+    b = O.DAEOracle(N, H, lr=0.01, seed=1, mode="b200")
+    x_pos = np.stack([rng.integers(0, B, 50), rng.integers(0, N, 50)], 1)
+    pa, pb = a.predict(x_pos, np.ones(50), B), b.predict(x_pos, np.ones(50), B)
+    np.testing.assert_allclose(pa, pb, rtol=1e-2)
+
+
+# ---------------------------------------------------------------- ranking + metrics vs the reference's own code
+def test_ranking_matches_reference_cand_generate():
+    g = np.load(os.path.join(GOLDEN, "ranking_golden.npz"), allow_pickle=False)
+    for s, c, sd in zip(g["scores"], g["cands"], g["seeds"]):
+        ours = ranking.topk_excluding_seeds(s, json.loads(str(sd)), 500)
+        assert np.array_equal(ours, c)
+
+
+def test_ranking_ties_canonical():
+    s = np.array([0.5, 1.0, 1.0, 0.5, 1.0], np.float32)
+    assert ranking.topk_excluding_seeds(s, [2], 3).tolist() == [1, 4, 0]
+
+
+def test_metrics_match_reference():
+    with open(os.path.join(GOLDEN, "metrics_golden.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        assert ranking.r_precision(c["answer"], c["cand"]) == pytest.approx(c["r_precision"], abs=0)
+        assert ranking.ndcg(c["answer"], c["cand"]) == pytest.approx(c["ndcg"], rel=1e-12)
+        assert ranking.rsc(c["answer"], c["cand"]) == c["rsc"]
+
+
+def test_merge_sharded_topk_equals_unsharded():
+    rng = np.random.default_rng(5)
+    T, K = 4000, 100
+    s = rng.permutation(T).astype(np.float32)
+    s[rng.integers(0, T, 500)] = 7.0      # ties
+    full = ranking.topk_excluding_seeds(s, [3, 5], K)
+    idxs, scs = [], []
+    for g in range(8):
+        lo, hi = g * T // 8, (g + 1) * T // 8
+        loc = ranking.topk_excluding_seeds(s[lo:hi], [x - lo for x in (3, 5) if lo <= x < hi], K)
+        idxs.append(loc + lo); scs.append(s[loc + lo])
+    m_idx, _ = ranking.merge_sharded_topk(idxs, scs, K)
+    assert np.array_equal(m_idx, full)
