@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- DAE train-step throughput (playlists/s) on B200, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg1]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "cfg2"): untied DAE (--dae), B=256 playlists per GPU, 250 000 tracks
++ 40 000 artists, latent 256, bf16 tensor-core operands / fp32 accumulate+master, synthetic MPD-shaped
+batches (tools/synth_mpd.py).  One step = one `sess.run([optimizer, cost])` of the reference:
+COO->CSR, encode, decode + weighted BCE + backward, dense TF1 Adam on every variable.
+
+Printed JSON (one line, rank 0):
+  value  : playlists/s, device-timed (CUDA events on the launching stream), inputs already staged in HBM
+  e2e    : the same metric through the public API (models.DAEs.DAE.train_step) with HOST buffers: pinned
+           H2D of the batch and D2H of the cost inside the timed region
+  roofline: dominant kernel (decoder Adam, HBM-bound): algorithmic bytes / measured launch time vs the
+           measured copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline: the TF1 graph restated op-for-op on torch-CPU (oracle/tf1_graph_cpu.py), bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_tracks, n_artists, hidden, batch, tied)
+    "cfg2": (250000, 40000, 256, 256, False),
+    "cfg1": (5000, 1000, 64, 128, True),
+}
+KP, KP_IN = 0.8, 0.75          # [DAE] keep_prob / input_kp of the shipped configs (0to1_inorder/config.ini:18-19)
+LR = 0.005
+
+
+def make_batches(wl, n, seed, rank=0):
+    from tools.synth_mpd import SynthMPD
+    T, A, H, B, tied = WORKLOADS[wl]
+    g = SynthMPD(T, A, n_clusters=64, seed=180610 + rank)
+    rng = np.random.default_rng(seed + 1000 * rank)
+    out = []
+    for i in range(n):
+        trk, art, y, titles, tv, av = g.coo_batch(B, rng)
+        # hide-and-seek: tracks-only or artists-only input, tracks+artists target (main_train.py:202-213)
+        x, xv = (trk, tv) if i % 2 == 0 else (art, av)
+        out.append((np.ascontiguousarray(x), xv.astype(np.float32), np.ascontiguousarray(y),
+                    np.ones(len(y), np.float32)))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference(wl, steps, warmup):
+    """The reference's CPU path (TF1 graph restated on torch-CPU, all host threads), bounded sample."""
+    import torch
+    from oracle.tf1_graph_cpu import TF1GraphCPU
+    T, A, H, B, tied = WORKLOADS[wl]
+    N = T + A
+    m = TF1GraphCPU(N, H, LR, tied=tied, seed=0)
+    batches = make_batches(wl, 2, seed=7)
+    for i in range(warmup):
+        m.train_step(*batches[i % 2], B, KP, KP_IN)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.train_step(*batches[i % 2], B, KP, KP_IN)
+    dt = time.perf_counter() - t0
+    return {"value": B * steps / dt, "unit": "playlists/s", "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": os.cpu_count(), "ms_per_step": 1e3 * dt / steps,
+            "sample": "%d steps (after %d warm-up) of the %s workload: dense fp32 TF1 graph of models/DAEs.py "
+                      "restated on torch-CPU (TF1 not installable: py3.12, no network)" % (steps, warmup, wl)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = args.workload
+    T, A, H, B, tied = WORKLOADS[wl]
+    N = T + A
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "%s: %s DAE train step, B=%d playlists/GPU, %d tracks + %d artists, latent %d"
+                          % (wl, "tied" if tied else "untied", B, T, A, H),
+              "global_batch": B * world, "parallelism": "dp%d" % world,
+              "l2": "working set per step (parameters + Adam state, %.1f GB) >> 126 MB L2; no explicit flush"
+                    % ((4 if not tied else 2) * 3 * N * H * 4 / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, args.cpu_steps if wl == "cfg2" else args.steps))
+        warm = max(1, min(args.warmup, 2))
+        base = cpu_reference(wl, steps, warm)
+        line = {"impl": "reference", "metric": "dae_train_playlists_per_sec", "value": base["value"],
+                "unit": "playlists/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "playlists/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from spotify_recsys_challenge_2018_b200.dp import DataParallelDAE
+    from spotify_recsys_challenge_2018_b200.models.DAEs import DAE, DAE_tied
+
+    class Conf:
+        pass
+    conf = Conf()
+    conf.save = "/tmp/bench_w"; conf.batch = B; conf.n_input = N; conf.n_tracks = T; conf.hidden = H
+    conf.lr = LR; conf.reg_lambda = 0.0; conf.initval = "NULL"; conf.seed = 0; conf.device = local_rank
+    stream = torch.cuda.Stream()
+    conf.stream = stream.cuda_stream
+    with torch.cuda.stream(stream):
+        model = (DAE_tied if tied else DAE)(conf).fit()
+        trainer = DataParallelDAE(model) if world > 1 else None
+        batches = make_batches(wl, 8, seed=7, rank=rank)
+        model.stage_batch(0, *batches[0])
+        model.stage_batch(1, *batches[1])
+
+        def step(i):
+            if trainer is not None:
+                trainer.train_step_staged(i & 1, KP, KP_IN)
+            else:
+                model.train_step_staged(i & 1, KP, KP_IN)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-timed throughput, inputs resident in HBM ------------------------------
+        for i in range(args.warmup):
+            step(i)
+        model.sync_cost()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = model.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        launches = model.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        cost = model.sync_cost()
+        clocks = sampler.stop() if rank == 0 else None
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        value = B * world * args.steps / (ms / 1e3)
+
+        # ---- end to end through the public API: host COO in, cost out ------------------------
+        e2e = None
+        if world == 1:
+            for i in range(3):
+                model.train_step(*batches[i % len(batches)], KP, KP_IN)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                model.train_step(*batches[i % len(batches)], KP, KP_IN)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            h2d = int(np.mean([x.nbytes + xv.nbytes + y.nbytes + yv.nbytes for x, xv, y, yv in batches]))
+            e2e = {"value": B * args.steps / dt, "unit": "playlists/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * dt / args.steps,
+                   "api": "models.DAEs.DAE.train_step (dae_model_train_step): host int64 COO + fp32 values in, "
+                          "cost out, synchronous"}
+        else:
+            # DP: per step every rank shards nothing on the host here (inputs are per-rank batches);
+            # H2D of the rank's batch + all-reduce + D2H of the cost inside the timed region
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                model.stage_batch(i & 1, *batches[i % len(batches)])
+                trainer.train_step_staged(i & 1, KP, KP_IN)
+                model.sync_cost()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            h2d = int(np.mean([x.nbytes + xv.nbytes + y.nbytes + yv.nbytes for x, xv, y, yv in batches]))
+            e2e = {"value": B * world * args.steps / float(dt.item()), "unit": "playlists/s",
+                   "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 8 * world,
+                   "ms_per_step": 1e3 * float(dt.item()) / args.steps,
+                   "api": "dp.DataParallelDAE over models.DAEs.DAE (stage_batch + train_step_staged + sync_cost)"}
+
+        # ---- per-phase device times (profiled steps; not part of `value`) -----------------------
+        model.set_profiling(True)
+        for i in range(min(args.steps, 20)):
+            step(i)
+        model.sync_cost()
+        phases = {k: (ms_ / max(n, 1)) for k, (ms_, n) in model.phase_times().items() if n}
+        model.set_profiling(False)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        # dominant kernel: k_adam_vec4 on the decoder matrix.  Algorithmic bytes per launch:
+        # read g,w,m,v (16 B) + write w,m,v (12 B) + write the bf16 operand shadow (2 B) = 30 B / parameter
+        adam_bytes = 30.0 * N * H
+        adam_ms = phases.get("adam_dec")
+        roofline = None
+        if adam_ms:
+            ach = adam_bytes / (adam_ms / 1e3) / 1e9
+            roofline = {"kernel": "k_adam_vec4 (decoder matrix, dense TF1 Adam + bf16 shadow)", "bound": "hbm",
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": adam_bytes,
+                        "launch_ms": adam_ms}
+        step_bytes = (30.0 + (24.0 if not tied else 0.0) + 2.0 + 4.0 + 2.0) * N * H   # + decode read, g write, dh read of W
+        line = {"metric": "dae_train_playlists_per_sec", "value": value, "unit": "playlists/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "phase_ms": phases, "last_cost": cost,
+                "step_hbm_gbs_algorithmic": step_bytes / (ms / args.steps / 1e3) / 1e9}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(wl, args.cpu_steps if wl == "cfg2" else 50, 2)
+        print(json.dumps(line))
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -106,6 +106,14 @@ int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t
 /* number of kernels launched by this model since creation (bench.py `gpu_launches`) */
 int64_t dae_model_launch_count(dae_model* m);
 
+/* Per-phase device timing (CUDA events on the model's stream around each phase of a train step;
+ * a profiled step synchronises once at its end).  Used by bench.py for the roofline of the
+ * dominant kernel; leave off for throughput runs. */
+int32_t dae_model_set_profiling(dae_model* m, int32_t on);
+int32_t dae_model_phase_count(void);
+const char* dae_model_phase_name(int32_t k);
+int32_t dae_model_phase_time(dae_model* m, int32_t k, double* total_ms, int64_t* count);
+
 /* ---- kernel-level entry points on caller-owned DEVICE memory (parity tests, other hosts) ------- */
 
 /* met.single_eval ranking on an existing score matrix.              metrics.py:58-68 */

@@ -43,6 +43,10 @@ SIGNATURES = {
     "dae_model_sync_cost": (_I32, [_P, C.POINTER(_F)]),
     "dae_model_buffer": (_I32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
     "dae_model_launch_count": (_I64, [_P]),
+    "dae_model_set_profiling": (_I32, [_P, _I32]),
+    "dae_model_phase_count": (_I32, []),
+    "dae_model_phase_name": (C.c_char_p, [_I32]),
+    "dae_model_phase_time": (_I32, [_P, _I32, C.POINTER(C.c_double), C.POINTER(_I64)]),
     "dae_topk_device": (_I32, [_P, _I64, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P]),
     "dae_adam_device": (_I32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P]),
     "dae_coo_to_csr_device": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -75,6 +75,12 @@ struct dae_model {
     size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
     int last_batch = 0, last_bpad = 0;
     long long launches = 0;
+    // optional per-phase device timing (bench.py roofline): events around each phase of a step
+    bool profiling = false;
+    cudaEvent_t ph_ev[2 * 16] = {};
+    bool ph_used[16] = {};
+    double ph_ms[16] = {};
+    long long ph_n[16] = {};
     std::vector<void*> dev_allocs, host_allocs;
 };
 
@@ -102,6 +108,27 @@ static int alloc_csr(dae_model* m, CsrWork* w, int B, int max_nnz) {
     TRY(dalloc(m, &w->col, max_nnz));
     TRY(dalloc(m, &w->val, max_nnz));
     return 0;
+}
+
+enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DW, PH_DH, PH_ENCODE_BWD, PH_ADAM_DEC, PH_ADAM_ENC,
+             PH_ADAM_BIAS, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"prepare_csr_ybits", "encode_fwd", "decode_loss_dz", "dw_dec", "dh",
+                                            "encode_bwd_scatter", "adam_dec", "adam_enc", "adam_bias"};
+static inline void ph_begin(dae_model* m, int k) {
+    if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], m->st); }
+}
+static inline void ph_end(dae_model* m, int k) {
+    if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k + 1], m->st); m->ph_used[k] = true; }
+}
+static void ph_collect(dae_model* m) {
+    if (!m->profiling) return;
+    cudaStreamSynchronize(m->st);
+    for (int k = 0; k < PH_COUNT; ++k) {
+        if (!m->ph_used[k]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->ph_ev[2 * k], m->ph_ev[2 * k + 1]) == cudaSuccess) { m->ph_ms[k] += ms; m->ph_n[k] += 1; }
+        m->ph_used[k] = false;
+    }
 }
 
 extern "C" int32_t dae_abi_version(void) { return DAE_B200_ABI_VERSION; }
@@ -306,15 +333,25 @@ static int check_device_flag(dae_model* m) {
 }
 
 // encode forward from a staged slot (shared by train / predict / recommend)
-static void run_encode(dae_model* m, const Slot& s, int rows_pad, float kp, float kp_in, int row_offset) {
+static void run_encode(dae_model* m, const Slot& s, int rows_pad, float kp, float kp_in, int row_offset,
+                       bool with_y = false) {
+    ph_begin(m, PH_PREPARE);
     launch_coo_to_csr(s.x_pos, s.x_val, s.nnz_x, s.batch, m->N, m->xw, m->err, m->st);
     m->launches += s.nnz_x > 0 ? 4 : 2;
+    if (with_y) {
+        launch_coo_to_csr(s.y_pos, s.y_val, s.nnz_y, s.batch, m->N, m->yw, m->err, m->st);
+        launch_ybits_set(m->yw, s.batch, m->ybits, m->ywords, 1, m->err, m->st);
+        m->launches += (s.nnz_y > 0 ? 4 : 2) + 1;
+    }
+    ph_end(m, PH_PREPARE);
+    ph_begin(m, PH_ENCODE);
     EncodeArgs e{};
     e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = m->xw; e.rowsum = m->rowsum; e.h = m->h; e.h_d = m->h_d;
     e.h_dT = m->h_dT; e.B = s.batch; e.bpad = rows_pad; e.H = m->H; e.kp = kp; e.kp_in = kp_in;
     e.seed = m->cfg.seed; e.step = (unsigned long long)m->step; e.row_offset = row_offset;
     launch_encode_fwd(e, m->st);
     m->launches += 1;
+    ph_end(m, PH_ENCODE);
 }
 
 extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
@@ -329,29 +366,33 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     const int gb = global_batch > 0 ? global_batch : B;
     m->last_batch = B; m->last_bpad = bpad;
 
-    run_encode(m, s, bpad, keep_prob, input_keep_prob, row_offset);
-    launch_coo_to_csr(s.y_pos, s.y_val, s.nnz_y, B, N, m->yw, m->err, m->st);
-    launch_ybits_set(m->yw, B, m->ybits, m->ywords, 1, m->err, m->st);
-    m->launches += (s.nnz_y > 0 ? 4 : 2) + 1;
+    run_encode(m, s, bpad, keep_prob, input_keep_prob, row_offset, true);
 
     DecodeArgs d{};
     d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
     d.ybits = m->ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.db_dec = m->g_b_dec;
     d.loss_partial = m->loss_partial; d.inv_batch = 1.0f / (float)gb;
     const int ngrid = decode_grid(N, 1);
+    ph_begin(m, PH_DECODE_LOSS);
     launch_decode_train(d, m->st);
+    ph_end(m, PH_DECODE_LOSS);
 
     DwArgs w{}; w.dzT = m->dzT; w.h_dT = m->h_dT; w.g = m->g_dec; w.N = N; w.H = H; w.bpad = bpad;
+    ph_begin(m, PH_DW);
     launch_dw(w, m->st);
+    ph_end(m, PH_DW);
 
     DhArgs q{}; q.dzT = m->dzT; q.W = m->W_dec_bf16; q.partial = m->dh_partial; q.N = N; q.H = H; q.bpad = bpad;
     q.nsplit = m->nsplit;
+    ph_begin(m, PH_DH);
     launch_dh(q, m->st);
+    ph_end(m, PH_DH);
 
     EncodeBwdArgs eb{};
     eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.x = m->xw; eb.da = m->da;
     eb.g_enc = m->g_enc; eb.touched = m->touched; eb.db_enc = m->g_b_enc; eb.B = B; eb.bpad = bpad; eb.H = H;
     eb.kp = keep_prob; eb.seed = m->cfg.seed; eb.step = (unsigned long long)m->step; eb.row_offset = row_offset;
+    ph_begin(m, PH_ENCODE_BWD);
     launch_encode_bwd(eb, m->st);
     launch_ybits_set(m->yw, B, m->ybits, m->ywords, 0, m->err, m->st);
     m->launches += 3 + 2 + 1;
@@ -369,6 +410,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     }
     launch_reduce_loss2(m->loss_partial, ngrid, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost, m->st);
     m->launches += 1;
+    ph_end(m, PH_ENCODE_BWD);
     return 0;
 }
 
@@ -382,21 +424,28 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     // decoder (or the tied matrix): dense gradient, refreshes the bf16 operand shadow
     a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.w_bf16 = m->W_dec_bf16;
     a.row_touched = nullptr; a.n = NH; a.row_len = m->H;
+    ph_begin(m, PH_ADAM_DEC);
     launch_adam(a, m->st);
+    ph_end(m, PH_ADAM_DEC);
     m->launches += 1;
-    if (!m->tied) {   // encoder: gradient rows exist only where the batch touched them; all rows still update
+    if (!m->tied) {
+        ph_begin(m, PH_ADAM_ENC);   // encoder: gradient rows exist only where the batch touched them; all rows still update
         a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = m->g_enc; a.w_bf16 = nullptr;
         a.row_touched = m->touched;
         launch_adam(a, m->st);
         launch_clear_flagged(m->N, m->H, m->g_enc, m->touched, m->st);
         m->launches += 2;
+        ph_end(m, PH_ADAM_ENC);
     }
+    ph_begin(m, PH_ADAM_BIAS);
     a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
     a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = m->H;
     launch_adam(a, m->st);
     a.w = m->b_dec; a.m = m->mb_dec; a.v = m->vb_dec; a.g = m->g_b_dec; a.n = m->N;
     launch_adam(a, m->st);
     m->launches += 2 + (m->N % 4 ? 1 : 0);
+    ph_end(m, PH_ADAM_BIAS);
+    ph_collect(m);
     m->b1_pow *= kBeta1;
     m->b2_pow *= kBeta2;
     m->step += 1;
@@ -539,6 +588,22 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
 }
 
 extern "C" int64_t dae_model_launch_count(dae_model* m) { return m ? m->launches : 0; }
+
+extern "C" int32_t dae_model_set_profiling(dae_model* m, int32_t on) {
+    if (!m) return fail("null model");
+    if (on && !m->ph_ev[0]) for (int i = 0; i < 2 * PH_COUNT; ++i) CK(cudaEventCreate(&m->ph_ev[i]));
+    m->profiling = on != 0;
+    for (int k = 0; k < PH_COUNT; ++k) { m->ph_ms[k] = 0.0; m->ph_n[k] = 0; m->ph_used[k] = false; }
+    return 0;
+}
+extern "C" int32_t dae_model_phase_count(void) { return PH_COUNT; }
+extern "C" const char* dae_model_phase_name(int32_t k) { return (k >= 0 && k < PH_COUNT) ? kPhaseNames[k] : ""; }
+extern "C" int32_t dae_model_phase_time(dae_model* m, int32_t k, double* total_ms, int64_t* count) {
+    if (!m || k < 0 || k >= PH_COUNT) return fail("bad phase");
+    if (total_ms) *total_ms = m->ph_ms[k];
+    if (count) *count = m->ph_n[k];
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // kernel-level entry points

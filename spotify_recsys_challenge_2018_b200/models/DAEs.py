@@ -169,6 +169,18 @@ class DAE_tied:
         _lib.check(self._lib.dae_model_sync_cost(self._h, C.byref(cost)))
         return float(cost.value)
 
+    def set_profiling(self, on):
+        _lib.check(self._lib.dae_model_set_profiling(self._h, int(bool(on))))
+
+    def phase_times(self):
+        """{phase name: (total ms, launches timed)} accumulated since set_profiling(True)."""
+        out = {}
+        for k in range(self._lib.dae_model_phase_count()):
+            ms = C.c_double(); n = C.c_int64()
+            _lib.check(self._lib.dae_model_phase_time(self._h, k, C.byref(ms), C.byref(n)))
+            out[self._lib.dae_model_phase_name(k).decode()] = (ms.value, n.value)
+        return out
+
     def launch_count(self):
         return int(self._lib.dae_model_launch_count(self._h))
 

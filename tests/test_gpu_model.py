@@ -1,0 +1,243 @@
+"""GPU parity tests, model level: one `sess.run([optimizer, cost])` / `sess.run(y_pred)` of the
+reference (restated by oracle/dae_oracle.py) against the CUDA path behind the C ABI, on the same
+seeded inputs, stage by stage; plus size-independent properties at BASELINE.json's full size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dae_oracle as O
+from oracle import ranking
+from spotify_recsys_challenge_2018_b200.models.DAEs import DAE, DAE_tied
+from tests.gpu_util import Conf, model_buf, random_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(tied, N, T, H, B, lr=0.005, lam=0.0, seed=11):
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=lr, reg_lambda=lam, seed=seed)
+    ora = O.DAEOracle(N, H, lr, reg_lambda=lam, tied=tied, seed=5, mode="b200")
+    ora.b_enc[:] = np.random.default_rng(1).normal(0, 0.1, H)
+    ora.b_dec[:] = np.random.default_rng(2).normal(0, 0.1, N)
+    m = (DAE_tied if tied else DAE)(conf).fit()
+    m.set_params(ora.params())
+    return conf, ora, m
+
+
+def _rel(a, b, floor):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+@pytest.mark.parametrize("tied,N,T,H,B", [(False, 1500, 1200, 64, 64), (True, 1500, 1200, 64, 64),
+                                          (False, 6007, 5000, 256, 250), (True, 3001, 2500, 128, 150),
+                                          (False, 20000, 17000, 256, 256)])
+def test_train_step_stage_by_stage(tied, N, T, H, B):
+    conf, ora, m = _mk(tied, N, T, H, B)
+    rng = np.random.default_rng(N + B)
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=25, empty_rows=(1,))
+    xv = np.ones(len(trk), np.float32); xv[::5] = 0.0          # firstN-style zeros, incl. "last value 0 wins"
+    yv = np.ones(len(y), np.float32)
+    kp, kp_in = 0.8, 0.75
+    m.stage_batch(0, trk, xv, y, yv)
+    m.backward_staged(0, kp, kp_in)
+    cost = m.sync_cost()
+    c_ora, g, f = ora.loss_and_grads(trk, xv, y, yv, B, kp, kp_in, seed=conf.seed, step=0)
+    bpad = (B + 63) // 64 * 64
+
+    # ---- sparse side: bit-exact structure ----------------------------------------------
+    rp = model_buf(m, "x_row_ptr", torch.int32).cpu().numpy()
+    rl = model_buf(m, "x_row_len", torch.int32).cpu().numpy()[:B]
+    col = model_buf(m, "x_col", torch.int32).cpu().numpy()
+    xn = model_buf(m, "x_val", torch.float32).cpu().numpy()
+    assert np.array_equal(rl, np.diff(f["row_ptr"]))
+    g_col = np.concatenate([col[rp[r]:rp[r] + rl[r]] for r in range(B)])
+    g_xn = np.concatenate([xn[rp[r]:rp[r] + rl[r]] for r in range(B)])
+    assert np.array_equal(g_col, f["col"])
+    assert np.array_equal(g_xn != 0, f["x_n"] != 0)                        # identical Philox keep mask
+    np.testing.assert_allclose(g_xn, f["x_n"], rtol=2e-6)
+    np.testing.assert_allclose(model_buf(m, "x_rowsum", torch.float32).cpu().numpy()[:B], f["s"], rtol=2e-6)
+
+    # ---- encode -----------------------------------------------------------------------
+    h = model_buf(m, "h", torch.float32).cpu().numpy()[:B * H].reshape(B, H)
+    np.testing.assert_allclose(h, f["h"], rtol=1e-5, atol=1e-6)
+    h_d = model_buf(m, "h_d", torch.bfloat16).float().cpu().numpy()[:bpad * H].reshape(bpad, H)
+    assert np.array_equal(h_d[:B] != 0, f["keep_h"])                       # identical hidden dropout mask
+    assert np.all(h_d[B:] == 0)
+    np.testing.assert_allclose(h_d[:B], f["h_dq"], rtol=8e-3)              # <= 1 bf16 ulp
+
+    # ---- decode + loss + dz -----------------------------------------------------------
+    assert abs(cost - c_ora) <= 1e-3 * abs(c_ora), (cost, c_ora)           # north_star: 1e-3 relative
+    dzT = model_buf(m, "dzT", torch.bfloat16).float().cpu().numpy()[:N * bpad].reshape(N, bpad)
+    assert np.all(dzT[:, B:] == 0)
+    dz_o = f["dzq"].T
+    assert np.array_equal(np.sign(dzT[:, :B]), np.sign(dz_o))              # y pattern (negative exactly where y == 1)
+    err = _rel(dzT[:, :B], dz_o, 1e-3 * np.abs(dz_o).max())
+    assert err.max() < 2e-2 and err.mean() < 2e-3                          # bf16 storage of dz: 2^-8 relative
+    np.testing.assert_allclose(model_buf(m, "g_b_dec", torch.float32).cpu().numpy(), g["b_dec"], rtol=5e-3,
+                               atol=1e-3 * np.abs(g["b_dec"]).max())
+
+    # ---- contractions: against torch on the device's own operands (tight), and the oracle (bf16-loose)
+    dz_dev = model_buf(m, "dzT", torch.bfloat16)[:N * bpad].view(N, bpad).float()
+    hd_dev = model_buf(m, "h_d", torch.bfloat16)[:bpad * H].view(bpad, H).float()
+    W16 = model_buf(m, "W_dec_bf16", torch.bfloat16).view(N, H).float()
+    dh_ref = dz_dev.T @ W16
+    ns = m._lib.dae_dh_nsplit(N)
+    dh = model_buf(m, "dh_partial", torch.float32)[:ns * bpad * H].view(ns, bpad, H).sum(0)
+    assert (dh - dh_ref).abs().max().item() < 2e-3 * dh_ref.abs().max().item()
+    np.testing.assert_allclose(dh[:B].cpu().numpy(), f["dh_d"], rtol=0, atol=3e-2 * np.abs(f["dh_d"]).max())
+
+    da = model_buf(m, "da", torch.float32).cpu().numpy()[:B * H].reshape(B, H)
+    np.testing.assert_allclose(da, f["da"], rtol=0, atol=3e-2 * np.abs(f["da"]).max())
+    np.testing.assert_allclose(model_buf(m, "g_b_enc", torch.float32).cpu().numpy(), g["b_enc"], rtol=0,
+                               atol=3e-2 * np.abs(g["b_enc"]).max())
+
+    g_dec = model_buf(m, "g_dec", torch.float32).view(N, H)
+    gw_ref = dz_dev @ hd_dev                                               # dW_dec from the device operands
+    if tied:
+        want = g["W_enc"] + g["W_dec"]
+        np.testing.assert_allclose(g_dec.cpu().numpy(), want, rtol=0, atol=3e-2 * np.abs(want).max())
+    else:
+        assert (g_dec - gw_ref).abs().max().item() < 1e-3 * gw_ref.abs().max().item()
+        np.testing.assert_allclose(g_dec.cpu().numpy(), g["W_dec"], rtol=0, atol=2e-2 * np.abs(g["W_dec"]).max())
+        g_enc = model_buf(m, "g_enc", torch.float32).view(N, H).cpu().numpy()
+        touched = model_buf(m, "touched", torch.uint8).cpu().numpy().astype(bool)
+        rows_o = np.zeros(N, bool); rows_o[f["col"][f["x_n"] != 0]] = True
+        assert np.array_equal(touched, rows_o)                             # exactly the rows present in x
+        assert np.all(g_enc[~touched] == 0)
+        np.testing.assert_allclose(g_enc, g["W_enc"], rtol=0, atol=3e-2 * np.abs(g["W_enc"]).max())
+
+    # ---- Adam ------------------------------------------------------------------------------
+    ora.apply_grads(g)
+    m.apply_adam()
+    m.sync_cost()
+    got = m.get_params()
+    for a, b, name in zip(got, ora.params(), ("W_enc", "W_dec", "b_enc", "b_dec")):
+        d = np.abs(a - b)
+        # the first Adam step is lr*sign(g): elements whose tiny gradient flips sign under bf16 noise move 2*lr
+        assert (d > 1e-3 * conf.lr).mean() < 5e-3 and d.max() <= 2.001 * conf.lr, name
+    if not tied:                                                            # gradient buffers are clean again
+        assert model_buf(m, "touched", torch.uint8).sum().item() == 0
+        assert model_buf(m, "g_enc", torch.float32).abs().sum().item() == 0
+    assert model_buf(m, "ybits", torch.int32).abs().sum().item() == 0
+    shadow = model_buf(m, "W_dec_bf16", torch.bfloat16).float().cpu().numpy().reshape(N, H)
+    assert np.array_equal(shadow, O.bf16_round(got[1]))                    # shadow == bf16(master), bit-exact
+    m.close()
+
+
+@pytest.mark.parametrize("tied", [False, True])
+def test_training_trajectory_matches_oracle(tied):
+    """20 steps on the same batch stream: cost trajectories within 1e-3 relative early, 1e-2 late."""
+    N, T, H, B = 3000, 2500, 64, 128
+    conf, ora, m = _mk(tied, N, T, H, B, lr=0.01)
+    rng = np.random.default_rng(3)
+    for step in range(20):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=20)
+        x, xv = (trk, np.ones(len(trk), np.float32)) if step % 2 == 0 else (art, np.ones(len(art), np.float32))
+        yv = np.ones(len(y), np.float32)
+        c_gpu = m.train_step(x, xv, y, yv, 0.8, 0.75)
+        c_ora = ora.train_step(x, xv, y, yv, B, 0.8, 0.75, seed=conf.seed)
+        tol = 1e-3 if step < 5 else 1e-2
+        assert abs(c_gpu - c_ora) <= tol * abs(c_ora), (step, c_gpu, c_ora)
+    m.close()
+
+
+def test_reg_lambda_cost_and_update():
+    N, T, H, B = 1500, 1200, 64, 64
+    conf, ora, m = _mk(False, N, T, H, B, lam=1e-3)
+    rng = np.random.default_rng(8)
+    trk, art, y = random_batch(rng, B, T, N - T)
+    c_gpu = m.train_step(trk, np.ones(len(trk)), y, np.ones(len(y)), 0.8, 0.75)
+    c_ora = ora.train_step(trk, np.ones(len(trk)), y, np.ones(len(y)), B, 0.8, 0.75, seed=conf.seed)
+    assert abs(c_gpu - c_ora) <= 1e-3 * abs(c_ora)
+    m.close()
+
+
+@pytest.mark.parametrize("N,T,H,B", [(1500, 1200, 64, 64), (6007, 5000, 256, 250), (9000, 8000, 256, 700)])
+def test_predict_and_recommend(N, T, H, B):
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.01, DAEval=None)
+    ora = O.DAEOracle(N, H, 0.01, tied=False, seed=5, mode="b200")
+    ora.b_dec[:] = np.random.default_rng(2).normal(0, 0.5, N)
+    m = DAE(conf)
+    m.trainable = False
+    m.fit()
+    m.set_params(ora.params())
+    rng = np.random.default_rng(N)
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=30, empty_rows=(2,))
+    xv = np.concatenate([np.ones(len(trk)), 0.5 * np.ones(len(art))]).astype(np.float32)
+    p_gpu = m.predict(y, xv)
+    p_ora = ora.predict(y, xv, B)
+    assert _rel(p_gpu, p_ora, 1e-6).max() < 1e-3                           # north_star: 1e-3 relative on scores
+    pt = m.predict(y, xv, tracks_only=True)
+    assert np.array_equal(pt, p_gpu[:, :T])
+    seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(B)]
+    idx, sc = m.recommend(y, xv, seeds, k=500, return_scores=True)
+    for r in range(0, B, max(B // 16, 1)):
+        want = ranking.topk_excluding_seeds(p_gpu[r, :T], seeds[r], 500)   # exact on the device's own scores
+        assert np.array_equal(idx[r], want), r
+        want_o = ranking.topk_excluding_seeds(p_ora[r, :T], seeds[r], 500)
+        # vs the oracle's scores: identical sets except items within 1e-3 of the K-th score
+        diff = set(idx[r].tolist()) ^ set(want_o.tolist())
+        kth = p_ora[r, want_o[-1]]
+        assert all(abs(p_ora[r, i] - kth) <= 1e-3 * kth for i in diff), (r, len(diff))
+    m.close()
+
+
+def test_errors_are_loud():
+    from spotify_recsys_challenge_2018_b200._lib import DaeError
+    conf = Conf(batch=8, n_input=100, n_tracks=80, hidden=64, lr=0.01)
+    m = DAE(conf).fit()
+    with pytest.raises(DaeError):
+        m.train_step(np.array([[0, 100]]), [1.0], np.array([[0, 1]]), [1.0], 0.8, 0.8)     # item id out of range
+    with pytest.raises(DaeError):
+        m.train_step(np.array([[9, 1]]), [1.0], np.array([[0, 1]]), [1.0], 0.8, 0.8)       # row outside the batch
+    with pytest.raises(DaeError):
+        m.train_step(np.array([[0, 1]]), [1.0], np.array([[0, 1]]), [0.5], 0.8, 0.8)       # non-binary target
+    c = m.train_step(np.zeros((0, 2)), [], np.array([[0, 1]]), [1.0], 0.8, 0.8)            # empty input is legal
+    assert np.isfinite(c)
+    m.close()
+    with pytest.raises(DaeError):
+        DAE(Conf(batch=8, n_input=100, n_tracks=80, hidden=48, lr=0.01)).fit()             # unsupported width
+
+
+def test_full_size_properties():
+    """BASELINE cfg2 size (B=256, N=290000, H=256): size-independent properties of one train step."""
+    N, T, H, B = 290000, 250000, 256, 256
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.005, seed=1)
+    m = DAE(conf).fit()
+    rng = np.random.default_rng(0)
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=66)
+    m.stage_batch(0, trk, np.ones(len(trk), np.float32), y, np.ones(len(y), np.float32))
+    m.backward_staged(0, 0.8, 0.75)
+    cost = m.sync_cost()
+    # at Xavier init p ~= 0.5 everywhere: cost ~= N*0.55*ln2 + nnz_y/B*(1-0.55)*ln2
+    nnz_y = len(np.unique(y, axis=0))
+    expect = N * 0.55 * np.log(2) + nnz_y / B * 0.45 * np.log(2)
+    assert abs(cost - expect) < 0.02 * expect, (cost, expect)
+    dz = model_buf(m, "dzT", torch.bfloat16).view(N, 256).float()
+    hd = model_buf(m, "h_d", torch.bfloat16).view(256, H).float()
+    W16 = model_buf(m, "W_dec_bf16", torch.bfloat16).view(N, H).float()
+    # db_dec == row sums of dz (computed from the unrounded values): loose bf16 tolerance
+    db = model_buf(m, "g_b_dec", torch.float32)
+    assert ((db - dz.sum(1)).abs().max() / db.abs().max()).item() < 1e-2
+    # dW_dec, dh: exact contractions of the stored operands
+    g_dec = model_buf(m, "g_dec", torch.float32).view(N, H)
+    ref = dz @ hd
+    assert ((g_dec - ref).abs().max() / ref.abs().max()).item() < 1e-3
+    ns = m._lib.dae_dh_nsplit(N)
+    dh = model_buf(m, "dh_partial", torch.float32)[:ns * 256 * H].view(ns, 256, H).sum(0)
+    ref = dz.T @ W16
+    assert ((dh - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    # y bitmask consistency: dz is negative exactly on the (row, item) pairs of y
+    neg = (dz < 0).sum().item()
+    assert neg == nnz_y, (neg, nnz_y)
+    m.apply_adam()
+    c2 = m.train_step(trk, np.ones(len(trk), np.float32), y, np.ones(len(y), np.float32), 0.8, 0.75)
+    assert np.isfinite(c2) and c2 < cost                                    # one Adam step lowers the loss on the same batch
+    # ranking at full width: sorted, seeds excluded, idempotent
+    seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(B)]
+    idx, sc = m.recommend(trk, np.ones(len(trk), np.float32), seeds, k=500, return_scores=True)
+    assert np.all(np.diff(sc, axis=1) <= 0)
+    for r in (0, 100, 255):
+        assert not (set(idx[r].tolist()) & set(seeds[r])) and len(set(idx[r].tolist())) == 500
+    idx2 = m.recommend(trk, np.ones(len(trk), np.float32), seeds, k=500)
+    assert np.array_equal(idx, idx2)
+    m.close()
