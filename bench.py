@@ -185,10 +185,13 @@ def main():
         model.stage_batch(1, *batches[1])
 
         def step(i):
+            # inputs stay resident in HBM; the slot's COO->CSR / bitmask preparation is re-run every step
+            # on the library's side stream, one step ahead of the main stream (dae_model_restage)
             if trainer is not None:
                 trainer.train_step_staged(i & 1, KP, KP_IN)
             else:
                 model.train_step_staged(i & 1, KP, KP_IN)
+            model.restage(i & 1)
 
         def barrier():
             if world > 1:

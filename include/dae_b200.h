@@ -82,9 +82,14 @@ int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_v
 
 /* ---- device-resident / asynchronous variants (bench `value`, data-parallel training) ---------- */
 
-/* Copy one batch (host COO) into device staging slot 0 or 1 (async on the model's stream). */
+/* Copy one batch (host COO) into device staging slot 0 or 1 and build its CSR / target bitmask, all
+ * asynchronously on the model's side stream (overlaps with a step running on the main stream). */
 int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
                               const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch);
+/* Re-run the device-side preparation (COO -> CSR, target bitmask) of the batch already resident in
+ * `slot` on the side stream: with inputs kept in HBM every step still does all of its own work,
+ * one step ahead of the main stream. */
+int32_t dae_model_restage(dae_model* m, int32_t slot);
 /* Forward + backward from a staged slot; gradients stay in device buffers; no host sync.
  * global_batch / row_offset: the loss is a mean over the GLOBAL batch (DAEs.py:100) and dropout is
  * keyed by the global row, so N ranks x B_local == one rank x (N*B_local). */

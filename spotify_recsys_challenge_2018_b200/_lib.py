@@ -37,6 +37,7 @@ SIGNATURES = {
     "dae_model_predict": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P]),
     "dae_model_recommend": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _I32, _P, _P]),
     "dae_model_stage_batch": (_I32, [_P, _I32, _P, _P, _I64, _P, _P, _I64, _I32]),
+    "dae_model_restage": (_I32, [_P, _I32]),
     "dae_model_backward_staged": (_I32, [_P, _I32, _F, _F, _I32, _I32]),
     "dae_model_apply_adam": (_I32, [_P]),
     "dae_model_train_step_staged": (_I32, [_P, _I32, _F, _F]),

@@ -40,15 +40,24 @@ struct Slot {
     float *x_val = nullptr, *y_val = nullptr;
     long long *hx_pos = nullptr, *hy_pos = nullptr; // pinned host mirrors
     float *hx_val = nullptr, *hy_val = nullptr;
-    int nnz_x = 0, nnz_y = 0, batch = 0;
+    int nnz_x = 0, nnz_y = 0, batch = 0, y_batch = 0;
+    bool has_y = false;
+    int yw_batch_dummy() const { return y_batch; }
+    CsrWork xw{}, yw{};                             // de-duplicated CSR of this slot's batch
+    uint32_t* ybits = nullptr;                      // item-major target bitmask of this slot's batch
+    bool y_live = false;                            // ybits currently holds the bits of yw
     cudaEvent_t h2d_done = nullptr;                 // the pinned mirror may be overwritten after this
+    cudaEvent_t prepared = nullptr;                 // side stream: CSR + ybits of this slot are ready
+    cudaEvent_t consumed = nullptr;                 // main stream: the step has finished reading this slot
 };
 
 struct dae_model {
     dae_config cfg{};
     int N = 0, T = 0, H = 0, Bmax = 0, rows_alloc = 0, max_nnz = 0;
     bool tied = false, trainable = true, own_stream = false;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;      // main stream: the step
+    cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
+    int cur = 0;                    // slot used by the last step (dae_model_buffer)
     float *W_enc = nullptr, *W_dec = nullptr, *b_enc = nullptr, *b_dec = nullptr;
     __nv_bfloat16* W_dec_bf16 = nullptr;
     float *mW_enc = nullptr, *vW_enc = nullptr, *mW_dec = nullptr, *vW_dec = nullptr;
@@ -58,10 +67,8 @@ struct dae_model {
     float *g_dec = nullptr, *g_enc = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
     unsigned char* touched = nullptr;
     Slot slots[2];
-    CsrWork xw{}, yw{};
     int* err = nullptr;
     int* err_host = nullptr;
-    uint32_t* ybits = nullptr;
     int ywords = 8;
     float *rowsum = nullptr, *h = nullptr, *da = nullptr, *dh_partial = nullptr;
     __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr;
@@ -114,14 +121,15 @@ enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DW, PH_DH, PH_ENCODE_
              PH_ADAM_BIAS, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"prepare_csr_ybits", "encode_fwd", "decode_loss_dz", "dw_dec", "dh",
                                             "encode_bwd_scatter", "adam_dec", "adam_enc", "adam_bias"};
-static inline void ph_begin(dae_model* m, int k) {
-    if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], m->st); }
+static inline void ph_begin(dae_model* m, int k, cudaStream_t s = nullptr) {
+    if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], s ? s : m->st); }
 }
-static inline void ph_end(dae_model* m, int k) {
-    if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k + 1], m->st); m->ph_used[k] = true; }
+static inline void ph_end(dae_model* m, int k, cudaStream_t s = nullptr) {
+    if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k + 1], s ? s : m->st); m->ph_used[k] = true; }
 }
 static void ph_collect(dae_model* m) {
     if (!m->profiling) return;
+    cudaStreamSynchronize(m->st2);
     cudaStreamSynchronize(m->st);
     for (int k = 0; k < PH_COUNT; ++k) {
         if (!m->ph_used[k]) continue;
@@ -159,6 +167,7 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     m->tied = cfg->tied != 0; m->trainable = cfg->trainable != 0;
     if (cfg->stream) { m->st = reinterpret_cast<cudaStream_t>(cfg->stream); }
     else { CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)); m->own_stream = true; }
+    CK(cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking));
     m->rows_alloc = m->Bmax <= kMaxBpad ? round_up(m->Bmax, 64) : round_up(m->Bmax, kMaxBpad);
     m->max_nnz = m->Bmax * 1024;
     const size_t NH = (size_t)m->N * m->H;
@@ -178,8 +187,6 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
         TRY(dalloc(m, &m->g_dec, NH));
         if (m->tied) m->g_enc = m->g_dec; else { TRY(dalloc(m, &m->g_enc, NH)); TRY(dalloc(m, &m->touched, N)); }
         TRY(dalloc(m, &m->g_b_enc, H)); TRY(dalloc(m, &m->g_b_dec, N));
-        TRY(alloc_csr(m, &m->yw, m->Bmax, m->max_nnz));
-        TRY(dalloc(m, &m->ybits, (size_t)N * m->ywords));
         TRY(dalloc(m, &m->da, (size_t)m->Bmax * H));
         TRY(dalloc(m, &m->dzT, (size_t)N * kMaxBpad));
         m->nsplit = dh_nsplit(N);
@@ -188,7 +195,6 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
         TRY(dalloc(m, &m->loss_partial, m->n_loss_partial));
         TRY(dalloc(m, &m->sq_partial, 4 * kSqBlocks));
     }
-    TRY(alloc_csr(m, &m->xw, m->Bmax, m->max_nnz));
     TRY(dalloc(m, &m->err, 1));
     TRY(halloc(m, &m->err_host, 1));
     TRY(dalloc(m, &m->rowsum, m->Bmax));
@@ -200,6 +206,13 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     for (int s = 0; s < 2; ++s) {
         Slot& sl = m->slots[s];
         CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.prepared, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
+        TRY(alloc_csr(m, &sl.xw, m->Bmax, m->max_nnz));
+        if (m->trainable) {
+            TRY(alloc_csr(m, &sl.yw, m->Bmax, m->max_nnz));
+            TRY(dalloc(m, &sl.ybits, (size_t)N * m->ywords));
+        }
         TRY(dalloc(m, &sl.x_pos, (size_t)m->max_nnz * 2)); TRY(dalloc(m, &sl.x_val, m->max_nnz));
         TRY(halloc(m, &sl.hx_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hx_val, m->max_nnz));
         if (m->trainable) {
@@ -222,7 +235,13 @@ extern "C" void dae_model_destroy(dae_model* m) {
     if (m->topk_score) cudaFree(m->topk_score);
     if (m->seed_ptr) cudaFree(m->seed_ptr);
     if (m->seed_idx) cudaFree(m->seed_idx);
-    for (int s = 0; s < 2; ++s) if (m->slots[s].h2d_done) cudaEventDestroy(m->slots[s].h2d_done);
+    cudaStreamSynchronize(m->st2);
+    for (int s = 0; s < 2; ++s) {
+        if (m->slots[s].h2d_done) cudaEventDestroy(m->slots[s].h2d_done);
+        if (m->slots[s].prepared) cudaEventDestroy(m->slots[s].prepared);
+        if (m->slots[s].consumed) cudaEventDestroy(m->slots[s].consumed);
+    }
+    cudaStreamDestroy(m->st2);
     if (m->own_stream) cudaStreamDestroy(m->st);
     delete m;
 }
@@ -289,9 +308,33 @@ extern "C" int32_t dae_model_get_adam_state(dae_model* m, float* m_W_enc, float*
 // ------------------------------------------------------------------------------------------
 // staging
 // ------------------------------------------------------------------------------------------
-extern "C" int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val,
-                                         int64_t nnz_x, const int64_t* y_pos, const float* y_val, int64_t nnz_y,
-                                         int32_t batch) {
+// Device-side preparation of a staged batch on the SIDE stream: COO -> CSR (x and y), y bitmask.
+// Independent of the parameters, so it overlaps with the previous step's GEMMs / Adam on the main stream.
+static int prepare_slot(dae_model* m, int slot) {
+    Slot& s = m->slots[slot];
+    CK(cudaStreamWaitEvent(m->st2, s.consumed, 0));       // the previous step on this slot no longer reads it
+    ph_begin(m, PH_PREPARE, m->st2);
+    if (s.y_live) {                                        // clear the bits of the batch this slot held before
+        launch_ybits_set(s.yw, s.yw_batch_dummy(), s.ybits, m->ywords, 0, m->err, m->st2);
+        s.y_live = false;
+        m->launches += 1;
+    }
+    launch_coo_to_csr(s.x_pos, s.x_val, s.nnz_x, s.batch, m->N, s.xw, m->err, m->st2);
+    m->launches += s.nnz_x > 0 ? 4 : 2;
+    if (s.has_y) {
+        launch_coo_to_csr(s.y_pos, s.y_val, s.nnz_y, s.batch, m->N, s.yw, m->err, m->st2);
+        launch_ybits_set(s.yw, s.batch, s.ybits, m->ywords, 1, m->err, m->st2);
+        s.y_live = true;
+        s.y_batch = s.batch;
+        m->launches += (s.nnz_y > 0 ? 4 : 2) + 1;
+    }
+    ph_end(m, PH_PREPARE, m->st2);
+    CK(cudaEventRecord(s.prepared, m->st2));
+    return 0;
+}
+
+static int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                      const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch, bool with_y) {
     if (!m) return fail("null model");
     if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
     if (batch <= 0 || batch > m->Bmax) return fail("batch %d outside (0, %d]", batch, m->Bmax);
@@ -301,24 +344,43 @@ extern "C" int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64
     if (nnz_y > 0 && !m->trainable) return fail("y given to an inference-only model");
     Slot& s = m->slots[slot];
     CK(cudaEventSynchronize(s.h2d_done));   // previous H2D out of this slot's pinned mirror has finished
+    CK(cudaStreamWaitEvent(m->st2, s.consumed, 0));
     s.nnz_x = (int)nnz_x; s.nnz_y = (int)nnz_y; s.batch = batch;
+    s.has_y = with_y;
     if (nnz_x > 0) {
         memcpy(s.hx_pos, x_pos, (size_t)nnz_x * 16);
         memcpy(s.hx_val, x_val, (size_t)nnz_x * 4);
-        CK(cudaMemcpyAsync(s.x_pos, s.hx_pos, (size_t)nnz_x * 16, cudaMemcpyHostToDevice, m->st));
-        CK(cudaMemcpyAsync(s.x_val, s.hx_val, (size_t)nnz_x * 4, cudaMemcpyHostToDevice, m->st));
+        CK(cudaMemcpyAsync(s.x_pos, s.hx_pos, (size_t)nnz_x * 16, cudaMemcpyHostToDevice, m->st2));
+        CK(cudaMemcpyAsync(s.x_val, s.hx_val, (size_t)nnz_x * 4, cudaMemcpyHostToDevice, m->st2));
     }
     if (nnz_y > 0) {
         memcpy(s.hy_pos, y_pos, (size_t)nnz_y * 16);
         memcpy(s.hy_val, y_val, (size_t)nnz_y * 4);
-        CK(cudaMemcpyAsync(s.y_pos, s.hy_pos, (size_t)nnz_y * 16, cudaMemcpyHostToDevice, m->st));
-        CK(cudaMemcpyAsync(s.y_val, s.hy_val, (size_t)nnz_y * 4, cudaMemcpyHostToDevice, m->st));
+        CK(cudaMemcpyAsync(s.y_pos, s.hy_pos, (size_t)nnz_y * 16, cudaMemcpyHostToDevice, m->st2));
+        CK(cudaMemcpyAsync(s.y_val, s.hy_val, (size_t)nnz_y * 4, cudaMemcpyHostToDevice, m->st2));
     }
-    CK(cudaEventRecord(s.h2d_done, m->st));
-    return 0;
+    CK(cudaEventRecord(s.h2d_done, m->st2));
+    return prepare_slot(m, slot);
+}
+
+extern "C" int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val,
+                                         int64_t nnz_x, const int64_t* y_pos, const float* y_val, int64_t nnz_y,
+                                         int32_t batch) {
+    // a trainable model stages training batches (targets may legitimately be empty)
+    return stage_impl(m, slot, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch, m && m->trainable);
+}
+
+// Re-run the device-side preparation of the COO batch already resident in `slot` (bench `value`
+// loop: inputs stay in HBM, every step still does its own COO->CSR / bitmask work, one step ahead).
+extern "C" int32_t dae_model_restage(dae_model* m, int32_t slot) {
+    if (!m) return fail("null model");
+    if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
+    if (m->slots[slot].batch <= 0) return fail("slot %d holds no batch", slot);
+    return prepare_slot(m, slot);
 }
 
 static int check_device_flag(dae_model* m) {
+    CK(cudaStreamSynchronize(m->st2));
     CK(cudaMemcpyAsync(m->err_host, m->err, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     CK(cudaStreamSynchronize(m->st));
     CK(cudaGetLastError());
@@ -333,20 +395,13 @@ static int check_device_flag(dae_model* m) {
 }
 
 // encode forward from a staged slot (shared by train / predict / recommend)
-static void run_encode(dae_model* m, const Slot& s, int rows_pad, float kp, float kp_in, int row_offset,
-                       bool with_y = false) {
-    ph_begin(m, PH_PREPARE);
-    launch_coo_to_csr(s.x_pos, s.x_val, s.nnz_x, s.batch, m->N, m->xw, m->err, m->st);
-    m->launches += s.nnz_x > 0 ? 4 : 2;
-    if (with_y) {
-        launch_coo_to_csr(s.y_pos, s.y_val, s.nnz_y, s.batch, m->N, m->yw, m->err, m->st);
-        launch_ybits_set(m->yw, s.batch, m->ybits, m->ywords, 1, m->err, m->st);
-        m->launches += (s.nnz_y > 0 ? 4 : 2) + 1;
-    }
-    ph_end(m, PH_PREPARE);
+static void run_encode(dae_model* m, int slot, int rows_pad, float kp, float kp_in, int row_offset) {
+    const Slot& s = m->slots[slot];
+    m->cur = slot;
+    cudaStreamWaitEvent(m->st, s.prepared, 0);
     ph_begin(m, PH_ENCODE);
     EncodeArgs e{};
-    e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = m->xw; e.rowsum = m->rowsum; e.h = m->h; e.h_d = m->h_d;
+    e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = s.xw; e.rowsum = m->rowsum; e.h = m->h; e.h_d = m->h_d;
     e.h_dT = m->h_dT; e.B = s.batch; e.bpad = rows_pad; e.H = m->H; e.kp = kp; e.kp_in = kp_in;
     e.seed = m->cfg.seed; e.step = (unsigned long long)m->step; e.row_offset = row_offset;
     launch_encode_fwd(e, m->st);
@@ -366,11 +421,12 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     const int gb = global_batch > 0 ? global_batch : B;
     m->last_batch = B; m->last_bpad = bpad;
 
-    run_encode(m, s, bpad, keep_prob, input_keep_prob, row_offset, true);
+    if (!s.has_y) return fail("slot %d was staged without targets", slot);
+    run_encode(m, slot, bpad, keep_prob, input_keep_prob, row_offset);
 
     DecodeArgs d{};
     d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
-    d.ybits = m->ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.db_dec = m->g_b_dec;
+    d.ybits = s.ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.db_dec = m->g_b_dec;
     d.loss_partial = m->loss_partial; d.inv_batch = 1.0f / (float)gb;
     const int ngrid = decode_grid(N, 1);
     ph_begin(m, PH_DECODE_LOSS);
@@ -389,13 +445,13 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     ph_end(m, PH_DH);
 
     EncodeBwdArgs eb{};
-    eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.x = m->xw; eb.da = m->da;
+    eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.x = s.xw; eb.da = m->da;
     eb.g_enc = m->g_enc; eb.touched = m->touched; eb.db_enc = m->g_b_enc; eb.B = B; eb.bpad = bpad; eb.H = H;
     eb.kp = keep_prob; eb.seed = m->cfg.seed; eb.step = (unsigned long long)m->step; eb.row_offset = row_offset;
     ph_begin(m, PH_ENCODE_BWD);
     launch_encode_bwd(eb, m->st);
-    launch_ybits_set(m->yw, B, m->ybits, m->ywords, 0, m->err, m->st);
-    m->launches += 3 + 2 + 1;
+    CK(cudaEventRecord(s.consumed, m->st));                 // the slot may be re-prepared from here on
+    m->launches += 3 + 2;
 
     int n_sq = 0;
     const float lam = m->cfg.reg_lambda;
@@ -484,12 +540,14 @@ static int ensure_scores(dae_model* m, size_t elems) {
     return 0;
 }
 
-static int run_predict(dae_model* m, const Slot& s, int n_cols, float* out_dev, long long ld) {
+static int run_predict(dae_model* m, int slot, int n_cols, float* out_dev, long long ld) {
+    const Slot& s = m->slots[slot];
     const int B = s.batch;
     int bpad, nbt;
     if (B <= kMaxBpad) { bpad = round_up(B, 64); nbt = 1; }
     else { bpad = kMaxBpad; nbt = (B + kMaxBpad - 1) / kMaxBpad; }
-    run_encode(m, s, bpad * nbt, 1.0f, 1.0f, 0);          // keep_prob = input_keep_prob = 1 (main_train.py:68)
+    run_encode(m, slot, bpad * nbt, 1.0f, 1.0f, 0);       // keep_prob = input_keep_prob = 1 (main_train.py:68)
+    CK(cudaEventRecord(s.consumed, m->st));
     DecodeArgs d{};
     d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
     d.n_batch_tiles = nbt; d.out = out_dev; d.ld_out = ld; d.n_out = n_cols;
@@ -502,9 +560,9 @@ extern "C" int32_t dae_model_predict(dae_model* m, const int64_t* x_pos, const f
                                      int32_t batch, int32_t n_cols, float* y_pred_out) {
     if (!m || !y_pred_out) return fail("null argument");
     if (n_cols <= 0 || n_cols > m->N) return fail("n_cols must be in (0, n_input]");
-    TRY(dae_model_stage_batch(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch));
+    TRY(stage_impl(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch, false));
     TRY(ensure_scores(m, (size_t)batch * n_cols));
-    TRY(run_predict(m, m->slots[0], n_cols, m->scores, n_cols));
+    TRY(run_predict(m, 0, n_cols, m->scores, n_cols));
     CK(cudaMemcpyAsync(y_pred_out, m->scores, (size_t)batch * n_cols * sizeof(float), cudaMemcpyDeviceToHost, m->st));
     return check_device_flag(m);
 }
@@ -523,7 +581,7 @@ extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const
                                        int32_t* out_idx, float* out_score) {
     if (!m || !out_idx) return fail("null argument");
     if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
-    TRY(dae_model_stage_batch(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch));
+    TRY(stage_impl(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch, false));
     const int T = m->T;
     TRY(ensure_scores(m, (size_t)batch * T));
     size_t tk = m->topk_elems;
@@ -540,7 +598,7 @@ extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const
         if (nseed > 0) CK(cudaMemcpyAsync(m->seed_idx, seed_idx, (size_t)nseed * 4, cudaMemcpyHostToDevice, m->st));
         sp = m->seed_ptr; si = m->seed_idx;
     }
-    TRY(run_predict(m, m->slots[0], T, m->scores, T));
+    TRY(run_predict(m, 0, T, m->scores, T));
     TopkArgs a{};
     a.scores = m->scores; a.ld = T; a.B = batch; a.T = T; a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.idx_base = 0;
     a.out_idx = m->topk_idx; a.out_score = m->topk_score;
@@ -558,6 +616,7 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
                                     int32_t* elem_size) {
     if (!m || !name || !dev_ptr) return fail("null argument");
     const int64_t NH = (int64_t)m->N * m->H;
+    const Slot& sl = m->slots[m->cur];
     struct E { const char* n; void* p; int64_t c; int32_t s; };
     const E table[] = {
         {"g_dec", m->g_dec, NH, 4}, {"g_enc", m->g_enc, NH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
@@ -568,10 +627,10 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
         {"h_dT", m->h_dT, (int64_t)m->rows_alloc * m->H, 2},
         {"dzT", m->dzT, (int64_t)m->N * kMaxBpad, 2},
         {"dh_partial", m->dh_partial, (int64_t)m->nsplit * kMaxBpad * m->H, 4}, {"da", m->da, (int64_t)m->Bmax * m->H, 4},
-        {"x_row_ptr", m->xw.row_ptr, m->Bmax + 1, 4}, {"x_row_len", m->xw.row_len, m->Bmax, 4},
-        {"x_col", m->xw.col, m->max_nnz, 4}, {"x_val", m->xw.val, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
-        {"y_row_ptr", m->yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", m->yw.row_len, m->Bmax, 4},
-        {"y_col", m->yw.col, m->max_nnz, 4}, {"ybits", m->ybits, (int64_t)m->N * m->ywords, 4},
+        {"x_row_ptr", sl.xw.row_ptr, m->Bmax + 1, 4}, {"x_row_len", sl.xw.row_len, m->Bmax, 4},
+        {"x_col", sl.xw.col, m->max_nnz, 4}, {"x_val", sl.xw.val, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
+        {"y_row_ptr", sl.yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", sl.yw.row_len, m->Bmax, 4},
+        {"y_col", sl.yw.col, m->max_nnz, 4}, {"ybits", sl.ybits, (int64_t)m->N * m->ywords, 4},
         {"scores", m->scores, (int64_t)m->scores_elems, 4},
         {"mW_dec", m->mW_dec, NH, 4}, {"vW_dec", m->vW_dec, NH, 4}, {"mW_enc", m->mW_enc, NH, 4}, {"vW_enc", m->vW_enc, NH, 4},
     };

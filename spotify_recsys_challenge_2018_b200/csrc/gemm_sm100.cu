@@ -72,6 +72,8 @@ static CUtensorMap make_map_bf16(const void* ptr, uint64_t inner, uint64_t outer
 enum { MODE_TRAIN = 0, MODE_PREDICT = 1, MODE_DW = 2 };
 
 constexpr int kStages = 6;
+constexpr int kEpiWarps = 8;                         // 2 warps per TMEM lane quadrant: each takes half the columns
+constexpr int kItemThreads = 64 + 32 * kEpiWarps;
 constexpr int kABytes = kTileItems * 128;           // one K-chunk of the streamed operand: 128 rows x 128 B
 constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the resident operand: <=256 rows x 128 B
 constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
@@ -104,7 +106,7 @@ struct ItemTileDev {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kItemThreads, 1)
 k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ItemTileDev p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -118,7 +120,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint64_t* tfull = bfull + 1;           // [2]
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [4]
+    float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -134,7 +136,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         mbar_init(bfull, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -200,12 +202,14 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp owns
         const int row_in_tile = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
         float loss_acc = 0.f;
         const int nchunks = p.n_cols >> 5;
+        const int c_lo = half * (nchunks >> 1), c_hi = c_lo + (nchunks >> 1);
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int item = tile * kTileItems + row_in_tile;
             const bool item_ok = item < p.n_items;
@@ -218,7 +222,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (MODE == MODE_TRAIN) {
                 if (item_ok) {
                     yrow = p.ybits + (size_t)item * p.ywords;
-                    yw_next = __ldg(yrow);
+                    yw_next = __ldg(yrow + c_lo);
                 }
             }
             float db = 0.f;
@@ -226,14 +230,14 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t r[32];
                 tmem_ld32(t_addr + c * 32, r);
                 tmem_ld_wait();
                 if (MODE == MODE_TRAIN) {
                     uint32_t packed[16];
                     const uint32_t w = yw_next;
-                    if (item_ok && c + 1 < nchunks) yw_next = __ldg(yrow + c + 1);
+                    if (item_ok && c + 1 < c_hi) yw_next = __ldg(yrow + c + 1);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         float dzv[2];
@@ -261,10 +265,9 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
                     }
                     if (item_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.dzT + (size_t)item * p.ld_dz + c * 32);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v)
-                            dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                        __nv_bfloat16* dst = p.dzT + (size_t)item * p.ld_dz + c * 32;   // 64 B: two full 32 B sectors
+                        st_global_v8(dst, packed);
+                        st_global_v8(dst + 16, packed + 8);
                     }
                 } else if (MODE == MODE_PREDICT) {
                     const bool col_ok = item < p.n_out;
@@ -284,16 +287,14 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     }
                 } else {  // MODE_DW
                     if (item_ok) {
-                        float4* dst = reinterpret_cast<float4*>(p.g + (size_t)item * p.n_cols + c * 32);
+                        float* dst = p.g + (size_t)item * p.n_cols + c * 32;             // 128 B: one full line
 #pragma unroll
-                        for (int v = 0; v < 8; ++v)
-                            dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                        for (int v = 0; v < 4; ++v) st_global_v8(dst + 8 * v, r + 8 * v);
                     }
                 }
             }
             if (MODE == MODE_TRAIN) {
-                if (item_ok) p.db_dec[item] = db;
+                if (item_ok) atomicAdd(p.db_dec + item, db);   // two addends per item (one per column half): order-independent
             }
             tc_fence_before();
             __syncwarp();
@@ -304,7 +305,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (MODE == MODE_TRAIN) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-            if (lane == 0) loss_smem[q] = loss_acc;
+            if (lane == 0) loss_smem[warp - 2] = loss_acc;
         }
     }
 
@@ -312,7 +313,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     __syncthreads();
     tc_fence_after();
     if (MODE == MODE_TRAIN) {
-        if (threadIdx.x == 0) p.loss_partial[blockIdx.x] = (loss_smem[0] + loss_smem[1]) + (loss_smem[2] + loss_smem[3]);
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < kEpiWarps; ++i) t += loss_smem[i];
+            p.loss_partial[blockIdx.x] = t;
+        }
     }
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
@@ -342,7 +347,7 @@ static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
         cudaFuncSetAttribute(k_itemtile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
         configured = true;
     }
-    k_itemtile<MODE><<<grid, 192, kSmemItemTile, st>>>(tmA, tmB, p);
+    k_itemtile<MODE><<<grid, kItemThreads, kSmemItemTile, st>>>(tmA, tmB, p);
 }
 
 static ItemTileDev decode_dev(const DecodeArgs& a) {
@@ -371,6 +376,7 @@ static ItemTileDev decode_dev(const DecodeArgs& a) {
 }
 
 void launch_decode_train(const DecodeArgs& a, cudaStream_t st) {
+    cudaMemsetAsync(a.db_dec, 0, sizeof(float) * a.N, st);   // the epilogue accumulates two column halves
     const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
     const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, a.bpad, a.bpad);
     ItemTileDev p = decode_dev(a);
@@ -515,11 +521,9 @@ k_dh(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
                 if (brow < p.bpad) {
-                    float4* dst = reinterpret_cast<float4*>(out + (size_t)brow * p.H + c * 32);
+                    float* dst = out + (size_t)brow * p.H + c * 32;
 #pragma unroll
-                    for (int v = 0; v < 8; ++v)
-                        dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                             __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    for (int v = 0; v < 4; ++v) st_global_v8(dst + 8 * v, r + 8 * v);
                 }
             }
         }

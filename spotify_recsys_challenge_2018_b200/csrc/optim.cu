@@ -29,10 +29,10 @@ __device__ __forceinline__ void adam_one(float& w, float& m, float& v, float g, 
 // n4 float4 groups; row_len4 = row_len/4 (groups per row) when row_touched != nullptr
 __global__ void __launch_bounds__(256)
 k_adam_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v, const float4* __restrict__ g,
-            uint2* __restrict__ wb, const unsigned char* __restrict__ touched, long long n4, int row_len4,
-            const AdamConst c) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            uint2* __restrict__ wb, const unsigned char* __restrict__ touched, unsigned int n4,
+            unsigned int row_len4, const AdamConst c) {
+    const unsigned int stride = gridDim.x * blockDim.x;                 // n4 < 2^31: 32-bit index math
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (touched == nullptr || touched[i / row_len4] != 0) gv = __ldcs(g + i);
         float4 wv = __ldcs(w + i), mv = __ldcs(m + i), vv = __ldcs(v + i);
@@ -80,8 +80,8 @@ void launch_adam(const AdamArgs& a, cudaStream_t st) {
         if (blocks > cap) blocks = cap;
         k_adam_vec4<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(a.w), reinterpret_cast<float4*>(a.m),
                                                  reinterpret_cast<float4*>(a.v), reinterpret_cast<const float4*>(a.g),
-                                                 reinterpret_cast<uint2*>(a.w_bf16), a.row_touched, n4,
-                                                 a.row_touched ? a.row_len / 4 : 1, c);
+                                                 reinterpret_cast<uint2*>(a.w_bf16), a.row_touched,
+                                                 (unsigned int)n4, (unsigned int)(a.row_touched ? a.row_len / 4 : 1), c);
     }
     const long long done = n4 * 4;
     if (done < a.n) {
@@ -159,20 +159,27 @@ void launch_reduce_loss2(const float* partial, int n, const float* sumsq_partial
     k_reduce_loss<<<1, 256, 0, st>>>(partial, n, sumsq_partial, n_sq, 0.5f * lambda, inv_batch, loss_out);
 }
 
-// zero every gradient row whose flag is set, and the flag (rows may have been touched by any rank)
+// zero every gradient row whose flag is set, and the flag (rows may have been touched by any rank).
+// One warp scans 32 flags with a coalesced read, then zeroes each flagged row cooperatively.
 __global__ void k_clear_flagged(int N, int H, float* __restrict__ g_enc, unsigned char* __restrict__ touched) {
-    const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
-    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < N; row += gridDim.x * warps_per_block) {
-        if (touched[row] != 0) {
-            for (int k = lane; k < H; k += 32) g_enc[(size_t)row * H + k] = 0.f;
-            __syncwarp();
-            if (lane == 0) touched[row] = 0;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp_global * 32; base < N; base += nwarps * 32) {
+        const int row = base + lane;
+        const bool f = row < N && touched[row] != 0;
+        unsigned int m = __ballot_sync(0xffffffffu, f);
+        if (f) touched[row] = 0;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            float4* dst = reinterpret_cast<float4*>(g_enc + (size_t)(base + b) * H);
+            for (int k = lane; k < (H >> 2); k += 32) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
 void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, cudaStream_t st) {
-    k_clear_flagged<<<592, 256, 0, st>>>(N, H, g_enc, touched);
+    k_clear_flagged<<<(N + 255) / 256, 256, 0, st>>>(N, H, g_enc, touched);
 }
 
 }  // namespace dae

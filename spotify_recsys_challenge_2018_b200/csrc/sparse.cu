@@ -186,7 +186,7 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
              float* __restrict__ rowsum, float* __restrict__ h, __nv_bfloat16* __restrict__ h_d,
              __nv_bfloat16* __restrict__ h_dT, int B, int bpad, int H, float kp, float kp_in,
              unsigned long long seed, unsigned long long step, int row_offset) {
-    __shared__ float s_x[kMaxRowNnz];
+    __shared__ __align__(16) float s_x[kMaxRowNnz];
     __shared__ int s_c[kMaxRowNnz];
     __shared__ float s_red[8];
     const int r = blockIdx.x;
@@ -222,26 +222,47 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     (void)inv;
     if (threadIdx.x == 0) rowsum[r] = s;
     __syncthreads();
+    // a4: a = sum_j x_n[j] * W_enc[col_j, :].  Thread (g, t): row group g takes entries j = g (mod G),
+    // lane t owns columns [4t, 4t+4) as one float4 -> every gathered row is a run of coalesced 16 B loads
+    // and up to 4*G rows are in flight per CTA.  Groups are combined through smem in a fixed order.
+    const int tpr = H >> 2;                      // threads per row
+    const int G = blockDim.x / tpr;              // concurrent row groups
+    const int g = threadIdx.x / tpr, t = threadIdx.x - g * tpr;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < G) {
+        int i = g;
+        for (; i + 3 * G < n; i += 4 * G) {
+            float x[4];
+            float4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[u] = s_x[i + u * G];
+                w[u] = x[u] != 0.f ? __ldg(reinterpret_cast<const float4*>(W + (size_t)s_c[i + u * G] * H) + t)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc.x = fmaf(x[u], w[u].x, acc.x); acc.y = fmaf(x[u], w[u].y, acc.y);
+                acc.z = fmaf(x[u], w[u].z, acc.z); acc.w = fmaf(x[u], w[u].w, acc.w);
+            }
+        }
+        for (; i < n; i += G) {
+            const float x0 = s_x[i];
+            if (x0 != 0.f) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)s_c[i] * H) + t);
+                acc.x = fmaf(x0, w0.x, acc.x); acc.y = fmaf(x0, w0.y, acc.y);
+                acc.z = fmaf(x0, w0.z, acc.z); acc.w = fmaf(x0, w0.w, acc.w);
+            }
+        }
+    }
+    __syncthreads();                              // s_x / s_c are dead from here: reuse s_x as the [G][H] staging area
+    float* s_acc = s_x;
+    if (g < G) *reinterpret_cast<float4*>(s_acc + g * H + 4 * t) = acc;
+    __syncthreads();
     if (k >= H) return;
-    // a4: a = sum_j x_n[j] * W_enc[col_j, k]   (4 independent accumulators -> 4 loads in flight)
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int i = 0;
-    for (; i + 4 <= n; i += 4) {
-        const float x0 = s_x[i], x1 = s_x[i + 1], x2 = s_x[i + 2], x3 = s_x[i + 3];
-        const float w0 = x0 != 0.f ? __ldg(W + (size_t)s_c[i] * H + k) : 0.f;
-        const float w1 = x1 != 0.f ? __ldg(W + (size_t)s_c[i + 1] * H + k) : 0.f;
-        const float w2 = x2 != 0.f ? __ldg(W + (size_t)s_c[i + 2] * H + k) : 0.f;
-        const float w3 = x3 != 0.f ? __ldg(W + (size_t)s_c[i + 3] * H + k) : 0.f;
-        a0 = fmaf(x0, w0, a0);
-        a1 = fmaf(x1, w1, a1);
-        a2 = fmaf(x2, w2, a2);
-        a3 = fmaf(x3, w3, a3);
-    }
-    for (; i < n; ++i) {
-        const float x0 = s_x[i];
-        if (x0 != 0.f) a0 = fmaf(x0, __ldg(W + (size_t)s_c[i] * H + k), a0);
-    }
-    const float a = ((a0 + a1) + (a2 + a3)) + b_enc[k];
+    float a = 0.f;
+    for (int gg = 0; gg < G; ++gg) a += s_acc[gg * H + k];
+    a += b_enc[k];
     const float hv = __fdividef(1.f, 1.f + __expf(-a));
     const bool keep = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(k), kp);
     const float hd = keep ? __fdiv_rn(hv, kp) : 0.f;
@@ -252,7 +273,7 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
 }
 
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st) {
-    const int threads = a.H <= 64 ? 64 : (a.H <= 128 ? 128 : 256);
+    const int threads = 256;                      // G = 1024 / H row groups of H/4 threads
     k_encode_fwd<<<a.bpad, threads, 0, st>>>(a.W_enc, a.b_enc, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val, a.rowsum,
                                              a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.kp, a.kp_in, a.seed, a.step,
                                              a.row_offset);
@@ -268,52 +289,71 @@ k_encode_bwd(const float* __restrict__ dh_partial, int nsplit, const float* __re
              const float* __restrict__ xn, float* __restrict__ da_out, float* __restrict__ g_enc,
              unsigned char* __restrict__ touched, int B, int bpad, int H, float kp, unsigned long long seed,
              unsigned long long step, int row_offset) {
+    __shared__ __align__(16) float s_da[256];
     const int r = blockIdx.x;
     const int k = threadIdx.x;
-    if (k >= H) return;
-    float dh = 0.f;
-    const size_t stride = (size_t)bpad * H;
-    const float* p = dh_partial + (size_t)r * H + k;
-    int s = 0;
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    for (; s + 4 <= nsplit; s += 4) {
-        d0 += p[(size_t)s * stride];
-        d1 += p[(size_t)(s + 1) * stride];
-        d2 += p[(size_t)(s + 2) * stride];
-        d3 += p[(size_t)(s + 3) * stride];
+    if (k < H) {
+        const size_t stride = (size_t)bpad * H;
+        const float* p = dh_partial + (size_t)r * H + k;
+        int s = 0;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        for (; s + 4 <= nsplit; s += 4) {                     // fixed order: deterministic
+            d0 += p[(size_t)s * stride];
+            d1 += p[(size_t)(s + 1) * stride];
+            d2 += p[(size_t)(s + 2) * stride];
+            d3 += p[(size_t)(s + 3) * stride];
+        }
+        for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
+        const float dh = (d0 + d1) + (d2 + d3);
+        const float hv = h[(size_t)r * H + k];
+        const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(r + row_offset),
+                                      static_cast<uint32_t>(k), kp);
+        const float da = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
+        da_out[(size_t)r * H + k] = da;
+        s_da[k] = da;
     }
-    for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
-    dh = (d0 + d1) + (d2 + d3);
-    const float hv = h[(size_t)r * H + k];
-    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(r + row_offset),
-                                  static_cast<uint32_t>(k), kp);
-    const float da = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
-    da_out[(size_t)r * H + k] = da;
+    __syncthreads();
+    // scatter-add: thread (g, t) takes entries j = g (mod G), lane t adds 4 columns with one 16-byte reduction
+    const int tpr = H >> 2, G = blockDim.x / tpr;
+    const int g = threadIdx.x / tpr, t = threadIdx.x - g * tpr;
+    if (g >= G) return;
+    const float4 dav = *reinterpret_cast<const float4*>(s_da + 4 * t);
     const int beg = row_ptr[r], n = row_len[r];
-    for (int i = 0; i < n; ++i) {
+    for (int i = g; i < n; i += G) {
         const float x = xn[beg + i];
         if (x != 0.f) {
             const int c = col[beg + i];
-            atomicAdd(g_enc + (size_t)c * H + k, x * da);
-            if (touched != nullptr && k == 0) touched[c] = 1;
+            float* dst = g_enc + (size_t)c * H + 4 * t;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x * dav.x), "f"(x * dav.y),
+                         "f"(x * dav.z), "f"(x * dav.w)
+                         : "memory");
+            if (touched != nullptr && t == 0) touched[c] = 1;
         }
     }
 }
 
+// db_enc[k] = sum_r da[r,k]: 8 row groups per block, combined in a fixed order
 __global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __restrict__ out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= H) return;
+    __shared__ float s_p[8][32];
+    const int k = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += x[(size_t)r * H + k];
-    out[k] = s;
+    if (k < H)
+        for (int r = threadIdx.y; r < rows; r += 8) s += x[(size_t)r * H + k];
+    s_p[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < H) {
+        float t = 0.f;
+        for (int g = 0; g < 8; ++g) t += s_p[g][threadIdx.x];
+        out[k] = t;
+    }
 }
 
 void launch_encode_bwd(const EncodeBwdArgs& a, cudaStream_t st) {
-    const int threads = a.H <= 64 ? 64 : (a.H <= 128 ? 128 : 256);
+    const int threads = 256;
     k_encode_bwd<<<a.B, threads, 0, st>>>(a.dh_partial, a.nsplit, a.h, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val,
                                           a.da, a.g_enc, a.touched, a.B, a.bpad, a.H, a.kp, a.seed, a.step,
                                           a.row_offset);
-    k_colsum<<<(a.H + 63) / 64, 64, 0, st>>>(a.da, a.B, a.H, a.db_enc);
+    k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.B, a.H, a.db_enc);
 }
 
 // zero the rows of g_enc that the step touched (and their flags) so the buffer is clean again

@@ -154,6 +154,9 @@ class DAE_tied:
         _lib.check(self._lib.dae_model_stage_batch(self._h, slot, _ptr(xp), _ptr(xv), xp.shape[0], _ptr(yp),
                                                    _ptr(yv), yp.shape[0], self.n_batch))
 
+    def restage(self, slot):
+        _lib.check(self._lib.dae_model_restage(self._h, slot))
+
     def train_step_staged(self, slot, keep_prob, input_keep_prob):
         _lib.check(self._lib.dae_model_train_step_staged(self._h, slot, float(keep_prob), float(input_keep_prob)))
 

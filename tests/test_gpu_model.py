@@ -117,7 +117,12 @@ def test_train_step_stage_by_stage(tied, N, T, H, B):
     if not tied:                                                            # gradient buffers are clean again
         assert model_buf(m, "touched", torch.uint8).sum().item() == 0
         assert model_buf(m, "g_enc", torch.float32).abs().sum().item() == 0
-    assert model_buf(m, "ybits", torch.int32).abs().sum().item() == 0
+    # re-staging the slot clears the previous batch's target bits before setting the new ones
+    trk2, art2, y2 = random_batch(np.random.default_rng(99), B, T, N - T, mean_len=10)
+    m.stage_batch(0, trk2, np.ones(len(trk2), np.float32), y2, np.ones(len(y2), np.float32))
+    m.sync_cost()
+    bits = model_buf(m, "ybits", torch.int32).cpu().numpy().view(np.uint32)
+    assert int(np.unpackbits(bits.view(np.uint8)).sum()) == len(np.unique(y2, axis=0))
     shadow = model_buf(m, "W_dec_bf16", torch.bfloat16).float().cpu().numpy().reshape(N, H)
     assert np.array_equal(shadow, O.bf16_round(got[1]))                    # shadow == bf16(master), bit-exact
     m.close()
