@@ -175,6 +175,7 @@ def main():
     conf = Conf()
     conf.save = "/tmp/bench_w"; conf.batch = B; conf.n_input = N; conf.n_tracks = T; conf.hidden = H
     conf.lr = LR; conf.reg_lambda = 0.0; conf.initval = "NULL"; conf.seed = 0; conf.device = local_rank
+    conf.world = world; conf.rank = rank
     stream = torch.cuda.Stream()
     conf.stream = stream.cuda_stream
     with torch.cuda.stream(stream):
@@ -240,8 +241,8 @@ def main():
                    "api": "models.DAEs.DAE.train_step (dae_model_train_step): host int64 COO + fp32 values in, "
                           "cost out, synchronous"}
         else:
-            # DP: per step every rank shards nothing on the host here (inputs are per-rank batches);
-            # H2D of the rank's batch + all-reduce + D2H of the cost inside the timed region
+            # DP: every rank feeds its own B rows of the global batch from host memory: H2D of the rank's batch,
+            # the step (NVLink exchange inside the kernels) and D2H of the cost inside the timed region
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -276,18 +277,24 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        # dominant kernel: k_adam_vec4 on the decoder matrix.  Algorithmic bytes per launch:
-        # read g,w,m,v (16 B) + write w,m,v (12 B) + write the bf16 operand shadow (2 B) = 30 B / parameter
-        adam_bytes = 30.0 * N * H
-        adam_ms = phases.get("adam_dec")
+        # dominant kernel: k_itemtile<DW> = dW_dec contraction + dense TF1 Adam in the epilogue, on the decoder rows
+        # this GPU owns (N/world).  Algorithmic bytes per launch: read w,m,v (12 B) + write w,m,v (12 B)
+        # + write the bf16 operand copy (2 B, x world copies of which world-1 go over NVLink) = 26 B / parameter,
+        # + the dz operand (2 B x world*Bpad columns per owned row).  The gradient itself never touches HBM.
+        n_own = N / world
+        adam_bytes = 26.0 * n_own * H + 2.0 * n_own * (world * ((B + 63) // 64 * 64))
+        adam_ms = phases.get("dw_adam_dec")
         roofline = None
         if adam_ms:
             ach = adam_bytes / (adam_ms / 1e3) / 1e9
-            roofline = {"kernel": "k_adam_vec4 (decoder matrix, dense TF1 Adam + bf16 shadow)", "bound": "hbm",
+            roofline = {"kernel": "k_itemtile<DW>: tcgen05 dW_dec = dz^T.h_d with the dense TF1 Adam update + bf16 "
+                                  "operand refresh fused into the TMEM epilogue", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": adam_bytes,
                         "launch_ms": adam_ms}
-        step_bytes = (30.0 + (24.0 if not tied else 0.0) + 2.0 + 4.0 + 2.0) * N * H   # + decode read, g write, dh read of W
+        # whole step (per GPU): fused decoder update 26 + encoder Adam 24 (untied) on the owned rows, + W operand read by
+        # decode and dh (2 + 2) + dz write (2) and re-read by dh and dW (2 + 2) over all N rows
+        step_bytes = (26.0 + (24.0 if not tied else 0.0)) * n_own * H + 10.0 * N * H
         line = {"metric": "dae_train_playlists_per_sec", "value": value, "unit": "playlists/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -297,6 +304,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(wl, args.cpu_steps if wl == "cfg2" else 50, 2)
         print(json.dumps(line))
+    barrier()          # no rank unmaps its arena while a peer may still read it
     model.close()
     if world > 1:
         dist.destroy_process_group()

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DAE_B200_ABI_VERSION 1
+#define DAE_B200_ABI_VERSION 2
 
 typedef struct dae_model dae_model; /* opaque: parameters, Adam state, workspaces, stream */
 
@@ -37,6 +37,8 @@ typedef struct dae_config {
     int32_t device;      /* CUDA device ordinal                                                    */
     int32_t trainable;   /* 0: inference only (no Adam state / gradient buffers; DAE_title's frozen DAE, DAEs.py:164-171) */
     void* stream;        /* cudaStream_t to run on, or NULL to create a private stream            */
+    int32_t world;       /* data-parallel ranks (GPUs of one NVSwitch box, <= 8); 0 or 1 = single GPU       */
+    int32_t rank;        /* this model's rank in [0, world)                                                  */
 } dae_config;
 
 int32_t dae_abi_version(void);
@@ -91,22 +93,47 @@ int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64_t* x_pos, 
  * one step ahead of the main stream. */
 int32_t dae_model_restage(dae_model* m, int32_t slot);
 /* Forward + backward from a staged slot; gradients stay in device buffers; no host sync.
- * global_batch / row_offset: the loss is a mean over the GLOBAL batch (DAEs.py:100) and dropout is
- * keyed by the global row, so N ranks x B_local == one rank x (N*B_local). */
+ * The loss is a mean over the GLOBAL batch (DAEs.py:100) and dropout is keyed by the global row, so
+ * N ranks x B_local == one rank x (N*B_local).  global_batch = 0: world * batch, row_offset = rank * batch.
+ * With world > 1 this enqueues a cross-GPU barrier first (all ranks must call it). */
 int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
                                   int32_t global_batch, int32_t row_offset);
-/* Dense TF1 Adam on every variable from the gradient buffers, then step += 1.   DAEs.py:102 */
+/* Dense TF1 Adam on every variable, then step += 1.  The decoder's dW_dec = dz^T h_d is contracted
+ * here, tile by tile in tensor memory, and consumed by the Adam update in the same epilogue.   DAEs.py:102 */
 int32_t dae_model_apply_adam(dae_model* m);
 /* backward_staged + apply_adam (single GPU). */
 int32_t dae_model_train_step_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob);
 /* Synchronise the stream, check the device-side error flag, return the last step's cost. */
 int32_t dae_model_sync_cost(dae_model* m, float* cost_out);
 
-/* Named device buffers (pointer, element count, element size) for collectives issued by the host
- * layer (torch.distributed / NCCL all-reduce of the gradients) and for parity tests.  Names:
- * "g_dec" "g_enc" "g_b_enc" "g_b_dec" "touched" "cost" "W_enc" "W_dec" "W_dec_bf16" "b_enc" "b_dec"
- * "h" "h_d" "dzT" "dh_partial" "da" "x_row_ptr" "x_row_len" "x_col" "x_val" "x_rowsum"
- * "y_row_ptr" "y_row_len" "y_col" "ybits" "scores". */
+/* ---- data parallelism over the GPUs of one box (the reference has none) --------------
+ * One process (or model) per GPU, `world` of them.  The train step shards by playlist: every rank
+ * runs encode / decode / loss / dh on its own batch rows, and the catalogue-sized state (W_enc,
+ * W_dec, Adam moments) is row-sharded tile-cyclically, ZeRO style.  All exchange is plain loads /
+ * stores into the peers' arenas over NVLink, fused into the producing kernels: the decode epilogue
+ * stores each item tile's dz on the tile's owner, the owner's dW + Adam epilogue stores the new bf16
+ * operand rows on every rank, encode gathers W_enc rows from their owners.  Two flag barriers per
+ * step order it.  Every rank must stage batches of the same size and call the step functions in the
+ * same order.  Attach once after dae_model_create on every rank:
+ *   dae_model_ipc_handle  -> 64-byte cudaIpcMemHandle_t of this rank's arena (exchange them out of band)
+ *   dae_model_attach_ipc  <- all `world` handles in rank order (own slot ignored)
+ *   dae_model_attach_local: peers living in the SAME process (tests; several models on one or more GPUs) */
+int32_t dae_model_ipc_handle(dae_model* m, void* handle_out64);
+int32_t dae_model_attach_ipc(dae_model* m, const void* handles, int32_t n_handles);
+int32_t dae_model_attach_local(dae_model* m, dae_model* const* peers, int32_t n_peers);
+int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
+
+/* debug flags: bit 0 = dae_model_backward_staged also materialises the raw dW_dec of the rows this
+ * rank owns (buffer "g_dec"); the train step itself never writes it (fused dW + Adam epilogue).
+ * bit 1 = it also runs the sparse-row dW_enc scatter ("g_enc", "touched"), which otherwise happens
+ * inside dae_model_apply_adam and is cleared by it. */
+int32_t dae_model_set_debug(dae_model* m, int32_t flags);
+
+/* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row
+ * buffers hold the rows this rank owns in local-tile order (== global order when world == 1).  Names:
+ * "g_dec" "g_enc" "g_b_enc" "g_b_dec" "g_b_enc_part" "g_b_dec_part" "touched" "cost" "W_enc" "W_dec"
+ * "W_dec_bf16" "b_enc" "b_dec" "h" "h_d" "h_dT" "dzT" "dz_all" "dh_partial" "da" "x_row_ptr" "x_row_len"
+ * "x_col" "x_val" "x_rowsum" "y_row_ptr" "y_row_len" "y_col" "ybits" "scores" "mW_dec" "vW_dec" "mW_enc" "vW_enc". */
 int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size);
 /* number of kernels launched by this model since creation (bench.py `gpu_launches`) */
 int64_t dae_model_launch_count(dae_model* m);

@@ -13,6 +13,7 @@ class DaeConfig(C.Structure):
         ("n_input", C.c_int32), ("n_tracks", C.c_int32), ("n_hidden", C.c_int32), ("max_batch", C.c_int32),
         ("tied", C.c_int32), ("lr", C.c_float), ("reg_lambda", C.c_float), ("seed", C.c_uint64),
         ("device", C.c_int32), ("trainable", C.c_int32), ("stream", C.c_void_p),
+        ("world", C.c_int32), ("rank", C.c_int32),
     ]
 
 
@@ -42,6 +43,11 @@ SIGNATURES = {
     "dae_model_apply_adam": (_I32, [_P]),
     "dae_model_train_step_staged": (_I32, [_P, _I32, _F, _F]),
     "dae_model_sync_cost": (_I32, [_P, C.POINTER(_F)]),
+    "dae_model_ipc_handle": (_I32, [_P, _P]),
+    "dae_model_attach_ipc": (_I32, [_P, _P, _I32]),
+    "dae_model_attach_local": (_I32, [_P, C.POINTER(_P), _I32]),
+    "dae_model_arena_bytes": (_I32, [_P, C.POINTER(_I64)]),
+    "dae_model_set_debug": (_I32, [_P, _I32]),
     "dae_model_buffer": (_I32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
     "dae_model_launch_count": (_I64, [_P]),
     "dae_model_set_profiling": (_I32, [_P, _I32]),

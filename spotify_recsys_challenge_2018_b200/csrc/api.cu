@@ -42,7 +42,6 @@ struct Slot {
     float *hx_val = nullptr, *hy_val = nullptr;
     int nnz_x = 0, nnz_y = 0, batch = 0, y_batch = 0;
     bool has_y = false;
-    int yw_batch_dummy() const { return y_batch; }
     CsrWork xw{}, yw{};                             // de-duplicated CSR of this slot's batch
     uint32_t* ybits = nullptr;                      // item-major target bitmask of this slot's batch
     bool y_live = false;                            // ybits currently holds the bits of yw
@@ -51,29 +50,57 @@ struct Slot {
     cudaEvent_t consumed = nullptr;                 // main stream: the step has finished reading this slot
 };
 
+// Bump allocator over ONE cudaMalloc per model.  Every rank lays its arena out identically, so a
+// peer's copy of any buffer is `peer base + same offset` (kernels.h: PeerTable / peer_ptr).
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 1023) & ~size_t(1023);
+        T* p = reinterpret_cast<T*>(base + off);     // base == nullptr during the measuring pass
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
 struct dae_model {
     dae_config cfg{};
     int N = 0, T = 0, H = 0, Bmax = 0, rows_alloc = 0, max_nnz = 0;
-    bool tied = false, trainable = true, own_stream = false;
+    int world = 1, rank = 0;
+    int n_local = 0;                // catalogue rows held by every rank (local tiles x 128)
+    bool tied = false, trainable = true, own_stream = false, attached = false;
     cudaStream_t st = nullptr;      // main stream: the step
     cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
     int cur = 0;                    // slot used by the last step (dae_model_buffer)
+    Arena arena;
+    PeerTable pt{};
+    void* ipc_opened[kMaxWorld] = {};
+    // parameters: catalogue matrices are row-sharded (tile-cyclic), biases replicated
     float *W_enc = nullptr, *W_dec = nullptr, *b_enc = nullptr, *b_dec = nullptr;
-    __nv_bfloat16* W_dec_bf16 = nullptr;
+    __nv_bfloat16* shadow[2] = {nullptr, nullptr};   // bf16 decoder operand, all N rows; double-buffered when world > 1
+    int cur_shadow = 0;
     float *mW_enc = nullptr, *vW_enc = nullptr, *mW_dec = nullptr, *vW_dec = nullptr;
     float *mb_enc = nullptr, *vb_enc = nullptr, *mb_dec = nullptr, *vb_dec = nullptr;
     float b1_pow = kBeta1, b2_pow = kBeta2;
     long long step = 0;
-    float *g_dec = nullptr, *g_enc = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
+    float *g_enc = nullptr;                          // sparse-row dW_enc of the rows this rank owns
     unsigned char* touched = nullptr;
+    float *g_b_enc_part = nullptr, *g_b_dec_part = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
+    float* g_dec_dbg = nullptr;                      // raw dW_dec, materialised only for parity tests
+    int debug = 0;
+    bool scatter_done = false;
     Slot slots[2];
+    PubInput pub{};
     int* err = nullptr;
     int* err_host = nullptr;
+    unsigned int* flags = nullptr;
+    unsigned int epoch = 0;
     int ywords = 8;
     float *rowsum = nullptr, *h = nullptr, *da = nullptr, *dh_partial = nullptr;
-    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr;
+    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr, *dz_all = nullptr;
     int nsplit = 0;
-    float *loss_partial = nullptr, *sq_partial = nullptr, *cost = nullptr, *cost_host = nullptr;
+    float *loss_partial = nullptr, *sq_partial = nullptr, *cost_part = nullptr, *cost = nullptr, *cost_host = nullptr;
     int n_loss_partial = 0;
     float* scores = nullptr;
     size_t scores_elems = 0;
@@ -88,16 +115,9 @@ struct dae_model {
     bool ph_used[16] = {};
     double ph_ms[16] = {};
     long long ph_n[16] = {};
-    std::vector<void*> dev_allocs, host_allocs;
+    std::vector<void*> host_allocs;
 };
 
-template <typename T>
-static int dalloc(dae_model* m, T** p, size_t n, bool zero = true) {
-    CK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T) + 16));
-    m->dev_allocs.push_back(*p);
-    if (zero) CK(cudaMemsetAsync(*p, 0, n * sizeof(T), m->st));
-    return 0;
-}
 template <typename T>
 static int halloc(dae_model* m, T** p, size_t n) {
     CK(cudaMallocHost(reinterpret_cast<void**>(p), n * sizeof(T)));
@@ -106,21 +126,79 @@ static int halloc(dae_model* m, T** p, size_t n) {
 }
 #define TRY(x) do { if (int rc_ = (x)) return rc_; } while (0)
 
-static int alloc_csr(dae_model* m, CsrWork* w, int B, int max_nnz) {
-    TRY(dalloc(m, &w->cnt, B));
-    TRY(dalloc(m, &w->row_ptr, B + 1));
-    TRY(dalloc(m, &w->cursor, B));
-    TRY(dalloc(m, &w->keys, max_nnz));
-    TRY(dalloc(m, &w->row_len, B));
-    TRY(dalloc(m, &w->col, max_nnz));
-    TRY(dalloc(m, &w->val, max_nnz));
-    return 0;
+static void layout_csr(Arena& A, CsrWork* w, int B, int max_nnz) {
+    w->cnt = A.take<int>(B);
+    w->row_ptr = A.take<int>(B + 1);
+    w->cursor = A.take<int>(B);
+    w->keys = A.take<unsigned long long>(max_nnz);
+    w->row_len = A.take<int>(B);
+    w->col = A.take<int>(max_nnz);
+    w->val = A.take<float>(max_nnz);
 }
 
-enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DW, PH_DH, PH_ENCODE_BWD, PH_ADAM_DEC, PH_ADAM_ENC,
-             PH_ADAM_BIAS, PH_COUNT };
-static const char* kPhaseNames[PH_COUNT] = {"prepare_csr_ybits", "encode_fwd", "decode_loss_dz", "dw_dec", "dh",
-                                            "encode_bwd_scatter", "adam_dec", "adam_enc", "adam_bias"};
+// Assign every device buffer of the model from the arena (called twice: measure, then place).
+static void layout(dae_model* m) {
+    Arena& A = m->arena;
+    A.off = 0;
+    const size_t LH = (size_t)m->n_local * m->H, NH = (size_t)m->N * m->H;
+    const int N = m->N, H = m->H, K = m->world * kMaxBpad;
+    m->flags = A.take<unsigned int>(kMaxWorld);
+    m->W_enc = A.take<float>(LH);
+    m->b_enc = A.take<float>(H);
+    m->b_dec = A.take<float>(N);
+    m->W_dec = m->tied ? m->W_enc : A.take<float>(LH);
+    m->shadow[0] = A.take<__nv_bfloat16>(NH);
+    m->shadow[1] = (m->world > 1 && m->trainable) ? A.take<__nv_bfloat16>(NH) : m->shadow[0];
+    if (m->trainable) {
+        m->mW_enc = A.take<float>(LH); m->vW_enc = A.take<float>(LH);
+        if (m->tied) { m->mW_dec = m->mW_enc; m->vW_dec = m->vW_enc; }
+        else { m->mW_dec = A.take<float>(LH); m->vW_dec = A.take<float>(LH); }
+        m->mb_enc = A.take<float>(H); m->vb_enc = A.take<float>(H);
+        m->mb_dec = A.take<float>(N); m->vb_dec = A.take<float>(N);
+        m->g_enc = A.take<float>(LH);
+        m->touched = A.take<unsigned char>(m->n_local);
+        m->g_b_enc_part = A.take<float>(H); m->g_b_dec_part = A.take<float>(N);
+        if (m->world > 1) { m->g_b_enc = A.take<float>(H); m->g_b_dec = A.take<float>(N); }
+        else { m->g_b_enc = m->g_b_enc_part; m->g_b_dec = m->g_b_dec_part; }
+        m->da = A.take<float>((size_t)m->Bmax * H);
+        m->dzT = A.take<__nv_bfloat16>((size_t)N * kMaxBpad);
+        m->dz_all = m->world > 1 ? A.take<__nv_bfloat16>((size_t)m->n_local * K) : m->dzT;
+        m->nsplit = dh_nsplit(N);
+        m->dh_partial = A.take<float>((size_t)m->nsplit * kMaxBpad * H);
+        m->n_loss_partial = 148 * 2;
+        m->loss_partial = A.take<float>(m->n_loss_partial);
+        m->sq_partial = A.take<float>(4 * kSqBlocks);
+        m->cost_part = A.take<float>(1);
+        m->cost = m->world > 1 ? A.take<float>(1) : m->cost_part;
+    }
+    m->err = A.take<int>(1);
+    m->rowsum = A.take<float>(m->Bmax);
+    m->h = A.take<float>((size_t)m->Bmax * H);
+    m->h_d = A.take<__nv_bfloat16>((size_t)m->rows_alloc * H);
+    m->h_dT = A.take<__nv_bfloat16>((size_t)H * (K > m->rows_alloc ? K : m->rows_alloc));
+    m->pub.row_ptr = A.take<int>(m->Bmax);
+    m->pub.row_len = A.take<int>(m->Bmax);
+    m->pub.col = A.take<int>(m->max_nnz);
+    m->pub.xn = A.take<float>(m->max_nnz);
+    for (int s = 0; s < 2; ++s) {
+        Slot& sl = m->slots[s];
+        layout_csr(A, &sl.xw, m->Bmax, m->max_nnz);
+        sl.x_pos = A.take<long long>((size_t)m->max_nnz * 2);
+        sl.x_val = A.take<float>(m->max_nnz);
+        if (m->trainable) {
+            layout_csr(A, &sl.yw, m->Bmax, m->max_nnz);
+            sl.ybits = A.take<uint32_t>((size_t)N * m->ywords);
+            sl.y_pos = A.take<long long>((size_t)m->max_nnz * 2);
+            sl.y_val = A.take<float>(m->max_nnz);
+        }
+    }
+    A.off = (A.off + 1023) & ~size_t(1023);
+}
+
+enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DH, PH_ENCODE_DA, PH_BARRIER, PH_DW_ADAM, PH_SCATTER,
+             PH_ADAM_ENC, PH_ADAM_BIAS, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"prepare_csr_ybits", "encode_fwd", "decode_loss_dz", "dh", "encode_da",
+                                            "barriers", "dw_adam_dec", "scatter_dw_enc", "adam_enc", "adam_bias"};
 static inline void ph_begin(dae_model* m, int k, cudaStream_t s = nullptr) {
     if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], s ? s : m->st); }
 }
@@ -153,6 +231,9 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     if (cfg->trainable && cfg->max_batch > kMaxBpad)
         return fail("training batch per GPU is limited to %d rows (one tensor-core batch tile); got %d", kMaxBpad,
                     cfg->max_batch);
+    const int world = cfg->world > 0 ? cfg->world : 1;
+    if (world > kMaxWorld || cfg->rank < 0 || cfg->rank >= world)
+        return fail("need 1 <= world <= %d and 0 <= rank < world (got world %d, rank %d)", kMaxWorld, cfg->world, cfg->rank);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("no CUDA device: libdae_b200 has no CPU fallback");
@@ -161,64 +242,39 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
+    preload_sparse(); preload_optim(); preload_gemm(); preload_topk();
+
     dae_model* m = new dae_model();
     m->cfg = *cfg;
     m->N = cfg->n_input; m->T = cfg->n_tracks; m->H = cfg->n_hidden; m->Bmax = cfg->max_batch;
     m->tied = cfg->tied != 0; m->trainable = cfg->trainable != 0;
+    m->world = world; m->rank = cfg->rank;
     if (cfg->stream) { m->st = reinterpret_cast<cudaStream_t>(cfg->stream); }
     else { CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)); m->own_stream = true; }
     CK(cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking));
     m->rows_alloc = m->Bmax <= kMaxBpad ? round_up(m->Bmax, 64) : round_up(m->Bmax, kMaxBpad);
     m->max_nnz = m->Bmax * 1024;
-    const size_t NH = (size_t)m->N * m->H;
-    const int N = m->N, H = m->H;
+    const int tiles_total = (m->N + kTileItems - 1) / kTileItems;
+    m->n_local = (tiles_total + world - 1) / world * kTileItems;
 
-    TRY(dalloc(m, &m->W_enc, NH));
-    TRY(dalloc(m, &m->b_enc, H));
-    TRY(dalloc(m, &m->b_dec, N));
-    if (m->tied) m->W_dec = m->W_enc; else TRY(dalloc(m, &m->W_dec, NH));
-    TRY(dalloc(m, &m->W_dec_bf16, NH));
-    if (m->trainable) {
-        TRY(dalloc(m, &m->mW_enc, NH)); TRY(dalloc(m, &m->vW_enc, NH));
-        if (m->tied) { m->mW_dec = m->mW_enc; m->vW_dec = m->vW_enc; }
-        else { TRY(dalloc(m, &m->mW_dec, NH)); TRY(dalloc(m, &m->vW_dec, NH)); }
-        TRY(dalloc(m, &m->mb_enc, H)); TRY(dalloc(m, &m->vb_enc, H));
-        TRY(dalloc(m, &m->mb_dec, N)); TRY(dalloc(m, &m->vb_dec, N));
-        TRY(dalloc(m, &m->g_dec, NH));
-        if (m->tied) m->g_enc = m->g_dec; else { TRY(dalloc(m, &m->g_enc, NH)); TRY(dalloc(m, &m->touched, N)); }
-        TRY(dalloc(m, &m->g_b_enc, H)); TRY(dalloc(m, &m->g_b_dec, N));
-        TRY(dalloc(m, &m->da, (size_t)m->Bmax * H));
-        TRY(dalloc(m, &m->dzT, (size_t)N * kMaxBpad));
-        m->nsplit = dh_nsplit(N);
-        TRY(dalloc(m, &m->dh_partial, (size_t)m->nsplit * kMaxBpad * H));
-        m->n_loss_partial = 148 * 2;
-        TRY(dalloc(m, &m->loss_partial, m->n_loss_partial));
-        TRY(dalloc(m, &m->sq_partial, 4 * kSqBlocks));
-    }
-    TRY(dalloc(m, &m->err, 1));
+    layout(m);                                            // measuring pass
+    const size_t bytes = m->arena.off;
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->arena.base), bytes));
+    CK(cudaMemsetAsync(m->arena.base, 0, bytes, m->st));
+    layout(m);
+    m->pt.world = world; m->pt.rank = m->rank;
+    m->pt.base[m->rank] = m->arena.base;
+    m->attached = world == 1;
+
     TRY(halloc(m, &m->err_host, 1));
-    TRY(dalloc(m, &m->rowsum, m->Bmax));
-    TRY(dalloc(m, &m->h, (size_t)m->Bmax * H));
-    TRY(dalloc(m, &m->h_d, (size_t)m->rows_alloc * H));
-    TRY(dalloc(m, &m->h_dT, (size_t)m->rows_alloc * H));
-    TRY(dalloc(m, &m->cost, 1));
     TRY(halloc(m, &m->cost_host, 1));
     for (int s = 0; s < 2; ++s) {
         Slot& sl = m->slots[s];
         CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sl.prepared, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
-        TRY(alloc_csr(m, &sl.xw, m->Bmax, m->max_nnz));
-        if (m->trainable) {
-            TRY(alloc_csr(m, &sl.yw, m->Bmax, m->max_nnz));
-            TRY(dalloc(m, &sl.ybits, (size_t)N * m->ywords));
-        }
-        TRY(dalloc(m, &sl.x_pos, (size_t)m->max_nnz * 2)); TRY(dalloc(m, &sl.x_val, m->max_nnz));
         TRY(halloc(m, &sl.hx_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hx_val, m->max_nnz));
-        if (m->trainable) {
-            TRY(dalloc(m, &sl.y_pos, (size_t)m->max_nnz * 2)); TRY(dalloc(m, &sl.y_val, m->max_nnz));
-            TRY(halloc(m, &sl.hy_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hy_val, m->max_nnz));
-        }
+        if (m->trainable) { TRY(halloc(m, &sl.hy_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hy_val, m->max_nnz)); }
     }
     CK(cudaStreamSynchronize(m->st));
     *out = m;
@@ -228,39 +284,127 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
 extern "C" void dae_model_destroy(dae_model* m) {
     if (!m) return;
     cudaStreamSynchronize(m->st);
-    for (void* p : m->dev_allocs) cudaFree(p);
+    cudaStreamSynchronize(m->st2);
+    for (int r = 0; r < kMaxWorld; ++r) if (m->ipc_opened[r]) cudaIpcCloseMemHandle(m->ipc_opened[r]);
+    if (m->arena.base) cudaFree(m->arena.base);
     for (void* p : m->host_allocs) cudaFreeHost(p);
+    if (m->g_dec_dbg) cudaFree(m->g_dec_dbg);
     if (m->scores) cudaFree(m->scores);
     if (m->topk_idx) cudaFree(m->topk_idx);
     if (m->topk_score) cudaFree(m->topk_score);
     if (m->seed_ptr) cudaFree(m->seed_ptr);
     if (m->seed_idx) cudaFree(m->seed_idx);
-    cudaStreamSynchronize(m->st2);
     for (int s = 0; s < 2; ++s) {
         if (m->slots[s].h2d_done) cudaEventDestroy(m->slots[s].h2d_done);
         if (m->slots[s].prepared) cudaEventDestroy(m->slots[s].prepared);
         if (m->slots[s].consumed) cudaEventDestroy(m->slots[s].consumed);
     }
+    if (m->ph_ev[0]) for (int i = 0; i < 2 * PH_COUNT; ++i) cudaEventDestroy(m->ph_ev[i]);
     cudaStreamDestroy(m->st2);
     if (m->own_stream) cudaStreamDestroy(m->st);
     delete m;
 }
 
-static void refresh_shadow(dae_model* m) {
-    launch_cast_bf16(m->W_dec, m->W_dec_bf16, (long long)m->N * m->H, m->st);
+// ------------------------------------------------------------------------------------------
+// data-parallel attachment: map every peer's arena (one process per GPU)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes) {
+    if (!m || !bytes) return fail("null argument");
+    *bytes = (int64_t)m->arena.off;
+    return 0;
+}
+
+extern "C" int32_t dae_model_ipc_handle(dae_model* m, void* handle_out64) {
+    if (!m || !handle_out64) return fail("null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, m->arena.base));
+    memcpy(handle_out64, &h, 64);
+    return 0;
+}
+
+extern "C" int32_t dae_model_attach_ipc(dae_model* m, const void* handles, int32_t n_handles) {
+    if (!m || !handles) return fail("null argument");
+    if (n_handles != m->world) return fail("expected %d IPC handles, got %d", m->world, n_handles);
+    CK(cudaSetDevice(m->cfg.device));
+    for (int r = 0; r < m->world; ++r) {
+        if (r == m->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        m->ipc_opened[r] = p;
+        m->pt.base[r] = static_cast<char*>(p);
+    }
+    m->attached = true;
+    return 0;
+}
+
+extern "C" int32_t dae_model_attach_local(dae_model* m, dae_model* const* peers, int32_t n_peers) {
+    if (!m || !peers) return fail("null argument");
+    if (n_peers != m->world) return fail("expected %d peers, got %d", m->world, n_peers);
+    for (int r = 0; r < m->world; ++r) {
+        if (!peers[r] || peers[r]->world != m->world || peers[r]->rank != r || peers[r]->arena.off != m->arena.off)
+            return fail("peer %d does not match this model's layout", r);
+        if (peers[r]->cfg.device != m->cfg.device) {
+            CK(cudaSetDevice(m->cfg.device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            (void)cudaGetLastError();
+        }
+        m->pt.base[r] = peers[r]->arena.base;
+    }
+    m->attached = true;
+    return 0;
+}
+
+static void barrier(dae_model* m) {
+    if (m->world == 1) return;
+    m->epoch += 1;
+    launch_barrier(m->flags, m->epoch, m->pt, m->st);
     m->launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+// Host matrix [N,H] (global row order) <-> the local-tile-ordered rows of rank `owner`: global tile
+// owner + k*world is local tile k, so one strided 2-D copy moves every full tile.
+static int copy_rows(dae_model* m, float* dev_local, float* host, int owner, bool to_device) {
+    const int N = m->N, H = m->H, W = m->world;
+    const int tiles_total = (N + kTileItems - 1) / kTileItems;
+    const size_t tile_bytes = (size_t)kTileItems * H * 4;
+    const int full_tiles = N / kTileItems;                       // global tiles that are complete
+    const int n_own = tiles_total > owner ? (tiles_total - owner + W - 1) / W : 0;
+    int n_full = full_tiles > owner ? (full_tiles - owner + W - 1) / W : 0;
+    if (n_full > n_own) n_full = n_own;
+    float* h0 = host + (size_t)owner * kTileItems * H;
+    if (n_full > 0) {
+        if (to_device) CK(cudaMemcpy2DAsync(dev_local, tile_bytes, h0, tile_bytes * W, tile_bytes, n_full, cudaMemcpyHostToDevice, m->st));
+        else CK(cudaMemcpy2DAsync(h0, tile_bytes * W, dev_local, tile_bytes, tile_bytes, n_full, cudaMemcpyDeviceToHost, m->st));
+    }
+    if (n_own > n_full) {                                        // the catalogue's last, partial tile
+        const int gt = owner + n_full * W;
+        const size_t rows = (size_t)N - (size_t)gt * kTileItems;
+        float* hp = host + (size_t)gt * kTileItems * H;
+        float* dp = dev_local + (size_t)n_full * kTileItems * H;
+        if (to_device) CK(cudaMemcpyAsync(dp, hp, rows * H * 4, cudaMemcpyHostToDevice, m->st));
+        else CK(cudaMemcpyAsync(hp, dp, rows * H * 4, cudaMemcpyDeviceToHost, m->st));
+    }
+    return 0;
 }
 
 extern "C" int32_t dae_model_init_xavier(dae_model* m, uint64_t seed) {
     if (!m) return fail("null model");
     const float lim = sqrtf(6.0f / (float)(m->N + m->H));
-    const long long NH = (long long)m->N * m->H;
-    launch_xavier_init(m->W_enc, NH, lim, seed, kStreamInit, m->st);
-    if (!m->tied) launch_xavier_init(m->W_dec, NH, lim, seed, kStreamInit + 1, m->st);
+    launch_xavier_init(m->W_enc, m->n_local, m->tied ? m->shadow[m->cur_shadow] : nullptr, m->N, m->H, lim, seed,
+                       kStreamInit, m->world, m->rank, m->st);
+    if (!m->tied)
+        launch_xavier_init(m->W_dec, m->n_local, m->shadow[m->cur_shadow], m->N, m->H, lim, seed, kStreamInit + 1,
+                           m->world, m->rank, m->st);
     CK(cudaMemsetAsync(m->b_enc, 0, sizeof(float) * m->H, m->st));
     CK(cudaMemsetAsync(m->b_dec, 0, sizeof(float) * m->N, m->st));
-    m->launches += m->tied ? 1 : 2;
-    refresh_shadow(m);
+    m->launches += m->tied ? 2 : 3;
     CK(cudaStreamSynchronize(m->st));
     return 0;
 }
@@ -268,24 +412,45 @@ extern "C" int32_t dae_model_init_xavier(dae_model* m, uint64_t seed) {
 extern "C" int32_t dae_model_set_params(dae_model* m, const float* W_enc, const float* W_dec, const float* b_enc,
                                         const float* b_dec) {
     if (!m || !W_enc || !b_enc || !b_dec) return fail("null argument");
-    const size_t NH = (size_t)m->N * m->H;
-    CK(cudaMemcpyAsync(m->W_enc, W_enc, NH * 4, cudaMemcpyHostToDevice, m->st));
-    if (!m->tied) {
-        if (!W_dec) return fail("W_dec required for the untied model");
-        CK(cudaMemcpyAsync(m->W_dec, W_dec, NH * 4, cudaMemcpyHostToDevice, m->st));
-    }
+    if (!m->tied && !W_dec) return fail("W_dec required for the untied model");
+    TRY(copy_rows(m, m->W_enc, const_cast<float*>(W_enc), m->rank, true));
+    if (!m->tied) TRY(copy_rows(m, m->W_dec, const_cast<float*>(W_dec), m->rank, true));
     CK(cudaMemcpyAsync(m->b_enc, b_enc, (size_t)m->H * 4, cudaMemcpyHostToDevice, m->st));
     CK(cudaMemcpyAsync(m->b_dec, b_dec, (size_t)m->N * 4, cudaMemcpyHostToDevice, m->st));
-    refresh_shadow(m);
+    // bf16 decoder operand, all N rows: own rows from the master, the other ranks' rows through a scratch block
+    const float* Wd = m->tied ? W_enc : W_dec;
+    launch_cast_rows_bf16(m->W_dec, m->n_local, m->shadow[m->cur_shadow], m->N, m->H, m->world, m->rank, m->st);
+    m->launches += 1;
+    if (m->world > 1) {
+        float* scratch = m->g_enc;
+        bool temp = false;
+        if (!scratch) { CK(cudaMalloc(reinterpret_cast<void**>(&scratch), (size_t)m->n_local * m->H * 4)); temp = true; }
+        for (int r = 0; r < m->world; ++r) {
+            if (r == m->rank) continue;
+            TRY(copy_rows(m, scratch, const_cast<float*>(Wd), r, true));
+            launch_cast_rows_bf16(scratch, m->n_local, m->shadow[m->cur_shadow], m->N, m->H, m->world, r, m->st);
+            m->launches += 1;
+        }
+        if (m->g_enc) CK(cudaMemsetAsync(m->g_enc, 0, (size_t)m->n_local * m->H * 4, m->st));
+        CK(cudaStreamSynchronize(m->st));
+        if (temp) CK(cudaFree(scratch));
+    }
     CK(cudaStreamSynchronize(m->st));
     return 0;
 }
 
+static int gather_rows(dae_model* m, float* host, float* dev_local) {
+    if (!host) return 0;
+    for (int r = 0; r < m->world; ++r) TRY(copy_rows(m, peer_ptr(m->pt, r, dev_local), host, r, false));
+    return 0;
+}
+
+// With world > 1 the caller must have synchronised every rank (no step in flight on any GPU).
 extern "C" int32_t dae_model_get_params(dae_model* m, float* W_enc, float* W_dec, float* b_enc, float* b_dec) {
     if (!m) return fail("null model");
-    const size_t NH = (size_t)m->N * m->H;
-    if (W_enc) CK(cudaMemcpyAsync(W_enc, m->W_enc, NH * 4, cudaMemcpyDeviceToHost, m->st));
-    if (W_dec) CK(cudaMemcpyAsync(W_dec, m->W_dec, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (!m->attached) return fail("peers are not attached");
+    TRY(gather_rows(m, W_enc, m->W_enc));
+    TRY(gather_rows(m, W_dec, m->W_dec));
     if (b_enc) CK(cudaMemcpyAsync(b_enc, m->b_enc, (size_t)m->H * 4, cudaMemcpyDeviceToHost, m->st));
     if (b_dec) CK(cudaMemcpyAsync(b_dec, m->b_dec, (size_t)m->N * 4, cudaMemcpyDeviceToHost, m->st));
     CK(cudaStreamSynchronize(m->st));
@@ -295,11 +460,11 @@ extern "C" int32_t dae_model_get_params(dae_model* m, float* W_enc, float* W_dec
 extern "C" int32_t dae_model_get_adam_state(dae_model* m, float* m_W_enc, float* v_W_enc, float* m_W_dec,
                                             float* v_W_dec, int64_t* step) {
     if (!m || !m->trainable) return fail("model is not trainable");
-    const size_t NH = (size_t)m->N * m->H;
-    if (m_W_enc) CK(cudaMemcpyAsync(m_W_enc, m->mW_enc, NH * 4, cudaMemcpyDeviceToHost, m->st));
-    if (v_W_enc) CK(cudaMemcpyAsync(v_W_enc, m->vW_enc, NH * 4, cudaMemcpyDeviceToHost, m->st));
-    if (m_W_dec) CK(cudaMemcpyAsync(m_W_dec, m->mW_dec, NH * 4, cudaMemcpyDeviceToHost, m->st));
-    if (v_W_dec) CK(cudaMemcpyAsync(v_W_dec, m->vW_dec, NH * 4, cudaMemcpyDeviceToHost, m->st));
+    if (!m->attached) return fail("peers are not attached");
+    TRY(gather_rows(m, m_W_enc, m->mW_enc));
+    TRY(gather_rows(m, v_W_enc, m->vW_enc));
+    TRY(gather_rows(m, m_W_dec, m->mW_dec));
+    TRY(gather_rows(m, v_W_dec, m->vW_dec));
     if (step) *step = m->step;
     CK(cudaStreamSynchronize(m->st));
     return 0;
@@ -315,7 +480,7 @@ static int prepare_slot(dae_model* m, int slot) {
     CK(cudaStreamWaitEvent(m->st2, s.consumed, 0));       // the previous step on this slot no longer reads it
     ph_begin(m, PH_PREPARE, m->st2);
     if (s.y_live) {                                        // clear the bits of the batch this slot held before
-        launch_ybits_set(s.yw, s.yw_batch_dummy(), s.ybits, m->ywords, 0, m->err, m->st2);
+        launch_ybits_set(s.yw, s.y_batch, s.ybits, m->ywords, 0, m->err, m->st2);
         s.y_live = false;
         m->launches += 1;
     }
@@ -395,113 +560,188 @@ static int check_device_flag(dae_model* m) {
 }
 
 // encode forward from a staged slot (shared by train / predict / recommend)
-static void run_encode(dae_model* m, int slot, int rows_pad, float kp, float kp_in, int row_offset) {
+static void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset,
+                       bool train) {
     const Slot& s = m->slots[slot];
     m->cur = slot;
     cudaStreamWaitEvent(m->st, s.prepared, 0);
     ph_begin(m, PH_ENCODE);
     EncodeArgs e{};
-    e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = s.xw; e.rowsum = m->rowsum; e.h = m->h; e.h_d = m->h_d;
-    e.h_dT = m->h_dT; e.B = s.batch; e.bpad = rows_pad; e.H = m->H; e.kp = kp; e.kp_in = kp_in;
+    e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = s.xw; e.pub = m->pub; e.rowsum = m->rowsum; e.h = m->h;
+    e.h_d = m->h_d; e.h_dT = m->h_dT; e.B = s.batch; e.bpad = rows_pad; e.H = m->H;
+    // training: this rank's h_d^T columns go into every rank's [H, world*bpad] operand of the dW contraction
+    e.hT_bcast = train ? 1 : 0;
+    e.K = train ? m->world * bpad : rows_pad;
+    e.hT_col0 = train ? m->rank * bpad : 0;
+    e.kp = kp; e.kp_in = kp_in;
     e.seed = m->cfg.seed; e.step = (unsigned long long)m->step; e.row_offset = row_offset;
+    e.pt = m->pt;
     launch_encode_fwd(e, m->st);
     m->launches += 1;
     ph_end(m, PH_ENCODE);
 }
 
+static AdamArgs adam_args(dae_model* m) {
+    AdamArgs a{};
+    a.alpha = m->cfg.lr * sqrtf(1.0f - m->b2_pow) / (1.0f - m->b1_pow);   // [TF1] ApplyAdam, fp32
+    a.one_minus_b1 = 1.0f - kBeta1; a.one_minus_b2 = 1.0f - kBeta2; a.eps = kAdamEps;
+    a.lambda = m->cfg.reg_lambda;
+    return a;
+}
+
+// sparse-row dW_enc of the rows this rank owns, from every rank's batch (after barrier B)
+static void run_scatter(dae_model* m, int B) {
+    ScatterArgs sc{};
+    sc.pub = m->pub; sc.da = m->da; sc.g_enc = m->g_enc; sc.touched = m->touched; sc.B = B; sc.H = m->H; sc.pt = m->pt;
+    ph_begin(m, PH_SCATTER);
+    launch_scatter_shard(sc, m->st);
+    ph_end(m, PH_SCATTER);
+    m->launches += 1;
+}
+
+static DwArgs dw_args(dae_model* m, int bpad) {
+    DwArgs w{};
+    w.dzT = m->dz_all; w.h_dT = m->h_dT; w.n_local = m->n_local; w.N = m->N; w.H = m->H; w.K = m->world * bpad;
+    w.pt = m->pt;
+    return w;
+}
+
 extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
                                              int32_t global_batch, int32_t row_offset) {
     if (!m || !m->trainable) return fail("model is not trainable");
+    if (!m->attached) return fail("world = %d but the peers are not attached (dae_model_attach_ipc)", m->world);
     if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
     const Slot& s = m->slots[slot];
     if (s.batch <= 0) return fail("slot %d holds no batch", slot);
     if (!(keep_prob > 0.f) || !(input_keep_prob > 0.f)) return fail("keep probabilities must be > 0");
     const int B = s.batch, bpad = round_up(B, 64), H = m->H, N = m->N;
     if (bpad > kMaxBpad) return fail("training batch %d exceeds %d", B, kMaxBpad);
-    const int gb = global_batch > 0 ? global_batch : B;
+    // the loss is a mean over the GLOBAL batch (DAEs.py:100); dropout is keyed by the global row
+    const int gb = global_batch > 0 ? global_batch : B * m->world;
+    if (global_batch <= 0) row_offset = m->rank * B;
     m->last_batch = B; m->last_bpad = bpad;
-
     if (!s.has_y) return fail("slot %d was staged without targets", slot);
-    run_encode(m, slot, bpad, keep_prob, input_keep_prob, row_offset);
+
+    // barrier A: every rank has finished the previous step (its Adam wrote W_enc rows and the operand
+    // copy this step reads; it no longer reads dz_all / h_dT / da / pub that this step overwrites)
+    ph_begin(m, PH_BARRIER);
+    barrier(m);
+    ph_end(m, PH_BARRIER);
+    run_encode(m, slot, bpad, bpad, keep_prob, input_keep_prob, row_offset, true);
 
     DecodeArgs d{};
-    d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
-    d.ybits = s.ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.db_dec = m->g_b_dec;
+    d.W = m->shadow[m->cur_shadow]; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
+    d.ybits = s.ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.dz_all = m->dz_all; d.K = m->world * bpad; d.pt = m->pt;
+    d.db_dec = m->g_b_dec_part;
     d.loss_partial = m->loss_partial; d.inv_batch = 1.0f / (float)gb;
     const int ngrid = decode_grid(N, 1);
     ph_begin(m, PH_DECODE_LOSS);
     launch_decode_train(d, m->st);
+    CK(cudaEventRecord(s.consumed, m->st));                 // the slot may be re-prepared from here on
     ph_end(m, PH_DECODE_LOSS);
 
-    DwArgs w{}; w.dzT = m->dzT; w.h_dT = m->h_dT; w.g = m->g_dec; w.N = N; w.H = H; w.bpad = bpad;
-    ph_begin(m, PH_DW);
-    launch_dw(w, m->st);
-    ph_end(m, PH_DW);
-
-    DhArgs q{}; q.dzT = m->dzT; q.W = m->W_dec_bf16; q.partial = m->dh_partial; q.N = N; q.H = H; q.bpad = bpad;
+    DhArgs q{}; q.dzT = m->dzT; q.W = m->shadow[m->cur_shadow]; q.partial = m->dh_partial; q.N = N; q.H = H; q.bpad = bpad;
     q.nsplit = m->nsplit;
     ph_begin(m, PH_DH);
     launch_dh(q, m->st);
     ph_end(m, PH_DH);
 
-    EncodeBwdArgs eb{};
-    eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.x = s.xw; eb.da = m->da;
-    eb.g_enc = m->g_enc; eb.touched = m->touched; eb.db_enc = m->g_b_enc; eb.B = B; eb.bpad = bpad; eb.H = H;
+    EncodeDaArgs eb{};
+    eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.da = m->da; eb.db_enc = m->g_b_enc_part;
+    eb.B = B; eb.bpad = bpad; eb.H = H;
     eb.kp = keep_prob; eb.seed = m->cfg.seed; eb.step = (unsigned long long)m->step; eb.row_offset = row_offset;
-    ph_begin(m, PH_ENCODE_BWD);
-    launch_encode_bwd(eb, m->st);
-    CK(cudaEventRecord(s.consumed, m->st));                 // the slot may be re-prepared from here on
-    m->launches += 3 + 2;
+    ph_begin(m, PH_ENCODE_DA);
+    launch_encode_da(eb, m->st);
+    m->launches += 2 + 1 + 2;
 
     int n_sq = 0;
     const float lam = m->cfg.reg_lambda;
-    if (lam != 0.f && row_offset == 0) {                    // l2 term once per global batch (DAEs.py:79-82, :147-150)
-        const long long NH = (long long)N * H;
-        launch_sumsq(m->W_enc, NH, m->sq_partial, kSqBlocks, m->st);
-        launch_sumsq(m->b_dec, N, m->sq_partial + kSqBlocks, kSqBlocks, m->st);
-        launch_sumsq(m->b_enc, H, m->sq_partial + 2 * kSqBlocks, kSqBlocks, m->st);
-        n_sq = 3 * kSqBlocks;
-        if (!m->tied) { launch_sumsq(m->W_dec, NH, m->sq_partial + 3 * kSqBlocks, kSqBlocks, m->st); n_sq = 4 * kSqBlocks; }
-        m->launches += m->tied ? 3 : 4;
+    if (lam != 0.f) {      // l2 term (DAEs.py:79-82, :147-150): own rows of the matrices; the replicated biases once (rank 0)
+        const long long LH = (long long)m->n_local * H;
+        launch_sumsq(m->W_enc, LH, m->sq_partial, kSqBlocks, m->st);
+        n_sq = kSqBlocks;
+        m->launches += 1;
+        if (!m->tied) { launch_sumsq(m->W_dec, LH, m->sq_partial + n_sq, kSqBlocks, m->st); n_sq += kSqBlocks; m->launches += 1; }
+        if (m->rank == 0) {
+            launch_sumsq(m->b_dec, N, m->sq_partial + n_sq, kSqBlocks, m->st); n_sq += kSqBlocks;
+            launch_sumsq(m->b_enc, H, m->sq_partial + n_sq, kSqBlocks, m->st); n_sq += kSqBlocks;
+            m->launches += 2;
+        }
     }
-    launch_reduce_loss2(m->loss_partial, ngrid, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost, m->st);
+    launch_reduce_loss2(m->loss_partial, ngrid, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost_part, m->st);
     m->launches += 1;
-    ph_end(m, PH_ENCODE_BWD);
+    ph_end(m, PH_ENCODE_DA);
+
+    if (m->debug & 3) {    // parity tests: materialise the raw dW_dec / scatter dW_enc now, where they can be inspected
+        barrier(m);
+        if (m->debug & 1) {
+            if (!m->g_dec_dbg) CK(cudaMalloc(reinterpret_cast<void**>(&m->g_dec_dbg), (size_t)m->n_local * H * 4));
+            DwArgs w = dw_args(m, bpad);
+            w.g = m->g_dec_dbg;
+            launch_dw(w, m->st);
+            m->launches += 1;
+        }
+        if (m->debug & 2) {
+            run_scatter(m, B);
+            m->scatter_done = true;
+        }
+    }
     return 0;
 }
 
 extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (!m || !m->trainable) return fail("model is not trainable");
-    const float alpha = m->cfg.lr * sqrtf(1.0f - m->b2_pow) / (1.0f - m->b1_pow);   // [TF1] ApplyAdam, fp32
-    AdamArgs a{};
-    a.alpha = alpha; a.one_minus_b1 = 1.0f - kBeta1; a.one_minus_b2 = 1.0f - kBeta2; a.eps = kAdamEps;
-    a.lambda = m->cfg.reg_lambda;
-    const long long NH = (long long)m->N * m->H;
-    // decoder (or the tied matrix): dense gradient, refreshes the bf16 operand shadow
-    a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.w_bf16 = m->W_dec_bf16;
-    a.row_touched = nullptr; a.n = NH; a.row_len = m->H;
-    ph_begin(m, PH_ADAM_DEC);
-    launch_adam(a, m->st);
-    ph_end(m, PH_ADAM_DEC);
+    if (m->last_bpad <= 0) return fail("no gradients: call dae_model_backward_staged first");
+    const int H = m->H, N = m->N, B = m->last_batch, bpad = m->last_bpad;
+    AdamArgs a = adam_args(m);
+    // barrier B: every rank's dz tiles, h_d columns, da, published input and bias partials have landed
+    ph_begin(m, PH_BARRIER);
+    barrier(m);
+    ph_end(m, PH_BARRIER);
+
+    if (!m->scatter_done) run_scatter(m, B);
+    m->scatter_done = false;
+
+    // decoder (or the tied matrix): dW_dec tile by tile in TMEM, dense Adam in the epilogue, new bf16 operand
+    // rows stored to every rank's copy
+    const int next_shadow = m->world > 1 ? (m->cur_shadow ^ 1) : m->cur_shadow;
+    DwArgs w = dw_args(m, bpad);
+    w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
+    w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
+    w.adam = AdamConst{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
+    w.shadow = m->shadow[next_shadow];
+    ph_begin(m, PH_DW_ADAM);
+    launch_dw(w, m->st);
+    ph_end(m, PH_DW_ADAM);
     m->launches += 1;
-    if (!m->tied) {
-        ph_begin(m, PH_ADAM_ENC);   // encoder: gradient rows exist only where the batch touched them; all rows still update
+
+    ph_begin(m, PH_ADAM_ENC);
+    if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
         a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = m->g_enc; a.w_bf16 = nullptr;
-        a.row_touched = m->touched;
+        a.row_touched = m->touched; a.n = (long long)m->n_local * H; a.row_len = H;
         launch_adam(a, m->st);
-        launch_clear_flagged(m->N, m->H, m->g_enc, m->touched, m->st);
-        m->launches += 2;
-        ph_end(m, PH_ADAM_ENC);
+        m->launches += 1;
     }
+    launch_clear_flagged(m->n_local, H, m->g_enc, m->touched, m->st);
+    m->launches += 1;
+    ph_end(m, PH_ADAM_ENC);
+
     ph_begin(m, PH_ADAM_BIAS);
+    if (m->world > 1) {   // bias gradients and the cost: every rank sums all partials in rank order -> identical replicas
+        launch_sum_partials(m->g_b_enc_part, m->g_b_enc, H, m->pt, m->st);
+        launch_sum_partials(m->g_b_dec_part, m->g_b_dec, N, m->pt, m->st);
+        launch_sum_partials(m->cost_part, m->cost, 1, m->pt, m->st);
+        m->launches += 3;
+    }
     a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
-    a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = m->H;
+    a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = H;
     launch_adam(a, m->st);
-    a.w = m->b_dec; a.m = m->mb_dec; a.v = m->vb_dec; a.g = m->g_b_dec; a.n = m->N;
+    a.w = m->b_dec; a.m = m->mb_dec; a.v = m->vb_dec; a.g = m->g_b_dec; a.n = N;
     launch_adam(a, m->st);
-    m->launches += 2 + (m->N % 4 ? 1 : 0);
+    m->launches += 2 + (N % 4 ? 1 : 0);
     ph_end(m, PH_ADAM_BIAS);
     ph_collect(m);
+    m->cur_shadow = next_shadow;
     m->b1_pow *= kBeta1;
     m->b2_pow *= kBeta2;
     m->step += 1;
@@ -529,6 +769,12 @@ extern "C" int32_t dae_model_train_step(dae_model* m, const int64_t* x_pos, cons
     return dae_model_sync_cost(m, cost_out);
 }
 
+extern "C" int32_t dae_model_set_debug(dae_model* m, int32_t flags) {
+    if (!m) return fail("null model");
+    m->debug = flags;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // inference
 // ------------------------------------------------------------------------------------------
@@ -546,10 +792,11 @@ static int run_predict(dae_model* m, int slot, int n_cols, float* out_dev, long 
     int bpad, nbt;
     if (B <= kMaxBpad) { bpad = round_up(B, 64); nbt = 1; }
     else { bpad = kMaxBpad; nbt = (B + kMaxBpad - 1) / kMaxBpad; }
-    run_encode(m, slot, bpad * nbt, 1.0f, 1.0f, 0);       // keep_prob = input_keep_prob = 1 (main_train.py:68)
+    if (!m->attached) return fail("world = %d but the peers are not attached (dae_model_attach_ipc)", m->world);
+    run_encode(m, slot, bpad, bpad * nbt, 1.0f, 1.0f, 0, false); // keep_prob = input_keep_prob = 1 (main_train.py:68)
     CK(cudaEventRecord(s.consumed, m->st));
     DecodeArgs d{};
-    d.W = m->W_dec_bf16; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
+    d.W = m->shadow[m->cur_shadow]; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
     d.n_batch_tiles = nbt; d.out = out_dev; d.ld_out = ld; d.n_out = n_cols;
     launch_decode_predict(d, m->st);
     m->launches += 1;
@@ -615,24 +862,25 @@ extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const
 extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t* n_elem,
                                     int32_t* elem_size) {
     if (!m || !name || !dev_ptr) return fail("null argument");
-    const int64_t NH = (int64_t)m->N * m->H;
+    const int64_t NH = (int64_t)m->N * m->H, LH = (int64_t)m->n_local * m->H;
     const Slot& sl = m->slots[m->cur];
     struct E { const char* n; void* p; int64_t c; int32_t s; };
     const E table[] = {
-        {"g_dec", m->g_dec, NH, 4}, {"g_enc", m->g_enc, NH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
-        {"g_b_dec", m->g_b_dec, m->N, 4}, {"touched", m->touched, m->N, 1}, {"cost", m->cost, 1, 4},
-        {"W_enc", m->W_enc, NH, 4}, {"W_dec", m->W_dec, NH, 4}, {"W_dec_bf16", m->W_dec_bf16, NH, 2},
+        {"g_dec", m->g_dec_dbg, LH, 4}, {"g_enc", m->g_enc, LH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
+        {"g_b_dec", m->g_b_dec, m->N, 4}, {"g_b_enc_part", m->g_b_enc_part, m->H, 4},
+        {"g_b_dec_part", m->g_b_dec_part, m->N, 4}, {"touched", m->touched, m->n_local, 1}, {"cost", m->cost, 1, 4},
+        {"W_enc", m->W_enc, LH, 4}, {"W_dec", m->W_dec, LH, 4}, {"W_dec_bf16", m->shadow[m->cur_shadow], NH, 2},
         {"b_enc", m->b_enc, m->H, 4}, {"b_dec", m->b_dec, m->N, 4},
         {"h", m->h, (int64_t)m->Bmax * m->H, 4}, {"h_d", m->h_d, (int64_t)m->rows_alloc * m->H, 2},
-        {"h_dT", m->h_dT, (int64_t)m->rows_alloc * m->H, 2},
-        {"dzT", m->dzT, (int64_t)m->N * kMaxBpad, 2},
+        {"h_dT", m->h_dT, (int64_t)m->H * m->world * kMaxBpad, 2},
+        {"dzT", m->dzT, (int64_t)m->N * kMaxBpad, 2}, {"dz_all", m->dz_all, (int64_t)m->n_local * m->world * kMaxBpad, 2},
         {"dh_partial", m->dh_partial, (int64_t)m->nsplit * kMaxBpad * m->H, 4}, {"da", m->da, (int64_t)m->Bmax * m->H, 4},
         {"x_row_ptr", sl.xw.row_ptr, m->Bmax + 1, 4}, {"x_row_len", sl.xw.row_len, m->Bmax, 4},
-        {"x_col", sl.xw.col, m->max_nnz, 4}, {"x_val", sl.xw.val, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
+        {"x_col", sl.xw.col, m->max_nnz, 4}, {"x_val", m->pub.xn, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
         {"y_row_ptr", sl.yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", sl.yw.row_len, m->Bmax, 4},
         {"y_col", sl.yw.col, m->max_nnz, 4}, {"ybits", sl.ybits, (int64_t)m->N * m->ywords, 4},
         {"scores", m->scores, (int64_t)m->scores_elems, 4},
-        {"mW_dec", m->mW_dec, NH, 4}, {"vW_dec", m->vW_dec, NH, 4}, {"mW_enc", m->mW_enc, NH, 4}, {"vW_enc", m->vW_enc, NH, 4},
+        {"mW_dec", m->mW_dec, LH, 4}, {"vW_dec", m->vW_dec, LH, 4}, {"mW_enc", m->mW_enc, LH, 4}, {"vW_enc", m->vW_enc, LH, 4},
     };
     for (const E& e : table) {
         if (strcmp(e.n, name) == 0) {
@@ -729,9 +977,11 @@ extern "C" int32_t dae_gemm_test_device(int32_t op, const uint16_t* a_dev, const
         DecodeArgs d{};
         d.W = A; d.h_d = Bm; d.bias = bias_dev; d.N = n_items; d.H = n_hidden; d.batch = batch; d.bpad = bpad;
         d.n_batch_tiles = (batch + bpad - 1) / bpad; d.out = out_dev; d.ld_out = n_items; d.n_out = n_items;
+        d.pt.world = 1;
         launch_decode_predict(d, st);
     } else if (op == 1) {
-        DwArgs w{}; w.dzT = A; w.h_dT = Bm; w.g = out_dev; w.N = n_items; w.H = n_hidden; w.bpad = bpad;
+        DwArgs w{}; w.dzT = A; w.h_dT = Bm; w.g = out_dev; w.n_local = n_items; w.N = n_items; w.H = n_hidden; w.K = bpad;
+        w.pt.world = 1;
         launch_dw(w, st);
     } else if (op == 2) {
         DhArgs q{}; q.dzT = A; q.W = Bm; q.partial = out_dev; q.N = n_items; q.H = n_hidden; q.bpad = bpad;

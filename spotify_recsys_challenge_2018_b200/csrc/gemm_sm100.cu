@@ -72,8 +72,11 @@ static CUtensorMap make_map_bf16(const void* ptr, uint64_t inner, uint64_t outer
 enum { MODE_TRAIN = 0, MODE_PREDICT = 1, MODE_DW = 2 };
 
 constexpr int kStages = 6;
-constexpr int kEpiWarps = 8;                         // 2 warps per TMEM lane quadrant: each takes half the columns
-constexpr int kItemThreads = 64 + 32 * kEpiWarps;
+constexpr int kStagesStreamB = 4;                    // stages of (16 KB item chunk + 32 KB second-operand chunk)
+// Epilogue warps per CTA (a multiple of 4: warp w may only read TMEM lanes [32*(w%4), +32), so the warps of one
+// lane quadrant split the accumulator columns).  The compute-bound G1 epilogues run 8 warps of up to 140 registers;
+// the fused dW + Adam epilogue is pure HBM streaming and needs bytes in flight, so it runs 16 leaner warps.
+template <int MODE> struct EpiCfg { static constexpr int kWarps = MODE == 2 ? 16 : 8; static constexpr int kThreads = 64 + 32 * kWarps; };
 constexpr int kABytes = kTileItems * 128;           // one K-chunk of the streamed operand: 128 rows x 128 B
 constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the resident operand: <=256 rows x 128 B
 constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
@@ -102,12 +105,24 @@ struct ItemTileDev {
     const float* mix_wp;
     const float* mix_wt;
     const float* title_score;
-    float* g;         // G2 output [n_items, n_cols]
+    float* g;         // G2 raw output [n_items, n_cols] (nullptr: not materialised)
+    // G2: B operand streamed with A (K > 256) and the fused Adam epilogue
+    int stream_b;
+    float* aw; float* am; float* av;
+    const float* g_extra;
+    const unsigned char* touched;
+    AdamConst adam;
+    __nv_bfloat16* shadow;   // [n_global, n_cols] refreshed on every rank
+    int n_global;            // catalogue size: bounds the last tile of G2 (local tiles map to global tiles cyclically)
+    // data-parallel: G1 also delivers each item tile's dz to the tile's owner (columns [dz_col0, +bpad) of its [rows, ld_all])
+    __nv_bfloat16* dz_all;
+    int ld_all, dz_col0;
+    PeerTable pt;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kItemThreads, 1)
-k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ItemTileDev p) {
+__global__ void __launch_bounds__(EpiCfg<MODE>::kThreads, 1)
+k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ItemTileDev p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -121,10 +136,16 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
+    constexpr int kEpiWarps = EpiCfg<MODE>::kWarps;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int bt = blockIdx.y;  // batch tile (PREDICT only; 0 otherwise)
+    // G2 with K > 256 (data-parallel: K = ranks x batch tile): the second operand no longer fits in shared
+    // memory, so its K-chunk rides in the same ring stage as the item tile's (it comes from L2).
+    const bool sb = (MODE == MODE_DW) && p.stream_b != 0;
+    const int nstages = sb ? kStagesStreamB : kStages;
+    const uint32_t stage_bytes = sb ? (kABytes + kBChunkBytes) : kABytes;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -151,18 +172,23 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (lane == 0) {
             const uint64_t pol_stream = policy_evict_first();
             const uint64_t pol_keep = policy_evict_last();
-            mbar_expect_tx(bfull, static_cast<uint32_t>(p.kchunks * p.b_rows_box * 128));
-            for (int kc = 0; kc < p.kchunks; ++kc)
-                tma_load_2d_hint(sB + kc * kBChunkBytes, &tmB, bfull, kc * 64, bt * p.b_rows_box, pol_keep);
+            if (!sb) {
+                mbar_expect_tx(bfull, static_cast<uint32_t>(p.kchunks * p.b_rows_box * 128));
+                for (int kc = 0; kc < p.kchunks; ++kc)
+                    tma_load_2d_hint(sB + kc * kBChunkBytes, &tmB, bfull, kc * 64, bt * p.b_rows_box, pol_keep);
+            }
+            uint8_t* ring = sb ? smem : sA;
+            const uint32_t tx = sb ? static_cast<uint32_t>(kABytes + p.b_rows_box * 128) : static_cast<uint32_t>(kABytes);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], kABytes);
-                    tma_load_2d_hint(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
+                    mbar_expect_tx(&full[stage], tx);
+                    tma_load_2d_hint(ring + stage * stage_bytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
                                      pol_stream);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (sb) tma_load_2d_hint(ring + stage * stage_bytes + kABytes, &tmB, &full[stage], kc * 64, 0, pol_keep);
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -170,8 +196,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kTileItems, static_cast<uint32_t>(p.n_cols), 0, 0);
-            mbar_wait(bfull, 0);
-            tc_fence_after();
+            if (!sb) {
+                mbar_wait(bfull, 0);
+                tc_fence_after();
+            }
+            uint8_t* ring = sb ? smem : sA;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -183,8 +212,8 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-                    const uint32_t b_addr = smem_u32(sB + kc * kBChunkBytes);
+                    const uint32_t a_addr = smem_u32(ring + stage * stage_bytes);
+                    const uint32_t b_addr = sb ? a_addr + kABytes : smem_u32(sB + kc * kBChunkBytes);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t ad = umma_smem_desc(a_addr + ks * 32, 16, 1024);
@@ -192,7 +221,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);
                 acc ^= 1;
@@ -202,17 +231,19 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp owns
+        const int half = (warp - 2) >> 2;          // which share of the accumulator columns this warp owns
         const int row_in_tile = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
         float loss_acc = 0.f;
+        constexpr int kParts = kEpiWarps / 4;
         const int nchunks = p.n_cols >> 5;
-        const int c_lo = half * (nchunks >> 1), c_hi = c_lo + (nchunks >> 1);
+        const int c_lo = half * (nchunks / kParts), c_hi = c_lo + (nchunks / kParts);   // 32-column chunks (G1)
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            const int item = tile * kTileItems + row_in_tile;
-            const bool item_ok = item < p.n_items;
+            const int item = tile * kTileItems + row_in_tile;   // row of the streamed operand
+            const int gitem = MODE == MODE_DW ? item_global(item, p.pt.world, p.pt.rank) : item;   // catalogue id
+            const bool item_ok = MODE == MODE_DW ? gitem < p.n_global : item < p.n_items;
             float bz = 0.f;
             uint32_t yw_next = 0;
             const uint32_t* yrow = nullptr;
@@ -226,11 +257,64 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
             float db = 0.f;
+            bool row_extra = false;
+            if (MODE == MODE_DW) row_extra = item_ok && p.g_extra != nullptr && p.touched[item] != 0;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
+            if (MODE == MODE_DW) {
+                // G2 epilogue: this warp owns n_cols / kParts columns of its 32 item rows, 16 columns (64 B) at a time
+                const int cols_per = p.n_cols / kParts;
+                const int col0 = half * cols_per;
 #pragma unroll 1
-            for (int c = c_lo; c < c_hi; ++c) {
+                for (int cc = col0; cc < col0 + cols_per; cc += 16) {
+                    uint32_t r[16];
+                    __syncwarp();                                                        // tcgen05.ld is warp-collective
+                    tmem_ld16(t_addr + cc, r);
+                    tmem_ld_wait();
+                    const size_t off = (size_t)item * p.n_cols + cc;
+                    if (item_ok && p.g != nullptr) {
+                        st_global_v8(p.g + off, r);
+                        st_global_v8(p.g + off + 8, r + 8);
+                    }
+                    if (item_ok && p.aw != nullptr) {
+                    // dense TF1 Adam on the 16 gradient values this thread just read from TMEM: the gradient
+                    // never goes to HBM (26 B / parameter instead of 34)
+                    uint32_t wv[16], mv[16], vv[16];
+                    ld_global_cs_v8(p.aw + off, wv); ld_global_cs_v8(p.aw + off + 8, wv + 8);
+                    ld_global_cs_v8(p.am + off, mv); ld_global_cs_v8(p.am + off + 8, mv + 8);
+                    ld_global_cs_v8(p.av + off, vv); ld_global_cs_v8(p.av + off + 8, vv + 8);
+                    if (row_extra) {                                                     // tied: + sparse-row dW_enc
+                        uint32_t ge[16];
+                        ld_global_cs_v8(p.g_extra + off, ge); ld_global_cs_v8(p.g_extra + off + 8, ge + 8);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(ge[j])));
+                    }
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float w0 = __uint_as_float(wv[j]), m0 = __uint_as_float(mv[j]), v0 = __uint_as_float(vv[j]);
+                        float w1 = __uint_as_float(wv[j + 1]), m1 = __uint_as_float(mv[j + 1]), v1 = __uint_as_float(vv[j + 1]);
+                        adam_one(w0, m0, v0, __uint_as_float(r[j]), p.adam);
+                        adam_one(w1, m1, v1, __uint_as_float(r[j + 1]), p.adam);
+                        wv[j] = __float_as_uint(w0); mv[j] = __float_as_uint(m0); vv[j] = __float_as_uint(v0);
+                        wv[j + 1] = __float_as_uint(w1); mv[j + 1] = __float_as_uint(m1); vv[j + 1] = __float_as_uint(v1);
+                        packed[j >> 1] = pack_bf16x2(w0, w1);
+                    }
+                    st_global_cs_v8(p.aw + off, wv); st_global_cs_v8(p.aw + off + 8, wv + 8);
+                    st_global_cs_v8(p.am + off, mv); st_global_cs_v8(p.am + off + 8, mv + 8);
+                    st_global_cs_v8(p.av + off, vv); st_global_cs_v8(p.av + off + 8, vv + 8);
+                    if (p.shadow != nullptr) {
+                        const size_t goff = (size_t)gitem * p.n_cols + cc;
+                        for (int sidx = 0; sidx < p.pt.world; ++sidx)                    // this GPU's operand copy and every peer's
+                            st_global_v8(peer_ptr(p.pt, sidx, p.shadow) + goff, packed);
+                    }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int c = c_lo; MODE != MODE_DW && c < c_hi; ++c) {
                 uint32_t r[32];
                 tmem_ld32(t_addr + c * 32, r);
                 tmem_ld_wait();
@@ -268,6 +352,12 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         __nv_bfloat16* dst = p.dzT + (size_t)item * p.ld_dz + c * 32;   // 64 B: two full 32 B sectors
                         st_global_v8(dst, packed);
                         st_global_v8(dst + 16, packed + 8);
+                        if (p.dz_all != nullptr) {       // the tile's owner contracts it with every rank's h_d (NVLink store)
+                            __nv_bfloat16* rdst = peer_ptr(p.pt, tile % p.pt.world, p.dz_all) +
+                                                  (size_t)item_local(item, p.pt.world) * p.ld_all + p.dz_col0 + c * 32;
+                            st_global_v8(rdst, packed);
+                            st_global_v8(rdst + 16, packed + 8);
+                        }
                     }
                 } else if (MODE == MODE_PREDICT) {
                     const bool col_ok = item < p.n_out;
@@ -284,12 +374,6 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                             }
                             p.out[o] = pr;   // lanes = consecutive items -> 128 B per warp store
                         }
-                    }
-                } else {  // MODE_DW
-                    if (item_ok) {
-                        float* dst = p.g + (size_t)item * p.n_cols + c * 32;             // 128 B: one full line
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) st_global_v8(dst + 8 * v, r + 8 * v);
                     }
                 }
             }
@@ -347,7 +431,7 @@ static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
         cudaFuncSetAttribute(k_itemtile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
         configured = true;
     }
-    k_itemtile<MODE><<<grid, kItemThreads, kSmemItemTile, st>>>(tmA, tmB, p);
+    k_itemtile<MODE><<<grid, EpiCfg<MODE>::kThreads, kSmemItemTile, st>>>(tmA, tmB, p);
 }
 
 static ItemTileDev decode_dev(const DecodeArgs& a) {
@@ -372,6 +456,11 @@ static ItemTileDev decode_dev(const DecodeArgs& a) {
     p.mix_wp = a.mix_wp;
     p.mix_wt = a.mix_wt;
     p.title_score = a.title_score;
+    p.pt = a.pt;
+    if (p.pt.world < 1) p.pt.world = 1;
+    p.dz_all = a.pt.world > 1 ? a.dz_all : nullptr;
+    p.ld_all = a.K;
+    p.dz_col0 = a.pt.rank * a.bpad;
     return p;
 }
 
@@ -394,16 +483,27 @@ void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
 }
 
 void launch_dw(const DwArgs& a, cudaStream_t st) {
-    const CUtensorMap tmA = make_map_bf16(a.dzT, a.bpad, a.N, kTileItems);
-    const CUtensorMap tmB = make_map_bf16(a.h_dT, a.bpad, a.H, a.H);
+    const CUtensorMap tmA = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
+    const CUtensorMap tmB = make_map_bf16(a.h_dT, a.K, a.H, a.H);
     ItemTileDev p{};
-    p.n_items = a.N;
-    p.tiles = (a.N + kTileItems - 1) / kTileItems;
-    p.kchunks = a.bpad / 64;
+    p.pt = a.pt;
+    if (p.pt.world < 1) p.pt.world = 1;
+    // local tiles that hold at least one valid catalogue row: global tile = local * world + rank
+    const int tiles_total = (a.N + kTileItems - 1) / kTileItems;
+    p.tiles = tiles_total > p.pt.rank ? (tiles_total - p.pt.rank + p.pt.world - 1) / p.pt.world : 0;
+    p.n_items = a.n_local;
+    p.n_global = a.N;
+    p.kchunks = a.K / 64;
     p.n_cols = a.H;
     p.b_rows_box = a.H;
     p.g = a.g;
-    launch_itemtile<MODE_DW>(tmA, tmB, p, dim3(decode_grid(a.N, 1), 1, 1), st);
+    p.stream_b = a.K > 256 ? 1 : 0;
+    p.aw = a.w; p.am = a.m; p.av = a.v;
+    p.g_extra = a.g_extra; p.touched = a.touched;
+    p.adam = a.adam;
+    p.shadow = a.w != nullptr ? a.shadow : nullptr;
+    if (p.tiles == 0) return;
+    launch_itemtile<MODE_DW>(tmA, tmB, p, dim3(decode_grid(p.tiles * kTileItems, 1), 1, 1), st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -558,6 +658,21 @@ void launch_dh(const DhArgs& a, cudaStream_t st) {
     p.sbo = a.sbo > 0 ? (uint32_t)a.sbo : 1024u;              // next 8 items along K
     p.partial = a.partial;
     k_dh<<<a.nsplit, 192, kSmemDh, st>>>(tmDz, tmW, p);
+}
+
+// Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
+// synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
+void preload_gemm() {
+    cudaFuncAttributes a;
+    cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_itemtile<MODE_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_itemtile<MODE_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
+    cudaFuncGetAttributes(&a, k_itemtile<MODE_TRAIN>);
+    cudaFuncGetAttributes(&a, k_itemtile<MODE_PREDICT>);
+    cudaFuncGetAttributes(&a, k_itemtile<MODE_DW>);
+    cudaFuncGetAttributes(&a, k_dh);
+    (void)cudaGetLastError();
 }
 
 }  // namespace dae

@@ -5,11 +5,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "adam.cuh"
+
 namespace dae {
 
 constexpr int kTileItems = 128;    // UMMA M: catalogue items per accumulator tile
 constexpr int kMaxBpad = 256;      // UMMA N limit: batch columns per tile
 constexpr int kMaxRowNnz = 2048;   // per-playlist COO entries the row sorter holds in smem
+constexpr int kMaxWorld = 8;       // GPUs of one NVSwitch box
 constexpr float kEpsLog = 1e-10f;  // DAEs.py:42,98-99
 constexpr float kNegWeight = 0.55f;  // DAEs.py:99
 
@@ -17,6 +20,28 @@ constexpr float kNegWeight = 0.55f;  // DAEs.py:99
 enum : int { kErrIndexRange = 1, kErrRowTooLong = 2, kErrYNotBinary = 4 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- data-parallel layout -------------------------------------------------------------------
+// Every rank allocates the same arena layout, so a buffer of rank r is `base[r] + (local - base[rank])`.
+// Peers are mapped with CUDA IPC (one process per GPU) and addressed by plain loads / stores over
+// NVLink / NVSwitch.  Catalogue rows (W_enc, W_dec, their Adam moments, the sparse-row gradient) are
+// owned tile-cyclically: 128-item tile t lives on rank t % world as local tile t / world, which
+// spreads the popularity-ranked head of the catalogue (Zipf ids) evenly over the GPUs.
+struct PeerTable {
+    char* base[kMaxWorld];
+    int world, rank;
+};
+template <typename T>
+__host__ __device__ __forceinline__ T* peer_ptr(const PeerTable& pt, int r, T* local) {
+    return reinterpret_cast<T*>(pt.base[r] + (reinterpret_cast<const char*>(local) - pt.base[pt.rank]));
+}
+__host__ __device__ __forceinline__ int item_owner(int item, int world) { return (item >> 7) % world; }
+__host__ __device__ __forceinline__ int item_local(int item, int world) {
+    return (((item >> 7) / world) << 7) | (item & 127);
+}
+__host__ __device__ __forceinline__ int item_global(int local, int world, int rank) {
+    return ((((local >> 7) * world) + rank) << 7) | (local & 127);
+}
 
 // ---- sparse.cu ---------------------------------------------------------------------------
 struct CsrWork {        // COO -> per-row sorted, de-duplicated (last occurrence wins) CSR-with-gaps
@@ -32,37 +57,61 @@ void launch_coo_to_csr(const long long* pos, const float* val, int nnz, int B, i
                        cudaStream_t st);
 void launch_ybits_set(const CsrWork& y, int B, uint32_t* ybits, int ywords, int set, int* err, cudaStream_t st);
 
+// The normalised input of the step in flight, published for the sparse-row scatter of every rank
+// (same offsets as the slot's CSR): x_n = x_d / (s + 1e-10) per kept entry.
+struct PubInput {
+    int* row_ptr;       // [B]
+    int* row_len;       // [B]
+    int* col;           // [max_nnz]
+    float* xn;          // [max_nnz]
+};
+
 struct EncodeArgs {
-    const float* W_enc;   // [N,H] fp32 master
+    const float* W_enc;   // this rank's rows of the fp32 master, local-tile order
     const float* b_enc;   // [H]
-    CsrWork x;            // val is overwritten with x_n (a3), needed again by the backward scatter
+    CsrWork x;            // read only
+    PubInput pub;         // written: col, x_n
     float* rowsum;        // [B] s = sum_j x_d (DAEs.py:41)
     float* h;             // [B,H] fp32 sigma(a)
     __nv_bfloat16* h_d;   // [bpad,H]  dropout(h), bf16, rows >= B zero
-    __nv_bfloat16* h_dT;  // [H,bpad]
-    int B, bpad, H;
+    __nv_bfloat16* h_dT;  // [H, K] K = world*bpad; this rank writes columns [rank*bpad, +bpad) on EVERY rank
+    int B, bpad, H, K;
+    int hT_col0;          // first h_dT column of this rank's rows
+    int hT_bcast;         // 1: store the h_dT columns into every rank's copy (training), 0: local only
     float kp, kp_in;
     unsigned long long seed, step;
     int row_offset;       // global row index of local row 0 (data-parallel shards)
+    PeerTable pt;
 };
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st);
 
-struct EncodeBwdArgs {
+struct EncodeDaArgs {
     const float* dh_partial;  // [nsplit, bpad, H]
     int nsplit;
     const float* h;           // [B,H]
-    CsrWork x;                // col, val = x_n
     float* da;                // [B,H]
-    float* g_enc;             // [N,H] scatter-add target (dW_enc rows, or the tied dW)
-    unsigned char* touched;   // [N] or nullptr
-    float* db_enc;            // [H]
+    float* db_enc;            // [H] this rank's column sums of da
     int B, bpad, H;
     float kp;
     unsigned long long seed, step;
     int row_offset;
 };
-void launch_encode_bwd(const EncodeBwdArgs& a, cudaStream_t st);
-void launch_clear_touched(const CsrWork& x, int B, int H, float* g_enc, unsigned char* touched, cudaStream_t st);
+void launch_encode_da(const EncodeDaArgs& a, cudaStream_t st);
+
+struct ScatterArgs {          // dW_enc rows owned by this rank, from every rank's published input and da
+    PubInput pub;             // local pointers; peers through pt
+    const float* da;          // [B,H]
+    float* g_enc;             // [local rows, H]
+    unsigned char* touched;   // [local rows]
+    int B, H;
+    PeerTable pt;
+};
+void launch_scatter_shard(const ScatterArgs& a, cudaStream_t st);
+
+// out[i] = sum over ranks (fixed order) of part[i] read from every rank's arena
+void launch_sum_partials(const float* part_local, float* out, int n, const PeerTable& pt, cudaStream_t st);
+// all ranks have reached `epoch` on their streams, and everything they wrote before is visible
+void launch_barrier(unsigned int* flags_local, unsigned int epoch, const PeerTable& pt, cudaStream_t st);
 
 // ---- gemm_sm100.cu -------------------------------------------------------------------------
 struct DecodeArgs {
@@ -76,7 +125,10 @@ struct DecodeArgs {
     // train
     const uint32_t* ybits;     // [N, ywords]
     int ywords;
-    __nv_bfloat16* dzT;        // [N,bpad]
+    __nv_bfloat16* dzT;        // [N,bpad] this rank's batch columns, every item (operand of dh)
+    __nv_bfloat16* dz_all;     // [local rows, K] on the OWNER of each item tile: columns [rank*bpad, +bpad); nullptr when world == 1
+    int K;
+    PeerTable pt;
     float* db_dec;             // [N]
     float* loss_partial;       // [grid]
     float inv_batch;
@@ -93,12 +145,20 @@ void launch_decode_train(const DecodeArgs& a, cudaStream_t st);    // G1: z, los
 void launch_decode_predict(const DecodeArgs& a, cudaStream_t st);  // G1: z, sigmoid, scores
 
 struct DwArgs {
-    const __nv_bfloat16* dzT;   // [N,bpad]
-    const __nv_bfloat16* h_dT;  // [H,bpad]
-    float* g;                   // [N,H] fp32, overwritten
-    int N, H, bpad;
+    const __nv_bfloat16* dzT;   // [local rows, K] d cost/dz of the item tiles this rank owns, all ranks' batch columns
+    const __nv_bfloat16* h_dT;  // [H, K]
+    float* g;                   // [local rows, H] fp32 raw dW_dec, overwritten (nullptr: not materialised)
+    int n_local;                // local rows (multiple of 128)
+    int N, H, K;                // N: catalogue size (global), bounds the last tile
+    // fused dense TF1 Adam on the tile while it is still in TMEM (w == nullptr: no update)
+    float* w; float* m; float* v;       // [local rows, H] fp32 master + moments
+    const float* g_extra;               // tied model: sparse-row dW_enc [local rows, H], added where touched[row] != 0
+    const unsigned char* touched;       // [local rows]
+    AdamConst adam;
+    __nv_bfloat16* shadow;              // [N,H] bf16 operand copy to refresh on this GPU and on every peer (global row order)
+    PeerTable pt;
 };
-void launch_dw(const DwArgs& a, cudaStream_t st);                  // G2: dW_dec = dz^T . h_d
+void launch_dw(const DwArgs& a, cudaStream_t st);                  // G2: dW_dec = dz^T . h_d (+ Adam)
 
 struct DhArgs {
     const __nv_bfloat16* dzT;   // [N,bpad]
@@ -121,9 +181,13 @@ struct AdamArgs {
     float alpha, one_minus_b1, one_minus_b2, eps, lambda;
 };
 void launch_adam(const AdamArgs& a, cudaStream_t st);
-void launch_xavier_init(float* w, long long n, float limit, unsigned long long seed, unsigned stream_id,
-                        cudaStream_t st);
-void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
+// U(-limit, limit) keyed by the GLOBAL element index; w: this rank's rows in local-tile order (or nullptr),
+// wb: bf16 copy of ALL N rows in global order (or nullptr)
+void launch_xavier_init(float* w, int n_local_rows, __nv_bfloat16* wb, int N, int H, float limit,
+                        unsigned long long seed, unsigned stream_id, int world, int rank, cudaStream_t st);
+// rows of a local-tile-ordered fp32 block of rank `owner_rank` -> bf16 rows of the global-order operand copy
+void launch_cast_rows_bf16(const float* src_local, int n_local_rows, __nv_bfloat16* dst_global, int N, int H, int world,
+                           int owner_rank, cudaStream_t st);
 void launch_sumsq(const float* x, long long n, float* partial, int nblocks, cudaStream_t st);
 void launch_reduce_loss2(const float* partial, int n, const float* sumsq_partial, int n_sq, float lambda,
                          float inv_batch, float* loss_out, cudaStream_t st);
@@ -141,5 +205,11 @@ struct TopkArgs {
     float* out_score;         // [B,k]
 };
 void launch_topk(const TopkArgs& a, cudaStream_t st);
+
+// load every kernel of a translation unit (see sparse.cu: preload_sparse)
+void preload_sparse();
+void preload_optim();
+void preload_gemm();
+void preload_topk();
 
 }  // namespace dae

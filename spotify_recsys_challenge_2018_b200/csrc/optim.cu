@@ -10,21 +10,11 @@
 // against the NumPy oracle given the same gradient.
 #include <cuda_runtime.h>
 
+#include "adam.cuh"
 #include "kernels.h"
 #include "philox.cuh"
 
 namespace dae {
-
-struct AdamConst {
-    float alpha, omb1, omb2, eps, lambda;
-};
-
-__device__ __forceinline__ void adam_one(float& w, float& m, float& v, float g, const AdamConst c) {
-    if (c.lambda != 0.f) g = __fadd_rn(g, __fmul_rn(c.lambda, w));          // d/dw of lambda * l2_loss(w)  (DAEs.py:100)
-    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), c.omb1));
-    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), c.omb2));
-    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(m, c.alpha), __fadd_rn(__fsqrt_rn(v), c.eps)));
-}
 
 // n4 float4 groups; row_len4 = row_len/4 (groups per row) when row_touched != nullptr
 __global__ void __launch_bounds__(256)
@@ -93,25 +83,45 @@ void launch_adam(const AdamArgs& a, cudaStream_t st) {
 }
 
 // tf.contrib.layers.xavier_initializer() [TF1]: U(-l, l), l = sqrt(6 / (fan_in + fan_out))   (DAEs.py:54-55)
-__global__ void k_xavier(float* __restrict__ w, long long n, float limit, unsigned long long seed, unsigned stream_id) {
+// Keyed by the GLOBAL element index, so the values do not depend on how the rows are spread over GPUs.
+__device__ __forceinline__ float xavier_value(long long gi, float limit, unsigned long long seed, unsigned stream_id) {
+    const float u = philox_uniform24(seed, stream_id, 0ull, static_cast<uint32_t>(gi >> 32), static_cast<uint32_t>(gi));
+    return (2.f * u - 1.f) * limit;
+}
+__global__ void k_xavier_local(float* __restrict__ w, long long n_local, int N, int H, float limit,
+                               unsigned long long seed, unsigned stream_id, int world, int rank) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float u = philox_uniform24(seed, stream_id, 0ull, static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(i));
-        w[i] = (2.f * u - 1.f) * limit;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
+        const int lrow = (int)(i / H), k = (int)(i - (long long)lrow * H);
+        const int grow = item_global(lrow, world, rank);
+        w[i] = grow < N ? xavier_value((long long)grow * H + k, limit, seed, stream_id) : 0.f;
     }
 }
-void launch_xavier_init(float* w, long long n, float limit, unsigned long long seed, unsigned stream_id,
-                        cudaStream_t st) {
-    k_xavier<<<1184, 256, 0, st>>>(w, n, limit, seed, stream_id);
-}
-
-__global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+__global__ void k_xavier_bf16(__nv_bfloat16* __restrict__ wb, long long n, float limit, unsigned long long seed,
+                              unsigned stream_id) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        dst[i] = __float2bfloat16(src[i]);
+        wb[i] = __float2bfloat16(xavier_value(i, limit, seed, stream_id));
 }
-void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {
-    k_cast_bf16<<<1184, 256, 0, st>>>(src, dst, n);
+void launch_xavier_init(float* w, int n_local_rows, __nv_bfloat16* wb, int N, int H, float limit,
+                        unsigned long long seed, unsigned stream_id, int world, int rank, cudaStream_t st) {
+    if (w != nullptr)
+        k_xavier_local<<<1184, 256, 0, st>>>(w, (long long)n_local_rows * H, N, H, limit, seed, stream_id, world, rank);
+    if (wb != nullptr) k_xavier_bf16<<<1184, 256, 0, st>>>(wb, (long long)N * H, limit, seed, stream_id);
+}
+
+__global__ void k_cast_rows_bf16(const float* __restrict__ src, long long n_local, __nv_bfloat16* __restrict__ dst,
+                                 int N, int H, int world, int owner) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
+        const int lrow = (int)(i / H), k = (int)(i - (long long)lrow * H);
+        const int grow = item_global(lrow, world, owner);
+        if (grow < N) dst[(size_t)grow * H + k] = __float2bfloat16(src[i]);
+    }
+}
+void launch_cast_rows_bf16(const float* src_local, int n_local_rows, __nv_bfloat16* dst_global, int N, int H, int world,
+                           int owner_rank, cudaStream_t st) {
+    k_cast_rows_bf16<<<1184, 256, 0, st>>>(src_local, (long long)n_local_rows * H, dst_global, N, H, world, owner_rank);
 }
 
 // sum of squares, one partial per block (tf.nn.l2_loss = sum(t^2)/2 [TF1], DAEs.py:79-82)
@@ -180,6 +190,21 @@ __global__ void k_clear_flagged(int N, int H, float* __restrict__ g_enc, unsigne
 }
 void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, cudaStream_t st) {
     k_clear_flagged<<<(N + 255) / 256, 256, 0, st>>>(N, H, g_enc, touched);
+}
+
+// Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
+// synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
+void preload_optim() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_adam_vec4);
+    cudaFuncGetAttributes(&a, k_adam_scalar);
+    cudaFuncGetAttributes(&a, k_xavier_local);
+    cudaFuncGetAttributes(&a, k_xavier_bf16);
+    cudaFuncGetAttributes(&a, k_cast_rows_bf16);
+    cudaFuncGetAttributes(&a, k_sumsq);
+    cudaFuncGetAttributes(&a, k_reduce_loss);
+    cudaFuncGetAttributes(&a, k_clear_flagged);
+    (void)cudaGetLastError();
 }
 
 }  // namespace dae

@@ -182,19 +182,23 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 
 __global__ void __launch_bounds__(256)
 k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const int* __restrict__ row_ptr,
-             const int* __restrict__ row_len, const int* __restrict__ col, float* __restrict__ val,
-             float* __restrict__ rowsum, float* __restrict__ h, __nv_bfloat16* __restrict__ h_d,
-             __nv_bfloat16* __restrict__ h_dT, int B, int bpad, int H, float kp, float kp_in,
-             unsigned long long seed, unsigned long long step, int row_offset) {
+             const int* __restrict__ row_len, const int* __restrict__ col, const float* __restrict__ val,
+             const __grid_constant__ PubInput pub, float* __restrict__ rowsum, float* __restrict__ h, __nv_bfloat16* __restrict__ h_d,
+             __nv_bfloat16* __restrict__ h_dT, int B, int bpad, int H, int K, int hT_col0, int hT_bcast, float kp,
+             float kp_in, unsigned long long seed, unsigned long long step, int row_offset, const __grid_constant__ PeerTable pt) {
     __shared__ __align__(16) float s_x[kMaxRowNnz];
     __shared__ int s_c[kMaxRowNnz];
     __shared__ float s_red[8];
     const int r = blockIdx.x;
     const int k = threadIdx.x;
+    const int world = pt.world;
+    const size_t hT_off = (size_t)k * K + hT_col0 + r;                  // this rank's column block of [H, K]
+    const int n_hT = hT_bcast ? world : 1;
     if (r >= B) {   // padding rows of the tensor-core operand
         if (k < H) {
-            h_d[(size_t)r * H + k] = __float2bfloat16(0.f);
-            h_dT[(size_t)k * bpad + r] = __float2bfloat16(0.f);
+            const __nv_bfloat16 z = __float2bfloat16(0.f);
+            h_d[(size_t)r * H + k] = z;
+            for (int s = 0; s < n_hT; ++s) (hT_bcast ? peer_ptr(pt, s, h_dT) : h_dT)[hT_off] = z;
         }
         return;
     }
@@ -212,23 +216,31 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
         part += xd;
     }
     const float s = block_sum(part, s_red);
-    const float inv = __fdiv_rn(1.f, s + kEpsLog);
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float xn = __fdiv_rn(s_x[i], s + kEpsLog);
         s_x[i] = xn;
-        val[beg + i] = xn;            // x_n is reused by the backward scatter
+        pub.xn[beg + i] = xn;         // x_n and its column are re-read by the sparse-row scatter of every rank
+        pub.col[beg + i] = s_c[i];
     }
-    (void)inv;
-    if (threadIdx.x == 0) rowsum[r] = s;
+    if (threadIdx.x == 0) {
+        rowsum[r] = s;
+        pub.row_ptr[r] = beg;
+        pub.row_len[r] = n;
+    }
     __syncthreads();
     // a4: a = sum_j x_n[j] * W_enc[col_j, :].  Thread (g, t): row group g takes entries j = g (mod G),
     // lane t owns columns [4t, 4t+4) as one float4 -> every gathered row is a run of coalesced 16 B loads
     // and up to 4*G rows are in flight per CTA.  Groups are combined through smem in a fixed order.
+    // Rows live on their owner GPU (tile-cyclic); remote rows are plain loads over NVLink.
     const int tpr = H >> 2;                      // threads per row
     const int G = blockDim.x / tpr;              // concurrent row groups
     const int g = threadIdx.x / tpr, t = threadIdx.x - g * tpr;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto row_of = [&](int c) -> const float4* {
+        const float* base = world == 1 ? W : peer_ptr(pt, item_owner(c, world), W);
+        return reinterpret_cast<const float4*>(base + (size_t)(world == 1 ? c : item_local(c, world)) * H) + t;
+    };
     if (g < G) {
         int i = g;
         for (; i + 3 * G < n; i += 4 * G) {
@@ -237,8 +249,7 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 x[u] = s_x[i + u * G];
-                w[u] = x[u] != 0.f ? __ldg(reinterpret_cast<const float4*>(W + (size_t)s_c[i + u * G] * H) + t)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u] = x[u] != 0.f ? __ldg(row_of(s_c[i + u * G])) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -249,7 +260,7 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
         for (; i < n; i += G) {
             const float x0 = s_x[i];
             if (x0 != 0.f) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)s_c[i] * H) + t);
+                const float4 w0 = __ldg(row_of(s_c[i]));
                 acc.x = fmaf(x0, w0.x, acc.x); acc.y = fmaf(x0, w0.y, acc.y);
                 acc.z = fmaf(x0, w0.z, acc.z); acc.w = fmaf(x0, w0.w, acc.w);
             }
@@ -269,67 +280,41 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     h[(size_t)r * H + k] = hv;
     const __nv_bfloat16 hb = __float2bfloat16(hd);
     h_d[(size_t)r * H + k] = hb;
-    h_dT[(size_t)k * bpad + r] = hb;
+    for (int s2 = 0; s2 < n_hT; ++s2) (hT_bcast ? peer_ptr(pt, s2, h_dT) : h_dT)[hT_off] = hb;
 }
 
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st) {
     const int threads = 256;                      // G = 1024 / H row groups of H/4 threads
-    k_encode_fwd<<<a.bpad, threads, 0, st>>>(a.W_enc, a.b_enc, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val, a.rowsum,
-                                             a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.kp, a.kp_in, a.seed, a.step,
-                                             a.row_offset);
+    k_encode_fwd<<<a.bpad, threads, 0, st>>>(a.W_enc, a.b_enc, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val, a.pub,
+                                             a.rowsum, a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.K, a.hT_col0, a.hT_bcast,
+                                             a.kp, a.kp_in, a.seed, a.step, a.row_offset, a.pt);
 }
 
 // ------------------------------------------------------------------------------------------
-// encode backward: reduce the split-K partials of dh, da = dh * (keep/kp) * h(1-h), then the
-// sparse-row scatter-add dW_enc[col_j,:] += x_n[j] * da[row,:]  (coalesced fp32 reductions).
+// encode backward, part 1: reduce the split-K partials of dh, da = dh * (keep/kp) * h(1-h)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_encode_bwd(const float* __restrict__ dh_partial, int nsplit, const float* __restrict__ h,
-             const int* __restrict__ row_ptr, const int* __restrict__ row_len, const int* __restrict__ col,
-             const float* __restrict__ xn, float* __restrict__ da_out, float* __restrict__ g_enc,
-             unsigned char* __restrict__ touched, int B, int bpad, int H, float kp, unsigned long long seed,
-             unsigned long long step, int row_offset) {
-    __shared__ __align__(16) float s_da[256];
+k_encode_da(const float* __restrict__ dh_partial, int nsplit, const float* __restrict__ h, float* __restrict__ da_out,
+            int B, int bpad, int H, float kp, unsigned long long seed, unsigned long long step, int row_offset) {
     const int r = blockIdx.x;
     const int k = threadIdx.x;
-    if (k < H) {
-        const size_t stride = (size_t)bpad * H;
-        const float* p = dh_partial + (size_t)r * H + k;
-        int s = 0;
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-        for (; s + 4 <= nsplit; s += 4) {                     // fixed order: deterministic
-            d0 += p[(size_t)s * stride];
-            d1 += p[(size_t)(s + 1) * stride];
-            d2 += p[(size_t)(s + 2) * stride];
-            d3 += p[(size_t)(s + 3) * stride];
-        }
-        for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
-        const float dh = (d0 + d1) + (d2 + d3);
-        const float hv = h[(size_t)r * H + k];
-        const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(r + row_offset),
-                                      static_cast<uint32_t>(k), kp);
-        const float da = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
-        da_out[(size_t)r * H + k] = da;
-        s_da[k] = da;
+    if (k >= H) return;
+    const size_t stride = (size_t)bpad * H;
+    const float* p = dh_partial + (size_t)r * H + k;
+    int s = 0;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    for (; s + 4 <= nsplit; s += 4) {                     // fixed order: deterministic
+        d0 += p[(size_t)s * stride];
+        d1 += p[(size_t)(s + 1) * stride];
+        d2 += p[(size_t)(s + 2) * stride];
+        d3 += p[(size_t)(s + 3) * stride];
     }
-    __syncthreads();
-    // scatter-add: thread (g, t) takes entries j = g (mod G), lane t adds 4 columns with one 16-byte reduction
-    const int tpr = H >> 2, G = blockDim.x / tpr;
-    const int g = threadIdx.x / tpr, t = threadIdx.x - g * tpr;
-    if (g >= G) return;
-    const float4 dav = *reinterpret_cast<const float4*>(s_da + 4 * t);
-    const int beg = row_ptr[r], n = row_len[r];
-    for (int i = g; i < n; i += G) {
-        const float x = xn[beg + i];
-        if (x != 0.f) {
-            const int c = col[beg + i];
-            float* dst = g_enc + (size_t)c * H + 4 * t;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x * dav.x), "f"(x * dav.y),
-                         "f"(x * dav.z), "f"(x * dav.w)
-                         : "memory");
-            if (touched != nullptr && t == 0) touched[c] = 1;
-        }
-    }
+    for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
+    const float dh = (d0 + d1) + (d2 + d3);
+    const float hv = h[(size_t)r * H + k];
+    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(r + row_offset),
+                                  static_cast<uint32_t>(k), kp);
+    da_out[(size_t)r * H + k] = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
 }
 
 // db_enc[k] = sum_r da[r,k]: 8 row groups per block, combined in a fixed order
@@ -348,29 +333,108 @@ __global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __
     }
 }
 
-void launch_encode_bwd(const EncodeBwdArgs& a, cudaStream_t st) {
-    const int threads = 256;
-    k_encode_bwd<<<a.B, threads, 0, st>>>(a.dh_partial, a.nsplit, a.h, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val,
-                                          a.da, a.g_enc, a.touched, a.B, a.bpad, a.H, a.kp, a.seed, a.step,
-                                          a.row_offset);
+void launch_encode_da(const EncodeDaArgs& a, cudaStream_t st) {
+    k_encode_da<<<a.B, 256, 0, st>>>(a.dh_partial, a.nsplit, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed, a.step,
+                                     a.row_offset);
     k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.B, a.H, a.db_enc);
 }
 
-// zero the rows of g_enc that the step touched (and their flags) so the buffer is clean again
-__global__ void k_clear_touched(const int* __restrict__ row_ptr, const int* __restrict__ row_len,
-                                const int* __restrict__ col, int H, float* __restrict__ g_enc,
-                                unsigned char* __restrict__ touched) {
-    const int r = blockIdx.x;
-    const int beg = row_ptr[r], n = row_len[r];
-    for (int i = 0; i < n; ++i) {
-        const int c = col[beg + i];
-        for (int k = threadIdx.x; k < H; k += blockDim.x) g_enc[(size_t)c * H + k] = 0.f;
-        if (threadIdx.x == 0) touched[c] = 0;
+// ------------------------------------------------------------------------------------------
+// encode backward, part 2: sparse-row scatter-add dW_enc[col_j,:] += x_n[j] * da[row,:] into the rows
+// THIS rank owns.  Block (r, s) walks row r of rank s's published input (read over NVLink when
+// s != rank: ~70 entries + one 1 KB da row) and keeps the entries whose item tile lives here.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_scatter_shard(const PubInput pub, const float* __restrict__ da, float* __restrict__ g_enc,
+                unsigned char* __restrict__ touched, int H, const __grid_constant__ PeerTable pt) {
+    __shared__ __align__(16) float s_da[256];
+    const int r = blockIdx.x, s = blockIdx.y;
+    const int world = pt.world;
+    const int* prow_ptr = world == 1 ? pub.row_ptr : peer_ptr(pt, s, pub.row_ptr);
+    const int* prow_len = world == 1 ? pub.row_len : peer_ptr(pt, s, pub.row_len);
+    const int* pcol = world == 1 ? pub.col : peer_ptr(pt, s, pub.col);
+    const float* pxn = world == 1 ? pub.xn : peer_ptr(pt, s, pub.xn);
+    const float* pda = world == 1 ? da : peer_ptr(pt, s, da);
+    if (threadIdx.x < H) s_da[threadIdx.x] = pda[(size_t)r * H + threadIdx.x];
+    __syncthreads();
+    // thread (g, t) takes entries j = g (mod G), lane t adds 4 columns with one 16-byte reduction
+    const int tpr = H >> 2, G = blockDim.x / tpr;
+    const int g = threadIdx.x / tpr, t = threadIdx.x - g * tpr;
+    if (g >= G) return;
+    const float4 dav = *reinterpret_cast<const float4*>(s_da + 4 * t);
+    const int beg = prow_ptr[r], n = prow_len[r];
+    for (int i = g; i < n; i += G) {
+        const int c = pcol[beg + i];
+        if (world != 1 && item_owner(c, world) != pt.rank) continue;
+        const float x = pxn[beg + i];
+        if (x != 0.f) {
+            const int lc = world == 1 ? c : item_local(c, world);
+            float* dst = g_enc + (size_t)lc * H + 4 * t;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x * dav.x), "f"(x * dav.y),
+                         "f"(x * dav.z), "f"(x * dav.w)
+                         : "memory");
+            if (t == 0) touched[lc] = 1;
+        }
     }
 }
 
-void launch_clear_touched(const CsrWork& x, int B, int H, float* g_enc, unsigned char* touched, cudaStream_t st) {
-    k_clear_touched<<<B, 256, 0, st>>>(x.row_ptr, x.row_len, x.col, H, g_enc, touched);
+void launch_scatter_shard(const ScatterArgs& a, cudaStream_t st) {
+    k_scatter_shard<<<dim3(a.B, a.pt.world), 256, 0, st>>>(a.pub, a.da, a.g_enc, a.touched, a.H, a.pt);
+}
+
+// out[i] = sum_s part_s[i], ranks in a fixed order (identical result on every rank)
+__global__ void k_sum_partials(const float* __restrict__ part, float* __restrict__ out, int n, const __grid_constant__ PeerTable pt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.f;
+    for (int s = 0; s < pt.world; ++s) t += peer_ptr(pt, s, part)[i];
+    out[i] = t;
+}
+void launch_sum_partials(const float* part_local, float* out, int n, const PeerTable& pt, cudaStream_t st) {
+    k_sum_partials<<<(n + 255) / 256, 256, 0, st>>>(part_local, out, n, pt);
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-GPU barrier on the stream: rank r stores `epoch` into slot r of every peer's flag array
+// (release, system scope), then waits until all of its own slots have reached `epoch`.  Kernels
+// enqueued before it have completed (stream order), so their NVLink stores are visible to the peers
+// that observe the flag.  Bounded spin: a lost peer traps instead of hanging the box.
+// ------------------------------------------------------------------------------------------
+__global__ void k_barrier(unsigned int* flags_local, unsigned int epoch, const __grid_constant__ PeerTable pt) {
+    const int t = threadIdx.x;
+    if (t >= pt.world) return;
+    __threadfence_system();
+    unsigned int* remote = peer_ptr(pt, t, flags_local) + pt.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const unsigned int* mine = flags_local + t;
+    unsigned int seen = 0;
+    for (unsigned long long spins = 0; spins < (1ull << 25); ++spins) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int)(seen - epoch) >= 0) return;
+        __nanosleep(64);
+    }
+    __trap();
+}
+void launch_barrier(unsigned int* flags_local, unsigned int epoch, const PeerTable& pt, cudaStream_t st) {
+    k_barrier<<<1, 32, 0, st>>>(flags_local, epoch, pt);
+}
+
+// Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
+// synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
+void preload_sparse() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_coo_count);
+    cudaFuncGetAttributes(&a, k_row_scan);
+    cudaFuncGetAttributes(&a, k_coo_fill);
+    cudaFuncGetAttributes(&a, k_row_sort_dedup);
+    cudaFuncGetAttributes(&a, k_ybits);
+    cudaFuncGetAttributes(&a, k_encode_fwd);
+    cudaFuncGetAttributes(&a, k_encode_da);
+    cudaFuncGetAttributes(&a, k_colsum);
+    cudaFuncGetAttributes(&a, k_scatter_shard);
+    cudaFuncGetAttributes(&a, k_sum_partials);
+    cudaFuncGetAttributes(&a, k_barrier);
+    (void)cudaGetLastError();
 }
 
 }  // namespace dae

@@ -229,4 +229,12 @@ void launch_topk(const TopkArgs& a, cudaStream_t st) {
                                          a.out_score);
 }
 
+// Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
+// synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
+void preload_topk() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_topk);
+    (void)cudaGetLastError();
+}
+
 }  // namespace dae

@@ -1,13 +1,15 @@
 """Data-parallel training of the DAE across the GPUs of one box (one process per GPU).
 
-The reference has no data parallelism; the train step shards naturally by playlist:
-every rank holds full replicas of the parameters and Adam state, processes B_local rows of the
-global batch, scales its gradients by 1/B_global (the loss is a mean over the GLOBAL batch,
-models/DAEs.py:100) and the gradients are sum-all-reduced once per step over NCCL / NVLink; then
-every rank applies the identical dense Adam update.  Dropout masks are keyed by the global row, so
-N ranks x B_local reproduce one rank x (N * B_local) up to fp32 summation order.
+The reference has no data parallelism.  The train step shards naturally by playlist:
+rank r runs encode / decode / loss / dh on rows [r*B, (r+1)*B) of the global batch (the loss is a
+mean over the GLOBAL batch, models/DAEs.py:100; dropout is keyed by the global row, so N ranks x B
+reproduce one rank x N*B).  The catalogue-sized state -- W_enc, W_dec, their Adam moments -- is
+row-sharded tile-cyclically over the ranks, and every exchange is done by the CUDA kernels
+themselves with loads / stores into the peers' memory over NVLink / NVSwitch (include/dae_b200.h,
+"data parallelism"): there is no collective call in the step.  torch.distributed is only the
+out-of-band channel that carries the 64-byte CUDA IPC handles at start-up.
 
-`shard_coo` and `allreduce_grads` are backend-agnostic (tested with gloo on CPU, world_size 2).
+`shard_coo` and `exchange_handles` are backend-agnostic (tested with gloo on CPU, world_size 2).
 """
 from __future__ import annotations
 
@@ -26,42 +28,64 @@ def shard_coo(positions, vals, rank, b_local):
     return out, val[keep]
 
 
-def allreduce_grads(tensors, group=None, flags=None):
-    """Sum-all-reduce every gradient tensor (and max-reduce the row flags) in place."""
+def tile_owner(item, world, tile=128):
+    """Rank that owns catalogue row `item` (csrc/kernels.h item_owner): 128-row tiles, cyclic."""
+    return (np.asarray(item) // tile) % world
+
+
+def tile_local_row(item, world, tile=128):
+    """Row of `item` inside its owner's shard (csrc/kernels.h item_local)."""
+    item = np.asarray(item)
+    return (item // tile // world) * tile + item % tile
+
+
+def exchange_handles(handle, group=None):
+    """All-gather one opaque bytes object per rank, in rank order."""
     import torch.distributed as dist
-    for t in tensors:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    if flags is not None:
-        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, bytes(handle), group=group)
+    return out
 
 
-class _DevArr:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+def attach_peers(model, group=None):
+    """Map every rank's arena into this rank's model (CUDA IPC), then line the ranks up."""
+    import torch.distributed as dist
+    model.attach_ipc(exchange_handles(model.ipc_handle(), group))
+    dist.barrier(group)
 
 
 class DataParallelDAE:
-    """Wraps a models.DAEs model created on this rank's GPU and stream."""
+    """A models.DAEs model created with conf.world / conf.rank on this rank's GPU, attached to its peers.
+
+    train_step_staged is the single-GPU call: the library enqueues the two cross-GPU flag barriers
+    of the step itself.  Every rank must stage batches of the same size and call in the same order."""
 
     def __init__(self, model, group=None):
-        import torch
         import torch.distributed as dist
         self.model, self.group = model, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        view = lambda name, ts: torch.as_tensor(_DevArr(*model.buffer(name)[:2], ts), device="cuda")
-        names = ["g_dec", "g_b_enc", "g_b_dec", "cost"] + ([] if model.tied else ["g_enc"])
-        self.grads = [view(n, "<f4") for n in names]
-        self.flags = None if model.tied else view("touched", "|u1")
+        if model.world != self.world or model.rank != self.rank:
+            raise ValueError("model was created for rank %d/%d, process group is %d/%d"
+                             % (model.rank, model.world, self.rank, self.world))
+        attach_peers(model, group)
 
     def train_step_staged(self, slot, keep_prob, input_keep_prob):
-        b = self.model.n_batch
-        self.model.backward_staged(slot, keep_prob, input_keep_prob, global_batch=b * self.world,
-                                   row_offset=b * self.rank)
-        allreduce_grads(self.grads, self.group, self.flags)
-        self.model.apply_adam()
+        self.model.train_step_staged(slot, keep_prob, input_keep_prob)
 
     def stage_global_batch(self, slot, x_positions, x_vals, y_positions, y_vals):
+        """Every rank is handed the GLOBAL reader batch and keeps its own rows."""
         b = self.model.n_batch
         xp, xv = shard_coo(x_positions, x_vals, self.rank, b)
         yp, yv = shard_coo(y_positions, y_vals, self.rank, b)
         self.model.stage_batch(slot, xp, xv, yp, yv)
+
+    def get_params(self):
+        """Gather the four parameter arrays on this rank (all ranks idle: barrier on both sides)."""
+        import torch
+        import torch.distributed as dist
+        self.model.sync_cost()
+        dist.barrier(self.group)
+        out = self.model.get_params()
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        return out

@@ -49,6 +49,8 @@ class DAE_tied:
         self.seed = int(getattr(conf, "seed", 0))
         self.device = int(getattr(conf, "device", 0))
         self.stream = getattr(conf, "stream", None)
+        self.world = int(getattr(conf, "world", 1))       # data-parallel ranks (one model per GPU), dp.py
+        self.rank = int(getattr(conf, "rank", 0))
         self._h = None
         self._lib = None
 
@@ -57,7 +59,7 @@ class DAE_tied:
         lib = _lib.load()
         cfg = _lib.DaeConfig(self.n_input, self.n_tracks, self.n_hidden, self.n_batch, int(self.tied),
                              self.learning_rate, self.reg_lambda, self.seed, self.device, int(self.trainable),
-                             self.stream)
+                             self.stream, self.world, self.rank)
         h = C.c_void_p()
         _lib.check(lib.dae_model_create(C.byref(cfg), C.byref(h)))
         self._h, self._lib = h, lib
@@ -71,6 +73,26 @@ class DAE_tied:
         self._create()
         self.init_weight()
         return self
+
+    # ---- data-parallel attachment (world > 1; see dp.py) ----------------------------------
+    def ipc_handle(self):
+        """64-byte CUDA IPC handle of this rank's arena."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self._lib.dae_model_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def attach_ipc(self, handles):
+        """Map the arenas of all ranks (handles in rank order, one per process)."""
+        blob = b"".join(handles)
+        _lib.check(self._lib.dae_model_attach_ipc(self._h, blob, len(handles)))
+
+    def attach_local(self, models):
+        """Peers living in this process (all ranks in rank order, including self)."""
+        arr = (C.c_void_p * len(models))(*[m._h for m in models])
+        _lib.check(self._lib.dae_model_attach_local(self._h, arr, len(models)))
+
+    def set_debug(self, flags):
+        _lib.check(self._lib.dae_model_set_debug(self._h, int(flags)))
 
     def close(self):
         if self._h is not None:

@@ -1,0 +1,183 @@
+"""GPU tests of the data-parallel train step: N ranks x B_local rows must reproduce one
+rank x N*B_local rows.  `world` models attached through dae_model_attach_local share ONE GPU in this
+process (the kernels, peer addressing and flag barriers are exactly those of the multi-GPU path);
+the multi-process CUDA-IPC variant needs >= 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dae_oracle as O
+from spotify_recsys_challenge_2018_b200.dp import shard_coo
+from spotify_recsys_challenge_2018_b200.models.DAEs import DAE, DAE_tied
+from tests.gpu_util import Conf, random_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(N, H, seed=5):
+    ora = O.DAEOracle(N, H, 0.005, tied=False, seed=seed)
+    ora.b_enc[:] = np.random.default_rng(1).normal(0, 0.1, H)
+    ora.b_dec[:] = np.random.default_rng(2).normal(0, 0.1, N)
+    return ora.params()
+
+
+def _run_single(cls, N, T, H, B, params, batches, lam=0.0):
+    m = cls(Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.005, seed=11, reg_lambda=lam)).fit()
+    m.set_params(params)
+    costs = [m.train_step(x, xv, y, yv, 0.8, 0.75) for x, xv, y, yv in batches]
+    out = m.get_params()
+    m.close()
+    return out, costs
+
+
+@pytest.mark.parametrize("tied,world,N,T,H,b_local,lam", [(False, 2, 3001, 2500, 64, 64, 0.0),
+                                                         (True, 2, 3001, 2500, 128, 128, 0.0),
+                                                         (False, 4, 20000, 17000, 256, 64, 1e-4),
+                                                         (False, 3, 1500, 1200, 64, 64, 0.0)])
+def test_dp_local_equals_single(tied, world, N, T, H, b_local, lam):
+    cls = DAE_tied if tied else DAE
+    B = world * b_local
+    params = _params(N, H)
+    rng = np.random.default_rng(N + world)
+    batches = []
+    for i in range(3):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=25, empty_rows=(1,))
+        x = trk if i % 2 == 0 else art
+        batches.append((x, np.ones(len(x), np.float32), y, np.ones(len(y), np.float32)))
+    want, want_costs = _run_single(cls, N, T, H, B, params, batches, lam)
+
+    ms = [cls(Conf(batch=b_local, n_input=N, n_tracks=T, hidden=H, lr=0.005, seed=11, reg_lambda=lam,
+                   world=world, rank=r)).fit() for r in range(world)]
+    for m in ms:
+        m.attach_local(ms)
+        m.set_params(params)
+    costs = []
+    for x, xv, y, yv in batches:
+        for r, m in enumerate(ms):
+            m.stage_batch(0, *shard_coo(x, xv, r, b_local), *shard_coo(y, yv, r, b_local))
+        for m in ms:
+            m.backward_staged(0, 0.8, 0.75)
+        for m in ms:
+            m.apply_adam()
+        cs = [m.sync_cost() for m in ms]
+        assert max(cs) == min(cs)                              # every rank sums the partial costs in the same order
+        costs.append(cs[0])
+    got = [m.get_params() for m in ms]
+    for g in got[1:]:
+        for a, b in zip(g, got[0]):
+            assert np.array_equal(a, b)                        # gathered parameters are identical on every rank
+    for c, w in zip(costs, want_costs):
+        assert abs(c - w) <= 1e-5 * abs(w)
+    W_enc, W_dec, b_enc, b_dec = got[0]
+    # decoder: same dz, same h_d, same contraction order over the batch columns -> bit-exact
+    if not tied and lam == 0.0 and world * ((b_local + 63) // 64 * 64) <= 256:
+        assert np.array_equal(W_dec, want[1])
+    for a, b, name in zip(got[0], want, ("W_enc", "W_dec", "b_enc", "b_dec")):
+        d = np.abs(a - b)
+        assert (d > 1e-6).mean() < 2e-3 and d.max() <= 3 * 2.001 * 0.005, (name, d.max(), (d > 1e-6).mean())
+    # every rank's operand copy == bf16 of the gathered master
+    for m in ms:
+        p, n, _ = m.buffer("W_dec_bf16")
+        from tests.gpu_util import dev_view
+        sh = dev_view(p, n, torch.bfloat16).float().cpu().numpy().reshape(N, H)
+        assert np.array_equal(sh, O.bf16_round(W_dec))
+    for m in ms:
+        m.close()
+
+
+def test_dp_streamed_operand_vs_oracle():
+    """world x bpad = 512 batch columns: the dW contraction streams BOTH operands (K > 256)."""
+    world, N, T, H, b_local = 4, 6007, 5000, 256, 128
+    B = world * b_local
+    ora = O.DAEOracle(N, H, 0.005, tied=False, seed=5, mode="b200")
+    ora.b_dec[:] = np.random.default_rng(2).normal(0, 0.1, N)
+    ms = [DAE(Conf(batch=b_local, n_input=N, n_tracks=T, hidden=H, lr=0.005, seed=11, world=world, rank=r)).fit()
+          for r in range(world)]
+    for m in ms:
+        m.attach_local(ms)
+        m.set_params(ora.params())
+    rng = np.random.default_rng(9)
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=25)
+    xv, yv = np.ones(len(trk), np.float32), np.ones(len(y), np.float32)
+    for r, m in enumerate(ms):
+        m.stage_batch(0, *shard_coo(trk, xv, r, b_local), *shard_coo(y, yv, r, b_local))
+    for m in ms:
+        m.backward_staged(0, 0.8, 0.75)
+    for m in ms:
+        m.apply_adam()
+    cost = ms[0].sync_cost()
+    for m in ms[1:]:
+        m.sync_cost()
+    c_ora = ora.train_step(trk, xv, y, yv, B, 0.8, 0.75, seed=11)
+    assert abs(cost - c_ora) <= 1e-3 * abs(c_ora)
+    got = ms[0].get_params()
+    for a, b, name in zip(got, ora.params(), ("W_enc", "W_dec", "b_enc", "b_dec")):
+        d = np.abs(a - b)
+        assert (d > 1e-3 * 0.005).mean() < 5e-3 and d.max() <= 2.001 * 0.005, name
+    for m in ms:
+        m.close()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _ipc_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from spotify_recsys_challenge_2018_b200.dp import DataParallelDAE
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, T, H, b_local = 6007, 5000, 256, 128
+    B = b_local * world
+    m = DAE(Conf(batch=b_local, n_input=N, n_tracks=T, hidden=H, lr=0.005, seed=11, world=world, rank=rank,
+                 device=rank)).fit()
+    dp = DataParallelDAE(m)
+    m.set_params(_params(N, H))
+    rng = np.random.default_rng(3)
+    costs = []
+    for i in range(4):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=25)
+        dp.stage_global_batch(i & 1, trk, np.ones(len(trk), np.float32), y, np.ones(len(y), np.float32))
+        dp.train_step_staged(i & 1, 0.8, 0.75)
+        costs.append(m.sync_cost())
+    params = dp.get_params()
+    if rank == 0:
+        q.put((params, costs))
+    dist.barrier()
+    m.close()
+    dist.destroy_process_group()
+
+
+def test_dp_ipc_two_gpus_equals_single():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, costs = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    N, T, H, b_local = 6007, 5000, 256, 128
+    B = b_local * world
+    rng = np.random.default_rng(3)
+    batches = []
+    for i in range(4):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=25)
+        batches.append((trk, np.ones(len(trk), np.float32), y, np.ones(len(y), np.float32)))
+    want, want_costs = _run_single(DAE, N, T, H, B, _params(N, H), batches)
+    for c, w in zip(costs, want_costs):
+        assert abs(c - w) <= 1e-5 * abs(w)
+    assert np.array_equal(got[1], want[1])                     # decoder bit-exact (see test_dp_local_equals_single)
+    for a, b, name in zip(got, want, ("W_enc", "W_dec", "b_enc", "b_dec")):
+        d = np.abs(a - b)
+        assert (d > 1e-6).mean() < 2e-3, (name, d.max())

@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 echo "== pytest kernels"; timeout 1200 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_kernels.log 2>&1; echo "rc=$?"; tail -25 gpurun_out/pytest_kernels.log
 echo "== pytest model"; timeout 1200 python -m pytest tests/test_gpu_model.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_model.log 2>&1; echo "rc=$?"; tail -40 gpurun_out/pytest_model.log
+echo "== pytest dp"; timeout 1200 python -m pytest tests/test_gpu_dp.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/pytest_dp.log 2>&1; echo "rc=$?"; tail -40 gpurun_out/pytest_dp.log
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 10 ${BENCH_ARGS} > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; echo "rc=$?"; python - <<'PY'
 import json
 try:
