@@ -277,24 +277,22 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        # dominant kernel: k_itemtile<DW> = dW_dec contraction + dense TF1 Adam in the epilogue, on the decoder rows
-        # this GPU owns (N/world).  Algorithmic bytes per launch: read w,m,v (12 B) + write w,m,v (12 B)
-        # + write the bf16 operand copy (2 B, x world copies of which world-1 go over NVLink) = 26 B / parameter,
-        # + the dz operand (2 B x world*Bpad columns per owned row).  The gradient itself never touches HBM.
+        # dominant kernel: k_adam_rows_vec4 on the decoder rows this GPU owns (N/world).  Algorithmic bytes per launch
+        # (SURVEY 8d): read g,w,m,v (16 B) + write w,m,v (12 B) + write the bf16 operand copy (2 B; x world copies of
+        # which world-1 leave over NVLink) = 30 B / parameter.
         n_own = N / world
-        adam_bytes = 26.0 * n_own * H + 2.0 * n_own * (world * ((B + 63) // 64 * 64))
-        adam_ms = phases.get("dw_adam_dec")
+        adam_bytes = 30.0 * n_own * H
+        adam_ms = phases.get("adam_dec")
         roofline = None
         if adam_ms:
             ach = adam_bytes / (adam_ms / 1e3) / 1e9
-            roofline = {"kernel": "k_itemtile<DW>: tcgen05 dW_dec = dz^T.h_d with the dense TF1 Adam update + bf16 "
-                                  "operand refresh fused into the TMEM epilogue", "bound": "hbm",
+            roofline = {"kernel": "k_adam_rows_vec4 (decoder rows: dense TF1 Adam + bf16 operand refresh)", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": adam_bytes,
                         "launch_ms": adam_ms}
-        # whole step (per GPU): fused decoder update 26 + encoder Adam 24 (untied) on the owned rows, + W operand read by
+        # whole step (per GPU): dW write 4 + decoder Adam 30 + encoder Adam 24 (untied) on the owned rows, + W operand read by
         # decode and dh (2 + 2) + dz write (2) and re-read by dh and dW (2 + 2) over all N rows
-        step_bytes = (26.0 + (24.0 if not tied else 0.0)) * n_own * H + 10.0 * N * H
+        step_bytes = (34.0 + (24.0 if not tied else 0.0)) * n_own * H + 10.0 * N * H
         line = {"metric": "dae_train_playlists_per_sec", "value": value, "unit": "playlists/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

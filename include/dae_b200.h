@@ -98,8 +98,8 @@ int32_t dae_model_restage(dae_model* m, int32_t slot);
  * With world > 1 this enqueues a cross-GPU barrier first (all ranks must call it). */
 int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
                                   int32_t global_batch, int32_t row_offset);
-/* Dense TF1 Adam on every variable, then step += 1.  The decoder's dW_dec = dz^T h_d is contracted
- * here, tile by tile in tensor memory, and consumed by the Adam update in the same epilogue.   DAEs.py:102 */
+/* dW_dec = dz^T h_d and the sparse-row dW_enc of the rows this rank owns, then the dense TF1 Adam
+ * update of every variable and step += 1.                                                      DAEs.py:102 */
 int32_t dae_model_apply_adam(dae_model* m);
 /* backward_staged + apply_adam (single GPU). */
 int32_t dae_model_train_step_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob);
@@ -123,10 +123,11 @@ int32_t dae_model_attach_ipc(dae_model* m, const void* handles, int32_t n_handle
 int32_t dae_model_attach_local(dae_model* m, dae_model* const* peers, int32_t n_peers);
 int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
 
-/* debug flags: bit 0 = dae_model_backward_staged also materialises the raw dW_dec of the rows this
- * rank owns (buffer "g_dec"); the train step itself never writes it (fused dW + Adam epilogue).
- * bit 1 = it also runs the sparse-row dW_enc scatter ("g_enc", "touched"), which otherwise happens
- * inside dae_model_apply_adam and is cleared by it. */
+/* debug / tuning flags.  bit 0: dae_model_backward_staged also forms dW_dec of the rows this rank owns
+ * (buffer "g_dec") and bit 1: the sparse-row dW_enc scatter ("g_enc", "touched") -- both otherwise
+ * happen inside dae_model_apply_adam, after the step's second barrier.  bit 2: apply_adam runs the
+ * decoder's Adam update inside the dW contraction's epilogue (the gradient never leaves tensor
+ * memory) instead of as a second kernel. */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row

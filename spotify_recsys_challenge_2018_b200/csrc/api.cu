@@ -32,6 +32,12 @@ static int fail(const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// load every kernel once per process (kernels.h: preload_*)
+static void ensure_loaded() {
+    static bool done = false;
+    if (!done) { preload_sparse(); preload_optim(); preload_gemm(); preload_topk(); done = true; }
+}
+
 constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;   // [TF1] AdamOptimizer defaults (DAEs.py:102)
 constexpr int kSqBlocks = 256;
 
@@ -87,7 +93,7 @@ struct dae_model {
     float *g_enc = nullptr;                          // sparse-row dW_enc of the rows this rank owns
     unsigned char* touched = nullptr;
     float *g_b_enc_part = nullptr, *g_b_dec_part = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
-    float* g_dec_dbg = nullptr;                      // raw dW_dec, materialised only for parity tests
+    float* g_dec = nullptr;                          // dW_dec of the rows this rank owns
     int debug = 0;
     bool scatter_done = false;
     Slot slots[2];
@@ -155,6 +161,7 @@ static void layout(dae_model* m) {
         else { m->mW_dec = A.take<float>(LH); m->vW_dec = A.take<float>(LH); }
         m->mb_enc = A.take<float>(H); m->vb_enc = A.take<float>(H);
         m->mb_dec = A.take<float>(N); m->vb_dec = A.take<float>(N);
+        m->g_dec = A.take<float>(LH);
         m->g_enc = A.take<float>(LH);
         m->touched = A.take<unsigned char>(m->n_local);
         m->g_b_enc_part = A.take<float>(H); m->g_b_dec_part = A.take<float>(N);
@@ -195,10 +202,10 @@ static void layout(dae_model* m) {
     A.off = (A.off + 1023) & ~size_t(1023);
 }
 
-enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DH, PH_ENCODE_DA, PH_BARRIER, PH_DW_ADAM, PH_SCATTER,
+enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DH, PH_ENCODE_DA, PH_BARRIER, PH_SCATTER, PH_DW, PH_ADAM_DEC,
              PH_ADAM_ENC, PH_ADAM_BIAS, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"prepare_csr_ybits", "encode_fwd", "decode_loss_dz", "dh", "encode_da",
-                                            "barriers", "dw_adam_dec", "scatter_dw_enc", "adam_enc", "adam_bias"};
+                                            "barriers", "scatter_dw_enc", "dw_dec", "adam_dec", "adam_enc", "adam_bias"};
 static inline void ph_begin(dae_model* m, int k, cudaStream_t s = nullptr) {
     if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], s ? s : m->st); }
 }
@@ -242,7 +249,7 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
-    preload_sparse(); preload_optim(); preload_gemm(); preload_topk();
+    ensure_loaded();
 
     dae_model* m = new dae_model();
     m->cfg = *cfg;
@@ -288,7 +295,6 @@ extern "C" void dae_model_destroy(dae_model* m) {
     for (int r = 0; r < kMaxWorld; ++r) if (m->ipc_opened[r]) cudaIpcCloseMemHandle(m->ipc_opened[r]);
     if (m->arena.base) cudaFree(m->arena.base);
     for (void* p : m->host_allocs) cudaFreeHost(p);
-    if (m->g_dec_dbg) cudaFree(m->g_dec_dbg);
     if (m->scores) cudaFree(m->scores);
     if (m->topk_idx) cudaFree(m->topk_idx);
     if (m->topk_score) cudaFree(m->topk_score);
@@ -675,9 +681,8 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     if (m->debug & 3) {    // parity tests: materialise the raw dW_dec / scatter dW_enc now, where they can be inspected
         barrier(m);
         if (m->debug & 1) {
-            if (!m->g_dec_dbg) CK(cudaMalloc(reinterpret_cast<void**>(&m->g_dec_dbg), (size_t)m->n_local * H * 4));
             DwArgs w = dw_args(m, bpad);
-            w.g = m->g_dec_dbg;
+            w.g = m->g_dec;
             launch_dw(w, m->st);
             m->launches += 1;
         }
@@ -702,24 +707,37 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (!m->scatter_done) run_scatter(m, B);
     m->scatter_done = false;
 
-    // decoder (or the tied matrix): dW_dec tile by tile in TMEM, dense Adam in the epilogue, new bf16 operand
-    // rows stored to every rank's copy
+    // decoder (or the tied matrix) rows this rank owns: dW_dec = dz^T h_d over every rank's batch columns, then the
+    // dense TF1 Adam update; the new bf16 operand rows are stored into every rank's copy (NVLink)
     const int next_shadow = m->world > 1 ? (m->cur_shadow ^ 1) : m->cur_shadow;
     DwArgs w = dw_args(m, bpad);
-    w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
-    w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
-    w.adam = AdamConst{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
-    w.shadow = m->shadow[next_shadow];
-    ph_begin(m, PH_DW_ADAM);
-    launch_dw(w, m->st);
-    ph_end(m, PH_DW_ADAM);
-    m->launches += 1;
+    if (m->debug & 4) {   // experimental: Adam inside the dW epilogue, the gradient never leaves tensor memory
+        w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
+        w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
+        w.adam = AdamConst{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
+        w.shadow = m->shadow[next_shadow];
+        ph_begin(m, PH_DW);
+        launch_dw(w, m->st);
+        ph_end(m, PH_DW);
+        m->launches += 1;
+    } else {
+        w.g = m->g_dec;
+        ph_begin(m, PH_DW);
+        launch_dw(w, m->st);
+        ph_end(m, PH_DW);
+        a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.row_touched = m->tied ? m->touched : nullptr;
+        a.n = (long long)m->n_local * H; a.row_len = H;
+        ph_begin(m, PH_ADAM_DEC);
+        launch_adam_rows(a, m->tied ? m->g_enc : nullptr, m->shadow[next_shadow], N, m->pt, m->st);
+        ph_end(m, PH_ADAM_DEC);
+        m->launches += 2;
+    }
 
     ph_begin(m, PH_ADAM_ENC);
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
-        a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = m->g_enc; a.w_bf16 = nullptr;
-        a.row_touched = m->touched; a.n = (long long)m->n_local * H; a.row_len = H;
-        launch_adam(a, m->st);
+        a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
+        a.n = (long long)m->n_local * H; a.row_len = H;
+        launch_adam_rows(a, m->g_enc, nullptr, N, m->pt, m->st);
         m->launches += 1;
     }
     launch_clear_flagged(m->n_local, H, m->g_enc, m->touched, m->st);
@@ -866,7 +884,7 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
     const Slot& sl = m->slots[m->cur];
     struct E { const char* n; void* p; int64_t c; int32_t s; };
     const E table[] = {
-        {"g_dec", m->g_dec_dbg, LH, 4}, {"g_enc", m->g_enc, LH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
+        {"g_dec", m->g_dec, LH, 4}, {"g_enc", m->g_enc, LH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
         {"g_b_dec", m->g_b_dec, m->N, 4}, {"g_b_enc_part", m->g_b_enc_part, m->H, 4},
         {"g_b_dec_part", m->g_b_dec_part, m->N, 4}, {"touched", m->touched, m->n_local, 1}, {"cost", m->cost, 1, 4},
         {"W_enc", m->W_enc, LH, 4}, {"W_dec", m->W_dec, LH, 4}, {"W_dec_bf16", m->shadow[m->cur_shadow], NH, 2},
@@ -918,6 +936,7 @@ extern "C" int32_t dae_model_phase_time(dae_model* m, int32_t k, double* total_m
 extern "C" int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t batch, int32_t n_tracks, int32_t k,
                                    const int32_t* seed_ptr_dev, const int32_t* seed_idx_dev, int32_t idx_base,
                                    int32_t* out_idx_dev, float* out_score_dev, void* stream) {
+    ensure_loaded();
     if (!scores_dev || !out_idx_dev || !out_score_dev) return fail("null argument");
     if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
     TopkArgs a{};
@@ -931,6 +950,7 @@ extern "C" int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t 
 extern "C" int32_t dae_adam_device(float* w_dev, float* m_dev, float* v_dev, const float* g_dev, uint16_t* w_bf16_dev,
                                    int64_t n, float lr, float beta1_power, float beta2_power, float reg_lambda,
                                    void* stream) {
+    ensure_loaded();
     AdamArgs a{};
     a.w = w_dev; a.m = m_dev; a.v = v_dev; a.g = g_dev; a.w_bf16 = reinterpret_cast<__nv_bfloat16*>(w_bf16_dev);
     a.n = n; a.row_len = 1;
@@ -944,6 +964,7 @@ extern "C" int32_t dae_adam_device(float* w_dev, float* m_dev, float* v_dev, con
 extern "C" int32_t dae_coo_to_csr_device(const int64_t* pos_dev, const float* val_dev, int64_t nnz, int32_t batch,
                                          int32_t n_input, int32_t* row_ptr_dev, int32_t* row_len_dev, int32_t* col_dev,
                                          float* val_out_dev, void* stream) {
+    ensure_loaded();
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CsrWork w{};
     int* scratch = nullptr;
@@ -969,6 +990,7 @@ extern "C" int32_t dae_gemm_test_device(int32_t op, const uint16_t* a_dev, const
                                         const float* bias_dev, float* out_dev, int32_t n_items, int32_t n_hidden,
                                         int32_t batch, int32_t bpad, int32_t lbo, int32_t sbo, int32_t* nsplit_out,
                                         void* stream) {
+    ensure_loaded();
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (n_hidden % 64 || n_hidden > 256 || bpad % 64 || bpad > 256) return fail("bad shape");
     const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(a_dev);

@@ -482,28 +482,257 @@ void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
     launch_itemtile<MODE_PREDICT>(tmA, tmB, p, dim3(decode_grid(p.n_items, nbt), nbt, 1), st);
 }
 
+// ------------------------------------------------------------------------------------------
+// G2: dW_dec^T tile = h_d^T . dz^T  with the dense TF1 Adam update fused into the epilogue
+// ------------------------------------------------------------------------------------------
+// Orientation: the accumulator holds dW^T -- TMEM lane = hidden unit h, TMEM column = item -- so that
+// for one item the 32 lanes of an epilogue warp touch 32 CONSECUTIVE floats of that item's row of
+// W / m / v (one full 128-byte line per warp access; the item-major layout is the reference's
+// [n_input, n_hidden], DAEs.py:54).  A = h_d^T [H, K] (K-major; resident in smem, or streamed when
+// K = ranks x batch tile > 256), B = dz tile [128 items, K] (K-major, streamed).  M = 128 per UMMA:
+// H = 256 takes two M-halves (TMEM columns [0,128) and [128,256) of the tile's buffer), H = 64 runs
+// with zero rows (TMA out-of-bounds fill).  192 + 16 epilogue warps: the epilogue is pure HBM
+// streaming (26 B / parameter) and needs bytes in flight, not registers.
+constexpr int kDwEpiWarps = 16;
+constexpr int kDwThreads = 64 + 32 * kDwEpiWarps;
+
+struct DwDev {
+    int tiles;        // local item tiles that hold at least one valid catalogue row
+    int kchunks;      // K / 64
+    int H;            // hidden units (valid TMEM lanes over the M-halves)
+    int mhalves;      // ceil(H / 128)
+    int stream_h;     // h_d^T chunk rides in the ring with the dz chunk (K > 256)
+    int n_global;     // catalogue size
+    float* g;         // raw dW_dec [local rows, H] or nullptr
+    float* aw; float* am; float* av;
+    const float* g_extra;
+    const unsigned char* touched;
+    AdamConst adam;
+    __nv_bfloat16* shadow;   // [n_global, H], refreshed on every rank
+    PeerTable pt;
+};
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmH,
+          const __grid_constant__ DwDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+    uint8_t* sH = smem;                    // resident h_d^T: kchunks x [256 rows x 128 B]
+    uint8_t* sA = smem + kSmemB;           // ring of dz chunks [128 items x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemB + kSmemA);
+    uint64_t* full = bars;                 // [kStages]
+    uint64_t* empty = bars + kStages;      // [kStages]
+    uint64_t* hfull = bars + 2 * kStages;  // [1]
+    uint64_t* tfull = hfull + 1;           // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool sh = p.stream_h != 0;
+    const int nstages = sh ? kStagesStreamB : kStages;
+    const uint32_t stage_bytes = sh ? (kABytes + kBChunkBytes) : kABytes;
+    const int hbox_rows = p.mhalves * 128;                       // rows per h_d^T box (rows >= H are zero-filled)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDz);
+        tma_prefetch_desc(&tmH);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(hfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], kDwEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const uint64_t pol_stream = policy_evict_first();
+            const uint64_t pol_keep = policy_evict_last();
+            if (!sh) {
+                mbar_expect_tx(hfull, static_cast<uint32_t>(p.kchunks * hbox_rows * 128));
+                for (int kc = 0; kc < p.kchunks; ++kc)
+                    tma_load_2d_hint(sH + kc * kBChunkBytes, &tmH, hfull, kc * 64, 0, pol_keep);
+            }
+            uint8_t* ring = sh ? smem : sA;
+            const uint32_t tx = static_cast<uint32_t>(kABytes + (sh ? hbox_rows * 128 : 0));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], tx);
+                    tma_load_2d_hint(ring + stage * stage_bytes, &tmDz, &full[stage], kc * 64, tile * kTileItems,
+                                     pol_stream);
+                    if (sh) tma_load_2d_hint(ring + stage * stage_bytes + kABytes, &tmH, &full[stage], kc * 64, 0, pol_keep);
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, kTileItems, 0, 0);
+            if (!sh) {
+                mbar_wait(hfull, 0);
+                tc_fence_after();
+            }
+            uint8_t* ring = sh ? smem : sA;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t dz_addr = smem_u32(ring + stage * stage_bytes);
+                    const uint32_t h_addr = sh ? dz_addr + kABytes : smem_u32(sH + kc * kBChunkBytes);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t bd = umma_smem_desc(dz_addr + ks * 32, 16, 1024);
+                        for (int mh = 0; mh < p.mhalves; ++mh) {
+                            const uint64_t ad = umma_smem_desc(h_addr + mh * (128 * 128) + ks * 32, 16, 1024);
+                            umma_bf16(d_tmem + static_cast<uint32_t>(mh * kTileItems), ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+        const int part = (warp - 2) >> 2;              // 0..3: which quarter of the tile's (M-half, item) columns
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int cols_per = p.mhalves * kTileItems / 4;   // 64 (H > 128) or 32
+        const int col_lo = part * cols_per;
+        const int mh = col_lo / kTileItems;
+        const int it_lo = col_lo % kTileItems;
+        const int h = mh * 128 + q * 32 + lane;
+        const bool h_ok = h < p.H;
+        const int world = p.pt.world;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256 + col_lo);
+#pragma unroll 1
+            for (int cc = 0; cc < cols_per; cc += 16) {
+                uint32_t r[16];
+                __syncwarp();                                                        // tcgen05.ld is warp-collective
+                tmem_ld16(t_addr + cc, r);
+                tmem_ld_wait();
+                const int item0 = tile * kTileItems + it_lo + cc;                    // local row of column cc
+                const int gitem0 = item_global(item0, world, p.pt.rank);             // 16 consecutive catalogue ids
+                const int nvalid = h_ok ? min(16, p.n_global - gitem0) : 0;
+                const size_t off0 = (size_t)item0 * p.H + h;
+                if (p.g != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < nvalid) p.g[off0 + (size_t)j * p.H] = __uint_as_float(r[j]);
+                }
+                if (p.aw != nullptr) {
+                    // dense TF1 Adam on the 16 gradient values this thread just read from TMEM: the gradient
+                    // never goes to HBM (26 B / parameter instead of 34)
+                    float wv[16], mv[16], vv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < nvalid) {
+                            const size_t o = off0 + (size_t)j * p.H;
+                            wv[j] = __ldcs(p.aw + o); mv[j] = __ldcs(p.am + o); vv[j] = __ldcs(p.av + o);
+                        } else {
+                            wv[j] = 0.f; mv[j] = 0.f; vv[j] = 0.f;
+                        }
+                    }
+                    if (p.g_extra != nullptr) {                                          // tied: + sparse-row dW_enc
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nvalid && p.touched[item0 + j] != 0)
+                                r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __ldcs(p.g_extra + off0 + (size_t)j * p.H)));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        adam_one(wv[j], mv[j], vv[j], __uint_as_float(r[j]), p.adam);
+                        if (j < nvalid) {
+                            const size_t o = off0 + (size_t)j * p.H;
+                            __stcs(p.aw + o, wv[j]); __stcs(p.am + o, mv[j]); __stcs(p.av + o, vv[j]);
+                        }
+                    }
+                    if (p.shadow != nullptr) {
+                        // bf16 operand rows: lanes pair up so that every lane stores one 4-byte (h, h+1) pair --
+                        // even lanes for item j, odd lanes for item j+1 -- into this GPU's copy and every peer's
+                        const size_t goff0 = (size_t)gitem0 * p.H + (h & ~1);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float give = (lane & 1) ? wv[j] : wv[j + 1];           // what the partner lane stores
+                            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+                            const int jj = j + (lane & 1);
+                            const uint32_t pk = (lane & 1) ? pack_bf16x2(got, wv[j + 1]) : pack_bf16x2(wv[j], got);
+                            if (jj < nvalid) {
+                                const size_t go = goff0 + (size_t)jj * p.H;
+                                for (int sidx = 0; sidx < world; ++sidx)
+                                    *reinterpret_cast<uint32_t*>(peer_ptr(p.pt, sidx, p.shadow) + go) = pk;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 void launch_dw(const DwArgs& a, cudaStream_t st) {
-    const CUtensorMap tmA = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
-    const CUtensorMap tmB = make_map_bf16(a.h_dT, a.K, a.H, a.H);
-    ItemTileDev p{};
+    DwDev p{};
     p.pt = a.pt;
     if (p.pt.world < 1) p.pt.world = 1;
     // local tiles that hold at least one valid catalogue row: global tile = local * world + rank
     const int tiles_total = (a.N + kTileItems - 1) / kTileItems;
     p.tiles = tiles_total > p.pt.rank ? (tiles_total - p.pt.rank + p.pt.world - 1) / p.pt.world : 0;
-    p.n_items = a.n_local;
+    if (p.tiles == 0) return;
     p.n_global = a.N;
     p.kchunks = a.K / 64;
-    p.n_cols = a.H;
-    p.b_rows_box = a.H;
+    p.H = a.H;
+    p.mhalves = (a.H + 127) / 128;
+    p.stream_h = a.K > 256 ? 1 : 0;
     p.g = a.g;
-    p.stream_b = a.K > 256 ? 1 : 0;
     p.aw = a.w; p.am = a.m; p.av = a.v;
     p.g_extra = a.g_extra; p.touched = a.touched;
     p.adam = a.adam;
     p.shadow = a.w != nullptr ? a.shadow : nullptr;
-    if (p.tiles == 0) return;
-    launch_itemtile<MODE_DW>(tmA, tmB, p, dim3(decode_grid(p.tiles * kTileItems, 1), 1, 1), st);
+    const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
+    const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
+    const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+    k_dw_adam<<<grid, kDwThreads, kSmemItemTile, st>>>(tmDz, tmH, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -666,11 +895,11 @@ void preload_gemm() {
     cudaFuncAttributes a;
     cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_itemtile<MODE_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
-    cudaFuncSetAttribute(k_itemtile<MODE_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_dw_adam, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
     cudaFuncGetAttributes(&a, k_itemtile<MODE_TRAIN>);
     cudaFuncGetAttributes(&a, k_itemtile<MODE_PREDICT>);
-    cudaFuncGetAttributes(&a, k_itemtile<MODE_DW>);
+    cudaFuncGetAttributes(&a, k_dw_adam);
     cudaFuncGetAttributes(&a, k_dh);
     (void)cudaGetLastError();
 }

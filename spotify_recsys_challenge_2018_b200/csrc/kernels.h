@@ -181,6 +181,10 @@ struct AdamArgs {
     float alpha, one_minus_b1, one_minus_b2, eps, lambda;
 };
 void launch_adam(const AdamArgs& a, cudaStream_t st);
+// matrices: a.w/m/v are this rank's rows [local rows, row_len] (row_len % 4 == 0); gradient = a.g (dense, or nullptr)
+// + g_sparse rows where a.row_touched != 0 (or nullptr); shadow [n_global, row_len] bf16 is refreshed on every rank
+void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, int n_global, const PeerTable& pt,
+                      cudaStream_t st);
 // U(-limit, limit) keyed by the GLOBAL element index; w: this rank's rows in local-tile order (or nullptr),
 // wb: bf16 copy of ALL N rows in global order (or nullptr)
 void launch_xavier_init(float* w, int n_local_rows, __nv_bfloat16* wb, int N, int H, float limit,

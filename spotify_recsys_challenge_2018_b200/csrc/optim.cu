@@ -43,6 +43,59 @@ k_adam_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__
     }
 }
 
+// Same update on the catalogue rows this rank owns ([local rows, H], local-tile order), with the bf16
+// operand copy of the rows refreshed on this GPU and on every peer (global row order, NVLink stores).
+__global__ void __launch_bounds__(256)
+k_adam_rows_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v, const float4* __restrict__ g,
+                 const float4* __restrict__ g_sparse, __nv_bfloat16* __restrict__ shadow,
+                 const unsigned char* __restrict__ touched, unsigned int n4,
+                 unsigned int row_len4, int n_global, const AdamConst c, const __grid_constant__ PeerTable pt) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const unsigned int lrow = i / row_len4;
+        // gradient = dense part (dW_dec) + sparse rows (dW_enc, read only where the step touched the row)
+        float4 gv = g != nullptr ? __ldcs(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g_sparse != nullptr && touched[lrow] != 0) {
+            const float4 gs = __ldcs(g_sparse + i);
+            gv.x = __fadd_rn(gv.x, gs.x); gv.y = __fadd_rn(gv.y, gs.y); gv.z = __fadd_rn(gv.z, gs.z); gv.w = __fadd_rn(gv.w, gs.w);
+        }
+        float4 wv = __ldcs(w + i), mv = __ldcs(m + i), vv = __ldcs(v + i);
+        adam_one(wv.x, mv.x, vv.x, gv.x, c);
+        adam_one(wv.y, mv.y, vv.y, gv.y, c);
+        adam_one(wv.z, mv.z, vv.z, gv.z, c);
+        adam_one(wv.w, mv.w, vv.w, gv.w, c);
+        __stcs(w + i, wv);
+        __stcs(m + i, mv);
+        __stcs(v + i, vv);
+        if (shadow != nullptr) {
+            const int grow = item_global((int)lrow, pt.world, pt.rank);
+            if (grow < n_global) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(wv.x, wv.y), hi = __floats2bfloat162_rn(wv.z, wv.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<unsigned int*>(&lo);
+                pk.y = *reinterpret_cast<unsigned int*>(&hi);
+                const size_t o = ((size_t)grow * row_len4 + (i - lrow * row_len4)) * 4;
+                for (int s = 0; s < pt.world; ++s) *reinterpret_cast<uint2*>(peer_ptr(pt, s, shadow) + o) = pk;
+            }
+        }
+    }
+}
+
+void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, int n_global, const PeerTable& pt,
+                      cudaStream_t st) {
+    AdamConst c{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
+    const long long n4 = a.n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = 148LL * 16;
+    if (blocks > cap) blocks = cap;
+    PeerTable t = pt;
+    if (t.world < 1) t.world = 1;
+    k_adam_rows_vec4<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(a.w), reinterpret_cast<float4*>(a.m),
+                                                  reinterpret_cast<float4*>(a.v), reinterpret_cast<const float4*>(a.g),
+                                                  reinterpret_cast<const float4*>(g_sparse), shadow, a.row_touched, (unsigned int)n4, (unsigned int)(a.row_len / 4),
+                                                  n_global, c, t);
+}
+
 __global__ void k_adam_scalar(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
                               const float* __restrict__ g, __nv_bfloat16* __restrict__ wb,
                               const unsigned char* __restrict__ touched, long long begin, long long n, int row_len,
@@ -197,6 +250,7 @@ void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, cu
 void preload_optim() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_adam_vec4);
+    cudaFuncGetAttributes(&a, k_adam_rows_vec4);
     cudaFuncGetAttributes(&a, k_adam_scalar);
     cudaFuncGetAttributes(&a, k_xavier_local);
     cudaFuncGetAttributes(&a, k_xavier_bf16);
