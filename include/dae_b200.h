@@ -35,7 +35,8 @@ typedef struct dae_config {
     float reg_lambda;    /* conf.reg_lambda                              (DAEs.py:21, :100)      */
     uint64_t seed;       /* Philox key of the dropout masks and of dae_model_init_xavier          */
     int32_t device;      /* CUDA device ordinal                                                    */
-    int32_t trainable;   /* 0: inference only (no Adam state / gradient buffers; DAE_title's frozen DAE, DAEs.py:164-171) */
+    int32_t trainable;   /* 1: trainable; 0: inference only (no Adam state / gradient buffers); 2: frozen but staged
+                            with targets -- the constant DAE inside DAE_title while the title branch trains (DAEs.py:164-171) */
     void* stream;        /* cudaStream_t to run on, or NULL to create a private stream            */
     int32_t world;       /* data-parallel ranks (GPUs of one NVSwitch box, <= 8); 0 or 1 = single GPU       */
     int32_t rank;        /* this model's rank in [0, world)                                                  */
@@ -146,6 +147,52 @@ int32_t dae_model_set_profiling(dae_model* m, int32_t on);
 int32_t dae_model_phase_count(void);
 const char* dae_model_phase_name(int32_t k);
 int32_t dae_model_phase_time(dae_model* m, int32_t k, double* total_ms, int64_t* count);
+
+/* ---- title branch: character CNN + output layer on top of a constant DAE --------------------------
+ * models/title_get.py:10-22 (get_model), models/title_models/Char_CNN.py:5-75 (Char_CNN) and
+ * models/DAEs.py:153-201 (DAE_title: y_pred = title_score * w_title + sigmoid(decoder) * w_playlist,
+ * weighted BCE on y_pred, only the title variables train).  The DAE model is created by the caller
+ * with trainable = 2 (training the title branch) or 0 (inference) and loaded from conf.DAEval with
+ * dae_model_set_params (DAEs.py:164-171); it must outlive the title object.  Batches of <= 256 rows. */
+typedef struct dae_title dae_title;
+typedef struct dae_title_config {
+    int32_t charsize;          /* conf.charsize   (Char_CNN.py:11)  */
+    int32_t strmaxlen;         /* conf.strmaxlen  (Char_CNN.py:9), <= 32 */
+    int32_t char_emb;          /* conf.char_emb   (Char_CNN.py:8), > 0 */
+    int32_t filter_num;        /* conf.filter_num (title_get.py:20) */
+    int32_t n_filter_sizes;    /* len(conf.filter_size), <= 8; filter_num * n_filter_sizes <= 512 */
+    int32_t filter_size[8];    /* conf.filter_size (title_get.py:19) */
+    float lr;                  /* [TITLE] lr (main.py:60) */
+    int32_t trainable;         /* 0: inference only */
+} dae_title_config;
+int32_t dae_title_create(dae_model* constant_dae, const dae_title_config* cfg, dae_title** out);
+void dae_title_destroy(dae_title* t);
+/* xavier_initializer(uniform=False) on every title variable                 Char_CNN.py:19, :45-47, :71-73 */
+int32_t dae_title_init(dae_title* t, uint64_t seed);
+/* Host fp32 arrays in the order [char_embedding, Conv_W0, Conv_b0, ..., Output_W, Output_b] with the
+ * reference's shapes: [charsize, char_emb]; [fs_i, char_emb, filter_num]; [filter_num]; [D, n_output]; [n_output]. */
+int32_t dae_title_param_count(dae_title* t);
+int32_t dae_title_param_size(dae_title* t, int32_t idx, int64_t* n_elem);
+int32_t dae_title_set_params(dae_title* t, const float* const* arrays);
+int32_t dae_title_get_params(dae_title* t, float* const* arrays);
+/* sess.run([optimizer, cost], {x, y, titles, keep_prob, title keep_prob, input_keep_prob, titles_use}) -> cost.
+ * titles: int64 [batch, strmaxlen] char ids (-1 = pad); titles_use: fp32 [batch].        main_train.py:214-221 */
+int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                             const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
+                             const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
+                             float title_keep_prob, float* cost_out);
+/* sess.run(y_pred, {..., titles, titles_use, keep probabilities 1}) -> [batch, n_cols] fp32.
+ *                                                                   main_train.py:69-79; main_challenge.py:80-85 */
+int32_t dae_title_predict(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x, const int64_t* titles,
+                          const float* titles_use, int32_t batch, int32_t n_cols, float* y_pred_out);
+/* y_pred[:, :n_tracks] + cand_generate on the device.                       main_challenge.py:26-36, :87-90 */
+int32_t dae_title_recommend(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                            const int64_t* titles, const float* titles_use, int32_t batch, const int32_t* seed_ptr,
+                            const int32_t* seed_idx, int32_t k, int32_t* out_idx, float* out_score);
+int64_t dae_title_launch_count(dae_title* t);
+/* named device buffers for parity tests: "feat" "argpos" "feat_d" "w_t" "w_p" "dzT" "d" "g_emb" "g_conv_W"
+ * "g_conv_b" "g_W_out" "g_b_out" "W_out" "W_out_bf16" */
+int32_t dae_title_buffer(dae_title* t, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size);
 
 /* ---- kernel-level entry points on caller-owned DEVICE memory (parity tests, other hosts) ------- */
 

@@ -17,6 +17,13 @@ class DaeConfig(C.Structure):
     ]
 
 
+class DaeTitleConfig(C.Structure):
+    _fields_ = [
+        ("charsize", C.c_int32), ("strmaxlen", C.c_int32), ("char_emb", C.c_int32), ("filter_num", C.c_int32),
+        ("n_filter_sizes", C.c_int32), ("filter_size", C.c_int32 * 8), ("lr", C.c_float), ("trainable", C.c_int32),
+    ]
+
+
 class DaeError(RuntimeError):
     pass
 
@@ -54,6 +61,18 @@ SIGNATURES = {
     "dae_model_phase_count": (_I32, []),
     "dae_model_phase_name": (C.c_char_p, [_I32]),
     "dae_model_phase_time": (_I32, [_P, _I32, C.POINTER(C.c_double), C.POINTER(_I64)]),
+    "dae_title_create": (_I32, [_P, C.POINTER(DaeTitleConfig), C.POINTER(_P)]),
+    "dae_title_destroy": (None, [_P]),
+    "dae_title_init": (_I32, [_P, C.c_uint64]),
+    "dae_title_param_count": (_I32, [_P]),
+    "dae_title_param_size": (_I32, [_P, _I32, C.POINTER(_I64)]),
+    "dae_title_set_params": (_I32, [_P, C.POINTER(_P)]),
+    "dae_title_get_params": (_I32, [_P, C.POINTER(_P)]),
+    "dae_title_train_step": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _I32, _F, _F, _F, C.POINTER(_F)]),
+    "dae_title_predict": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _I32, _P]),
+    "dae_title_recommend": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P, _I32, _P, _P]),
+    "dae_title_launch_count": (_I64, [_P]),
+    "dae_title_buffer": (_I32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
     "dae_topk_device": (_I32, [_P, _I64, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P]),
     "dae_adam_device": (_I32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P]),
     "dae_coo_to_csr_device": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -9,15 +9,12 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dae_b200.h"
-#include "kernels.h"
+#include "model.h"
 #include "philox.cuh"
 
-using namespace dae;
-
 static thread_local std::string g_err;
-
-static int fail(const char* fmt, ...) {
+std::string& dae_err() { return g_err; }
+int fail(const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -26,111 +23,10 @@ static int fail(const char* fmt, ...) {
     g_err = buf;
     return 1;
 }
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-// load every kernel once per process (kernels.h: preload_*)
-static void ensure_loaded() {
+void ensure_loaded() {
     static bool done = false;
-    if (!done) { preload_sparse(); preload_optim(); preload_gemm(); preload_topk(); done = true; }
+    if (!done) { preload_sparse(); preload_optim(); preload_gemm(); preload_topk(); preload_title(); done = true; }
 }
-
-constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;   // [TF1] AdamOptimizer defaults (DAEs.py:102)
-constexpr int kSqBlocks = 256;
-
-struct Slot {
-    long long *x_pos = nullptr, *y_pos = nullptr;   // device
-    float *x_val = nullptr, *y_val = nullptr;
-    long long *hx_pos = nullptr, *hy_pos = nullptr; // pinned host mirrors
-    float *hx_val = nullptr, *hy_val = nullptr;
-    int nnz_x = 0, nnz_y = 0, batch = 0, y_batch = 0;
-    bool has_y = false;
-    CsrWork xw{}, yw{};                             // de-duplicated CSR of this slot's batch
-    uint32_t* ybits = nullptr;                      // item-major target bitmask of this slot's batch
-    bool y_live = false;                            // ybits currently holds the bits of yw
-    cudaEvent_t h2d_done = nullptr;                 // the pinned mirror may be overwritten after this
-    cudaEvent_t prepared = nullptr;                 // side stream: CSR + ybits of this slot are ready
-    cudaEvent_t consumed = nullptr;                 // main stream: the step has finished reading this slot
-};
-
-// Bump allocator over ONE cudaMalloc per model.  Every rank lays its arena out identically, so a
-// peer's copy of any buffer is `peer base + same offset` (kernels.h: PeerTable / peer_ptr).
-struct Arena {
-    char* base = nullptr;
-    size_t off = 0;
-    template <typename T>
-    T* take(size_t n) {
-        off = (off + 1023) & ~size_t(1023);
-        T* p = reinterpret_cast<T*>(base + off);     // base == nullptr during the measuring pass
-        off += n * sizeof(T);
-        return p;
-    }
-};
-
-struct dae_model {
-    dae_config cfg{};
-    int N = 0, T = 0, H = 0, Bmax = 0, rows_alloc = 0, max_nnz = 0;
-    int world = 1, rank = 0;
-    int n_local = 0;                // catalogue rows held by every rank (local tiles x 128)
-    bool tied = false, trainable = true, own_stream = false, attached = false;
-    cudaStream_t st = nullptr;      // main stream: the step
-    cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
-    int cur = 0;                    // slot used by the last step (dae_model_buffer)
-    Arena arena;
-    PeerTable pt{};
-    void* ipc_opened[kMaxWorld] = {};
-    // parameters: catalogue matrices are row-sharded (tile-cyclic), biases replicated
-    float *W_enc = nullptr, *W_dec = nullptr, *b_enc = nullptr, *b_dec = nullptr;
-    __nv_bfloat16* shadow[2] = {nullptr, nullptr};   // bf16 decoder operand, all N rows; double-buffered when world > 1
-    int cur_shadow = 0;
-    float *mW_enc = nullptr, *vW_enc = nullptr, *mW_dec = nullptr, *vW_dec = nullptr;
-    float *mb_enc = nullptr, *vb_enc = nullptr, *mb_dec = nullptr, *vb_dec = nullptr;
-    float b1_pow = kBeta1, b2_pow = kBeta2;
-    long long step = 0;
-    float *g_enc = nullptr;                          // sparse-row dW_enc of the rows this rank owns
-    unsigned char* touched = nullptr;
-    float *g_b_enc_part = nullptr, *g_b_dec_part = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
-    float* g_dec = nullptr;                          // dW_dec of the rows this rank owns
-    int debug = 0;
-    bool scatter_done = false;
-    Slot slots[2];
-    PubInput pub{};
-    int* err = nullptr;
-    int* err_host = nullptr;
-    unsigned int* flags = nullptr;
-    unsigned int epoch = 0;
-    int ywords = 8;
-    float *rowsum = nullptr, *h = nullptr, *da = nullptr, *dh_partial = nullptr;
-    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr, *dz_all = nullptr;
-    int nsplit = 0;
-    float *loss_partial = nullptr, *sq_partial = nullptr, *cost_part = nullptr, *cost = nullptr, *cost_host = nullptr;
-    int n_loss_partial = 0;
-    float* scores = nullptr;
-    size_t scores_elems = 0;
-    int *topk_idx = nullptr, *seed_ptr = nullptr, *seed_idx = nullptr;
-    float* topk_score = nullptr;
-    size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
-    int last_batch = 0, last_bpad = 0;
-    long long launches = 0;
-    // optional per-phase device timing (bench.py roofline): events around each phase of a step
-    bool profiling = false;
-    cudaEvent_t ph_ev[2 * 16] = {};
-    bool ph_used[16] = {};
-    double ph_ms[16] = {};
-    long long ph_n[16] = {};
-    std::vector<void*> host_allocs;
-};
-
-template <typename T>
-static int halloc(dae_model* m, T** p, size_t n) {
-    CK(cudaMallocHost(reinterpret_cast<void**>(p), n * sizeof(T)));
-    m->host_allocs.push_back(*p);
-    return 0;
-}
-#define TRY(x) do { if (int rc_ = (x)) return rc_; } while (0)
 
 static void layout_csr(Arena& A, CsrWork* w, int B, int max_nnz) {
     w->cnt = A.take<int>(B);
@@ -192,7 +88,7 @@ static void layout(dae_model* m) {
         layout_csr(A, &sl.xw, m->Bmax, m->max_nnz);
         sl.x_pos = A.take<long long>((size_t)m->max_nnz * 2);
         sl.x_val = A.take<float>(m->max_nnz);
-        if (m->trainable) {
+        if (m->needs_y) {
             layout_csr(A, &sl.yw, m->Bmax, m->max_nnz);
             sl.ybits = A.take<uint32_t>((size_t)N * m->ywords);
             sl.y_pos = A.take<long long>((size_t)m->max_nnz * 2);
@@ -235,7 +131,7 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     if (cfg->n_input <= 0 || cfg->n_tracks <= 0 || cfg->n_tracks > cfg->n_input)
         return fail("need 0 < n_tracks <= n_input (got %d, %d)", cfg->n_tracks, cfg->n_input);
     if (cfg->max_batch <= 0) return fail("max_batch must be positive");
-    if (cfg->trainable && cfg->max_batch > kMaxBpad)
+    if (cfg->trainable != 0 && cfg->max_batch > kMaxBpad)
         return fail("training batch per GPU is limited to %d rows (one tensor-core batch tile); got %d", kMaxBpad,
                     cfg->max_batch);
     const int world = cfg->world > 0 ? cfg->world : 1;
@@ -254,7 +150,7 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     dae_model* m = new dae_model();
     m->cfg = *cfg;
     m->N = cfg->n_input; m->T = cfg->n_tracks; m->H = cfg->n_hidden; m->Bmax = cfg->max_batch;
-    m->tied = cfg->tied != 0; m->trainable = cfg->trainable != 0;
+    m->tied = cfg->tied != 0; m->trainable = cfg->trainable == 1; m->needs_y = cfg->trainable != 0;
     m->world = world; m->rank = cfg->rank;
     if (cfg->stream) { m->st = reinterpret_cast<cudaStream_t>(cfg->stream); }
     else { CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)); m->own_stream = true; }
@@ -281,7 +177,7 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
         CK(cudaEventCreateWithFlags(&sl.prepared, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming));
         TRY(halloc(m, &sl.hx_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hx_val, m->max_nnz));
-        if (m->trainable) { TRY(halloc(m, &sl.hy_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hy_val, m->max_nnz)); }
+        if (m->needs_y) { TRY(halloc(m, &sl.hy_pos, (size_t)m->max_nnz * 2)); TRY(halloc(m, &sl.hy_val, m->max_nnz)); }
     }
     CK(cudaStreamSynchronize(m->st));
     *out = m;
@@ -504,7 +400,7 @@ static int prepare_slot(dae_model* m, int slot) {
     return 0;
 }
 
-static int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
                       const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch, bool with_y) {
     if (!m) return fail("null model");
     if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
@@ -512,7 +408,7 @@ static int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const fl
     if (nnz_x < 0 || nnz_x > m->max_nnz || nnz_y < 0 || nnz_y > m->max_nnz)
         return fail("nnz (%lld, %lld) exceeds the staging capacity %d", (long long)nnz_x, (long long)nnz_y, m->max_nnz);
     if ((nnz_x > 0 && (!x_pos || !x_val)) || (nnz_y > 0 && (!y_pos || !y_val))) return fail("null COO pointer");
-    if (nnz_y > 0 && !m->trainable) return fail("y given to an inference-only model");
+    if (nnz_y > 0 && !m->needs_y) return fail("y given to an inference-only model");
     Slot& s = m->slots[slot];
     CK(cudaEventSynchronize(s.h2d_done));   // previous H2D out of this slot's pinned mirror has finished
     CK(cudaStreamWaitEvent(m->st2, s.consumed, 0));
@@ -538,7 +434,7 @@ extern "C" int32_t dae_model_stage_batch(dae_model* m, int32_t slot, const int64
                                          int64_t nnz_x, const int64_t* y_pos, const float* y_val, int64_t nnz_y,
                                          int32_t batch) {
     // a trainable model stages training batches (targets may legitimately be empty)
-    return stage_impl(m, slot, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch, m && m->trainable);
+    return stage_impl(m, slot, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch, m && m->needs_y);
 }
 
 // Re-run the device-side preparation of the COO batch already resident in `slot` (bench `value`
@@ -550,7 +446,7 @@ extern "C" int32_t dae_model_restage(dae_model* m, int32_t slot) {
     return prepare_slot(m, slot);
 }
 
-static int check_device_flag(dae_model* m) {
+int check_device_flag(dae_model* m) {
     CK(cudaStreamSynchronize(m->st2));
     CK(cudaMemcpyAsync(m->err_host, m->err, sizeof(int), cudaMemcpyDeviceToHost, m->st));
     CK(cudaStreamSynchronize(m->st));
@@ -566,7 +462,7 @@ static int check_device_flag(dae_model* m) {
 }
 
 // encode forward from a staged slot (shared by train / predict / recommend)
-static void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset,
+void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset,
                        bool train) {
     const Slot& s = m->slots[slot];
     m->cur = slot;

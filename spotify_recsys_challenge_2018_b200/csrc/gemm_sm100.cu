@@ -21,50 +21,10 @@
 #include <stdlib.h>
 
 #include "kernels.h"
+#include "tmap.h"
 #include "umma.cuh"
 
 namespace dae {
-
-// ------------------------------------------------------------------------------------------
-// host: tensor maps
-// ------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
-static PFN_tmapEncodeTiled tmap_encoder() {
-    static PFN_tmapEncodeTiled fn = []() -> PFN_tmapEncodeTiled {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess || p == nullptr) {
-            fprintf(stderr, "dae_b200: cuTensorMapEncodeTiled not available from the driver\n");
-            abort();
-        }
-        return reinterpret_cast<PFN_tmapEncodeTiled>(p);
-    }();
-    return fn;
-}
-
-// Row-major bf16 matrix [outer, inner]; box = [box_outer rows, 64 elements (128 B)], SWIZZLE_128B,
-// out-of-bounds elements read as zero.
-static CUtensorMap make_map_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint32_t box_outer) {
-    CUtensorMap m;
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {inner * sizeof(__nv_bfloat16)};
-    cuuint32_t box[2] = {64, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = tmap_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
-                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        fprintf(stderr, "dae_b200: cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu box=%u\n", (int)r,
-                (unsigned long long)inner, (unsigned long long)outer, box_outer);
-        abort();
-    }
-    return m;
-}
 
 // ------------------------------------------------------------------------------------------
 // G1 / G2: item-tile kernels
@@ -510,6 +470,7 @@ struct DwDev {
     AdamConst adam;
     __nv_bfloat16* shadow;   // [n_global, H], refreshed on every rank
     PeerTable pt;
+    int ld, col0;            // row stride and first column of the row-major outputs
 };
 
 __global__ void __launch_bounds__(kDwThreads, 1)
@@ -645,11 +606,11 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
                 const int item0 = tile * kTileItems + it_lo + cc;                    // local row of column cc
                 const int gitem0 = item_global(item0, world, p.pt.rank);             // 16 consecutive catalogue ids
                 const int nvalid = h_ok ? min(16, p.n_global - gitem0) : 0;
-                const size_t off0 = (size_t)item0 * p.H + h;
+                const size_t off0 = (size_t)item0 * p.ld + p.col0 + h;
                 if (p.g != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (j < nvalid) p.g[off0 + (size_t)j * p.H] = __uint_as_float(r[j]);
+                        if (j < nvalid) p.g[off0 + (size_t)j * p.ld] = __uint_as_float(r[j]);
                 }
                 if (p.aw != nullptr) {
                     // dense TF1 Adam on the 16 gradient values this thread just read from TMEM: the gradient
@@ -658,7 +619,7 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if (j < nvalid) {
-                            const size_t o = off0 + (size_t)j * p.H;
+                            const size_t o = off0 + (size_t)j * p.ld;
                             wv[j] = __ldcs(p.aw + o); mv[j] = __ldcs(p.am + o); vv[j] = __ldcs(p.av + o);
                         } else {
                             wv[j] = 0.f; mv[j] = 0.f; vv[j] = 0.f;
@@ -668,20 +629,20 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (j < nvalid && p.touched[item0 + j] != 0)
-                                r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __ldcs(p.g_extra + off0 + (size_t)j * p.H)));
+                                r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __ldcs(p.g_extra + off0 + (size_t)j * p.ld)));
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         adam_one(wv[j], mv[j], vv[j], __uint_as_float(r[j]), p.adam);
                         if (j < nvalid) {
-                            const size_t o = off0 + (size_t)j * p.H;
+                            const size_t o = off0 + (size_t)j * p.ld;
                             __stcs(p.aw + o, wv[j]); __stcs(p.am + o, mv[j]); __stcs(p.av + o, vv[j]);
                         }
                     }
                     if (p.shadow != nullptr) {
                         // bf16 operand rows: lanes pair up so that every lane stores one 4-byte (h, h+1) pair --
                         // even lanes for item j, odd lanes for item j+1 -- into this GPU's copy and every peer's
-                        const size_t goff0 = (size_t)gitem0 * p.H + (h & ~1);
+                        const size_t goff0 = (size_t)gitem0 * p.ld + p.col0 + (h & ~1);
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             const float give = (lane & 1) ? wv[j] : wv[j + 1];           // what the partner lane stores
@@ -689,7 +650,7 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
                             const int jj = j + (lane & 1);
                             const uint32_t pk = (lane & 1) ? pack_bf16x2(got, wv[j + 1]) : pack_bf16x2(wv[j], got);
                             if (jj < nvalid) {
-                                const size_t go = goff0 + (size_t)jj * p.H;
+                                const size_t go = goff0 + (size_t)jj * p.ld;
                                 for (int sidx = 0; sidx < world; ++sidx)
                                     *reinterpret_cast<uint32_t*>(peer_ptr(p.pt, sidx, p.shadow) + go) = pk;
                             }
@@ -729,6 +690,8 @@ void launch_dw(const DwArgs& a, cudaStream_t st) {
     p.g_extra = a.g_extra; p.touched = a.touched;
     p.adam = a.adam;
     p.shadow = a.w != nullptr ? a.shadow : nullptr;
+    p.ld = a.ld > 0 ? a.ld : a.H;
+    p.col0 = a.col0;
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
     const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
     const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
@@ -876,7 +839,7 @@ void launch_dh(const DhArgs& a, cudaStream_t st) {
         configured = true;
     }
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.bpad, a.N, 64);
-    const CUtensorMap tmW = make_map_bf16(a.W, a.H, a.N, 64);
+    const CUtensorMap tmW = make_map_bf16(a.W, a.H, a.N, 64, a.ldW);
     DhDev p{};
     p.kchunks_total = (a.N + 63) / 64;
     p.mboxes = a.bpad / 64;

@@ -157,6 +157,7 @@ struct DwArgs {
     AdamConst adam;
     __nv_bfloat16* shadow;              // [N,H] bf16 operand copy to refresh on this GPU and on every peer (global row order)
     PeerTable pt;
+    int ld, col0;                       // row stride (0: H) and first column of g / w / m / v / shadow (title head: two 256-column halves of [N, 512])
 };
 void launch_dw(const DwArgs& a, cudaStream_t st);                  // G2: dW_dec = dz^T . h_d (+ Adam)
 
@@ -166,6 +167,7 @@ struct DhArgs {
     float* partial;             // [nsplit,bpad,H]
     int N, H, bpad, nsplit;
     int lbo, sbo;               // MN-major descriptor strides (bytes); 0 -> defaults
+    int ldW;                    // row stride of W in elements (0: H)
 };
 int dh_nsplit(int N);
 void launch_dh(const DhArgs& a, cudaStream_t st);                  // G3: dh = dz . W_dec (split-K)
@@ -197,6 +199,73 @@ void launch_reduce_loss2(const float* partial, int n, const float* sumsq_partial
                          float inv_batch, float* loss_out, cudaStream_t st);
 void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, cudaStream_t st);
 
+// ---- title.cu / title_sm100.cu: the title branch (Char_CNN.py:16-75, DAEs.py:153-201) ----------
+constexpr int kTitleFpad = 512;    // feature columns of the output layer's operands (D = filters x widths <= 512, zero padded)
+constexpr int kTitleMaxLen = 32;   // strmaxlen limit (25 in every shipped config)
+constexpr int kTitleMaxWidths = 8;
+
+struct CnnShape {
+    int C, L, E, F, n_widths;            // charsize, strmaxlen, char_emb, filter_num, len(filter_size)
+    int width[kTitleMaxWidths];          // filter_size
+    int w_off[kTitleMaxWidths];          // offset of width i's [w][E][F] block inside conv_W
+};
+struct CnnFwdArgs {
+    const long long* titles;             // [B, L] char ids, -1 = pad
+    const float* emb; const float* conv_W; const float* conv_b;
+    CnnShape shape;
+    float* feat;                         // [B, D] max-over-time features (before dropout)
+    unsigned char* argpos;               // [B, D] arg-max position
+    __nv_bfloat16* feat_d;               // [bpad, 512] dropout(feat), bf16
+    __nv_bfloat16* feat_dT;              // [512, bpad]
+    int B, bpad;
+    float kp_t;
+    unsigned long long seed, step;
+    int row_offset;
+};
+void launch_charcnn_fwd(const CnnFwdArgs& a, cudaStream_t st);
+void launch_mix_weights(const float* rowsum, const float* titles_use, float kp_in, int B, int bpad, float* w_t,
+                        float* w_p, cudaStream_t st);
+struct CnnBwdArgs {
+    const long long* titles;
+    const float* emb; const float* conv_W;
+    CnnShape shape;
+    const float* dh_partial;             // [2 halves][nsplit][bpad][256] split-K partials of d cost / d feat_d
+    int nsplit, bpad, B;
+    const float* feat; const unsigned char* argpos;
+    float kp_t;
+    unsigned long long seed, step;
+    int row_offset;
+    float* d;                            // [B, D] workspace: gradient at the arg-max positions
+    float* g_emb; float* g_conv_W; float* g_conv_b;
+};
+void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st);
+void launch_trunc_normal(float* w, long long rows, int row_len, int ld, float stddev, unsigned long long seed,
+                         unsigned stream_id, cudaStream_t st);
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
+void launch_transpose_pad(const float* src, float* dst, int D, int N, int ld, int to_item_major, cudaStream_t st);
+
+struct TitleTileArgs {                   // y_pred = title_score * w_t + sigmoid(z_dae) * w_p over one batch tile  (DAEs.py:175-181)
+    const __nv_bfloat16* W_dec;          // [N, H]   frozen DAE decoder operand
+    const __nv_bfloat16* h_d;            // [bpad, H]
+    const float* b_dec;                  // [N]
+    const __nv_bfloat16* W_out;          // [N, 512] title output layer (item-major)
+    const __nv_bfloat16* feat_d;         // [bpad, 512]
+    const float* b_out;                  // [N]
+    const float* w_t; const float* w_p;  // [bpad]
+    int N, H, batch, bpad;
+    int kf;                              // 64-column chunks of the feature operand actually used (ceil(D / 64))
+    // train (DAEs.py:194-196)
+    const uint32_t* ybits; int ywords;
+    __nv_bfloat16* dzT;                  // [N, bpad] d cost / d z_title
+    float* db_out;                       // [N]
+    float* loss_partial;
+    float inv_batch;
+    // predict
+    float* out; long long ld_out; int n_out;
+};
+void launch_title_train(const TitleTileArgs& a, cudaStream_t st);
+void launch_title_predict(const TitleTileArgs& a, cudaStream_t st);
+
 // ---- topk.cu --------------------------------------------------------------------------------
 struct TopkArgs {
     const float* scores;      // [B, ld]
@@ -215,5 +284,8 @@ void preload_sparse();
 void preload_optim();
 void preload_gemm();
 void preload_topk();
+void preload_title_cnn();
+void preload_title_gemm();
+inline void preload_title() { preload_title_cnn(); preload_title_gemm(); }
 
 }  // namespace dae

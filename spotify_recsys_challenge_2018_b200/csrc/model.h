@@ -1,0 +1,126 @@
+// Internal: the model object behind the C ABI (include/dae_b200.h), shared by api.cu (DAE path) and
+// api_title.cu (title branch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dae_b200.h"
+#include "kernels.h"
+
+using namespace dae;
+
+std::string& dae_err();                      // last error of the calling thread
+int fail(const char* fmt, ...);               // records the message, returns 1
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+void ensure_loaded();                         // load every kernel once per process (kernels.h: preload_*)
+
+constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;   // [TF1] AdamOptimizer defaults (DAEs.py:102)
+constexpr int kSqBlocks = 256;
+
+struct Slot {
+    long long *x_pos = nullptr, *y_pos = nullptr;   // device
+    float *x_val = nullptr, *y_val = nullptr;
+    long long *hx_pos = nullptr, *hy_pos = nullptr; // pinned host mirrors
+    float *hx_val = nullptr, *hy_val = nullptr;
+    int nnz_x = 0, nnz_y = 0, batch = 0, y_batch = 0;
+    bool has_y = false;
+    CsrWork xw{}, yw{};                             // de-duplicated CSR of this slot's batch
+    uint32_t* ybits = nullptr;                      // item-major target bitmask of this slot's batch
+    bool y_live = false;                            // ybits currently holds the bits of yw
+    cudaEvent_t h2d_done = nullptr;                 // the pinned mirror may be overwritten after this
+    cudaEvent_t prepared = nullptr;                 // side stream: CSR + ybits of this slot are ready
+    cudaEvent_t consumed = nullptr;                 // main stream: the step has finished reading this slot
+};
+
+// Bump allocator over ONE cudaMalloc per model.  Every rank lays its arena out identically, so a
+// peer's copy of any buffer is `peer base + same offset` (kernels.h: PeerTable / peer_ptr).
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 1023) & ~size_t(1023);
+        T* p = reinterpret_cast<T*>(base + off);     // base == nullptr during the measuring pass
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct dae_model {
+    dae_config cfg{};
+    int N = 0, T = 0, H = 0, Bmax = 0, rows_alloc = 0, max_nnz = 0;
+    int world = 1, rank = 0;
+    int n_local = 0;                // catalogue rows held by every rank (local tiles x 128)
+    bool tied = false, trainable = true, needs_y = true, own_stream = false, attached = false;
+    cudaStream_t st = nullptr;      // main stream: the step
+    cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
+    int cur = 0;                    // slot used by the last step (dae_model_buffer)
+    Arena arena;
+    PeerTable pt{};
+    void* ipc_opened[kMaxWorld] = {};
+    // parameters: catalogue matrices are row-sharded (tile-cyclic), biases replicated
+    float *W_enc = nullptr, *W_dec = nullptr, *b_enc = nullptr, *b_dec = nullptr;
+    __nv_bfloat16* shadow[2] = {nullptr, nullptr};   // bf16 decoder operand, all N rows; double-buffered when world > 1
+    int cur_shadow = 0;
+    float *mW_enc = nullptr, *vW_enc = nullptr, *mW_dec = nullptr, *vW_dec = nullptr;
+    float *mb_enc = nullptr, *vb_enc = nullptr, *mb_dec = nullptr, *vb_dec = nullptr;
+    float b1_pow = kBeta1, b2_pow = kBeta2;
+    long long step = 0;
+    float *g_enc = nullptr;                          // sparse-row dW_enc of the rows this rank owns
+    unsigned char* touched = nullptr;
+    float *g_b_enc_part = nullptr, *g_b_dec_part = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
+    float* g_dec = nullptr;                          // dW_dec of the rows this rank owns
+    int debug = 0;
+    bool scatter_done = false;
+    Slot slots[2];
+    PubInput pub{};
+    int* err = nullptr;
+    int* err_host = nullptr;
+    unsigned int* flags = nullptr;
+    unsigned int epoch = 0;
+    int ywords = 8;
+    float *rowsum = nullptr, *h = nullptr, *da = nullptr, *dh_partial = nullptr;
+    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr, *dz_all = nullptr;
+    int nsplit = 0;
+    float *loss_partial = nullptr, *sq_partial = nullptr, *cost_part = nullptr, *cost = nullptr, *cost_host = nullptr;
+    int n_loss_partial = 0;
+    float* scores = nullptr;
+    size_t scores_elems = 0;
+    int *topk_idx = nullptr, *seed_ptr = nullptr, *seed_idx = nullptr;
+    float* topk_score = nullptr;
+    size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
+    int last_batch = 0, last_bpad = 0;
+    long long launches = 0;
+    // optional per-phase device timing (bench.py roofline): events around each phase of a step
+    bool profiling = false;
+    cudaEvent_t ph_ev[2 * 16] = {};
+    bool ph_used[16] = {};
+    double ph_ms[16] = {};
+    long long ph_n[16] = {};
+    std::vector<void*> host_allocs;
+};
+
+template <typename T>
+static int halloc(dae_model* m, T** p, size_t n) {
+    CK(cudaMallocHost(reinterpret_cast<void**>(p), n * sizeof(T)));
+    m->host_allocs.push_back(*p);
+    return 0;
+}
+#define TRY(x) do { if (int rc_ = (x)) return rc_; } while (0)
+
+
+// api.cu internals used by the title branch
+int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+               const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch, bool with_y);
+int check_device_flag(dae_model* m);
+void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset, bool train);

@@ -1,0 +1,282 @@
+// Title branch, CUDA-core part: the character CNN of models/title_models/Char_CNN.py:16-75
+// (embedding -> parallel VALID convolutions over time -> bias -> ReLU -> max over time -> concat ->
+// dropout) forward and backward, the mixing weights of DAE_title (models/DAEs.py:159-162), and the
+// truncated-normal initialiser.  All of it is tiny next to the catalogue-sized output layer
+// (~1.2 GFLOP per 256 titles): plain fp32 FMA, weights served from L2, no tensor cores.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace dae {
+
+// ------------------------------------------------------------------------------------------
+// forward: one CTA per title, one thread per (width, filter) feature
+// ------------------------------------------------------------------------------------------
+// conv_W: widths back to back, each [w][E][F] (the reference's [fs, E, 1, F], Char_CNN.py:43); conv_b: [n_widths][F].
+__global__ void __launch_bounds__(512)
+k_charcnn_fwd(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ conv_W,
+              const float* __restrict__ conv_b, const CnnShape s, float* __restrict__ feat,
+              unsigned char* __restrict__ argpos, __nv_bfloat16* __restrict__ feat_d, __nv_bfloat16* __restrict__ feat_dT,
+              int B, int bpad, float kp_t, unsigned long long seed, unsigned long long step, int row_offset) {
+    extern __shared__ float s_x[];                 // [L][E] embedded title, pad rows zero
+    const int b = blockIdx.x;
+    const int j = threadIdx.x;                     // feature index in [0, D)
+    const int D = s.F * s.n_widths;
+    if (b >= B) {                                  // padding rows of the tensor-core operand
+        for (int c = j; c < kTitleFpad; c += blockDim.x) {
+            feat_d[(size_t)b * kTitleFpad + c] = __float2bfloat16(0.f);
+            feat_dT[(size_t)c * bpad + b] = __float2bfloat16(0.f);
+        }
+        return;
+    }
+    for (int i = j; i < s.L * s.E; i += blockDim.x) {
+        const int pos = i / s.E, e = i - pos * s.E;
+        const long long id = titles[(size_t)b * s.L + pos];
+        s_x[i] = (id >= 0 && id < s.C) ? emb[(size_t)id * s.E + e] : 0.f;      // pad id -1 -> zero vector
+    }
+    __syncthreads();
+    float best = 0.f;
+    int best_pos = 0;
+    if (j < D) {
+        const int wi = j / s.F, f = j - wi * s.F;
+        const int w = s.width[wi];
+        const float* W = conv_W + s.w_off[wi] + f;                             // [k][e][f]: threads read consecutive f
+        const int P = s.L - w + 1;
+        float acc[kTitleMaxLen];
+#pragma unroll
+        for (int p = 0; p < kTitleMaxLen; ++p) acc[p] = 0.f;
+        for (int k = 0; k < w; ++k) {
+            for (int e = 0; e < s.E; ++e) {
+                const float wv = __ldg(W + (size_t)(k * s.E + e) * s.F);
+#pragma unroll
+                for (int p = 0; p < kTitleMaxLen; ++p)
+                    if (p < P) acc[p] = fmaf(s_x[(p + k) * s.E + e], wv, acc[p]);
+            }
+        }
+        const float bias = conv_b[wi * s.F + f];
+        best = fmaxf(acc[0] + bias, 0.f);                                      // bias_add, relu, reduce_max (Char_CNN.py:50-58)
+#pragma unroll
+        for (int p = 1; p < kTitleMaxLen; ++p) {
+            if (p < P) {
+                const float v = fmaxf(acc[p] + bias, 0.f);
+                if (v > best) { best = v; best_pos = p; }
+            }
+        }
+        feat[(size_t)b * D + j] = best;
+        argpos[(size_t)b * D + j] = static_cast<unsigned char>(best_pos);
+    }
+    // dropout (Char_CNN.py:67) and the bf16 operand copies [bpad, 512] / [512, bpad]; columns >= D stay zero
+    for (int c = j; c < kTitleFpad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < D && c == j) {
+            const bool keep = philox_keep(seed, kStreamTitle, step, static_cast<uint32_t>(b + row_offset),
+                                          static_cast<uint32_t>(c), kp_t);
+            v = keep ? __fdiv_rn(best, kp_t) : 0.f;
+        }
+        const __nv_bfloat16 hb = __float2bfloat16(v);
+        feat_d[(size_t)b * kTitleFpad + c] = hb;
+        feat_dT[(size_t)c * bpad + b] = hb;
+    }
+}
+
+void launch_charcnn_fwd(const CnnFwdArgs& a, cudaStream_t st) {
+    const int D = a.shape.F * a.shape.n_widths;
+    const int threads = ((D > kTitleFpad ? D : kTitleFpad) + 31) / 32 * 32;
+    k_charcnn_fwd<<<a.bpad, threads, sizeof(float) * a.shape.L * a.shape.E, st>>>(
+        a.titles, a.emb, a.conv_W, a.conv_b, a.shape, a.feat, a.argpos, a.feat_d, a.feat_dT, a.B, a.bpad, a.kp_t, a.seed,
+        a.step, a.row_offset);
+}
+
+// x_count = s * kp_in ; w_t = u / (u + x_count + 1e-10) ; w_p = x_count / (u + x_count + 1e-10)     DAEs.py:159-162
+__global__ void k_mix_weights(const float* __restrict__ rowsum, const float* __restrict__ titles_use, float kp_in,
+                              int B, int bpad, float* __restrict__ w_t, float* __restrict__ w_p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bpad) return;
+    float wt = 0.f, wp = 0.f;
+    if (b < B) {
+        const float xc = rowsum[b] * kp_in, u = titles_use[b];
+        const float deno = (u + xc) + kEpsLog;
+        wt = __fdiv_rn(u, deno);
+        wp = __fdiv_rn(xc, deno);
+    }
+    w_t[b] = wt;
+    w_p[b] = wp;
+}
+void launch_mix_weights(const float* rowsum, const float* titles_use, float kp_in, int B, int bpad, float* w_t,
+                        float* w_p, cudaStream_t st) {
+    k_mix_weights<<<(bpad + 127) / 128, 128, 0, st>>>(rowsum, titles_use, kp_in, B, bpad, w_t, w_p);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+// d[b, j] = (sum of the split-K partials of dfeat_d[b, j]) * keep / kp_t * (feat > 0)      (dropout, ReLU, max)
+__global__ void k_title_dfeat(const float* __restrict__ partial, int nsplit, int bpad, const float* __restrict__ feat,
+                              int B, int D, float kp_t, unsigned long long seed, unsigned long long step,
+                              int row_offset, float* __restrict__ d) {
+    const int b = blockIdx.x, j = threadIdx.x;
+    if (j >= D) return;
+    const int half = j / 256, c = j - half * 256;                             // two 256-column launches of the dh kernel
+    const float* p = partial + (size_t)half * nsplit * bpad * 256 + (size_t)b * 256 + c;
+    float s0 = 0.f, s1 = 0.f;
+    int sidx = 0;
+    for (; sidx + 2 <= nsplit; sidx += 2) {                                    // fixed order: deterministic
+        s0 += p[(size_t)sidx * bpad * 256];
+        s1 += p[(size_t)(sidx + 1) * bpad * 256];
+    }
+    for (; sidx < nsplit; ++sidx) s0 += p[(size_t)sidx * bpad * 256];
+    const bool keep = philox_keep(seed, kStreamTitle, step, static_cast<uint32_t>(b + row_offset), static_cast<uint32_t>(j), kp_t);
+    const float f = feat[(size_t)b * D + j];
+    d[(size_t)b * D + j] = (keep && f > 0.f) ? (s0 + s1) * __fdiv_rn(1.f, kp_t) : 0.f;
+}
+
+// dW[k][e][f] = sum_b x[b, arg[b,f] + k, e] * d[b, f];  db[f] = sum_b d[b, f].  One CTA per feature: no atomics.
+__global__ void __launch_bounds__(512)
+k_charcnn_bwd_w(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ d,
+                const unsigned char* __restrict__ argpos, const CnnShape s, int B, float* __restrict__ g_W,
+                float* __restrict__ g_b) {
+    const int j = blockIdx.x;
+    const int D = s.F * s.n_widths;
+    const int wi = j / s.F, f = j - wi * s.F;
+    const int w = s.width[wi];
+    const int t = threadIdx.x;                     // (k, e) pair
+    const int k = t / s.E, e = t - k * s.E;
+    float acc = 0.f, accb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float dv = d[(size_t)b * D + j];
+        if (dv == 0.f) continue;                   // uniform over the CTA
+        accb += dv;
+        if (k < w) {
+            const long long id = titles[(size_t)b * s.L + argpos[(size_t)b * D + j] + k];
+            if (id >= 0 && id < s.C) acc = fmaf(emb[(size_t)id * s.E + e], dv, acc);
+        }
+    }
+    if (k < w) g_W[s.w_off[wi] + (size_t)(k * s.E + e) * s.F + f] = acc;
+    if (t == 0) g_b[wi * s.F + f] = accb;
+}
+
+// demb[c][e] += sum_{j, k : title[b, arg+k] == c} W[k][e][f] * d[b, j].  One CTA per title, positions accumulated in
+// shared memory, then one atomic row add per (position, e).
+__global__ void __launch_bounds__(256)
+k_charcnn_bwd_emb(const long long* __restrict__ titles, const float* __restrict__ conv_W, const float* __restrict__ d,
+                  const unsigned char* __restrict__ argpos, const CnnShape s, float* __restrict__ g_emb) {
+    extern __shared__ float s_dx[];                // [L][E]
+    const int b = blockIdx.x;
+    const int D = s.F * s.n_widths;
+    for (int i = threadIdx.x; i < s.L * s.E; i += blockDim.x) s_dx[i] = 0.f;
+    __syncthreads();
+    // thread -> embedding column e (strided); loop features: every thread adds its own e, so no smem conflicts
+    for (int e = threadIdx.x; e < s.E; e += blockDim.x) {
+        for (int j = 0; j < D; ++j) {
+            const float dv = d[(size_t)b * D + j];
+            if (dv == 0.f) continue;
+            const int wi = j / s.F, f = j - wi * s.F;
+            const int w = s.width[wi];
+            const int p0 = argpos[(size_t)b * D + j];
+            const float* W = conv_W + s.w_off[wi] + f;
+            for (int k = 0; k < w; ++k) s_dx[(p0 + k) * s.E + e] = fmaf(__ldg(W + (size_t)(k * s.E + e) * s.F), dv, s_dx[(p0 + k) * s.E + e]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s.L * s.E; i += blockDim.x) {
+        const int pos = i / s.E, e = i - pos * s.E;
+        const long long id = titles[(size_t)b * s.L + pos];
+        const float v = s_dx[i];
+        if (id >= 0 && id < s.C && v != 0.f) atomicAdd(g_emb + (size_t)id * s.E + e, v);
+    }
+}
+
+void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st) {
+    const int D = a.shape.F * a.shape.n_widths;
+    k_title_dfeat<<<a.B, (D + 31) / 32 * 32, 0, st>>>(a.dh_partial, a.nsplit, a.bpad, a.feat, a.B, D, a.kp_t, a.seed, a.step,
+                                                      a.row_offset, a.d);
+    int maxw = 0;
+    for (int i = 0; i < a.shape.n_widths; ++i) maxw = a.shape.width[i] > maxw ? a.shape.width[i] : maxw;
+    k_charcnn_bwd_w<<<D, (maxw * a.shape.E + 31) / 32 * 32, 0, st>>>(a.titles, a.emb, a.d, a.argpos, a.shape, a.B, a.g_conv_W,
+                                                                     a.g_conv_b);
+    cudaMemsetAsync(a.g_emb, 0, sizeof(float) * a.shape.C * a.shape.E, st);
+    k_charcnn_bwd_emb<<<a.B, 64, sizeof(float) * a.shape.L * a.shape.E, st>>>(a.titles, a.conv_W, a.d, a.argpos, a.shape, a.g_emb);
+}
+
+// ------------------------------------------------------------------------------------------
+// tf.contrib.layers.xavier_initializer(uniform=False) [TF1]: truncated normal, stddev sqrt(2.6 / (fan_in + fan_out)),
+// samples beyond two standard deviations redrawn (Char_CNN.py:19, :45-47, :71-73).  Philox -> Box-Muller.
+// ------------------------------------------------------------------------------------------
+__global__ void k_trunc_normal(float* __restrict__ w, long long n, int row_len, int ld, float stddev,
+                               unsigned long long seed, unsigned stream_id) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float z = 0.f;
+        for (unsigned long long attempt = 0; attempt < 64; ++attempt) {
+            const float u1 = philox_uniform24(seed, stream_id, 2 * attempt, static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(i));
+            const float u2 = philox_uniform24(seed, stream_id, 2 * attempt + 1, static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(i));
+            z = sqrtf(-2.f * logf(u1 + 5.9604645e-8f)) * cospif(2.f * u2);
+            if (fabsf(z) <= 2.f) break;
+            z = 0.f;
+        }
+        const long long r = i / row_len, c = i - r * row_len;
+        w[r * ld + c] = z * stddev;
+    }
+}
+void launch_trunc_normal(float* w, long long rows, int row_len, int ld, float stddev, unsigned long long seed,
+                         unsigned stream_id, cudaStream_t st) {
+    k_trunc_normal<<<1184, 256, 0, st>>>(w, rows * row_len, row_len, ld, stddev, seed, stream_id);
+}
+
+// fp32 [rows, ld] -> bf16 [rows, ld] (operand copy of the output layer)
+__global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16(src[i]);
+}
+void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {
+    k_cast_bf16<<<1184, 256, 0, st>>>(src, dst, n);
+}
+
+// [D, N] (the reference's Output_W layout, Char_CNN.py:72) <-> item-major [N, ld] with zero padding columns
+__global__ void k_transpose_pad(const float* __restrict__ src, float* __restrict__ dst, int D, int N, int ld, int to_item_major) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    if (to_item_major) {
+        const int n = n0 + threadIdx.x, d = d0 + threadIdx.y;
+        for (int yy = 0; yy < 32; yy += 8) {
+            const int dd = d + yy;
+            tile[threadIdx.y + yy][threadIdx.x] = (dd < D && n < N) ? src[(size_t)dd * N + n] : 0.f;
+        }
+        __syncthreads();
+        for (int yy = 0; yy < 32; yy += 8) {
+            const int nn = n0 + threadIdx.y + yy, dd = d0 + threadIdx.x;
+            if (nn < N && dd < ld) dst[(size_t)nn * ld + dd] = tile[threadIdx.x][threadIdx.y + yy];
+        }
+    } else {
+        for (int yy = 0; yy < 32; yy += 8) {
+            const int nn = n0 + threadIdx.y + yy, dd = d0 + threadIdx.x;
+            tile[threadIdx.y + yy][threadIdx.x] = (nn < N && dd < D) ? src[(size_t)nn * ld + dd] : 0.f;
+        }
+        __syncthreads();
+        for (int yy = 0; yy < 32; yy += 8) {
+            const int dd = d0 + threadIdx.y + yy, nn = n0 + threadIdx.x;
+            if (dd < D && nn < N) dst[(size_t)dd * N + nn] = tile[threadIdx.x][threadIdx.y + yy];
+        }
+    }
+}
+void launch_transpose_pad(const float* src, float* dst, int D, int N, int ld, int to_item_major, cudaStream_t st) {
+    const int dcols = to_item_major ? ld : D;
+    k_transpose_pad<<<dim3((N + 31) / 32, (dcols + 31) / 32), dim3(32, 8), 0, st>>>(src, dst, D, N, ld, to_item_major);
+}
+
+void preload_title_cnn() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_charcnn_fwd);
+    cudaFuncGetAttributes(&a, k_mix_weights);
+    cudaFuncGetAttributes(&a, k_title_dfeat);
+    cudaFuncGetAttributes(&a, k_charcnn_bwd_w);
+    cudaFuncGetAttributes(&a, k_charcnn_bwd_emb);
+    cudaFuncGetAttributes(&a, k_trunc_normal);
+    cudaFuncGetAttributes(&a, k_cast_bf16);
+    cudaFuncGetAttributes(&a, k_transpose_pad);
+    (void)cudaGetLastError();
+}
+
+}  // namespace dae

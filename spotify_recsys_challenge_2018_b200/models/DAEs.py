@@ -236,17 +236,34 @@ class DAE(DAE_tied):
 
 
 class DAE_title(DAE):
-    """Frozen DAE whose scores are mixed with a title model's scores (reference models/DAEs.py:153-201).
+    """Constant DAE whose scores are mixed with a title model's scores (reference models/DAEs.py:153-201).
 
-    The DAE weights come from conf.DAEval and are constants (DAEs.py:164-171): the device model is
-    created inference-only.  The mixing weights follow DAEs.py:159-162:
-        x_count = rowsum(x_dropout) * input_keep_prob ; w_t = u / (u + x_count + 1e-10) ; w_p = x_count / (...)
+    The DAE weights come from conf.DAEval and are constants (DAEs.py:164-171): the device model holds
+    no Adam state; it is created "frozen with targets" (trainable = 2) so the title branch can train
+    against y.  The mixing (DAEs.py:159-162, :180), the loss on y_pred (:194-196) and the title
+    variables live in the title model (models/title_models/Char_CNN.py), which is attached with
+    `title_model.fit(self)`; `train_step` / `predict` / `recommend` here forward to it.
     """
 
-    trainable = False
+    trainable = 2
 
     def __init__(self, conf, title_score=None):
         DAE_tied.__init__(self, conf)
         self.DAEval_dir = conf.DAEval                     # DAEs.py:156
         self.initval_dir = conf.DAEval
-        self.title_score = title_score
+        self.title_score = title_score                    # the Char_CNN object (the reference passes its .output tensor)
+
+    def train_step(self, x_positions, x_vals, y_positions, y_vals, keep_prob, input_keep_prob, titles=None,
+                   titles_use=1.0, title_keep_prob=1.0):
+        return self.title_score.train_step(self, x_positions, x_vals, titles, keep_prob, title_keep_prob,
+                                           input_keep_prob, y_positions, y_vals, titles_use)
+
+    def predict(self, x_positions, x_vals, titles=None, titles_use=1.0, tracks_only=False):
+        if self.title_score is None or titles is None:    # no title branch attached: titles_use = 0 -> the DAE's own scores
+            return DAE.predict(self, x_positions, x_vals, tracks_only)
+        return self.title_score.predict(self, x_positions, x_vals, titles, titles_use, tracks_only)
+
+    def recommend(self, x_positions, x_vals, seeds, titles=None, titles_use=1.0, k=500, return_scores=False):
+        if self.title_score is None or titles is None:
+            return DAE.recommend(self, x_positions, x_vals, seeds, k, return_scores)
+        return self.title_score.recommend(self, x_positions, x_vals, titles, seeds, titles_use, k, return_scores)

@@ -220,3 +220,77 @@ def test_merge_sharded_topk_equals_unsharded():
         idxs.append(loc + lo); scs.append(s[loc + lo])
     m_idx, _ = ranking.merge_sharded_topk(idxs, scs, K)
     assert np.array_equal(m_idx, full)
+
+
+# ---------------------------------------------------------------- title branch (Char_CNN.py, DAEs.py:153-201)
+def _title_setup(B=6, N=40, H=8, seed=0):
+    from oracle import title_oracle as TO
+    dae = O.DAEOracle(N, H, 0.01, tied=False, seed=seed)
+    dae.b_dec[:] = np.random.default_rng(1).normal(0, 0.3, N)
+    cnn = TO.CharCNNOracle(charsize=11, strmaxlen=12, char_emb=5, filter_num=4, filter_size=[3, 5], n_output=N, seed=seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    titles = rng.integers(0, 11, (B, 12))
+    titles[0, 7:] = -1; titles[1, :] = -1; titles[2, 3:] = -1          # padded, empty and short titles
+    n = B * 5
+    x = np.stack([np.sort(rng.integers(0, B, n)), rng.integers(0, N, n)], 1)
+    y = np.stack([np.sort(rng.integers(0, B, 2 * n)), rng.integers(0, N, 2 * n)], 1)
+    use = (rng.random(B) < 0.7).astype(np.float32)
+    return TO, dae, cnn, titles, x, np.ones(n, np.float32), y, np.ones(2 * n, np.float32), use
+
+
+def test_title_backward_matches_autograd():
+    """Closed-form backward of the title branch vs torch autograd in fp64 on the same masks."""
+    import torch
+    TO, dae, cnn, titles, x, xv, y, yv, use = _title_setup()
+    B = titles.shape[0]
+    m = TO.DAETitleOracle(dae, cnn, 0.01)
+    cost, grads, f = m.loss_and_grads(x, xv, y, yv, titles, use, B, 0.8, 0.7, 0.6, seed=3, step=2)
+    # torch restatement, differentiable w.r.t. every title variable
+    P = [torch.tensor(p.astype(np.float64), requires_grad=True) for p in cnn.params()]
+    emb = P[0]
+    tt = torch.tensor(titles)
+    ok = (tt >= 0).double().unsqueeze(-1)
+    xe = emb[tt.clamp(min=0)] * ok                                       # [B, L, E]
+    feats = []
+    for i, w in enumerate(cnn.fs):
+        W, b = P[1 + 2 * i], P[2 + 2 * i]
+        win = xe.unfold(1, w, 1).permute(0, 1, 3, 2)                       # [B, P, w, E]
+        conv = torch.relu(torch.einsum("bpke,kef->bpf", win, W) + b)
+        feats.append(conv.max(1).values)
+    feat = torch.cat(feats, 1)
+    keep = torch.tensor(f["title"]["keep"].astype(np.float64))
+    feat_d = feat / 0.6 * keep
+    t = torch.sigmoid(feat_d @ P[-2] + P[-1])
+    p = torch.tensor(f["dae"]["p"].astype(np.float64))
+    q = t * torch.tensor(f["w_t"].astype(np.float64)) + p * torch.tensor(f["w_p"].astype(np.float64))
+    yt = torch.tensor(f["y"].astype(np.float64))
+    L = -(yt * torch.log(q + 1e-10) + 0.55 * (1 - yt) * torch.log(1 - q + 1e-10)).sum(1)
+    c = L.mean()
+    c.backward()
+    assert abs(float(c) - cost) < 1e-5 * abs(cost)
+    for g, pt in zip(grads, P):
+        ref = pt.grad.numpy()
+        assert np.abs(g - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-6), (g.shape, np.abs(g - ref).max())
+
+
+def test_title_mix_weights_and_padding():
+    TO, dae, cnn, titles, x, xv, y, yv, use = _title_setup()
+    B = titles.shape[0]
+    m = TO.DAETitleOracle(dae, cnn, 0.01)
+    f = m.forward(x, xv, titles, use, B)
+    # titles_use == 0 -> pure DAE score; an all-pad title still produces a finite score
+    for r in range(B):
+        if use[r] == 0 and f["dae"]["s"][r] > 0:
+            np.testing.assert_allclose(f["q"][r], f["dae"]["p"][r], rtol=1e-6)
+    assert np.isfinite(f["q"]).all()
+    xe, ok = cnn.embed(titles)
+    assert np.all(xe[1] == 0) and not ok[1].any()                       # pad id -1 embeds to zeros (SURVEY a9)
+    np.testing.assert_allclose(f["w_t"] + f["w_p"], np.where((use[:, None] + f["dae"]["s"][:, None]) > 0, 1.0, 0.0), atol=1e-6)
+
+
+def test_title_training_lowers_cost():
+    TO, dae, cnn, titles, x, xv, y, yv, use = _title_setup()
+    B = titles.shape[0]
+    m = TO.DAETitleOracle(dae, cnn, 0.02)
+    costs = [m.train_step(x, xv, y, yv, titles, np.ones(B, np.float32), B, 1.0, 1.0, 1.0) for _ in range(15)]
+    assert costs[-1] < costs[0]
