@@ -38,6 +38,9 @@ WORKLOADS = {
     # name: (n_tracks, n_artists, hidden, batch, tied)
     "cfg2": (250000, 40000, 256, 256, False),
     "cfg1": (5000, 1000, 64, 128, True),
+    # secondary lines (not the headline; measured through the host API, H2D inside the timed region):
+    "cfg3": (250000, 40000, 256, 256, False),     # DAE + char-CNN title head train step (--title)
+    "cfg5": (2000000, 0, 256, 4096, False),       # challenge inference: top-500 over a 2M-item decoder, batch 4096
 }
 KP, KP_IN = 0.8, 0.75          # [DAE] keep_prob / input_kp of the shipped configs (0to1_inorder/config.ini:18-19)
 LR = 0.005
@@ -122,6 +125,79 @@ def cpu_reference(wl, steps, warmup):
                       "restated on torch-CPU (TF1 not installable: py3.12, no network)" % (steps, warmup, wl)}
 
 
+def aux_workload(args, wl):
+    """cfg3 (title-mode train step) / cfg5 (challenge inference) through the public host API on one GPU."""
+    import torch
+    from spotify_recsys_challenge_2018_b200.models.DAEs import DAE, DAE_title
+    from spotify_recsys_challenge_2018_b200.models.title_get import get_model
+    from tools.synth_mpd import SynthMPD
+    T, A, H, B, tied = WORKLOADS[wl]
+    N = T + A
+
+    class Conf:
+        pass
+    conf = Conf()
+    conf.save = "/tmp/bench_w"; conf.n_input = N; conf.n_tracks = T; conf.n_output = N; conf.hidden = H
+    conf.lr = LR; conf.reg_lambda = 0.0; conf.initval = "NULL"; conf.DAEval = "NULL"; conf.seed = 0; conf.device = 0
+    conf.charsize = 41; conf.strmaxlen = 25; conf.char_emb = 50; conf.char_model = "Char_CNN"
+    conf.filter_num = 100; conf.filter_size = [3, 5, 7, 9]                    # */config.ini [TITLE]
+    g = SynthMPD(T, max(A, 1), n_clusters=64, seed=180610)
+    rng = np.random.default_rng(7)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if wl == "cfg3":
+        conf.batch = B
+        tm = get_model(conf)
+        m = DAE_title(conf, tm).fit()
+        tm.fit(m)
+        batches = []
+        for i in range(4):
+            trk, art, y, titles, tv, av = g.coo_batch(B, rng)
+            batches.append((np.ascontiguousarray(y), np.ones(len(y), np.float32), np.asarray(titles, np.int64)))
+        run = lambda i: tm.train_step(m, batches[i % 4][0], batches[i % 4][1], batches[i % 4][2], KP, 0.7, 0.01)
+        h2d = int(np.mean([2 * (y.nbytes + v.nbytes) + t.nbytes for y, v, t in batches]))
+        d2h, units, metric = 4, B, "dae_title_train_playlists_per_sec"
+        desc = "cfg3: DAE + char-CNN title head train step (--title), B=%d, %d tracks + %d artists, latent %d, 4x100 filters" % (B, T, A, H)
+        launches = lambda: tm.launch_count() + m.launch_count()
+    else:
+        Bt = 256                                                              # device batch tile; 4096 = 16 calls
+        conf.batch = Bt
+        m = DAE(conf)
+        m.trainable = False
+        m.fit()
+        batches = []
+        for i in range(B // Bt):
+            trk, art, y, titles, tv, av = g.coo_batch(Bt, rng)
+            seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(Bt)]
+            batches.append((np.ascontiguousarray(trk), tv.astype(np.float32), seeds))
+        def run(i):
+            for x, xv, seeds in batches:
+                m.recommend(x, xv, seeds, k=500)
+        h2d = int(sum(x.nbytes + xv.nbytes for x, xv, _ in batches))
+        d2h, units, metric = B * 500 * 4, B, "dae_challenge_topk_playlists_per_sec"
+        desc = "cfg5: challenge inference, top-500 over a %d-item decoder, batch %d (16 device tiles of 256 rows), latent %d, 1 GPU" % (T, B, H)
+        launches = m.launch_count
+    for i in range(max(args.warmup, 3) if wl == "cfg3" else 1):
+        run(i)
+    torch.cuda.synchronize()
+    steps = args.steps if wl == "cfg3" else max(1, min(args.steps, 5))
+    l0 = launches()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    line = {"metric": metric, "value": units * steps / dt, "unit": "playlists/s", "n_gpus": 1, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "note": "secondary line: timed through the host API (H2D + D2H inside)"},
+            "e2e": {"value": units * steps / dt, "unit": "playlists/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches() - l0)}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +240,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    if wl in ("cfg3", "cfg5"):
+        return aux_workload(args, wl) if rank == 0 else 0
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
