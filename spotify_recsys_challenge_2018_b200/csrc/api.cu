@@ -44,13 +44,14 @@ static void layout(dae_model* m) {
     A.off = 0;
     const size_t LH = (size_t)m->n_local * m->H, NH = (size_t)m->N * m->H;
     const int N = m->N, H = m->H, K = m->world * kMaxBpad;
+    const int rows_h = K > m->rows_alloc ? K : m->rows_alloc;            // training: the global batch; inference: batch tiles
     m->flags = A.take<unsigned int>(kMaxWorld);
     m->W_enc = A.take<float>(LH);
     m->b_enc = A.take<float>(H);
     m->b_dec = A.take<float>(N);
     m->W_dec = m->tied ? m->W_enc : A.take<float>(LH);
-    m->shadow[0] = A.take<__nv_bfloat16>(NH);
-    m->shadow[1] = (m->world > 1 && m->trainable) ? A.take<__nv_bfloat16>(NH) : m->shadow[0];
+    m->shadow = A.take<__nv_bfloat16>(LH);                               // this rank's rows of the decoder operand
+    m->shadow_full = m->world > 1 ? A.take<__nv_bfloat16>(NH) : m->shadow;   // all rows, gathered lazily for inference
     if (m->trainable) {
         m->mW_enc = A.take<float>(LH); m->vW_enc = A.take<float>(LH);
         if (m->tied) { m->mW_dec = m->mW_enc; m->vW_dec = m->vW_enc; }
@@ -60,25 +61,26 @@ static void layout(dae_model* m) {
         m->g_dec = A.take<float>(LH);
         m->g_enc = A.take<float>(LH);
         m->touched = A.take<unsigned char>(m->n_local);
-        m->g_b_enc_part = A.take<float>(H); m->g_b_dec_part = A.take<float>(N);
-        if (m->world > 1) { m->g_b_enc = A.take<float>(H); m->g_b_dec = A.take<float>(N); }
-        else { m->g_b_enc = m->g_b_enc_part; m->g_b_dec = m->g_b_dec_part; }
-        m->da = A.take<float>((size_t)m->Bmax * H);
-        m->dzT = A.take<__nv_bfloat16>((size_t)N * kMaxBpad);
-        m->dz_all = m->world > 1 ? A.take<__nv_bfloat16>((size_t)m->n_local * K) : m->dzT;
-        m->nsplit = dh_nsplit(N);
-        m->dh_partial = A.take<float>((size_t)m->nsplit * kMaxBpad * H);
+        m->g_b_enc = A.take<float>(H);
+        m->g_b_dec_sh = A.take<float>(m->n_local);
+        m->g_b_dec = m->world > 1 ? A.take<float>(N) : m->g_b_dec_sh;
+        m->da = A.take<float>((size_t)K * H);
+        m->dz_all = A.take<__nv_bfloat16>((size_t)m->n_local * K);
+        m->nsplit = dh_nsplit(m->n_local, m->world);
+        m->dh_partial = A.take<float>((size_t)m->world * m->nsplit * kMaxBpad * H);
+        m->dh_sum = A.take<float>((size_t)K * H);
         m->n_loss_partial = 148 * 2;
         m->loss_partial = A.take<float>(m->n_loss_partial);
         m->sq_partial = A.take<float>(4 * kSqBlocks);
         m->cost_part = A.take<float>(1);
         m->cost = m->world > 1 ? A.take<float>(1) : m->cost_part;
     }
+    if (m->needs_y) m->ybits = A.take<uint32_t>((size_t)m->n_local * (K / 32));
     m->err = A.take<int>(1);
     m->rowsum = A.take<float>(m->Bmax);
-    m->h = A.take<float>((size_t)m->Bmax * H);
-    m->h_d = A.take<__nv_bfloat16>((size_t)m->rows_alloc * H);
-    m->h_dT = A.take<__nv_bfloat16>((size_t)H * (K > m->rows_alloc ? K : m->rows_alloc));
+    m->h = A.take<float>((size_t)rows_h * H);
+    m->h_d = A.take<__nv_bfloat16>((size_t)rows_h * H);
+    m->h_dT = A.take<__nv_bfloat16>((size_t)H * rows_h);
     m->pub.row_ptr = A.take<int>(m->Bmax);
     m->pub.row_len = A.take<int>(m->Bmax);
     m->pub.col = A.take<int>(m->max_nnz);
@@ -90,7 +92,6 @@ static void layout(dae_model* m) {
         sl.x_val = A.take<float>(m->max_nnz);
         if (m->needs_y) {
             layout_csr(A, &sl.yw, m->Bmax, m->max_nnz);
-            sl.ybits = A.take<uint32_t>((size_t)N * m->ywords);
             sl.y_pos = A.take<long long>((size_t)m->max_nnz * 2);
             sl.y_val = A.take<float>(m->max_nnz);
         }
@@ -98,9 +99,9 @@ static void layout(dae_model* m) {
     A.off = (A.off + 1023) & ~size_t(1023);
 }
 
-enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_DECODE_LOSS, PH_DH, PH_ENCODE_DA, PH_BARRIER, PH_SCATTER, PH_DW, PH_ADAM_DEC,
+enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_YBITS, PH_DECODE_LOSS, PH_DH, PH_DA, PH_BARRIER, PH_SCATTER, PH_DW, PH_ADAM_DEC,
              PH_ADAM_ENC, PH_ADAM_BIAS, PH_COUNT };
-static const char* kPhaseNames[PH_COUNT] = {"prepare_csr_ybits", "encode_fwd", "decode_loss_dz", "dh", "encode_da",
+static const char* kPhaseNames[PH_COUNT] = {"prepare_csr", "encode_fwd", "ybits", "decode_loss_dz", "dh", "da_all",
                                             "barriers", "scatter_dw_enc", "dw_dec", "adam_dec", "adam_enc", "adam_bias"};
 static inline void ph_begin(dae_model* m, int k, cudaStream_t s = nullptr) {
     if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], s ? s : m->st); }
@@ -296,17 +297,21 @@ static int copy_rows(dae_model* m, float* dev_local, float* host, int owner, boo
     return 0;
 }
 
+static void refresh_shadow(dae_model* m) {
+    launch_cast_bf16(m->W_dec, m->shadow, (long long)m->n_local * m->H, m->st);
+    m->full_stale = true;
+    m->launches += 1;
+}
+
 extern "C" int32_t dae_model_init_xavier(dae_model* m, uint64_t seed) {
     if (!m) return fail("null model");
     const float lim = sqrtf(6.0f / (float)(m->N + m->H));
-    launch_xavier_init(m->W_enc, m->n_local, m->tied ? m->shadow[m->cur_shadow] : nullptr, m->N, m->H, lim, seed,
-                       kStreamInit, m->world, m->rank, m->st);
-    if (!m->tied)
-        launch_xavier_init(m->W_dec, m->n_local, m->shadow[m->cur_shadow], m->N, m->H, lim, seed, kStreamInit + 1,
-                           m->world, m->rank, m->st);
+    launch_xavier_init(m->W_enc, m->n_local, m->N, m->H, lim, seed, kStreamInit, m->world, m->rank, m->st);
+    if (!m->tied) launch_xavier_init(m->W_dec, m->n_local, m->N, m->H, lim, seed, kStreamInit + 1, m->world, m->rank, m->st);
     CK(cudaMemsetAsync(m->b_enc, 0, sizeof(float) * m->H, m->st));
     CK(cudaMemsetAsync(m->b_dec, 0, sizeof(float) * m->N, m->st));
-    m->launches += m->tied ? 2 : 3;
+    m->launches += m->tied ? 1 : 2;
+    refresh_shadow(m);
     CK(cudaStreamSynchronize(m->st));
     return 0;
 }
@@ -319,24 +324,7 @@ extern "C" int32_t dae_model_set_params(dae_model* m, const float* W_enc, const 
     if (!m->tied) TRY(copy_rows(m, m->W_dec, const_cast<float*>(W_dec), m->rank, true));
     CK(cudaMemcpyAsync(m->b_enc, b_enc, (size_t)m->H * 4, cudaMemcpyHostToDevice, m->st));
     CK(cudaMemcpyAsync(m->b_dec, b_dec, (size_t)m->N * 4, cudaMemcpyHostToDevice, m->st));
-    // bf16 decoder operand, all N rows: own rows from the master, the other ranks' rows through a scratch block
-    const float* Wd = m->tied ? W_enc : W_dec;
-    launch_cast_rows_bf16(m->W_dec, m->n_local, m->shadow[m->cur_shadow], m->N, m->H, m->world, m->rank, m->st);
-    m->launches += 1;
-    if (m->world > 1) {
-        float* scratch = m->g_enc;
-        bool temp = false;
-        if (!scratch) { CK(cudaMalloc(reinterpret_cast<void**>(&scratch), (size_t)m->n_local * m->H * 4)); temp = true; }
-        for (int r = 0; r < m->world; ++r) {
-            if (r == m->rank) continue;
-            TRY(copy_rows(m, scratch, const_cast<float*>(Wd), r, true));
-            launch_cast_rows_bf16(scratch, m->n_local, m->shadow[m->cur_shadow], m->N, m->H, m->world, r, m->st);
-            m->launches += 1;
-        }
-        if (m->g_enc) CK(cudaMemsetAsync(m->g_enc, 0, (size_t)m->n_local * m->H * 4, m->st));
-        CK(cudaStreamSynchronize(m->st));
-        if (temp) CK(cudaFree(scratch));
-    }
+    refresh_shadow(m);
     CK(cudaStreamSynchronize(m->st));
     return 0;
 }
@@ -381,19 +369,11 @@ static int prepare_slot(dae_model* m, int slot) {
     Slot& s = m->slots[slot];
     CK(cudaStreamWaitEvent(m->st2, s.consumed, 0));       // the previous step on this slot no longer reads it
     ph_begin(m, PH_PREPARE, m->st2);
-    if (s.y_live) {                                        // clear the bits of the batch this slot held before
-        launch_ybits_set(s.yw, s.y_batch, s.ybits, m->ywords, 0, m->err, m->st2);
-        s.y_live = false;
-        m->launches += 1;
-    }
     launch_coo_to_csr(s.x_pos, s.x_val, s.nnz_x, s.batch, m->N, s.xw, m->err, m->st2);
     m->launches += s.nnz_x > 0 ? 4 : 2;
     if (s.has_y) {
         launch_coo_to_csr(s.y_pos, s.y_val, s.nnz_y, s.batch, m->N, s.yw, m->err, m->st2);
-        launch_ybits_set(s.yw, s.batch, s.ybits, m->ywords, 1, m->err, m->st2);
-        s.y_live = true;
-        s.y_batch = s.batch;
-        m->launches += (s.nnz_y > 0 ? 4 : 2) + 1;
+        m->launches += s.nnz_y > 0 ? 4 : 2;
     }
     ph_end(m, PH_PREPARE, m->st2);
     CK(cudaEventRecord(s.prepared, m->st2));
@@ -462,25 +442,35 @@ int check_device_flag(dae_model* m) {
 }
 
 // encode forward from a staged slot (shared by train / predict / recommend)
-void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset,
-                       bool train) {
+void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset, bool train) {
     const Slot& s = m->slots[slot];
     m->cur = slot;
-    cudaStreamWaitEvent(m->st, s.prepared, 0);
     ph_begin(m, PH_ENCODE);
     EncodeArgs e{};
     e.W_enc = m->W_enc; e.b_enc = m->b_enc; e.x = s.xw; e.pub = m->pub; e.rowsum = m->rowsum; e.h = m->h;
     e.h_d = m->h_d; e.h_dT = m->h_dT; e.B = s.batch; e.bpad = rows_pad; e.H = m->H;
-    // training: this rank's h_d^T columns go into every rank's [H, world*bpad] operand of the dW contraction
-    e.hT_bcast = train ? 1 : 0;
+    // training: this rank's rows of h / h_d (and columns of h_d^T) go into every rank's copy of the global batch
+    e.bcast = train ? 1 : 0;
     e.K = train ? m->world * bpad : rows_pad;
-    e.hT_col0 = train ? m->rank * bpad : 0;
+    e.row0 = train ? m->rank * bpad : 0;
     e.kp = kp; e.kp_in = kp_in;
     e.seed = m->cfg.seed; e.step = (unsigned long long)m->step; e.row_offset = row_offset;
     e.pt = m->pt;
     launch_encode_fwd(e, m->st);
     m->launches += 1;
     ph_end(m, PH_ENCODE);
+}
+
+// target bitmask of the global batch over this rank's item rows, from every rank's slot CSR
+void build_ybits(dae_model* m, int slot, int B, int bpad) {
+    const Slot& s = m->slots[slot];
+    YbitsArgs y{};
+    y.y = s.yw; y.ybits = m->ybits; y.n_local = m->n_local; y.ywords = m->world * bpad / 32; y.B = B; y.bpad = bpad;
+    y.err = m->err; y.pt = m->pt;
+    ph_begin(m, PH_YBITS);
+    launch_ybits_shard(y, m->st);
+    ph_end(m, PH_YBITS);
+    m->launches += 1;
 }
 
 static AdamArgs adam_args(dae_model* m) {
@@ -491,10 +481,11 @@ static AdamArgs adam_args(dae_model* m) {
     return a;
 }
 
-// sparse-row dW_enc of the rows this rank owns, from every rank's batch (after barrier B)
-static void run_scatter(dae_model* m, int B) {
+// sparse-row dW_enc of the rows this rank owns, from every rank's batch
+static void run_scatter(dae_model* m, int B, int bpad) {
     ScatterArgs sc{};
-    sc.pub = m->pub; sc.da = m->da; sc.g_enc = m->g_enc; sc.touched = m->touched; sc.B = B; sc.H = m->H; sc.pt = m->pt;
+    sc.pub = m->pub; sc.da = m->da; sc.g_enc = m->g_enc; sc.touched = m->touched; sc.B = B; sc.bpad = bpad; sc.H = m->H;
+    sc.pt = m->pt;
     ph_begin(m, PH_SCATTER);
     launch_scatter_shard(sc, m->st);
     ph_end(m, PH_SCATTER);
@@ -508,6 +499,12 @@ static DwArgs dw_args(dae_model* m, int bpad) {
     return w;
 }
 
+// Forward + backward of one step up to the gradients of the batch side (da, db_enc, db_dec, cost).  Three
+// cross-GPU barriers order the exchanges (none when world == 1):
+//   A  the previous step is over on every rank (its Adam wrote W_enc rows this step gathers; nobody still reads the
+//      h / pub / dh_sum buffers this step overwrites) and every rank's slot CSR is prepared
+//   B1 every rank's rows of h_d / h_d^T / h have landed  -> decode, dh over the global batch
+//   B2 every rank's dh sums, db_dec rows and cost partial are complete -> da for the global batch
 extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob,
                                              int32_t global_batch, int32_t row_offset) {
     if (!m || !m->trainable) return fail("model is not trainable");
@@ -516,45 +513,40 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     const Slot& s = m->slots[slot];
     if (s.batch <= 0) return fail("slot %d holds no batch", slot);
     if (!(keep_prob > 0.f) || !(input_keep_prob > 0.f)) return fail("keep probabilities must be > 0");
-    const int B = s.batch, bpad = round_up(B, 64), H = m->H, N = m->N;
+    const int B = s.batch, bpad = round_up(B, 64), H = m->H, N = m->N, R = m->world;
     if (bpad > kMaxBpad) return fail("training batch %d exceeds %d", B, kMaxBpad);
     // the loss is a mean over the GLOBAL batch (DAEs.py:100); dropout is keyed by the global row
-    const int gb = global_batch > 0 ? global_batch : B * m->world;
+    const int gb = global_batch > 0 ? global_batch : B * R;
     if (global_batch <= 0) row_offset = m->rank * B;
     m->last_batch = B; m->last_bpad = bpad;
     if (!s.has_y) return fail("slot %d was staged without targets", slot);
 
-    // barrier A: every rank has finished the previous step (its Adam wrote W_enc rows and the operand
-    // copy this step reads; it no longer reads dz_all / h_dT / da / pub that this step overwrites)
+    CK(cudaStreamWaitEvent(m->st, s.prepared, 0));
     ph_begin(m, PH_BARRIER);
-    barrier(m);
+    barrier(m);                                                               // A
     ph_end(m, PH_BARRIER);
     run_encode(m, slot, bpad, bpad, keep_prob, input_keep_prob, row_offset, true);
+    build_ybits(m, slot, B, bpad);
+    barrier(m);                                                               // B1
+    CK(cudaEventRecord(s.consumed, m->st));                 // every rank has read this slot: it may be re-prepared
 
     DecodeArgs d{};
-    d.W = m->shadow[m->cur_shadow]; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
-    d.ybits = s.ybits; d.ywords = m->ywords; d.dzT = m->dzT; d.dz_all = m->dz_all; d.K = m->world * bpad; d.pt = m->pt;
-    d.db_dec = m->g_b_dec_part;
+    d.W = m->shadow; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
+    d.n_batch_tiles = R; d.n_local = m->n_local; d.pt = m->pt;
+    d.ybits = m->ybits; d.ywords = R * bpad / 32; d.dzT = m->dz_all;
+    d.db_dec = m->g_b_dec_sh;
     d.loss_partial = m->loss_partial; d.inv_batch = 1.0f / (float)gb;
-    const int ngrid = decode_grid(N, 1);
     ph_begin(m, PH_DECODE_LOSS);
     launch_decode_train(d, m->st);
-    CK(cudaEventRecord(s.consumed, m->st));                 // the slot may be re-prepared from here on
     ph_end(m, PH_DECODE_LOSS);
 
-    DhArgs q{}; q.dzT = m->dzT; q.W = m->shadow[m->cur_shadow]; q.partial = m->dh_partial; q.N = N; q.H = H; q.bpad = bpad;
-    q.nsplit = m->nsplit;
+    DhArgs q{}; q.dzT = m->dz_all; q.W = m->shadow; q.partial = m->dh_partial; q.N = m->n_local; q.H = H; q.bpad = bpad;
+    q.nsplit = m->nsplit; q.n_batch_tiles = R; q.ld_dz = R * bpad;
     ph_begin(m, PH_DH);
     launch_dh(q, m->st);
+    launch_reduce_splits(m->dh_partial, m->nsplit, bpad, H, R, m->dh_sum, m->st);
     ph_end(m, PH_DH);
-
-    EncodeDaArgs eb{};
-    eb.dh_partial = m->dh_partial; eb.nsplit = m->nsplit; eb.h = m->h; eb.da = m->da; eb.db_enc = m->g_b_enc_part;
-    eb.B = B; eb.bpad = bpad; eb.H = H;
-    eb.kp = keep_prob; eb.seed = m->cfg.seed; eb.step = (unsigned long long)m->step; eb.row_offset = row_offset;
-    ph_begin(m, PH_ENCODE_DA);
-    launch_encode_da(eb, m->st);
-    m->launches += 2 + 1 + 2;
+    m->launches += 3 + 2;
 
     int n_sq = 0;
     const float lam = m->cfg.reg_lambda;
@@ -570,48 +562,54 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
             m->launches += 2;
         }
     }
-    launch_reduce_loss2(m->loss_partial, ngrid, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost_part, m->st);
+    launch_reduce_loss2(m->loss_partial, m->n_loss_partial, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost_part, m->st);
     m->launches += 1;
-    ph_end(m, PH_ENCODE_DA);
 
-    if (m->debug & 3) {    // parity tests: materialise the raw dW_dec / scatter dW_enc now, where they can be inspected
-        barrier(m);
-        if (m->debug & 1) {
-            DwArgs w = dw_args(m, bpad);
-            w.g = m->g_dec;
-            launch_dw(w, m->st);
-            m->launches += 1;
-        }
-        if (m->debug & 2) {
-            run_scatter(m, B);
-            m->scatter_done = true;
-        }
+    ph_begin(m, PH_BARRIER);
+    barrier(m);                                                               // B2
+    ph_end(m, PH_BARRIER);
+    DaArgs da{};
+    da.dh_sum = m->dh_sum; da.h = m->h; da.da = m->da; da.db_enc = m->g_b_enc; da.B = B; da.bpad = bpad; da.H = H;
+    da.kp = keep_prob; da.seed = m->cfg.seed; da.step = (unsigned long long)m->step; da.pt = m->pt;
+    ph_begin(m, PH_DA);
+    launch_da_all(da, m->st);
+    m->launches += 2;
+    if (R > 1) {   // db_dec rows from their owners; the cost is the rank-ordered sum of every rank's partial
+        launch_gather_items_f32(m->g_b_dec_sh, m->g_b_dec, N, m->pt, m->st);
+        launch_sum_partials(m->cost_part, m->cost, 1, m->pt, m->st);
+        m->launches += 2;
+    }
+    ph_end(m, PH_DA);
+
+    if (m->debug & 1) {    // parity tests: form dW_dec / dW_enc now, where they can be inspected before Adam consumes them
+        DwArgs w = dw_args(m, bpad);
+        w.g = m->g_dec;
+        launch_dw(w, m->st);
+        m->launches += 1;
+    }
+    if (m->debug & 2) {
+        run_scatter(m, B, bpad);
+        m->scatter_done = true;
     }
     return 0;
 }
 
+// dW_dec = dz^T h_d and the sparse-row dW_enc of the rows this rank owns, then the dense TF1 Adam update of every
+// variable.  Purely local: no cross-GPU traffic except the (tiny) reads of the peers' published sparse inputs.
 extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (!m || !m->trainable) return fail("model is not trainable");
     if (m->last_bpad <= 0) return fail("no gradients: call dae_model_backward_staged first");
     const int H = m->H, N = m->N, B = m->last_batch, bpad = m->last_bpad;
     AdamArgs a = adam_args(m);
-    // barrier B: every rank's dz tiles, h_d columns, da, published input and bias partials have landed
-    ph_begin(m, PH_BARRIER);
-    barrier(m);
-    ph_end(m, PH_BARRIER);
-
-    if (!m->scatter_done) run_scatter(m, B);
+    if (!m->scatter_done) run_scatter(m, B, bpad);
     m->scatter_done = false;
 
-    // decoder (or the tied matrix) rows this rank owns: dW_dec = dz^T h_d over every rank's batch columns, then the
-    // dense TF1 Adam update; the new bf16 operand rows are stored into every rank's copy (NVLink)
-    const int next_shadow = m->world > 1 ? (m->cur_shadow ^ 1) : m->cur_shadow;
     DwArgs w = dw_args(m, bpad);
     if (m->debug & 4) {   // experimental: Adam inside the dW epilogue, the gradient never leaves tensor memory
         w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
         w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
         w.adam = AdamConst{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
-        w.shadow = m->shadow[next_shadow];
+        w.shadow = m->shadow;
         ph_begin(m, PH_DW);
         launch_dw(w, m->st);
         ph_end(m, PH_DW);
@@ -624,16 +622,17 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
         a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.row_touched = m->tied ? m->touched : nullptr;
         a.n = (long long)m->n_local * H; a.row_len = H;
         ph_begin(m, PH_ADAM_DEC);
-        launch_adam_rows(a, m->tied ? m->g_enc : nullptr, m->shadow[next_shadow], N, m->pt, m->st);
+        launch_adam_rows(a, m->tied ? m->g_enc : nullptr, m->shadow, m->st);
         ph_end(m, PH_ADAM_DEC);
         m->launches += 2;
     }
+    m->full_stale = true;
 
     ph_begin(m, PH_ADAM_ENC);
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
         a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
         a.n = (long long)m->n_local * H; a.row_len = H;
-        launch_adam_rows(a, m->g_enc, nullptr, N, m->pt, m->st);
+        launch_adam_rows(a, m->g_enc, nullptr, m->st);
         m->launches += 1;
     }
     launch_clear_flagged(m->n_local, H, m->g_enc, m->touched, m->st);
@@ -641,12 +640,6 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     ph_end(m, PH_ADAM_ENC);
 
     ph_begin(m, PH_ADAM_BIAS);
-    if (m->world > 1) {   // bias gradients and the cost: every rank sums all partials in rank order -> identical replicas
-        launch_sum_partials(m->g_b_enc_part, m->g_b_enc, H, m->pt, m->st);
-        launch_sum_partials(m->g_b_dec_part, m->g_b_dec, N, m->pt, m->st);
-        launch_sum_partials(m->cost_part, m->cost, 1, m->pt, m->st);
-        m->launches += 3;
-    }
     a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
     a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = H;
     launch_adam(a, m->st);
@@ -655,7 +648,6 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     m->launches += 2 + (N % 4 ? 1 : 0);
     ph_end(m, PH_ADAM_BIAS);
     ph_collect(m);
-    m->cur_shadow = next_shadow;
     m->b1_pow *= kBeta1;
     m->b2_pow *= kBeta2;
     m->step += 1;
@@ -707,10 +699,16 @@ static int run_predict(dae_model* m, int slot, int n_cols, float* out_dev, long 
     if (B <= kMaxBpad) { bpad = round_up(B, 64); nbt = 1; }
     else { bpad = kMaxBpad; nbt = (B + kMaxBpad - 1) / kMaxBpad; }
     if (!m->attached) return fail("world = %d but the peers are not attached (dae_model_attach_ipc)", m->world);
+    if (m->world > 1 && m->full_stale) {   // inference scores every item: gather the operand rows from their owners
+        launch_gather_rows_bf16(m->shadow, m->shadow_full, m->N, m->H, m->pt, m->st);   // (all ranks idle: caller's contract)
+        m->launches += 1;
+    }
+    m->full_stale = false;
+    CK(cudaStreamWaitEvent(m->st, s.prepared, 0));
     run_encode(m, slot, bpad, bpad * nbt, 1.0f, 1.0f, 0, false); // keep_prob = input_keep_prob = 1 (main_train.py:68)
     CK(cudaEventRecord(s.consumed, m->st));
     DecodeArgs d{};
-    d.W = m->shadow[m->cur_shadow]; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
+    d.W = m->shadow_full; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
     d.n_batch_tiles = nbt; d.out = out_dev; d.ld_out = ld; d.n_out = n_cols;
     launch_decode_predict(d, m->st);
     m->launches += 1;
@@ -779,20 +777,22 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
     const int64_t NH = (int64_t)m->N * m->H, LH = (int64_t)m->n_local * m->H;
     const Slot& sl = m->slots[m->cur];
     struct E { const char* n; void* p; int64_t c; int32_t s; };
+    const int64_t KH = (int64_t)m->world * kMaxBpad * m->H;
     const E table[] = {
         {"g_dec", m->g_dec, LH, 4}, {"g_enc", m->g_enc, LH, 4}, {"g_b_enc", m->g_b_enc, m->H, 4},
-        {"g_b_dec", m->g_b_dec, m->N, 4}, {"g_b_enc_part", m->g_b_enc_part, m->H, 4},
-        {"g_b_dec_part", m->g_b_dec_part, m->N, 4}, {"touched", m->touched, m->n_local, 1}, {"cost", m->cost, 1, 4},
-        {"W_enc", m->W_enc, LH, 4}, {"W_dec", m->W_dec, LH, 4}, {"W_dec_bf16", m->shadow[m->cur_shadow], NH, 2},
+        {"g_b_dec", m->g_b_dec, m->N, 4}, {"g_b_dec_sh", m->g_b_dec_sh, m->n_local, 4},
+        {"touched", m->touched, m->n_local, 1}, {"cost", m->cost, 1, 4},
+        {"W_enc", m->W_enc, LH, 4}, {"W_dec", m->W_dec, LH, 4}, {"W_dec_bf16", m->shadow, LH, 2},
+        {"W_dec_bf16_full", m->shadow_full, NH, 2},
         {"b_enc", m->b_enc, m->H, 4}, {"b_dec", m->b_dec, m->N, 4},
-        {"h", m->h, (int64_t)m->Bmax * m->H, 4}, {"h_d", m->h_d, (int64_t)m->rows_alloc * m->H, 2},
-        {"h_dT", m->h_dT, (int64_t)m->H * m->world * kMaxBpad, 2},
-        {"dzT", m->dzT, (int64_t)m->N * kMaxBpad, 2}, {"dz_all", m->dz_all, (int64_t)m->n_local * m->world * kMaxBpad, 2},
-        {"dh_partial", m->dh_partial, (int64_t)m->nsplit * kMaxBpad * m->H, 4}, {"da", m->da, (int64_t)m->Bmax * m->H, 4},
+        {"h", m->h, KH, 4}, {"h_d", m->h_d, KH, 2}, {"h_dT", m->h_dT, KH, 2},
+        {"dzT", m->dz_all, (int64_t)m->n_local * m->world * kMaxBpad, 2},
+        {"dh_partial", m->dh_partial, (int64_t)m->world * m->nsplit * kMaxBpad * m->H, 4}, {"dh_sum", m->dh_sum, KH, 4},
+        {"da", m->da, KH, 4},
         {"x_row_ptr", sl.xw.row_ptr, m->Bmax + 1, 4}, {"x_row_len", sl.xw.row_len, m->Bmax, 4},
         {"x_col", sl.xw.col, m->max_nnz, 4}, {"x_val", m->pub.xn, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
         {"y_row_ptr", sl.yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", sl.yw.row_len, m->Bmax, 4},
-        {"y_col", sl.yw.col, m->max_nnz, 4}, {"ybits", sl.ybits, (int64_t)m->N * m->ywords, 4},
+        {"y_col", sl.yw.col, m->max_nnz, 4}, {"ybits", m->ybits, (int64_t)m->n_local * m->world * (kMaxBpad / 32), 4},
         {"scores", m->scores, (int64_t)m->scores_elems, 4},
         {"mW_dec", m->mW_dec, LH, 4}, {"vW_dec", m->vW_dec, LH, 4}, {"mW_enc", m->mW_enc, LH, 4}, {"vW_enc", m->vW_enc, LH, 4},
     };
@@ -880,7 +880,7 @@ extern "C" int32_t dae_coo_to_csr_device(const int64_t* pos_dev, const float* va
     return 0;
 }
 
-extern "C" int32_t dae_dh_nsplit(int32_t n_items) { return dh_nsplit(n_items); }
+extern "C" int32_t dae_dh_nsplit(int32_t n_items) { return dh_nsplit(n_items, 1); }
 
 extern "C" int32_t dae_gemm_test_device(int32_t op, const uint16_t* a_dev, const uint16_t* b_dev,
                                         const float* bias_dev, float* out_dev, int32_t n_items, int32_t n_hidden,
@@ -903,7 +903,7 @@ extern "C" int32_t dae_gemm_test_device(int32_t op, const uint16_t* a_dev, const
         launch_dw(w, st);
     } else if (op == 2) {
         DhArgs q{}; q.dzT = A; q.W = Bm; q.partial = out_dev; q.N = n_items; q.H = n_hidden; q.bpad = bpad;
-        q.nsplit = dh_nsplit(n_items); q.lbo = lbo; q.sbo = sbo;
+        q.nsplit = dh_nsplit(n_items, 1); q.lbo = lbo; q.sbo = sbo;
         if (nsplit_out) *nsplit_out = q.nsplit;
         launch_dh(q, st);
     } else {

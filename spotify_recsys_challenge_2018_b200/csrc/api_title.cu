@@ -203,7 +203,9 @@ static int title_forward(dae_title* t, const int64_t* x_pos, const float* x_val,
     CK(cudaMemcpyAsync(t->titles_use, t->h_titles_use, sizeof(float) * batch, cudaMemcpyHostToDevice, t->st));
     const int bpad = round_up(batch, 64);
     m->step = t->step;                                    // dropout masks are keyed by the title model's step
+    CK(cudaStreamWaitEvent(t->st, m->slots[0].prepared, 0));
     run_encode(m, 0, bpad, bpad, kp, kp_in, 0, false);
+    if (with_y) build_ybits(m, 0, batch, bpad);
     CnnFwdArgs c{};
     c.titles = t->titles; c.emb = t->emb; c.conv_W = t->conv_W; c.conv_b = t->conv_b; c.shape = s;
     c.feat = t->feat; c.argpos = t->argpos; c.feat_d = t->feat_d; c.feat_dT = t->feat_dT; c.B = batch; c.bpad = bpad;
@@ -218,7 +220,7 @@ static int title_forward(dae_title* t, const int64_t* x_pos, const float* x_val,
 static TitleTileArgs tile_args(dae_title* t, int batch) {
     dae_model* m = t->dae;
     TitleTileArgs a{};
-    a.W_dec = m->shadow[m->cur_shadow]; a.h_d = m->h_d; a.b_dec = m->b_dec;
+    a.W_dec = m->shadow_full; a.h_d = m->h_d; a.b_dec = m->b_dec;
     a.W_out = t->W_out_bf16; a.feat_d = t->feat_d; a.b_out = t->b_out; a.w_t = t->w_t; a.w_p = t->w_p;
     a.N = t->N; a.H = t->H; a.batch = batch; a.bpad = round_up(batch, 64); a.kf = (t->D + 63) / 64;
     return a;
@@ -237,7 +239,7 @@ extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, cons
     const int bpad = round_up(batch, 64), N = t->N;
     const Slot& sl = m->slots[0];
     TitleTileArgs a = tile_args(t, batch);
-    a.ybits = sl.ybits; a.ywords = m->ywords; a.dzT = t->dzT; a.db_out = t->g_b_out; a.loss_partial = t->loss_partial;
+    a.ybits = m->ybits; a.ywords = bpad / 32; a.dzT = t->dzT; a.db_out = t->g_b_out; a.loss_partial = t->loss_partial;
     a.inv_batch = 1.0f / (float)batch;
     launch_title_train(a, t->st);
     CK(cudaEventRecord(sl.consumed, t->st));
@@ -271,8 +273,7 @@ extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, cons
     ad.row_touched = nullptr; ad.w_bf16 = nullptr;
     ad.w = t->W_out; ad.m = t->m_W_out; ad.v = t->v_W_out; ad.g = t->g_W_out; ad.n = (long long)N * kTitleFpad;
     ad.row_len = kTitleFpad;
-    PeerTable one{}; one.world = 1; one.rank = 0;
-    launch_adam_rows(ad, nullptr, t->W_out_bf16, N, one, t->st);
+    launch_adam_rows(ad, nullptr, t->W_out_bf16, t->st);
     ad.row_len = 1;
     const CnnShape& s = t->shape;
     ad.w = t->b_out; ad.m = t->m_b_out; ad.v = t->v_b_out; ad.g = t->g_b_out; ad.n = N; launch_adam(ad, t->st);

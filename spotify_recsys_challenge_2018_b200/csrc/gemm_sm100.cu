@@ -29,14 +29,12 @@ namespace dae {
 // ------------------------------------------------------------------------------------------
 // G1 / G2: item-tile kernels
 // ------------------------------------------------------------------------------------------
-enum { MODE_TRAIN = 0, MODE_PREDICT = 1, MODE_DW = 2 };
+enum { MODE_TRAIN = 0, MODE_PREDICT = 1 };
 
 constexpr int kStages = 6;
-constexpr int kStagesStreamB = 4;                    // stages of (16 KB item chunk + 32 KB second-operand chunk)
-// Epilogue warps per CTA (a multiple of 4: warp w may only read TMEM lanes [32*(w%4), +32), so the warps of one
-// lane quadrant split the accumulator columns).  The compute-bound G1 epilogues run 8 warps of up to 140 registers;
-// the fused dW + Adam epilogue is pure HBM streaming and needs bytes in flight, so it runs 16 leaner warps.
-template <int MODE> struct EpiCfg { static constexpr int kWarps = MODE == 2 ? 16 : 8; static constexpr int kThreads = 64 + 32 * kWarps; };
+constexpr int kStagesStreamB = 4;                    // G2, K > 256: stages of (16 KB item chunk + 32 KB second-operand chunk)
+constexpr int kEpiWarps = 8;                         // 2 warps per TMEM lane quadrant: each takes half the columns
+constexpr int kItemThreads = 64 + 32 * kEpiWarps;
 constexpr int kABytes = kTileItems * 128;           // one K-chunk of the streamed operand: 128 rows x 128 B
 constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the resident operand: <=256 rows x 128 B
 constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
@@ -45,12 +43,13 @@ constexpr int kSmemBars = 256;
 constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + 1024;  // + alignment slack
 
 struct ItemTileDev {
-    int n_items;      // valid rows of the streamed operand
-    int tiles;        // ceil(n_items / 128)
-    int kchunks;      // K / 64
-    int n_cols;       // UMMA N: rows of the resident operand (bpad for G1, H for G2)
-    int batch;        // valid batch rows (G1)
-    int b_rows_box;   // rows per resident-operand box
+    int n_rows;       // rows of the streamed operand (TRAIN: this rank's item rows; PREDICT: catalogue columns kept)
+    int n_global;     // catalogue size
+    int tiles;        // 128-row tiles to process
+    int kchunks;      // H / 64
+    int n_cols;       // UMMA N: rows of one batch tile
+    int batch;        // valid rows per batch tile
+    int world, rank;  // TRAIN: local row -> catalogue id (tile-cyclic ownership)
     const float* bias;
     const uint32_t* ybits;
     int ywords;
@@ -65,23 +64,12 @@ struct ItemTileDev {
     const float* mix_wp;
     const float* mix_wt;
     const float* title_score;
-    float* g;         // G2 raw output [n_items, n_cols] (nullptr: not materialised)
-    // G2: B operand streamed with A (K > 256) and the fused Adam epilogue
-    int stream_b;
-    float* aw; float* am; float* av;
-    const float* g_extra;
-    const unsigned char* touched;
-    AdamConst adam;
-    __nv_bfloat16* shadow;   // [n_global, n_cols] refreshed on every rank
-    int n_global;            // catalogue size: bounds the last tile of G2 (local tiles map to global tiles cyclically)
-    // data-parallel: G1 also delivers each item tile's dz to the tile's owner (columns [dz_col0, +bpad) of its [rows, ld_all])
-    __nv_bfloat16* dz_all;
-    int ld_all, dz_col0;
-    PeerTable pt;
 };
 
+// blockIdx.y = batch tile: TRAIN decodes this rank's item rows against every rank's rows of the global batch
+// (tile bt = rank bt's playlists), PREDICT tiles an inference batch of more than 256 rows.
 template <int MODE>
-__global__ void __launch_bounds__(EpiCfg<MODE>::kThreads, 1)
+__global__ void __launch_bounds__(kItemThreads, 1)
 k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ItemTileDev p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -96,16 +84,10 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
-    constexpr int kEpiWarps = EpiCfg<MODE>::kWarps;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int bt = blockIdx.y;  // batch tile (PREDICT only; 0 otherwise)
-    // G2 with K > 256 (data-parallel: K = ranks x batch tile): the second operand no longer fits in shared
-    // memory, so its K-chunk rides in the same ring stage as the item tile's (it comes from L2).
-    const bool sb = (MODE == MODE_DW) && p.stream_b != 0;
-    const int nstages = sb ? kStagesStreamB : kStages;
-    const uint32_t stage_bytes = sb ? (kABytes + kBChunkBytes) : kABytes;
+    const int bt = blockIdx.y;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -132,23 +114,19 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (lane == 0) {
             const uint64_t pol_stream = policy_evict_first();
             const uint64_t pol_keep = policy_evict_last();
-            if (!sb) {
-                mbar_expect_tx(bfull, static_cast<uint32_t>(p.kchunks * p.b_rows_box * 128));
-                for (int kc = 0; kc < p.kchunks; ++kc)
-                    tma_load_2d_hint(sB + kc * kBChunkBytes, &tmB, bfull, kc * 64, bt * p.b_rows_box, pol_keep);
-            }
-            uint8_t* ring = sb ? smem : sA;
-            const uint32_t tx = sb ? static_cast<uint32_t>(kABytes + p.b_rows_box * 128) : static_cast<uint32_t>(kABytes);
+            mbar_expect_tx(bfull, static_cast<uint32_t>(p.kchunks * p.n_cols * 128));
+            for (int kc = 0; kc < p.kchunks; ++kc)
+                tma_load_2d_hint(sB + kc * kBChunkBytes, &tmB, bfull, kc * 64, bt * p.n_cols, pol_keep);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1u);
-                    mbar_expect_tx(&full[stage], tx);
-                    tma_load_2d_hint(ring + stage * stage_bytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
-                                     pol_stream);
-                    if (sb) tma_load_2d_hint(ring + stage * stage_bytes + kABytes, &tmB, &full[stage], kc * 64, 0, pol_keep);
-                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                    mbar_expect_tx(&full[stage], kABytes);
+                    // several batch tiles re-read the same item tile: keep it in L2 then, stream it otherwise
+                    tma_load_2d_hint(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
+                                     gridDim.y > 1 ? pol_keep : pol_stream);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -156,11 +134,8 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kTileItems, static_cast<uint32_t>(p.n_cols), 0, 0);
-            if (!sb) {
-                mbar_wait(bfull, 0);
-                tc_fence_after();
-            }
-            uint8_t* ring = sb ? smem : sA;
+            mbar_wait(bfull, 0);
+            tc_fence_after();
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -172,8 +147,8 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ring + stage * stage_bytes);
-                    const uint32_t b_addr = sb ? a_addr + kABytes : smem_u32(sB + kc * kBChunkBytes);
+                    const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+                    const uint32_t b_addr = smem_u32(sB + kc * kBChunkBytes);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t ad = umma_smem_desc(a_addr + ks * 32, 16, 1024);
@@ -181,7 +156,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);
                 acc ^= 1;
@@ -191,90 +166,35 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;          // which share of the accumulator columns this warp owns
+        const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp owns
         const int row_in_tile = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
         float loss_acc = 0.f;
-        constexpr int kParts = kEpiWarps / 4;
         const int nchunks = p.n_cols >> 5;
-        const int c_lo = half * (nchunks / kParts), c_hi = c_lo + (nchunks / kParts);   // 32-column chunks (G1)
+        const int c_lo = half * (nchunks >> 1), c_hi = c_lo + (nchunks >> 1);
+        const int yword0 = bt * (p.n_cols >> 5);   // this batch tile's words inside a row of the target bitmask
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-            const int item = tile * kTileItems + row_in_tile;   // row of the streamed operand
-            const int gitem = MODE == MODE_DW ? item_global(item, p.pt.world, p.pt.rank) : item;   // catalogue id
-            const bool item_ok = MODE == MODE_DW ? gitem < p.n_global : item < p.n_items;
+            const int row = tile * kTileItems + row_in_tile;                                   // row of the streamed operand
+            const int item = MODE == MODE_TRAIN ? item_global(row, p.world, p.rank) : row;     // catalogue id
+            const bool item_ok = row < p.n_rows && item < p.n_global;
             float bz = 0.f;
             uint32_t yw_next = 0;
             const uint32_t* yrow = nullptr;
-            if (MODE != MODE_DW) {
-                if (item_ok) bz = __ldg(p.bias + item);
-            }
+            if (item_ok) bz = __ldg(p.bias + item);
             if (MODE == MODE_TRAIN) {
                 if (item_ok) {
-                    yrow = p.ybits + (size_t)item * p.ywords;
+                    yrow = p.ybits + (size_t)row * p.ywords + yword0;
                     yw_next = __ldg(yrow + c_lo);
                 }
             }
             float db = 0.f;
-            bool row_extra = false;
-            if (MODE == MODE_DW) row_extra = item_ok && p.g_extra != nullptr && p.touched[item] != 0;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
-            if (MODE == MODE_DW) {
-                // G2 epilogue: this warp owns n_cols / kParts columns of its 32 item rows, 16 columns (64 B) at a time
-                const int cols_per = p.n_cols / kParts;
-                const int col0 = half * cols_per;
 #pragma unroll 1
-                for (int cc = col0; cc < col0 + cols_per; cc += 16) {
-                    uint32_t r[16];
-                    __syncwarp();                                                        // tcgen05.ld is warp-collective
-                    tmem_ld16(t_addr + cc, r);
-                    tmem_ld_wait();
-                    const size_t off = (size_t)item * p.n_cols + cc;
-                    if (item_ok && p.g != nullptr) {
-                        st_global_v8(p.g + off, r);
-                        st_global_v8(p.g + off + 8, r + 8);
-                    }
-                    if (item_ok && p.aw != nullptr) {
-                    // dense TF1 Adam on the 16 gradient values this thread just read from TMEM: the gradient
-                    // never goes to HBM (26 B / parameter instead of 34)
-                    uint32_t wv[16], mv[16], vv[16];
-                    ld_global_cs_v8(p.aw + off, wv); ld_global_cs_v8(p.aw + off + 8, wv + 8);
-                    ld_global_cs_v8(p.am + off, mv); ld_global_cs_v8(p.am + off + 8, mv + 8);
-                    ld_global_cs_v8(p.av + off, vv); ld_global_cs_v8(p.av + off + 8, vv + 8);
-                    if (row_extra) {                                                     // tied: + sparse-row dW_enc
-                        uint32_t ge[16];
-                        ld_global_cs_v8(p.g_extra + off, ge); ld_global_cs_v8(p.g_extra + off + 8, ge + 8);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(ge[j])));
-                    }
-                    uint32_t packed[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        float w0 = __uint_as_float(wv[j]), m0 = __uint_as_float(mv[j]), v0 = __uint_as_float(vv[j]);
-                        float w1 = __uint_as_float(wv[j + 1]), m1 = __uint_as_float(mv[j + 1]), v1 = __uint_as_float(vv[j + 1]);
-                        adam_one(w0, m0, v0, __uint_as_float(r[j]), p.adam);
-                        adam_one(w1, m1, v1, __uint_as_float(r[j + 1]), p.adam);
-                        wv[j] = __float_as_uint(w0); mv[j] = __float_as_uint(m0); vv[j] = __float_as_uint(v0);
-                        wv[j + 1] = __float_as_uint(w1); mv[j + 1] = __float_as_uint(m1); vv[j + 1] = __float_as_uint(v1);
-                        packed[j >> 1] = pack_bf16x2(w0, w1);
-                    }
-                    st_global_cs_v8(p.aw + off, wv); st_global_cs_v8(p.aw + off + 8, wv + 8);
-                    st_global_cs_v8(p.am + off, mv); st_global_cs_v8(p.am + off + 8, mv + 8);
-                    st_global_cs_v8(p.av + off, vv); st_global_cs_v8(p.av + off + 8, vv + 8);
-                    if (p.shadow != nullptr) {
-                        const size_t goff = (size_t)gitem * p.n_cols + cc;
-                        for (int sidx = 0; sidx < p.pt.world; ++sidx)                    // this GPU's operand copy and every peer's
-                            st_global_v8(peer_ptr(p.pt, sidx, p.shadow) + goff, packed);
-                    }
-                    }
-                }
-            }
-#pragma unroll 1
-            for (int c = c_lo; MODE != MODE_DW && c < c_hi; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t r[32];
                 tmem_ld32(t_addr + c * 32, r);
                 tmem_ld_wait();
@@ -309,24 +229,18 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
                     }
                     if (item_ok) {
-                        __nv_bfloat16* dst = p.dzT + (size_t)item * p.ld_dz + c * 32;   // 64 B: two full 32 B sectors
+                        __nv_bfloat16* dst = p.dzT + (size_t)row * p.ld_dz + bt * p.n_cols + c * 32;   // 64 B: two full sectors
                         st_global_v8(dst, packed);
                         st_global_v8(dst + 16, packed + 8);
-                        if (p.dz_all != nullptr) {       // the tile's owner contracts it with every rank's h_d (NVLink store)
-                            __nv_bfloat16* rdst = peer_ptr(p.pt, tile % p.pt.world, p.dz_all) +
-                                                  (size_t)item_local(item, p.pt.world) * p.ld_all + p.dz_col0 + c * 32;
-                            st_global_v8(rdst, packed);
-                            st_global_v8(rdst + 16, packed + 8);
-                        }
                     }
-                } else if (MODE == MODE_PREDICT) {
+                } else {
                     const bool col_ok = item < p.n_out;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int b = bt * p.b_rows_box + c * 32 + j;
+                        const int b = bt * p.n_cols + c * 32 + j;
                         const float z = __uint_as_float(r[j]) + bz;
                         float pr = __fdividef(1.f, 1.f + __expf(-z));
-                        if (b < p.batch && col_ok) {
+                        if (b < p.batch && col_ok && item_ok) {
                             const size_t o = (size_t)b * p.ld_out + item;
                             if (p.mix_wp != nullptr) {
                                 const float ts = p.title_score ? __ldg(p.title_score + o) : 0.f;
@@ -338,7 +252,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
             if (MODE == MODE_TRAIN) {
-                if (item_ok) atomicAdd(p.db_dec + item, db);   // two addends per item (one per column half): order-independent
+                if (item_ok) atomicAdd(p.db_dec + row, db);   // 2 column halves x batch tiles addends per item
             }
             tc_fence_before();
             __syncwarp();
@@ -360,7 +274,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (threadIdx.x == 0) {
             float t = 0.f;
             for (int i = 0; i < kEpiWarps; ++i) t += loss_smem[i];
-            p.loss_partial[blockIdx.x] = t;
+            p.loss_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
         }
     }
     if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -386,60 +300,54 @@ int decode_grid(int N, int n_batch_tiles) {
 template <int MODE>
 static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, const ItemTileDev& p, dim3 grid,
                             cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_itemtile<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
-        configured = true;
-    }
-    k_itemtile<MODE><<<grid, EpiCfg<MODE>::kThreads, kSmemItemTile, st>>>(tmA, tmB, p);
-}
-
-static ItemTileDev decode_dev(const DecodeArgs& a) {
-    ItemTileDev p{};
-    p.n_items = a.N;
-    p.tiles = (a.N + kTileItems - 1) / kTileItems;
-    p.kchunks = a.H / 64;
-    p.n_cols = a.bpad;
-    p.batch = a.batch;
-    p.b_rows_box = a.bpad;
-    p.bias = a.bias;
-    p.ybits = a.ybits;
-    p.ywords = a.ywords;
-    p.dzT = a.dzT;
-    p.ld_dz = a.bpad;
-    p.db_dec = a.db_dec;
-    p.loss_partial = a.loss_partial;
-    p.inv_batch = a.inv_batch;
-    p.out = a.out;
-    p.ld_out = a.ld_out;
-    p.n_out = a.n_out;
-    p.mix_wp = a.mix_wp;
-    p.mix_wt = a.mix_wt;
-    p.title_score = a.title_score;
-    p.pt = a.pt;
-    if (p.pt.world < 1) p.pt.world = 1;
-    p.dz_all = a.pt.world > 1 ? a.dz_all : nullptr;
-    p.ld_all = a.K;
-    p.dz_col0 = a.pt.rank * a.bpad;
-    return p;
+    k_itemtile<MODE><<<grid, kItemThreads, kSmemItemTile, st>>>(tmA, tmB, p);
 }
 
 void launch_decode_train(const DecodeArgs& a, cudaStream_t st) {
-    cudaMemsetAsync(a.db_dec, 0, sizeof(float) * a.N, st);   // the epilogue accumulates two column halves
-    const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
-    const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, a.bpad, a.bpad);
-    ItemTileDev p = decode_dev(a);
-    launch_itemtile<MODE_TRAIN>(tmA, tmB, p, dim3(decode_grid(a.N, 1), 1, 1), st);
+    const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
+    cudaMemsetAsync(a.db_dec, 0, sizeof(float) * a.n_local, st);   // the epilogue accumulates column halves / batch tiles
+    ItemTileDev p{};
+    p.world = a.pt.world > 0 ? a.pt.world : 1;
+    p.rank = a.pt.rank;
+    p.n_rows = a.n_local;
+    p.n_global = a.N;
+    // local tiles that hold at least one valid catalogue row: global tile = local * world + rank
+    const int tiles_total = (a.N + kTileItems - 1) / kTileItems;
+    p.tiles = tiles_total > p.rank ? (tiles_total - p.rank + p.world - 1) / p.world : 0;
+    p.kchunks = a.H / 64;
+    p.n_cols = a.bpad;
+    p.batch = a.batch;
+    p.bias = a.bias;
+    p.ybits = a.ybits; p.ywords = a.ywords;
+    p.dzT = a.dzT; p.ld_dz = nbt * a.bpad;
+    p.db_dec = a.db_dec; p.loss_partial = a.loss_partial; p.inv_batch = a.inv_batch;
+    const int gx = decode_grid(p.tiles * kTileItems, nbt);
+    if (p.tiles == 0) {                                             // a rank may own no tile of a tiny catalogue
+        cudaMemsetAsync(a.loss_partial, 0, sizeof(float) * 2 * 148, st);
+        return;
+    }
+    cudaMemsetAsync(a.loss_partial, 0, sizeof(float) * 2 * 148, st);
+    const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.n_local, kTileItems);
+    const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
+    launch_itemtile<MODE_TRAIN>(tmA, tmB, p, dim3(gx, nbt, 1), st);
 }
 
 void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
     const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
+    ItemTileDev p{};
+    p.world = 1; p.rank = 0;
+    p.n_rows = a.n_out < a.N ? a.n_out : a.N;       // only the columns that are kept (tracks) are scored
+    p.n_global = a.N;
+    p.tiles = (p.n_rows + kTileItems - 1) / kTileItems;
+    p.kchunks = a.H / 64;
+    p.n_cols = a.bpad;
+    p.batch = a.batch;
+    p.bias = a.bias;
+    p.out = a.out; p.ld_out = a.ld_out; p.n_out = a.n_out;
+    p.mix_wp = a.mix_wp; p.mix_wt = a.mix_wt; p.title_score = a.title_score;
     const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
     const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
-    ItemTileDev p = decode_dev(a);
-    p.n_items = a.n_out < a.N ? a.n_out : a.N;       // only the columns that are kept (tracks) are scored
-    p.tiles = (p.n_items + kTileItems - 1) / kTileItems;
-    launch_itemtile<MODE_PREDICT>(tmA, tmB, p, dim3(decode_grid(p.n_items, nbt), nbt, 1), st);
+    launch_itemtile<MODE_PREDICT>(tmA, tmB, p, dim3(decode_grid(p.n_rows, nbt), nbt, 1), st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -468,7 +376,7 @@ struct DwDev {
     const float* g_extra;
     const unsigned char* touched;
     AdamConst adam;
-    __nv_bfloat16* shadow;   // [n_global, H], refreshed on every rank
+    __nv_bfloat16* shadow;   // bf16 copy of the same rows as aw (same indexing)
     PeerTable pt;
     int ld, col0;            // row stride and first column of the row-major outputs
 };
@@ -640,20 +548,16 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
                         }
                     }
                     if (p.shadow != nullptr) {
-                        // bf16 operand rows: lanes pair up so that every lane stores one 4-byte (h, h+1) pair --
-                        // even lanes for item j, odd lanes for item j+1 -- into this GPU's copy and every peer's
-                        const size_t goff0 = (size_t)gitem0 * p.ld + p.col0 + (h & ~1);
+                        // bf16 operand rows (same indexing as w): lanes pair up so that every lane stores one 4-byte
+                        // (h, h+1) pair -- even lanes for item j, odd lanes for item j+1
+                        const size_t soff0 = (size_t)item0 * p.ld + p.col0 + (h & ~1);
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             const float give = (lane & 1) ? wv[j] : wv[j + 1];           // what the partner lane stores
                             const float got = __shfl_xor_sync(0xffffffffu, give, 1);
                             const int jj = j + (lane & 1);
                             const uint32_t pk = (lane & 1) ? pack_bf16x2(got, wv[j + 1]) : pack_bf16x2(wv[j], got);
-                            if (jj < nvalid) {
-                                const size_t go = goff0 + (size_t)jj * p.ld;
-                                for (int sidx = 0; sidx < world; ++sidx)
-                                    *reinterpret_cast<uint32_t*>(peer_ptr(p.pt, sidx, p.shadow) + go) = pk;
-                            }
+                            if (jj < nvalid) *reinterpret_cast<uint32_t*>(p.shadow + soff0 + (size_t)jj * p.ld) = pk;
                         }
                     }
                 }
@@ -712,7 +616,7 @@ struct DhDev {
     int nboxes;          // H / 64
     int H, bpad;
     uint32_t lbo, sbo;
-    float* partial;      // [gridDim.x, bpad, H]
+    float* partial;      // [gridDim.y][gridDim.x][bpad][H]
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -765,7 +669,8 @@ k_dh(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
                 uint8_t* sa = smem + stage * kDhStageBytes;
                 uint8_t* sb = sa + 4 * kDhBox;
                 const int item0 = (kc0 + k) * 64;
-                for (int m = 0; m < p.mboxes; ++m) tma_load_2d_hint(sa + m * kDhBox, &tmDz, &full[stage], m * 64, item0, pol);
+                for (int m = 0; m < p.mboxes; ++m)
+                    tma_load_2d_hint(sa + m * kDhBox, &tmDz, &full[stage], blockIdx.y * p.bpad + m * 64, item0, pol);
                 for (int n = 0; n < p.nboxes; ++n) tma_load_2d_hint(sb + n * kDhBox, &tmW, &full[stage], n * 64, item0, pol);
                 if (++stage == kDhStages) { stage = 0; phase ^= 1u; }
             }
@@ -796,7 +701,7 @@ k_dh(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
     } else {
         const int q = warp & 3;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        float* out = p.partial + (size_t)blockIdx.x * p.bpad * p.H;
+        float* out = p.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.bpad * p.H;
         if (nk > 0) {
             mbar_wait(tfull, 0);
             tc_fence_after();
@@ -826,19 +731,17 @@ k_dh(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-int dh_nsplit(int N) {
+int dh_nsplit(int N, int n_batch_tiles) {
     const int chunks = (N + 63) / 64;
-    const int sms = sm_count();
+    int sms = sm_count() / (n_batch_tiles > 0 ? n_batch_tiles : 1);
+    if (sms < 1) sms = 1;
     return chunks < sms ? chunks : sms;
 }
 
 void launch_dh(const DhArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
-        configured = true;
-    }
-    const CUtensorMap tmDz = make_map_bf16(a.dzT, a.bpad, a.N, 64);
+    const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
+    const int ld_dz = a.ld_dz > 0 ? a.ld_dz : a.bpad;
+    const CUtensorMap tmDz = make_map_bf16(a.dzT, ld_dz, a.N, 64);
     const CUtensorMap tmW = make_map_bf16(a.W, a.H, a.N, 64, a.ldW);
     DhDev p{};
     p.kchunks_total = (a.N + 63) / 64;
@@ -849,11 +752,9 @@ void launch_dh(const DhArgs& a, cudaStream_t st) {
     p.lbo = a.lbo > 0 ? (uint32_t)a.lbo : (uint32_t)kDhBox;   // next 64 elements along M/N: the next box
     p.sbo = a.sbo > 0 ? (uint32_t)a.sbo : 1024u;              // next 8 items along K
     p.partial = a.partial;
-    k_dh<<<a.nsplit, 192, kSmemDh, st>>>(tmDz, tmW, p);
+    k_dh<<<dim3(a.nsplit, nbt), 192, kSmemDh, st>>>(tmDz, tmW, p);
 }
 
-// Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
-// synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
 void preload_gemm() {
     cudaFuncAttributes a;
     cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);

@@ -21,12 +21,16 @@ enum : int { kErrIndexRange = 1, kErrRowTooLong = 2, kErrYNotBinary = 4 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// ---- data-parallel layout -------------------------------------------------------------------
+// ---- multi-GPU layout ------------------------------------------------------------------------
 // Every rank allocates the same arena layout, so a buffer of rank r is `base[r] + (local - base[rank])`.
 // Peers are mapped with CUDA IPC (one process per GPU) and addressed by plain loads / stores over
-// NVLink / NVSwitch.  Catalogue rows (W_enc, W_dec, their Adam moments, the sparse-row gradient) are
-// owned tile-cyclically: 128-item tile t lives on rank t % world as local tile t / world, which
-// spreads the popularity-ranked head of the catalogue (Zipf ids) evenly over the GPUs.
+// NVLink / NVSwitch.  Catalogue rows (W_enc, W_dec, their Adam moments, gradients, the bf16 decoder
+// operand, the dz tiles) are owned tile-cyclically: 128-item tile t lives on rank t % world as local
+// tile t / world, which spreads the popularity-ranked head of the catalogue (Zipf ids)
+// evenly over the GPUs.  The batch is sharded by playlist for the sparse side (encode, dW_enc) and
+// all-gathered (K = world x batch-tile rows of h_d, 128 KB each) for the dense side: every rank
+// decodes ITS item rows against the GLOBAL batch, so dz, dW_dec and the Adam update never leave
+// the GPU that owns the rows; only h_d / h rows, split-K sums of dh and the sparse inputs cross NVLink.
 struct PeerTable {
     char* base[kMaxWorld];
     int world, rank;
@@ -55,7 +59,6 @@ struct CsrWork {        // COO -> per-row sorted, de-duplicated (last occurrence
 };
 void launch_coo_to_csr(const long long* pos, const float* val, int nnz, int B, int N, CsrWork w, int* err,
                        cudaStream_t st);
-void launch_ybits_set(const CsrWork& y, int B, uint32_t* ybits, int ywords, int set, int* err, cudaStream_t st);
 
 // The normalised input of the step in flight, published for the sparse-row scatter of every rank
 // (same offsets as the slot's CSR): x_n = x_d / (s + 1e-10) per kept entry.
@@ -72,41 +75,59 @@ struct EncodeArgs {
     CsrWork x;            // read only
     PubInput pub;         // written: col, x_n
     float* rowsum;        // [B] s = sum_j x_d (DAEs.py:41)
-    float* h;             // [B,H] fp32 sigma(a)
-    __nv_bfloat16* h_d;   // [bpad,H]  dropout(h), bf16, rows >= B zero
-    __nv_bfloat16* h_dT;  // [H, K] K = world*bpad; this rank writes columns [rank*bpad, +bpad) on EVERY rank
-    int B, bpad, H, K;
-    int hT_col0;          // first h_dT column of this rank's rows
-    int hT_bcast;         // 1: store the h_dT columns into every rank's copy (training), 0: local only
+    float* h;             // [rows, H] fp32 sigma(a)
+    __nv_bfloat16* h_d;   // [rows, H] dropout(h), bf16, padding rows zero
+    __nv_bfloat16* h_dT;  // [H, K]
+    int B, bpad, H, K;    // K: columns of h_dT (train: world * bpad)
+    int row0;             // first row / h_dT column of this rank's block (train: rank * bpad)
+    int bcast;            // 1: store h / h_d rows and h_dT columns into EVERY rank's copy (training), 0: local only
     float kp, kp_in;
     unsigned long long seed, step;
-    int row_offset;       // global row index of local row 0 (data-parallel shards)
+    int row_offset;       // global row index of local row 0 for the dropout keys (rank * B)
     PeerTable pt;
 };
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st);
 
-struct EncodeDaArgs {
-    const float* dh_partial;  // [nsplit, bpad, H]
-    int nsplit;
-    const float* h;           // [B,H]
-    float* da;                // [B,H]
-    float* db_enc;            // [H] this rank's column sums of da
-    int B, bpad, H;
+// y of the GLOBAL batch restricted to the item rows this rank owns, as a bitmask [local rows, K/32 words]:
+// bit (s * bpad + i) of row item_local(c) is set when row i of rank s's target CSR contains column c.
+struct YbitsArgs {
+    CsrWork y;                // this rank's slot CSR (local pointers; peers' through pt)
+    uint32_t* ybits;          // [local rows, ywords], zeroed by the launcher
+    int n_local, ywords, B, bpad;
+    int* err;
+    PeerTable pt;
+};
+void launch_ybits_shard(const YbitsArgs& a, cudaStream_t st);
+
+// dh of the global batch over this rank's item rows: fixed-order sum of the split-K partials -> dh_sum [K, H]
+void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, int n_batch_tiles, float* dh_sum, cudaStream_t st);
+
+struct DaArgs {               // da = dh * (keep/kp) * h(1-h) for EVERY row of the global batch (each rank computes all of it)
+    const float* dh_sum;      // [K, H] this rank's item-shard contribution; peers' through pt, summed in rank order
+    const float* h;           // [K, H] fp32 (rows written by their owners' encode)
+    float* da;                // [K, H]
+    float* db_enc;            // [H] column sums over the global batch
+    int B, bpad, H;           // rows per rank, padded rows per rank
     float kp;
     unsigned long long seed, step;
-    int row_offset;
+    PeerTable pt;
 };
-void launch_encode_da(const EncodeDaArgs& a, cudaStream_t st);
+void launch_da_all(const DaArgs& a, cudaStream_t st);
 
-struct ScatterArgs {          // dW_enc rows owned by this rank, from every rank's published input and da
+struct ScatterArgs {          // dW_enc rows owned by this rank, from every rank's published input and the local da
     PubInput pub;             // local pointers; peers through pt
-    const float* da;          // [B,H]
+    const float* da;          // [K, H] (local)
     float* g_enc;             // [local rows, H]
     unsigned char* touched;   // [local rows]
-    int B, H;
+    int B, bpad, H;
     PeerTable pt;
 };
 void launch_scatter_shard(const ScatterArgs& a, cudaStream_t st);
+
+// out[global item] = src_of_owner[local item] for every catalogue item (fp32 vector / bf16 rows of H)
+void launch_gather_items_f32(const float* src_local, float* out, int N, const PeerTable& pt, cudaStream_t st);
+void launch_gather_rows_bf16(const __nv_bfloat16* src_local, __nv_bfloat16* out, int N, int H, const PeerTable& pt,
+                             cudaStream_t st);
 
 // out[i] = sum over ranks (fixed order) of part[i] read from every rank's arena
 void launch_sum_partials(const float* part_local, float* out, int n, const PeerTable& pt, cudaStream_t st);
@@ -115,22 +136,21 @@ void launch_barrier(unsigned int* flags_local, unsigned int epoch, const PeerTab
 
 // ---- gemm_sm100.cu -------------------------------------------------------------------------
 struct DecodeArgs {
-    const __nv_bfloat16* W;    // [N,H] bf16 decoder operand
-    const __nv_bfloat16* h_d;  // [rows_alloc,H] bf16
-    const float* bias;         // [N]
-    int N, H;
-    int batch;                 // valid rows
+    const __nv_bfloat16* W;    // bf16 decoder operand: train [local rows, H] (this rank's items), predict [N, H]
+    const __nv_bfloat16* h_d;  // [n_batch_tiles * bpad, H] bf16
+    const float* bias;         // [N] (global item order)
+    int N, H;                  // catalogue size (global)
+    int batch;                 // valid rows per batch tile
     int bpad;                  // rows per batch tile (multiple of 64, <= 256)
-    int n_batch_tiles;         // predict only
+    int n_batch_tiles;         // train: world (the global batch), predict: ceil(batch / 256)
     // train
-    const uint32_t* ybits;     // [N, ywords]
+    int n_local;               // item rows held by this rank (multiple of 128)
+    PeerTable pt;              // world / rank: local item -> catalogue id
+    const uint32_t* ybits;     // [local rows, ywords]
     int ywords;
-    __nv_bfloat16* dzT;        // [N,bpad] this rank's batch columns, every item (operand of dh)
-    __nv_bfloat16* dz_all;     // [local rows, K] on the OWNER of each item tile: columns [rank*bpad, +bpad); nullptr when world == 1
-    int K;
-    PeerTable pt;
-    float* db_dec;             // [N]
-    float* loss_partial;       // [grid]
+    __nv_bfloat16* dzT;        // [local rows, n_batch_tiles * bpad]
+    float* db_dec;             // [local rows]
+    float* loss_partial;       // [grid.x * grid.y]
     float inv_batch;
     // predict
     float* out;                // [batch, ld_out] fp32 scores
@@ -155,21 +175,23 @@ struct DwArgs {
     const float* g_extra;               // tied model: sparse-row dW_enc [local rows, H], added where touched[row] != 0
     const unsigned char* touched;       // [local rows]
     AdamConst adam;
-    __nv_bfloat16* shadow;              // [N,H] bf16 operand copy to refresh on this GPU and on every peer (global row order)
-    PeerTable pt;
+    __nv_bfloat16* shadow;              // bf16 operand copy of the same rows (same indexing as w), or nullptr
+    PeerTable pt;                       // world / rank: which catalogue rows the local tiles are
     int ld, col0;                       // row stride (0: H) and first column of g / w / m / v / shadow (title head: two 256-column halves of [N, 512])
 };
 void launch_dw(const DwArgs& a, cudaStream_t st);                  // G2: dW_dec = dz^T . h_d (+ Adam)
 
 struct DhArgs {
-    const __nv_bfloat16* dzT;   // [N,bpad]
-    const __nv_bfloat16* W;     // [N,H]
-    float* partial;             // [nsplit,bpad,H]
-    int N, H, bpad, nsplit;
+    const __nv_bfloat16* dzT;   // [rows, ld_dz]: batch tile bt is columns [bt * bpad, +bpad)
+    const __nv_bfloat16* W;     // [rows, H] (row stride ldW)
+    float* partial;             // [n_batch_tiles][nsplit][bpad][H]
+    int N;                      // rows contracted over
+    int H, bpad, nsplit;        // nsplit: split-K CTAs per batch tile
+    int n_batch_tiles, ld_dz;   // 0 -> 1 tile, ld_dz = bpad
     int lbo, sbo;               // MN-major descriptor strides (bytes); 0 -> defaults
     int ldW;                    // row stride of W in elements (0: H)
 };
-int dh_nsplit(int N);
+int dh_nsplit(int N, int n_batch_tiles = 1);   // split-K CTAs per batch tile
 void launch_dh(const DhArgs& a, cudaStream_t st);                  // G3: dh = dz . W_dec (split-K)
 
 // ---- optim.cu -------------------------------------------------------------------------------
@@ -183,17 +205,12 @@ struct AdamArgs {
     float alpha, one_minus_b1, one_minus_b2, eps, lambda;
 };
 void launch_adam(const AdamArgs& a, cudaStream_t st);
-// matrices: a.w/m/v are this rank's rows [local rows, row_len] (row_len % 4 == 0); gradient = a.g (dense, or nullptr)
-// + g_sparse rows where a.row_touched != 0 (or nullptr); shadow [n_global, row_len] bf16 is refreshed on every rank
-void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, int n_global, const PeerTable& pt,
-                      cudaStream_t st);
-// U(-limit, limit) keyed by the GLOBAL element index; w: this rank's rows in local-tile order (or nullptr),
-// wb: bf16 copy of ALL N rows in global order (or nullptr)
-void launch_xavier_init(float* w, int n_local_rows, __nv_bfloat16* wb, int N, int H, float limit,
-                        unsigned long long seed, unsigned stream_id, int world, int rank, cudaStream_t st);
-// rows of a local-tile-ordered fp32 block of rank `owner_rank` -> bf16 rows of the global-order operand copy
-void launch_cast_rows_bf16(const float* src_local, int n_local_rows, __nv_bfloat16* dst_global, int N, int H, int world,
-                           int owner_rank, cudaStream_t st);
+// matrices: a.w/m/v are [rows, row_len] (row_len % 4 == 0); gradient = a.g (dense, or nullptr) + g_sparse rows where
+// a.row_touched != 0 (or nullptr); shadow: bf16 copy of the same rows (same indexing), or nullptr
+void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, cudaStream_t st);
+// U(-limit, limit) keyed by the GLOBAL element index; w: this rank's rows in local-tile order
+void launch_xavier_init(float* w, int n_local_rows, int N, int H, float limit, unsigned long long seed,
+                        unsigned stream_id, int world, int rank, cudaStream_t st);
 void launch_sumsq(const float* x, long long n, float* partial, int nblocks, cudaStream_t st);
 void launch_reduce_loss2(const float* partial, int n, const float* sumsq_partial, int n_sq, float lambda,
                          float inv_batch, float* loss_out, cudaStream_t st);

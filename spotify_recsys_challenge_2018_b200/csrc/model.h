@@ -35,8 +35,6 @@ struct Slot {
     int nnz_x = 0, nnz_y = 0, batch = 0, y_batch = 0;
     bool has_y = false;
     CsrWork xw{}, yw{};                             // de-duplicated CSR of this slot's batch
-    uint32_t* ybits = nullptr;                      // item-major target bitmask of this slot's batch
-    bool y_live = false;                            // ybits currently holds the bits of yw
     cudaEvent_t h2d_done = nullptr;                 // the pinned mirror may be overwritten after this
     cudaEvent_t prepared = nullptr;                 // side stream: CSR + ybits of this slot are ready
     cudaEvent_t consumed = nullptr;                 // main stream: the step has finished reading this slot
@@ -70,15 +68,17 @@ struct dae_model {
     void* ipc_opened[kMaxWorld] = {};
     // parameters: catalogue matrices are row-sharded (tile-cyclic), biases replicated
     float *W_enc = nullptr, *W_dec = nullptr, *b_enc = nullptr, *b_dec = nullptr;
-    __nv_bfloat16* shadow[2] = {nullptr, nullptr};   // bf16 decoder operand, all N rows; double-buffered when world > 1
-    int cur_shadow = 0;
+    __nv_bfloat16* shadow = nullptr;                 // bf16 decoder operand: the rows this rank owns (training)
+    __nv_bfloat16* shadow_full = nullptr;            // all N rows in catalogue order (inference); == shadow when world == 1
+    bool full_stale = true;
     float *mW_enc = nullptr, *vW_enc = nullptr, *mW_dec = nullptr, *vW_dec = nullptr;
     float *mb_enc = nullptr, *vb_enc = nullptr, *mb_dec = nullptr, *vb_dec = nullptr;
     float b1_pow = kBeta1, b2_pow = kBeta2;
     long long step = 0;
     float *g_enc = nullptr;                          // sparse-row dW_enc of the rows this rank owns
     unsigned char* touched = nullptr;
-    float *g_b_enc_part = nullptr, *g_b_dec_part = nullptr, *g_b_enc = nullptr, *g_b_dec = nullptr;
+    float *g_b_enc = nullptr, *g_b_dec_sh = nullptr, *g_b_dec = nullptr;
+    uint32_t* ybits = nullptr;                       // targets of the global batch over this rank's item rows
     float* g_dec = nullptr;                          // dW_dec of the rows this rank owns
     int debug = 0;
     bool scatter_done = false;
@@ -90,7 +90,8 @@ struct dae_model {
     unsigned int epoch = 0;
     int ywords = 8;
     float *rowsum = nullptr, *h = nullptr, *da = nullptr, *dh_partial = nullptr;
-    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dzT = nullptr, *dz_all = nullptr;
+    __nv_bfloat16 *h_d = nullptr, *h_dT = nullptr, *dz_all = nullptr;
+    float* dh_sum = nullptr;
     int nsplit = 0;
     float *loss_partial = nullptr, *sq_partial = nullptr, *cost_part = nullptr, *cost = nullptr, *cost_host = nullptr;
     int n_loss_partial = 0;
@@ -124,3 +125,4 @@ int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_
                const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch, bool with_y);
 int check_device_flag(dae_model* m);
 void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset, bool train);
+void build_ybits(dae_model* m, int slot, int B, int bpad);

@@ -43,13 +43,13 @@ k_adam_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__
     }
 }
 
-// Same update on the catalogue rows this rank owns ([local rows, H], local-tile order), with the bf16
-// operand copy of the rows refreshed on this GPU and on every peer (global row order, NVLink stores).
+// Same update on a row-major matrix [rows, row_len] (the catalogue rows this rank owns), gradient = dense part +
+// sparse rows, with the bf16 tensor-core operand copy of the rows refreshed in the same pass.
 __global__ void __launch_bounds__(256)
 k_adam_rows_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v, const float4* __restrict__ g,
                  const float4* __restrict__ g_sparse, __nv_bfloat16* __restrict__ shadow,
                  const unsigned char* __restrict__ touched, unsigned int n4,
-                 unsigned int row_len4, int n_global, const AdamConst c, const __grid_constant__ PeerTable pt) {
+                 unsigned int row_len4, const AdamConst c) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const unsigned int lrow = i / row_len4;
@@ -68,32 +68,24 @@ k_adam_rows_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restr
         __stcs(m + i, mv);
         __stcs(v + i, vv);
         if (shadow != nullptr) {
-            const int grow = item_global((int)lrow, pt.world, pt.rank);
-            if (grow < n_global) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(wv.x, wv.y), hi = __floats2bfloat162_rn(wv.z, wv.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<unsigned int*>(&lo);
-                pk.y = *reinterpret_cast<unsigned int*>(&hi);
-                const size_t o = ((size_t)grow * row_len4 + (i - lrow * row_len4)) * 4;
-                for (int s = 0; s < pt.world; ++s) *reinterpret_cast<uint2*>(peer_ptr(pt, s, shadow) + o) = pk;
-            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(wv.x, wv.y), hi = __floats2bfloat162_rn(wv.z, wv.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned int*>(&lo);
+            pk.y = *reinterpret_cast<unsigned int*>(&hi);
+            reinterpret_cast<uint2*>(shadow)[i] = pk;      // default policy: the operand copy is re-read by the next step's decode
         }
     }
 }
 
-void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, int n_global, const PeerTable& pt,
-                      cudaStream_t st) {
+void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, cudaStream_t st) {
     AdamConst c{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
     const long long n4 = a.n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = 148LL * 16;
     if (blocks > cap) blocks = cap;
-    PeerTable t = pt;
-    if (t.world < 1) t.world = 1;
     k_adam_rows_vec4<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(a.w), reinterpret_cast<float4*>(a.m),
                                                   reinterpret_cast<float4*>(a.v), reinterpret_cast<const float4*>(a.g),
-                                                  reinterpret_cast<const float4*>(g_sparse), shadow, a.row_touched, (unsigned int)n4, (unsigned int)(a.row_len / 4),
-                                                  n_global, c, t);
+                                                  reinterpret_cast<const float4*>(g_sparse), shadow, a.row_touched, (unsigned int)n4, (unsigned int)(a.row_len / 4), c);
 }
 
 __global__ void k_adam_scalar(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
@@ -150,31 +142,9 @@ __global__ void k_xavier_local(float* __restrict__ w, long long n_local, int N, 
         w[i] = grow < N ? xavier_value((long long)grow * H + k, limit, seed, stream_id) : 0.f;
     }
 }
-__global__ void k_xavier_bf16(__nv_bfloat16* __restrict__ wb, long long n, float limit, unsigned long long seed,
-                              unsigned stream_id) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        wb[i] = __float2bfloat16(xavier_value(i, limit, seed, stream_id));
-}
-void launch_xavier_init(float* w, int n_local_rows, __nv_bfloat16* wb, int N, int H, float limit,
-                        unsigned long long seed, unsigned stream_id, int world, int rank, cudaStream_t st) {
-    if (w != nullptr)
-        k_xavier_local<<<1184, 256, 0, st>>>(w, (long long)n_local_rows * H, N, H, limit, seed, stream_id, world, rank);
-    if (wb != nullptr) k_xavier_bf16<<<1184, 256, 0, st>>>(wb, (long long)N * H, limit, seed, stream_id);
-}
-
-__global__ void k_cast_rows_bf16(const float* __restrict__ src, long long n_local, __nv_bfloat16* __restrict__ dst,
-                                 int N, int H, int world, int owner) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += stride) {
-        const int lrow = (int)(i / H), k = (int)(i - (long long)lrow * H);
-        const int grow = item_global(lrow, world, owner);
-        if (grow < N) dst[(size_t)grow * H + k] = __float2bfloat16(src[i]);
-    }
-}
-void launch_cast_rows_bf16(const float* src_local, int n_local_rows, __nv_bfloat16* dst_global, int N, int H, int world,
-                           int owner_rank, cudaStream_t st) {
-    k_cast_rows_bf16<<<1184, 256, 0, st>>>(src_local, (long long)n_local_rows * H, dst_global, N, H, world, owner_rank);
+void launch_xavier_init(float* w, int n_local_rows, int N, int H, float limit, unsigned long long seed,
+                        unsigned stream_id, int world, int rank, cudaStream_t st) {
+    k_xavier_local<<<1184, 256, 0, st>>>(w, (long long)n_local_rows * H, N, H, limit, seed, stream_id, world, rank);
 }
 
 // sum of squares, one partial per block (tf.nn.l2_loss = sum(t^2)/2 [TF1], DAEs.py:79-82)
@@ -253,8 +223,6 @@ void preload_optim() {
     cudaFuncGetAttributes(&a, k_adam_rows_vec4);
     cudaFuncGetAttributes(&a, k_adam_scalar);
     cudaFuncGetAttributes(&a, k_xavier_local);
-    cudaFuncGetAttributes(&a, k_xavier_bf16);
-    cudaFuncGetAttributes(&a, k_cast_rows_bf16);
     cudaFuncGetAttributes(&a, k_sumsq);
     cudaFuncGetAttributes(&a, k_reduce_loss);
     cudaFuncGetAttributes(&a, k_clear_flagged);

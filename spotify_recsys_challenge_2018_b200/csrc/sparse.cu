@@ -140,30 +140,6 @@ void launch_coo_to_csr(const long long* pos, const float* val, int nnz, int B, i
     k_row_sort_dedup<<<B, 256, 0, st>>>(w.row_ptr, w.keys, val, w.row_len, w.col, w.val);
 }
 
-// y as an item-major bitmask: bit b of ybits[item*ywords + b/32] == y[b, item] (y in {0,1}; the
-// runner feeds ones, main_train.py:206).  set=1 writes the bits, set=0 clears the same words.
-__global__ void k_ybits(const int* __restrict__ row_ptr, const int* __restrict__ row_len, const int* __restrict__ col,
-                        const float* __restrict__ val, int B, uint32_t* __restrict__ ybits, int ywords, int set,
-                        int* __restrict__ err) {
-    const int r = blockIdx.x;
-    const int beg = row_ptr[r], n = row_len[r];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = col[beg + i];
-        uint32_t* wp = ybits + (size_t)c * ywords + (r >> 5);
-        if (set) {
-            const float v = val[beg + i];
-            if (v == 1.0f) atomicOr(wp, 1u << (r & 31));
-            else if (v != 0.0f) atomicOr(err, kErrYNotBinary);
-        } else {
-            *wp = 0u;
-        }
-    }
-}
-
-void launch_ybits_set(const CsrWork& y, int B, uint32_t* ybits, int ywords, int set, int* err, cudaStream_t st) {
-    k_ybits<<<B, 128, 0, st>>>(y.row_ptr, y.row_len, y.col, y.val, B, ybits, ywords, set, err);
-}
-
 // ------------------------------------------------------------------------------------------
 // encode forward: one CTA per playlist row, blockDim = H threads (H <= 256), thread k owns
 // hidden unit k; every gathered W_enc row is one fully coalesced H*4-byte read.
@@ -184,7 +160,7 @@ __global__ void __launch_bounds__(256)
 k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const int* __restrict__ row_ptr,
              const int* __restrict__ row_len, const int* __restrict__ col, const float* __restrict__ val,
              const __grid_constant__ PubInput pub, float* __restrict__ rowsum, float* __restrict__ h, __nv_bfloat16* __restrict__ h_d,
-             __nv_bfloat16* __restrict__ h_dT, int B, int bpad, int H, int K, int hT_col0, int hT_bcast, float kp,
+             __nv_bfloat16* __restrict__ h_dT, int B, int bpad, int H, int K, int row0, int bcast, float kp,
              float kp_in, unsigned long long seed, unsigned long long step, int row_offset, const __grid_constant__ PeerTable pt) {
     __shared__ __align__(16) float s_x[kMaxRowNnz];
     __shared__ int s_c[kMaxRowNnz];
@@ -192,13 +168,19 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     const int r = blockIdx.x;
     const int k = threadIdx.x;
     const int world = pt.world;
-    const size_t hT_off = (size_t)k * K + hT_col0 + r;                  // this rank's column block of [H, K]
-    const int n_hT = hT_bcast ? world : 1;
+    // this rank's rows of h / h_d ([rows, H]) and columns of h_d^T ([H, K]); training stores them into EVERY rank's
+    // copy (the dense side contracts over the global batch), inference keeps them local
+    const size_t hT_off = (size_t)k * K + row0 + r;
+    const size_t h_off = (size_t)(row0 + r) * H + k;
+    const int n_dst = bcast ? world : 1;
     if (r >= B) {   // padding rows of the tensor-core operand
         if (k < H) {
             const __nv_bfloat16 z = __float2bfloat16(0.f);
-            h_d[(size_t)r * H + k] = z;
-            for (int s = 0; s < n_hT; ++s) (hT_bcast ? peer_ptr(pt, s, h_dT) : h_dT)[hT_off] = z;
+            for (int s = 0; s < n_dst; ++s) {
+                (bcast ? peer_ptr(pt, s, h_d) : h_d)[h_off] = z;
+                (bcast ? peer_ptr(pt, s, h_dT) : h_dT)[hT_off] = z;
+                (bcast ? peer_ptr(pt, s, h) : h)[h_off] = 0.f;
+            }
         }
         return;
     }
@@ -277,30 +259,58 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     const float hv = __fdividef(1.f, 1.f + __expf(-a));
     const bool keep = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(k), kp);
     const float hd = keep ? __fdiv_rn(hv, kp) : 0.f;
-    h[(size_t)r * H + k] = hv;
     const __nv_bfloat16 hb = __float2bfloat16(hd);
-    h_d[(size_t)r * H + k] = hb;
-    for (int s2 = 0; s2 < n_hT; ++s2) (hT_bcast ? peer_ptr(pt, s2, h_dT) : h_dT)[hT_off] = hb;
+    for (int s2 = 0; s2 < n_dst; ++s2) {
+        (bcast ? peer_ptr(pt, s2, h) : h)[h_off] = hv;
+        (bcast ? peer_ptr(pt, s2, h_d) : h_d)[h_off] = hb;
+        (bcast ? peer_ptr(pt, s2, h_dT) : h_dT)[hT_off] = hb;
+    }
 }
 
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st) {
     const int threads = 256;                      // G = 1024 / H row groups of H/4 threads
     k_encode_fwd<<<a.bpad, threads, 0, st>>>(a.W_enc, a.b_enc, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val, a.pub,
-                                             a.rowsum, a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.K, a.hT_col0, a.hT_bcast,
+                                             a.rowsum, a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.K, a.row0, a.bcast,
                                              a.kp, a.kp_in, a.seed, a.step, a.row_offset, a.pt);
 }
 
 // ------------------------------------------------------------------------------------------
-// encode backward, part 1: reduce the split-K partials of dh, da = dh * (keep/kp) * h(1-h)
+// y of the global batch over the item rows this rank owns (bitmask for the decode epilogue)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_encode_da(const float* __restrict__ dh_partial, int nsplit, const float* __restrict__ h, float* __restrict__ da_out,
-            int B, int bpad, int H, float kp, unsigned long long seed, unsigned long long step, int row_offset) {
-    const int r = blockIdx.x;
-    const int k = threadIdx.x;
+__global__ void k_ybits_shard(const int* __restrict__ row_ptr, const int* __restrict__ row_len,
+                              const int* __restrict__ col, const float* __restrict__ val, uint32_t* __restrict__ ybits,
+                              int ywords, int bpad, int* __restrict__ err, const __grid_constant__ PeerTable pt) {
+    const int r = blockIdx.x, s = blockIdx.y;                  // row r of rank s's batch
+    const int world = pt.world;
+    const int* prow_ptr = world == 1 ? row_ptr : peer_ptr(pt, s, row_ptr);
+    const int* prow_len = world == 1 ? row_len : peer_ptr(pt, s, row_len);
+    const int* pcol = world == 1 ? col : peer_ptr(pt, s, col);
+    const float* pval = world == 1 ? val : peer_ptr(pt, s, val);
+    const int beg = prow_ptr[r], n = prow_len[r];
+    const int bit = s * bpad + r;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = pcol[beg + i];
+        if (world != 1 && item_owner(c, world) != pt.rank) continue;
+        const float v = pval[beg + i];
+        if (v == 1.0f) atomicOr(ybits + (size_t)(world == 1 ? c : item_local(c, world)) * ywords + (bit >> 5), 1u << (bit & 31));
+        else if (v != 0.0f) atomicOr(err, kErrYNotBinary);     // the runner feeds ones (main_train.py:206)
+    }
+}
+void launch_ybits_shard(const YbitsArgs& a, cudaStream_t st) {
+    cudaMemsetAsync(a.ybits, 0, sizeof(uint32_t) * (size_t)a.n_local * a.ywords, st);
+    k_ybits_shard<<<dim3(a.B, a.pt.world), 128, 0, st>>>(a.y.row_ptr, a.y.row_len, a.y.col, a.y.val, a.ybits, a.ywords, a.bpad,
+                                                         a.err, a.pt);
+}
+
+// ------------------------------------------------------------------------------------------
+// encode backward, part 1: dh -> da for the whole global batch
+// ------------------------------------------------------------------------------------------
+// fixed-order sum of the split-K partials [bt][split][bpad][H] -> dh_sum [bt * bpad + row][H]
+__global__ void k_reduce_splits(const float* __restrict__ partial, int nsplit, int bpad, int H, float* __restrict__ out) {
+    const int bt = blockIdx.y, r = blockIdx.x, k = threadIdx.x;
     if (k >= H) return;
     const size_t stride = (size_t)bpad * H;
-    const float* p = dh_partial + (size_t)r * H + k;
+    const float* p = partial + (size_t)bt * nsplit * stride + (size_t)r * H + k;
     int s = 0;
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
     for (; s + 4 <= nsplit; s += 4) {                     // fixed order: deterministic
@@ -310,11 +320,27 @@ k_encode_da(const float* __restrict__ dh_partial, int nsplit, const float* __res
         d3 += p[(size_t)(s + 3) * stride];
     }
     for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
-    const float dh = (d0 + d1) + (d2 + d3);
-    const float hv = h[(size_t)r * H + k];
-    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(r + row_offset),
-                                  static_cast<uint32_t>(k), kp);
-    da_out[(size_t)r * H + k] = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
+    out[((size_t)bt * bpad + r) * H + k] = (d0 + d1) + (d2 + d3);
+}
+void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, int n_batch_tiles, float* dh_sum, cudaStream_t st) {
+    k_reduce_splits<<<dim3(bpad, n_batch_tiles), 256, 0, st>>>(partial, nsplit, bpad, H, dh_sum);
+}
+
+// Row g = s * bpad + i of the global batch: dh = sum over ranks (fixed order) of their item-shard sums,
+// da = dh * (keep / kp) * h (1 - h).  Every rank computes every row (K x H values), so da itself never crosses NVLink.
+__global__ void __launch_bounds__(256)
+k_da_all(const float* __restrict__ dh_sum, const float* __restrict__ h, float* __restrict__ da_out, int B, int bpad, int H,
+         float kp, unsigned long long seed, unsigned long long step, const __grid_constant__ PeerTable pt) {
+    const int i = blockIdx.x, s = blockIdx.y;
+    const int k = threadIdx.x;
+    if (k >= H) return;
+    const size_t o = ((size_t)s * bpad + i) * H + k;
+    if (i >= B) { da_out[o] = 0.f; return; }
+    float dh = 0.f;
+    for (int q = 0; q < pt.world; ++q) dh += (pt.world == 1 ? dh_sum : peer_ptr(pt, q, dh_sum))[o];
+    const float hv = h[o];
+    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(s * B + i), static_cast<uint32_t>(k), kp);
+    da_out[o] = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
 }
 
 // db_enc[k] = sum_r da[r,k]: 8 row groups per block, combined in a fixed order
@@ -333,20 +359,19 @@ __global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __
     }
 }
 
-void launch_encode_da(const EncodeDaArgs& a, cudaStream_t st) {
-    k_encode_da<<<a.B, 256, 0, st>>>(a.dh_partial, a.nsplit, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed, a.step,
-                                     a.row_offset);
-    k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.B, a.H, a.db_enc);
+void launch_da_all(const DaArgs& a, cudaStream_t st) {
+    k_da_all<<<dim3(a.bpad, a.pt.world), 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed, a.step, a.pt);
+    k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.bpad * a.pt.world, a.H, a.db_enc);
 }
 
 // ------------------------------------------------------------------------------------------
 // encode backward, part 2: sparse-row scatter-add dW_enc[col_j,:] += x_n[j] * da[row,:] into the rows
 // THIS rank owns.  Block (r, s) walks row r of rank s's published input (read over NVLink when
-// s != rank: ~70 entries + one 1 KB da row) and keeps the entries whose item tile lives here.
+// s != rank: ~70 entries) and keeps the entries whose item tile lives here; da is local.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_scatter_shard(const PubInput pub, const float* __restrict__ da, float* __restrict__ g_enc,
-                unsigned char* __restrict__ touched, int H, const __grid_constant__ PeerTable pt) {
+k_scatter_shard(const __grid_constant__ PubInput pub, const float* __restrict__ da, float* __restrict__ g_enc,
+                unsigned char* __restrict__ touched, int bpad, int H, const __grid_constant__ PeerTable pt) {
     __shared__ __align__(16) float s_da[256];
     const int r = blockIdx.x, s = blockIdx.y;
     const int world = pt.world;
@@ -354,8 +379,7 @@ k_scatter_shard(const PubInput pub, const float* __restrict__ da, float* __restr
     const int* prow_len = world == 1 ? pub.row_len : peer_ptr(pt, s, pub.row_len);
     const int* pcol = world == 1 ? pub.col : peer_ptr(pt, s, pub.col);
     const float* pxn = world == 1 ? pub.xn : peer_ptr(pt, s, pub.xn);
-    const float* pda = world == 1 ? da : peer_ptr(pt, s, da);
-    if (threadIdx.x < H) s_da[threadIdx.x] = pda[(size_t)r * H + threadIdx.x];
+    if (threadIdx.x < H) s_da[threadIdx.x] = da[((size_t)s * bpad + r) * H + threadIdx.x];
     __syncthreads();
     // thread (g, t) takes entries j = g (mod G), lane t adds 4 columns with one 16-byte reduction
     const int tpr = H >> 2, G = blockDim.x / tpr;
@@ -379,7 +403,30 @@ k_scatter_shard(const PubInput pub, const float* __restrict__ da, float* __restr
 }
 
 void launch_scatter_shard(const ScatterArgs& a, cudaStream_t st) {
-    k_scatter_shard<<<dim3(a.B, a.pt.world), 256, 0, st>>>(a.pub, a.da, a.g_enc, a.touched, a.H, a.pt);
+    k_scatter_shard<<<dim3(a.B, a.pt.world), 256, 0, st>>>(a.pub, a.da, a.g_enc, a.touched, a.bpad, a.H, a.pt);
+}
+
+// out[global item] = the owner's src[local item]
+__global__ void k_gather_items_f32(const float* __restrict__ src, float* __restrict__ out, int N, const __grid_constant__ PeerTable pt) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    out[g] = pt.world == 1 ? src[g] : peer_ptr(pt, item_owner(g, pt.world), src)[item_local(g, pt.world)];
+}
+void launch_gather_items_f32(const float* src_local, float* out, int N, const PeerTable& pt, cudaStream_t st) {
+    k_gather_items_f32<<<(N + 255) / 256, 256, 0, st>>>(src_local, out, N, pt);
+}
+__global__ void k_gather_rows_bf16(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ out, int N, int H8,
+                                   const __grid_constant__ PeerTable pt) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * H8; i += stride) {
+        const int g = (int)(i / H8), c = (int)(i - (long long)g * H8);
+        const uint4* row = reinterpret_cast<const uint4*>(peer_ptr(pt, item_owner(g, pt.world), src)) + (size_t)item_local(g, pt.world) * H8;
+        reinterpret_cast<uint4*>(out)[i] = row[c];
+    }
+}
+void launch_gather_rows_bf16(const __nv_bfloat16* src_local, __nv_bfloat16* out, int N, int H, const PeerTable& pt,
+                             cudaStream_t st) {
+    k_gather_rows_bf16<<<1184, 256, 0, st>>>(src_local, out, N, H / 8, pt);
 }
 
 // out[i] = sum_s part_s[i], ranks in a fixed order (identical result on every rank)
@@ -427,9 +474,12 @@ void preload_sparse() {
     cudaFuncGetAttributes(&a, k_row_scan);
     cudaFuncGetAttributes(&a, k_coo_fill);
     cudaFuncGetAttributes(&a, k_row_sort_dedup);
-    cudaFuncGetAttributes(&a, k_ybits);
+    cudaFuncGetAttributes(&a, k_ybits_shard);
+    cudaFuncGetAttributes(&a, k_reduce_splits);
+    cudaFuncGetAttributes(&a, k_da_all);
+    cudaFuncGetAttributes(&a, k_gather_items_f32);
+    cudaFuncGetAttributes(&a, k_gather_rows_bf16);
     cudaFuncGetAttributes(&a, k_encode_fwd);
-    cudaFuncGetAttributes(&a, k_encode_da);
     cudaFuncGetAttributes(&a, k_colsum);
     cudaFuncGetAttributes(&a, k_scatter_shard);
     cudaFuncGetAttributes(&a, k_sum_partials);

@@ -73,17 +73,22 @@ def test_dp_local_equals_single(tied, world, N, T, H, b_local, lam):
         assert abs(c - w) <= 1e-5 * abs(w)
     W_enc, W_dec, b_enc, b_dec = got[0]
     # decoder: same dz, same h_d, same contraction order over the batch columns -> bit-exact
-    if not tied and lam == 0.0 and world * ((b_local + 63) // 64 * 64) <= 256:
-        assert np.array_equal(W_dec, want[1])
+    # (not asserted bit-exact: the fp32 atomics of the dW_enc scatter commute differently per layout, which
+    #  reaches W_dec through h_d from the second step on)
     for a, b, name in zip(got[0], want, ("W_enc", "W_dec", "b_enc", "b_dec")):
         d = np.abs(a - b)
         assert (d > 1e-6).mean() < 2e-3 and d.max() <= 3 * 2.001 * 0.005, (name, d.max(), (d > 1e-6).mean())
-    # every rank's operand copy == bf16 of the gathered master
+    # inference on any rank scores every item: the gathered operand copy == bf16 of the gathered master
+    x, xv, y, yv = batches[0]
+    xs = shard_coo(x, xv, 0, b_local)
+    ps = [m.predict(*xs) for m in ms]
     for m in ms:
-        p, n, _ = m.buffer("W_dec_bf16")
+        p, n, _ = m.buffer("W_dec_bf16_full")
         from tests.gpu_util import dev_view
         sh = dev_view(p, n, torch.bfloat16).float().cpu().numpy().reshape(N, H)
         assert np.array_equal(sh, O.bf16_round(W_dec))
+    for p_ in ps[1:]:
+        assert np.array_equal(p_, ps[0])
     for m in ms:
         m.close()
 
