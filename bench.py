@@ -306,18 +306,21 @@ def main():
         e2e = None
         if world == 1:
             for i in range(3):
-                model.train_step(*batches[i % len(batches)], KP, KP_IN)
+                model.train_step_async(*batches[i % len(batches)], KP, KP_IN)
+            model.flush()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(args.steps):
-                model.train_step(*batches[i % len(batches)], KP, KP_IN)
+                model.train_step_async(*batches[i % len(batches)], KP, KP_IN)   # returns the previous step's cost
+            model.flush()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             h2d = int(np.mean([x.nbytes + xv.nbytes + y.nbytes + yv.nbytes for x, xv, y, yv in batches]))
             e2e = {"value": B * args.steps / dt, "unit": "playlists/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 8, "ms_per_step": 1e3 * dt / args.steps,
-                   "api": "models.DAEs.DAE.train_step (dae_model_train_step): host int64 COO + fp32 values in, "
-                          "cost out, synchronous"}
+                   "api": "models.DAEs.DAE.train_step_async (dae_model_train_step_async), the call main_runner/main_train.py "
+                          "makes: host int64 COO + fp32 values in (pinned H2D every step), every step's cost read back "
+                          "(D2H, one step late), final flush inside the timed region"}
         else:
             # DP: every rank feeds its own B rows of the global batch from host memory: H2D of the rank's batch,
             # the step (NVLink exchange inside the kernels) and D2H of the cost inside the timed region
@@ -326,9 +329,8 @@ def main():
                 dist.barrier()
             t0 = time.perf_counter()
             for i in range(args.steps):
-                model.stage_batch(i & 1, *batches[i % len(batches)])
-                trainer.train_step_staged(i & 1, KP, KP_IN)
-                model.sync_cost()
+                model.train_step_async(*batches[i % len(batches)], KP, KP_IN)
+            model.flush()
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], device="cuda")
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -336,7 +338,8 @@ def main():
             e2e = {"value": B * world * args.steps / float(dt.item()), "unit": "playlists/s",
                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 8 * world,
                    "ms_per_step": 1e3 * float(dt.item()) / args.steps,
-                   "api": "dp.DataParallelDAE over models.DAEs.DAE (stage_batch + train_step_staged + sync_cost)"}
+                   "api": "models.DAEs.DAE.train_step_async on every rank (world = N model attached with dp.DataParallelDAE): "
+                          "per-rank host COO in, per-step cost back"}
 
         # ---- per-phase device times (profiled steps; not part of `value`) -----------------------
         model.set_profiling(True)

@@ -75,6 +75,15 @@ int32_t dae_model_train_step(dae_model* m, const int64_t* x_pos, const float* x_
 int32_t dae_model_predict(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
                           int32_t n_cols, float* y_pred_out);
 
+/* The same step, pipelined for a training loop (the reference's loop only accumulates the cost,
+ * main_train.py:223): stages this batch while the previous step is still running, enqueues the step
+ * and returns the PREVIOUS step's cost (*has_prev = 0 on the first call).  dae_model_train_flush
+ * returns the last pending cost (epoch end / before reading parameters). */
+int32_t dae_model_train_step_async(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                   const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch,
+                                   float keep_prob, float input_keep_prob, float* prev_cost_out, int32_t* has_prev);
+int32_t dae_model_train_flush(dae_model* m, float* cost_out, int32_t* has_cost);
+
 /* y_pred + np.argsort + seed removal + [:k] fused on the device: met.single_eval /
  * cand_generate.  seed_ptr [batch+1] / seed_idx: CSR of the seed track ids to exclude (host).
  * out_idx [batch,k] int32 (-1 padded), out_score [batch,k] fp32 (may be NULL).

@@ -42,6 +42,8 @@ SIGNATURES = {
     "dae_model_get_params": (_I32, [_P, _P, _P, _P, _P]),
     "dae_model_get_adam_state": (_I32, [_P, _P, _P, _P, _P, C.POINTER(_I64)]),
     "dae_model_train_step": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _F, _F, C.POINTER(_F)]),
+    "dae_model_train_step_async": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _I32, _F, _F, C.POINTER(_F), C.POINTER(_I32)]),
+    "dae_model_train_flush": (_I32, [_P, C.POINTER(_F), C.POINTER(_I32)]),
     "dae_model_predict": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P]),
     "dae_model_recommend": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _I32, _P, _P]),
     "dae_model_stage_batch": (_I32, [_P, _I32, _P, _P, _I64, _P, _P, _I64, _I32]),

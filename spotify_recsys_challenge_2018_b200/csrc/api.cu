@@ -172,6 +172,9 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
 
     TRY(halloc(m, &m->err_host, 1));
     TRY(halloc(m, &m->cost_host, 1));
+    TRY(halloc(m, &m->cost_ring, 2));
+    TRY(halloc(m, &m->err_ring, 2));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&m->ev_cost[i], cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
         Slot& sl = m->slots[s];
         CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
@@ -203,6 +206,7 @@ extern "C" void dae_model_destroy(dae_model* m) {
         if (m->slots[s].consumed) cudaEventDestroy(m->slots[s].consumed);
     }
     if (m->ph_ev[0]) for (int i = 0; i < 2 * PH_COUNT; ++i) cudaEventDestroy(m->ph_ev[i]);
+    for (int i = 0; i < 2; ++i) if (m->ev_cost[i]) cudaEventDestroy(m->ev_cost[i]);
     cudaStreamDestroy(m->st2);
     if (m->own_stream) cudaStreamDestroy(m->st);
     delete m;
@@ -426,6 +430,7 @@ extern "C" int32_t dae_model_restage(dae_model* m, int32_t slot) {
     return prepare_slot(m, slot);
 }
 
+static int invalid_batch(int e);
 int check_device_flag(dae_model* m) {
     CK(cudaStreamSynchronize(m->st2));
     CK(cudaMemcpyAsync(m->err_host, m->err, sizeof(int), cudaMemcpyDeviceToHost, m->st));
@@ -434,9 +439,7 @@ int check_device_flag(dae_model* m) {
     const int e = *m->err_host;
     if (e != 0) {
         cudaMemsetAsync(m->err, 0, sizeof(int), m->st);
-        return fail("invalid sparse batch:%s%s%s", (e & kErrIndexRange) ? " index out of range" : "",
-                    (e & kErrRowTooLong) ? " row longer than 2048 entries" : "",
-                    (e & kErrYNotBinary) ? " y values must be 0 or 1" : "");
+        return invalid_batch(e);
     }
     return 0;
 }
@@ -667,12 +670,62 @@ extern "C" int32_t dae_model_sync_cost(dae_model* m, float* cost_out) {
     return 0;
 }
 
+extern "C" int32_t dae_model_train_flush(dae_model* m, float* cost_out, int32_t* has_cost);
 extern "C" int32_t dae_model_train_step(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
                                         const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch,
                                         float keep_prob, float input_keep_prob, float* cost_out) {
+    if (m && m->async_pending) TRY(dae_model_train_flush(m, nullptr, nullptr));   // drain a pipelined step first
     TRY(dae_model_stage_batch(m, 0, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch));
     TRY(dae_model_train_step_staged(m, 0, keep_prob, input_keep_prob));
     return dae_model_sync_cost(m, cost_out);
+}
+
+static int invalid_batch(int e) {
+    return fail("invalid sparse batch:%s%s%s", (e & kErrIndexRange) ? " index out of range" : "",
+                (e & kErrRowTooLong) ? " row longer than 2048 entries" : "", (e & kErrYNotBinary) ? " y values must be 0 or 1" : "");
+}
+
+// wait for the step issued from `slot` by dae_model_train_step_async and fetch its cost / validation flag
+static int collect_async(dae_model* m, int slot, float* cost_out) {
+    CK(cudaEventSynchronize(m->ev_cost[slot]));
+    const int e = m->err_ring[slot];
+    if (e != 0) {
+        cudaMemsetAsync(m->err, 0, sizeof(int), m->st);
+        return invalid_batch(e);
+    }
+    if (cost_out) *cost_out = m->cost_ring[slot];
+    return 0;
+}
+
+// Pipelined form of dae_model_train_step for a training loop: the batch is staged into the slot the device is not
+// using (H2D + COO->CSR on the side stream, overlapping the step in flight), the step is enqueued, and the call
+// returns the cost of the PREVIOUS step (*has_prev = 0 on the first call) without waiting for this one.
+extern "C" int32_t dae_model_train_step_async(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                              const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch,
+                                              float keep_prob, float input_keep_prob, float* prev_cost_out,
+                                              int32_t* has_prev) {
+    if (!m || !m->trainable) return fail("model is not trainable");
+    const int slot = m->async_slot ^ 1;
+    TRY(dae_model_stage_batch(m, slot, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch));
+    TRY(dae_model_train_step_staged(m, slot, keep_prob, input_keep_prob));
+    CK(cudaMemcpyAsync(m->cost_ring + slot, m->cost, sizeof(float), cudaMemcpyDeviceToHost, m->st));
+    CK(cudaMemcpyAsync(m->err_ring + slot, m->err, sizeof(int), cudaMemcpyDeviceToHost, m->st));
+    CK(cudaEventRecord(m->ev_cost[slot], m->st));
+    const bool had = m->async_pending;
+    m->async_slot = slot;
+    m->async_pending = true;
+    if (has_prev) *has_prev = had ? 1 : 0;
+    if (had) return collect_async(m, slot ^ 1, prev_cost_out);
+    return 0;
+}
+
+// cost of the last step issued by dae_model_train_step_async (*has_cost = 0 if none is pending)
+extern "C" int32_t dae_model_train_flush(dae_model* m, float* cost_out, int32_t* has_cost) {
+    if (!m) return fail("null model");
+    if (has_cost) *has_cost = m->async_pending ? 1 : 0;
+    if (!m->async_pending) return 0;
+    m->async_pending = false;
+    return collect_async(m, m->async_slot, cost_out);
 }
 
 extern "C" int32_t dae_model_set_debug(dae_model* m, int32_t flags) {

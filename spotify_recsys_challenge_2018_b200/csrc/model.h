@@ -102,6 +102,12 @@ struct dae_model {
     size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
     int last_batch = 0, last_bpad = 0;
     long long launches = 0;
+    // pipelined train loop (dae_model_train_step_async): the host runs one step ahead of the device
+    int async_slot = 1;
+    bool async_pending = false;
+    cudaEvent_t ev_cost[2] = {nullptr, nullptr};
+    float* cost_ring = nullptr;      // pinned [2]
+    int* err_ring = nullptr;         // pinned [2]
     // optional per-phase device timing (bench.py roofline): events around each phase of a step
     bool profiling = false;
     cudaEvent_t ph_ev[2 * 16] = {};

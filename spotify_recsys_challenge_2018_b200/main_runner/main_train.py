@@ -115,18 +115,23 @@ def run(conf, only_testmode):
         end_idx = reader.train_idx
         input_kp = random.uniform(kp_range[0], kp_range[-1])                  # main_train.py:199
         if conf.mode in ("pretrain", "dae"):
+            # pipelined step: the device works on this batch while the reader builds the next one; the cost that
+            # comes back is the previous step's (the loop only accumulates it, main_train.py:223)
             y_ones = np.ones(len(y_positions), np.float32)
             if np.random.randint(2) == 0:                                     # main_train.py:202-213
-                l = model.train_step(trk_positions, trk_val, y_positions, y_ones, conf.kp, input_kp)
+                l = model.train_step_async(trk_positions, trk_val, y_positions, y_ones, conf.kp, input_kp)
             else:
-                l = model.train_step(art_positions, art_val, y_positions, y_ones, conf.kp, input_kp)
+                l = model.train_step_async(art_positions, art_val, y_positions, y_ones, conf.kp, input_kp)
         else:                                                                  # main_train.py:214-221
             l = model_title.train_step(model, y_positions, np.ones(len(y_positions), np.float32), titles,
                                        conf.kp, conf.title_kp, input_kp)
-        loss += l
+        if l is not None:
+            loss += l
         it += 1
         n_seen += conf.batch
         if start_idx > end_idx or end_idx == 0:                               # main_train.py:227
+            if conf.mode in ("pretrain", "dae"):
+                loss += model.flush() or 0.0                                  # the epoch's last step
             epoch += 1
             loss = loss / it
             log_write(conf, "epoch " + str(epoch))

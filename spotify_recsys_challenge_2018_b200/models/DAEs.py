@@ -142,6 +142,22 @@ class DAE_tied:
                                                   float(input_keep_prob), C.byref(cost)))
         return float(cost.value)
 
+    def train_step_async(self, x_positions, x_vals, y_positions, y_vals, keep_prob, input_keep_prob):
+        """The same step, pipelined: returns the cost of the PREVIOUS step (None on the first call) while this one
+        runs; `flush()` returns the last pending cost.  The runner only accumulates the cost (main_train.py:223)."""
+        xp, xv = _coo(x_positions, x_vals)
+        yp, yv = _coo(y_positions, y_vals)
+        cost = C.c_float(); has = C.c_int32()
+        _lib.check(self._lib.dae_model_train_step_async(self._h, _ptr(xp), _ptr(xv), xp.shape[0], _ptr(yp), _ptr(yv),
+                                                        yp.shape[0], self.n_batch, float(keep_prob),
+                                                        float(input_keep_prob), C.byref(cost), C.byref(has)))
+        return float(cost.value) if has.value else None
+
+    def flush(self):
+        cost = C.c_float(); has = C.c_int32()
+        _lib.check(self._lib.dae_model_train_flush(self._h, C.byref(cost), C.byref(has)))
+        return float(cost.value) if has.value else None
+
     def predict(self, x_positions, x_vals, tracks_only=False):
         """`sess.run(y_pred, keep_prob=1, input_keep_prob=1)` (main_train.py:66-68) -> [batch, n_input]
         (or [batch, n_tracks], the slice the runner keeps, main_train.py:86)."""

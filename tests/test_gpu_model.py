@@ -142,6 +142,29 @@ def test_training_trajectory_matches_oracle(tied):
     m.close()
 
 
+def test_pipelined_step_equals_synchronous_step():
+    """train_step_async (the runner's call) returns the same costs as train_step, one call late, and leaves the
+    same parameters."""
+    N, T, H, B = 3000, 2500, 64, 128
+    rng = np.random.default_rng(3)
+    batches = []
+    for step in range(6):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=20)
+        batches.append((trk, np.ones(len(trk), np.float32), y, np.ones(len(y), np.float32)))
+    conf, ora, m1 = _mk(False, N, T, H, B, lr=0.01)
+    sync_costs = [m1.train_step(*b, 0.8, 0.75) for b in batches]
+    p1 = m1.get_params(); m1.close()
+    conf, ora, m2 = _mk(False, N, T, H, B, lr=0.01)
+    got = [m2.train_step_async(*b, 0.8, 0.75) for b in batches]
+    assert got[0] is None
+    got = got[1:] + [m2.flush()]
+    assert m2.flush() is None
+    p2 = m2.get_params(); m2.close()
+    np.testing.assert_allclose(got, sync_costs, rtol=1e-6)
+    for a, b in zip(p1, p2):
+        assert (np.abs(a - b) > 1e-6).mean() < 2e-3            # identical up to the scatter's atomic ordering
+
+
 def test_reg_lambda_cost_and_update():
     N, T, H, B = 1500, 1200, 64, 64
     conf, ora, m = _mk(False, N, T, H, B, lam=1e-3)
