@@ -66,6 +66,71 @@ struct ItemTileDev {
     const float* title_score;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// G1 TRAIN epilogue on 32 accumulator values of one item row (32 batch columns): p = sigmoid(z), the weighted BCE
+// term (DAEs.py:98-99), d cost / d z packed to bf16.  `yw` bit j = y[b0 + j, item].  The hot loop keeps
+// the cheap gradient form ratio = (1-p | p), which equals p(1-p)/((p | 1-p) + 1e-10) to fp32 rounding unless the
+// denominator is tiny; `minden` tells the caller when train_chunk_exact has to redo the chunk.  MASKED: columns
+// >= n_valid are padding of the batch tile.
+template <bool MASKED>
+__device__ __forceinline__ void train_chunk(const uint32_t (&r)[32], uint32_t yw, float c1, float c2, float wl_pos,
+                                            float wl_neg, float c_pos, float c_neg, int n_valid, float& loss,
+                                            float& db, float& minden, uint32_t (&packed)[16]) {
+    float md = 1.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        float dzv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[j + u]), c1, c2));
+            const float pr = rcp_approx(1.f + e);
+            const float omp = 1.f - pr;
+            const bool yb = (yw >> (j + u)) & 1u;
+            const float den = (yb ? pr : omp) + kEpsLog;
+            float wl = yb ? wl_pos : wl_neg;
+            float cz = yb ? c_pos : c_neg;
+            if (MASKED) {
+                const bool live = (j + u) < n_valid;
+                wl = live ? wl : 0.f;
+                cz = live ? cz : 0.f;
+            }
+            md = fminf(md, den);
+            loss = fmaf(wl, lg2_approx(den), loss);
+            const float dz = (yb ? omp : pr) * cz;
+            db += dz;
+            dzv[u] = dz;
+        }
+        packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
+    }
+    minden = md;
+}
+
+// the exact gradient form near saturation (p == 1.0f in fp32 -> p(1-p) == 0 -> dz == 0, as TF computes it)
+__device__ __forceinline__ void train_chunk_exact(const uint32_t (&r)[32], uint32_t yw, float c1, float c2, float c_pos,
+                                               float c_neg, int n_valid, float& db, uint32_t (&packed)[16]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {        // static register indices: the arrays must stay in registers
+        float dzv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float e = ex2_approx(fmaf(__uint_as_float(r[j + u]), c1, c2));
+            const float pr = rcp_approx(1.f + e);
+            const float omp = 1.f - pr;
+            const bool yb = (yw >> (j + u)) & 1u;
+            const float den = (yb ? pr : omp) + kEpsLog;
+            const float cz = (j + u) < n_valid ? (yb ? c_pos : c_neg) : 0.f;
+            const float fast = (yb ? omp : pr) * cz;
+            const float exact = den < 2e-3f ? __fdividef(pr * omp, den) * cz : fast;
+            db += exact - fast;
+            dzv[u] = exact;
+        }
+        packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
+    }
+}
+
 // blockIdx.y = batch tile: TRAIN decodes this rank's item rows against every rank's rows of the global batch
 // (tile bt = rank bt's playlists), PREDICT tiles an inference batch of more than 256 rows.
 template <int MODE>
@@ -189,7 +254,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     yw_next = __ldg(yrow + c_lo);
                 }
             }
-            float db = 0.f;
+            float db = 0.f, lt = 0.f;
+            // e^-z = 2^(acc * c1 + c2) with the bias folded in; -w ln(den) = wl * lg2(den); dz = ratio * (c_pos | c_neg)
+            const float c1 = -1.4426950408889634f, c2 = bz * c1;
+            const float wl_pos = -0.6931471805599453f, wl_neg = kNegWeight * wl_pos;
+            const float c_pos = -p.inv_batch, c_neg = kNegWeight * p.inv_batch;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
@@ -199,35 +268,14 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 tmem_ld32(t_addr + c * 32, r);
                 tmem_ld_wait();
                 if (MODE == MODE_TRAIN) {
-                    uint32_t packed[16];
                     const uint32_t w = yw_next;
                     if (item_ok && c + 1 < c_hi) yw_next = __ldg(yrow + c + 1);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float dzv[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int b = c * 32 + j + u;
-                            const float z = __uint_as_float(r[j + u]) + bz;
-                            const float e = __expf(-z);
-                            const float pr = __fdividef(1.f, 1.f + e);
-                            const float omp = 1.f - pr;
-                            const bool yb = (w >> (j + u)) & 1u;
-                            const float den = (yb ? pr : omp) + kEpsLog;
-                            const float wgt = yb ? 1.f : kNegWeight;
-                            const float pq = pr * omp;
-                            float ratio = yb ? omp : pr;                   // pq/den when eps is below half an ulp of den
-                            if (den < 2e-3f) ratio = __fdividef(pq, den);  // exact form near saturation (p==1.0f -> 0)
-                            const bool live = item_ok && (b < p.batch);
-                            const float lterm = -wgt * __logf(den);
-                            loss_acc += live ? lterm : 0.f;
-                            float dz = (yb ? -ratio : kNegWeight * ratio) * p.inv_batch;
-                            dz = live ? dz : 0.f;
-                            db += dz;
-                            dzv[u] = dz;
-                        }
-                        packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
-                    }
+                    uint32_t packed[16];
+                    float minden;
+                    if ((c + 1) * 32 <= p.batch) train_chunk<false>(r, w, c1, c2, wl_pos, wl_neg, c_pos, c_neg, 0, lt, db, minden, packed);
+                    else train_chunk<true>(r, w, c1, c2, wl_pos, wl_neg, c_pos, c_neg, p.batch - c * 32, lt, db, minden, packed);
+                    if (minden < 2e-3f)     // some p (or 1-p) is within reach of the 1e-10 inside the logs: exact gradient form
+                        train_chunk_exact(r, w, c1, c2, c_pos, c_neg, p.batch - c * 32, db, packed);
                     if (item_ok) {
                         __nv_bfloat16* dst = p.dzT + (size_t)row * p.ld_dz + bt * p.n_cols + c * 32;   // 64 B: two full sectors
                         st_global_v8(dst, packed);
@@ -252,7 +300,10 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
             if (MODE == MODE_TRAIN) {
-                if (item_ok) atomicAdd(p.db_dec + row, db);   // 2 column halves x batch tiles addends per item
+                if (item_ok) {
+                    atomicAdd(p.db_dec + row, db);            // 2 column halves x batch tiles addends per item
+                    loss_acc += lt;
+                }
             }
             tc_fence_before();
             __syncwarp();
