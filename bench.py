@@ -42,6 +42,7 @@ WORKLOADS = {
     "cfg3": (250000, 40000, 256, 256, False),     # DAE + char-CNN title head train step (--title)
     "cfg5": (2000000, 0, 256, 4096, False),       # challenge inference: top-500 over a 2M-item decoder, batch 4096
 }
+ROOF_KERNEL = "k_adam_rows_vec4"     # dominant kernel of the step (first capture in profiles/traffic.json = decoder launch)
 KP, KP_IN = 0.8, 0.75          # [DAE] keep_prob / input_kp of the shipped configs (0to1_inorder/config.ini:18-19)
 LR = 0.005
 
@@ -365,11 +366,21 @@ def main():
         adam_bytes = 30.0 * n_own * H
         adam_ms = phases.get("adam_dec")
         roofline = None
+        # DRAM bytes of the same launch from the committed ncu --set full capture (profiles/traffic.json, written by
+        # tools/summarize_profile.py): only quoted for the single-GPU shape it was captured on
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                caps = json.load(f)["kernels"].get(ROOF_KERNEL, [])
+            if caps and world == 1 and wl == "cfg2":
+                traffic = caps[0]["dram_bytes"]
+        except Exception:
+            pass
         if adam_ms:
             ach = adam_bytes / (adam_ms / 1e3) / 1e9
             roofline = {"kernel": "k_adam_rows_vec4 (decoder rows: dense TF1 Adam + bf16 operand refresh)", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": adam_bytes,
+                        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": adam_bytes,
                         "launch_ms": adam_ms}
         # whole step (per GPU): dW write 4 + decoder Adam 30 + encoder Adam 24 (untied) on the owned rows, + W operand read by
         # decode and dh (2 + 2) + dz write (2) and re-read by dh and dW (2 + 2) over all N rows
