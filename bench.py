@@ -42,7 +42,6 @@ WORKLOADS = {
     "cfg3": (250000, 40000, 256, 256, False),     # DAE + char-CNN title head train step (--title)
     "cfg5": (2000000, 0, 256, 4096, False),       # challenge inference: top-500 over a 2M-item decoder, batch 4096
 }
-ROOF_KERNEL = "k_adam_rows_vec4"     # dominant kernel of the step (first capture in profiles/traffic.json = decoder launch)
 KP, KP_IN = 0.8, 0.75          # [DAE] keep_prob / input_kp of the shipped configs (0to1_inorder/config.ini:18-19)
 LR = 0.005
 
@@ -208,6 +207,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--two-kernel", action="store_true", help="decoder dW and Adam as two kernels (gradient through HBM)")
     args = ap.parse_args()
     wl = args.workload
     T, A, H, B, tied = WORKLOADS[wl]
@@ -259,6 +259,8 @@ def main():
     conf.stream = stream.cuda_stream
     with torch.cuda.stream(stream):
         model = (DAE_tied if tied else DAE)(conf).fit()
+        if args.two_kernel:
+            model.set_debug(4)
         trainer = DataParallelDAE(model) if world > 1 else None
         batches = make_batches(wl, 8, seed=7, rank=rank)
         model.stage_batch(0, *batches[0])
@@ -359,32 +361,40 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        # dominant kernel: k_adam_rows_vec4 on the decoder rows this GPU owns (N/world).  Algorithmic bytes per launch
-        # (SURVEY 8d): read g,w,m,v (16 B) + write w,m,v (12 B) + write the bf16 operand copy (2 B; x world copies of
-        # which world-1 leave over NVLink) = 30 B / parameter.
+        # dominant kernel.  Default step: k_dw_adam_fused = dW_dec tile in tensor memory + dense TF1 Adam on the decoder
+        # rows this GPU owns (N/world): algorithmic bytes per launch = dz read 2 B x K/256 + w,m,v read 12 B
+        # + w,m,v write 12 B + bf16 operand copy 2 B = 28 B / parameter at K = 256 (the gradient never exists in HBM).
+        # --two-kernel (debug bit 2): k_adam_rows_vec4 = 30 B / parameter (g read 4 + 24 + 2).
         n_own = N / world
-        adam_bytes = 30.0 * n_own * H
-        adam_ms = phases.get("adam_dec")
+        fused = "adam_dec" not in phases
+        if fused:
+            roof_kernel, roof_ms = "k_dw_adam_fused", phases.get("dw_dec")
+            roof_bytes = (26.0 + 2.0 * world) * n_own * H
+            roof_desc = "k_dw_adam_fused (dW_dec tile in TMEM + dense TF1 Adam on the decoder rows + bf16 operand refresh)"
+        else:
+            roof_kernel, roof_ms = "k_adam_rows_vec4", phases.get("adam_dec")
+            roof_bytes = 30.0 * n_own * H
+            roof_desc = "k_adam_rows_vec4 (decoder rows: dense TF1 Adam + bf16 operand refresh)"
         roofline = None
         # DRAM bytes of the same launch from the committed ncu --set full capture (profiles/traffic.json, written by
         # tools/summarize_profile.py): only quoted for the single-GPU shape it was captured on
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                caps = json.load(f)["kernels"].get(ROOF_KERNEL, [])
+                caps = json.load(f)["kernels"].get(roof_kernel, [])
             if caps and world == 1 and wl == "cfg2":
                 traffic = caps[0]["dram_bytes"]
         except Exception:
             pass
-        if adam_ms:
-            ach = adam_bytes / (adam_ms / 1e3) / 1e9
-            roofline = {"kernel": "k_adam_rows_vec4 (decoder rows: dense TF1 Adam + bf16 operand refresh)", "bound": "hbm",
+        if roof_ms:
+            ach = roof_bytes / (roof_ms / 1e3) / 1e9
+            roofline = {"kernel": roof_desc, "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": adam_bytes,
-                        "launch_ms": adam_ms}
-        # whole step (per GPU): dW write 4 + decoder Adam 30 + encoder Adam 24 (untied) on the owned rows, + W operand read by
-        # decode and dh (2 + 2) + dz write (2) and re-read by dh and dW (2 + 2) over all N rows
-        step_bytes = (34.0 + (24.0 if not tied else 0.0)) * n_own * H + 10.0 * N * H
+                        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": roof_bytes,
+                        "launch_ms": roof_ms}
+        # whole step (per GPU): decoder dW+Adam 26 (fused; 34 as two kernels) + encoder Adam 24 (untied) on the owned rows,
+        # + W operand read by decode and dh (2 + 2) + dz write (2) and re-read by dh and dW (2 + 2) over all N rows
+        step_bytes = ((26.0 if fused else 34.0) + (24.0 if not tied else 0.0)) * n_own * H + 10.0 * N * H
         line = {"metric": "dae_train_playlists_per_sec", "value": value, "unit": "playlists/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

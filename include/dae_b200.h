@@ -135,9 +135,9 @@ int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
 
 /* debug / tuning flags.  bit 0: dae_model_backward_staged also forms dW_dec of the rows this rank owns
  * (buffer "g_dec") and bit 1: the sparse-row dW_enc scatter ("g_enc", "touched") -- both otherwise
- * happen inside dae_model_apply_adam, after the step's second barrier.  bit 2: apply_adam runs the
- * decoder's Adam update inside the dW contraction's epilogue (the gradient never leaves tensor
- * memory) instead of as a second kernel. */
+ * happen inside dae_model_apply_adam, after the step's second barrier.  bit 2: apply_adam forms dW_dec
+ * in HBM and runs the decoder's Adam update as a second kernel, instead of the default fused kernel
+ * that applies Adam to the dW tile while it is still in tensor memory. */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row

@@ -608,7 +608,7 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     m->scatter_done = false;
 
     DwArgs w = dw_args(m, bpad);
-    if (m->debug & 4) {   // experimental: Adam inside the dW epilogue, the gradient never leaves tensor memory
+    if (!(m->debug & 4)) {   // default: Adam applied to the dW tile while it is in tensor memory (gradient never in HBM)
         w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
         w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
         w.adam = AdamConst{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
@@ -617,7 +617,7 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
         launch_dw(w, m->st);
         ph_end(m, PH_DW);
         m->launches += 1;
-    } else {
+    } else {                 // debug bit 2: two kernels, the gradient goes through HBM (buffer "g_dec")
         w.g = m->g_dec;
         ph_begin(m, PH_DW);
         launch_dw(w, m->st);

@@ -422,18 +422,13 @@ struct DwDev {
     int mhalves;      // ceil(H / 128)
     int stream_h;     // h_d^T chunk rides in the ring with the dz chunk (K > 256)
     int n_global;     // catalogue size
-    float* g;         // raw dW_dec [local rows, H] or nullptr
-    float* aw; float* am; float* av;
-    const float* g_extra;
-    const unsigned char* touched;
-    AdamConst adam;
-    __nv_bfloat16* shadow;   // bf16 copy of the same rows as aw (same indexing)
+    float* g;         // raw dW_dec [local rows, H]
     PeerTable pt;
     int ld, col0;            // row stride and first column of the row-major outputs
 };
 
 __global__ void __launch_bounds__(kDwThreads, 1)
-k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmH,
+k_dw(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmH,
           const __grid_constant__ DwDev p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -566,52 +561,9 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
                 const int gitem0 = item_global(item0, world, p.pt.rank);             // 16 consecutive catalogue ids
                 const int nvalid = h_ok ? min(16, p.n_global - gitem0) : 0;
                 const size_t off0 = (size_t)item0 * p.ld + p.col0 + h;
-                if (p.g != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < nvalid) p.g[off0 + (size_t)j * p.ld] = __uint_as_float(r[j]);
-                }
-                if (p.aw != nullptr) {
-                    // dense TF1 Adam on the 16 gradient values this thread just read from TMEM: the gradient
-                    // never goes to HBM (26 B / parameter instead of 34)
-                    float wv[16], mv[16], vv[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < nvalid) {
-                            const size_t o = off0 + (size_t)j * p.ld;
-                            wv[j] = __ldcs(p.aw + o); mv[j] = __ldcs(p.am + o); vv[j] = __ldcs(p.av + o);
-                        } else {
-                            wv[j] = 0.f; mv[j] = 0.f; vv[j] = 0.f;
-                        }
-                    }
-                    if (p.g_extra != nullptr) {                                          // tied: + sparse-row dW_enc
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < nvalid && p.touched[item0 + j] != 0)
-                                r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __ldcs(p.g_extra + off0 + (size_t)j * p.ld)));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        adam_one(wv[j], mv[j], vv[j], __uint_as_float(r[j]), p.adam);
-                        if (j < nvalid) {
-                            const size_t o = off0 + (size_t)j * p.ld;
-                            __stcs(p.aw + o, wv[j]); __stcs(p.am + o, mv[j]); __stcs(p.av + o, vv[j]);
-                        }
-                    }
-                    if (p.shadow != nullptr) {
-                        // bf16 operand rows (same indexing as w): lanes pair up so that every lane stores one 4-byte
-                        // (h, h+1) pair -- even lanes for item j, odd lanes for item j+1
-                        const size_t soff0 = (size_t)item0 * p.ld + p.col0 + (h & ~1);
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float give = (lane & 1) ? wv[j] : wv[j + 1];           // what the partner lane stores
-                            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
-                            const int jj = j + (lane & 1);
-                            const uint32_t pk = (lane & 1) ? pack_bf16x2(got, wv[j + 1]) : pack_bf16x2(wv[j], got);
-                            if (jj < nvalid) *reinterpret_cast<uint32_t*>(p.shadow + soff0 + (size_t)jj * p.ld) = pk;
-                        }
-                    }
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (j < nvalid) p.g[off0 + (size_t)j * p.ld] = __uint_as_float(r[j]);
             }
             tc_fence_before();
             __syncwarp();
@@ -627,7 +579,259 @@ k_dw_adam(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUte
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// G2 + K5: dW_dec^T tile in tensor memory, dense TF1 Adam applied to it from there (the
+// gradient never exists in HBM: 2 (dz) + 24 (w, m, v read + write) + 2 (bf16 operand) = 28 B / parameter
+// instead of 2 + 4 (dW write) + 30 for the two-kernel path)
+// ------------------------------------------------------------------------------------------
+// Same W^T orientation as k_dw (TMEM lane = hidden unit, column = item).  The optimizer state never passes
+// through registers as global loads: one I/O thread streams 8-item row groups of w / m / v (8 x H fp32 = 8 KB
+// each, contiguous in the item-major layout) into a 5-stage shared-memory ring with 1-D bulk copies
+// (cp.async.bulk, mbarrier complete_tx), the 16 epilogue warps (two groups of 8, alternating row groups)
+// read their accumulator columns with tcgen05.ld, update the stage IN PLACE (conflict-free: lanes =
+// consecutive h), and the I/O thread writes the stage back with bulk stores (bulk async-groups; a stage is
+// re-loaded once its store has finished reading it).  Bytes in flight come from the copy engine, not from
+// warps stalled on loads, so the epilogue keeps HBM busy with 16 warps.  The bf16 operand copy of the
+// updated rows goes out as 64-byte warp stores.  MMA operands: both the dz chunk and the h_d^T chunk ride
+// a 2-stage ring (h_d^T is 128 KB and L2-resident); the MMA of tile t+1 overlaps the epilogue of tile t
+// through the two TMEM accumulators, and is ~10x shorter than it.
+constexpr int kFuItems = 8;                                    // rows of w / m / v per staging stage
+constexpr int kFuSub = kTileItems / kFuItems;                  // 16 row groups per tile
+constexpr int kFuStages = 5;
+constexpr int kFuMmaStages = 2;
+constexpr int kFuMmaStageBytes = kABytes + kBChunkBytes;       // 16 KB dz chunk + 32 KB h_d^T chunk
+constexpr int kFuStageBytes = 3 * kFuItems * 256 * 4;          // 24 KB at H = 256
+constexpr int kFuEpiWarps = 16;
+constexpr int kFuThreads = 128 + 32 * kFuEpiWarps;             // producer, MMA, I/O, (idle), 16 epilogue warps
+constexpr int kSmemFused = kFuMmaStages * kFuMmaStageBytes + kFuStages * kFuStageBytes + 256 + 1024;
+
+struct FusedDev {
+    int tiles, kchunks, H, mhalves, n_global, world, rank;
+    float* w; float* m; float* v;          // [local rows, H]
+    const float* g_extra;                  // tied: sparse-row dW_enc, added where touched
+    const unsigned char* touched;
+    __nv_bfloat16* shadow;                 // [local rows, H] or nullptr
+    AdamConst adam;
+};
+
+__global__ void __launch_bounds__(kFuThreads, 1)
+k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmH,
+                const __grid_constant__ FusedDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+    uint8_t* sS = smem + kFuMmaStages * kFuMmaStageBytes;            // optimizer-state staging ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + kFuStages * kFuStageBytes);
+    uint64_t* full = bars;                         // [2] MMA operand stage loaded
+    uint64_t* empty = full + kFuMmaStages;         // [2] MMA operand stage consumed
+    uint64_t* tfull = empty + kFuMmaStages;        // [2] accumulator complete
+    uint64_t* tempty = tfull + 2;                  // [2] accumulator drained
+    uint64_t* ld_full = tempty + 2;                // [5] w / m / v rows of the stage have landed
+    uint64_t* done = ld_full + kFuStages;          // [5] the stage holds the updated rows
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + kFuStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int hbox_rows = p.mhalves * 128;
+    const int n_my = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDz);
+        tma_prefetch_desc(&tmH);
+        for (int s = 0; s < kFuMmaStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], kFuEpiWarps);
+        }
+        for (int s = 0; s < kFuStages; ++s) {
+            mbar_init(&ld_full[s], 1);
+            mbar_init(&done[s], kFuEpiWarps / 2);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer: MMA operands =================
+        if (lane == 0) {
+            const uint64_t pol_stream = policy_evict_first();
+            const uint64_t pol_keep = policy_evict_last();
+            const uint32_t tx = static_cast<uint32_t>(kABytes + hbox_rows * 128);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int tile = blockIdx.x + t * gridDim.x;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_expect_tx(&full[stage], tx);
+                    uint8_t* dst = smem + stage * kFuMmaStageBytes;
+                    tma_load_2d_hint(dst, &tmDz, &full[stage], kc * 64, tile * kTileItems, pol_stream);
+                    tma_load_2d_hint(dst + kABytes, &tmH, &full[stage], kc * 64, 0, pol_keep);
+                    if (++stage == kFuMmaStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, kTileItems, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int acc = t & 1;
+                mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t dz_addr = smem_u32(smem + stage * kFuMmaStageBytes);
+                    const uint32_t h_addr = dz_addr + kABytes;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t bd = umma_smem_desc(dz_addr + ks * 32, 16, 1024);
+                        for (int mh = 0; mh < p.mhalves; ++mh) {
+                            const uint64_t ad = umma_smem_desc(h_addr + mh * (128 * 128) + ks * 32, 16, 1024);
+                            umma_bf16(d_tmem + static_cast<uint32_t>(mh * kTileItems), ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kFuMmaStages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp == 2) {
+        // ================= I/O thread: optimizer state through the staging ring =================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            const uint32_t abytes = static_cast<uint32_t>(kFuItems * p.H * 4);   // one array's rows of a stage
+            const int total = n_my * kFuSub;
+            auto elem_off = [&](int i) -> size_t {
+                const int tile = blockIdx.x + (i / kFuSub) * gridDim.x;
+                return ((size_t)tile * kTileItems + (size_t)(i % kFuSub) * kFuItems) * p.H;
+            };
+            auto issue_load = [&](int i) {
+                const int s = i % kFuStages;
+                uint8_t* dst = sS + s * kFuStageBytes;
+                const size_t off = elem_off(i);
+                mbar_expect_tx(&ld_full[s], 3u * abytes);
+                bulk_load_hint(dst, p.w + off, abytes, &ld_full[s], pol);
+                bulk_load_hint(dst + abytes, p.m + off, abytes, &ld_full[s], pol);
+                bulk_load_hint(dst + 2 * abytes, p.v + off, abytes, &ld_full[s], pol);
+            };
+            for (int i = 0; i < kFuStages && i < total; ++i) issue_load(i);
+            for (int i = 0; i < total; ++i) {
+                const int s = i % kFuStages;
+                mbar_wait(&done[s], static_cast<uint32_t>((i / kFuStages) & 1));
+                const uint8_t* src = sS + s * kFuStageBytes;
+                const size_t off = elem_off(i);
+                bulk_store_hint(p.w + off, src, abytes, pol);
+                bulk_store_hint(p.m + off, src + abytes, abytes, pol);
+                bulk_store_hint(p.v + off, src + 2 * abytes, abytes, pol);
+                bulk_commit_group();
+                if (i >= 1) {
+                    bulk_wait_group_read<1>();           // the store of row group i-1 no longer reads its stage
+                    if (i - 1 + kFuStages < total) issue_load(i - 1 + kFuStages);
+                }
+            }
+            bulk_wait_group<0>();
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue warps: Adam on the accumulator columns =================
+        const int ew = warp - 4;
+        const int grp = ew >> 3;                       // row groups grp, grp + 2, ...
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+        const int mh = (ew & 7) >> 2;                  // M-half (hidden units 0-127 / 128-255)
+        const int h = mh * 128 + q * 32 + lane;
+        const bool h_ok = h < p.H;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int astride = kFuItems * p.H;            // floats between the w, m and v blocks of a stage
+        for (int t = 0; t < n_my; ++t) {
+            const int tile = blockIdx.x + t * gridDim.x;
+            const int acc = t & 1;
+            mbar_wait(&tfull[acc], static_cast<uint32_t>((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256 + mh * kTileItems);
+#pragma unroll 1
+            for (int sub = grp; sub < kFuSub; sub += 2) {
+                const int i = t * kFuSub + sub;
+                const int s = i % kFuStages;
+                uint32_t r[8];
+                __syncwarp();                                                    // tcgen05.ld is warp-collective
+                tmem_ld8(t_addr + sub * kFuItems, r);
+                mbar_wait(&ld_full[s], static_cast<uint32_t>((i / kFuStages) & 1));
+                tmem_ld_wait();
+                const int item0 = tile * kTileItems + sub * kFuItems;            // local row of column 0 of the group
+                const int gitem0 = item_global(item0, p.world, p.rank);          // 8 consecutive catalogue ids
+                const int nvalid = h_ok ? max(0, min(kFuItems, p.n_global - gitem0)) : 0;
+                float* sw = reinterpret_cast<float*>(sS + s * kFuStageBytes) + h;
+#pragma unroll
+                for (int j = 0; j < kFuItems; ++j) {
+                    if (j < nvalid) {
+                        float* pw = sw + j * p.H;
+                        float wv = pw[0], mv = pw[astride], vv = pw[2 * astride];
+                        float g = __uint_as_float(r[j]);
+                        if (p.g_extra != nullptr && p.touched[item0 + j] != 0)   // tied: + sparse-row dW_enc
+                            g = __fadd_rn(g, __ldcs(p.g_extra + (size_t)(item0 + j) * p.H + h));
+                        adam_one(wv, mv, vv, g, p.adam);
+                        pw[0] = wv; pw[astride] = mv; pw[2 * astride] = vv;
+                        if (p.shadow != nullptr) p.shadow[(size_t)(item0 + j) * p.H + h] = __float2bfloat16_rn(wv);
+                    }
+                }
+                fence_proxy_async_smem();              // the bulk store (async proxy) must see these writes
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&done[s]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
+    if ((a.ld != 0 && a.ld != a.H) || a.col0 != 0 || a.H % 64 != 0 || a.H > 256) {
+        fprintf(stderr, "dae_b200: launch_dw_adam_fused needs dense [rows, H <= 256] state (ld=%d col0=%d H=%d)\n", a.ld, a.col0, a.H);
+        abort();
+    }
+    FusedDev p{};
+    p.world = a.pt.world > 0 ? a.pt.world : 1;
+    p.rank = a.pt.rank;
+    const int tiles_total = (a.N + kTileItems - 1) / kTileItems;
+    p.tiles = tiles_total > p.rank ? (tiles_total - p.rank + p.world - 1) / p.world : 0;
+    if (p.tiles == 0) return;
+    p.n_global = a.N;
+    p.kchunks = a.K / 64;
+    p.H = a.H;
+    p.mhalves = (a.H + 127) / 128;
+    p.w = a.w; p.m = a.m; p.v = a.v;
+    p.g_extra = a.g_extra; p.touched = a.touched;
+    p.shadow = a.shadow;
+    p.adam = a.adam;
+    const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
+    const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
+    const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
+    k_dw_adam_fused<<<grid, kFuThreads, kSmemFused, st>>>(tmDz, tmH, p);
+}
+
 void launch_dw(const DwArgs& a, cudaStream_t st) {
+    if (a.w != nullptr) {        // Adam applied to the tile while it is in tensor memory
+        launch_dw_adam_fused(a, st);
+        return;
+    }
     DwDev p{};
     p.pt = a.pt;
     if (p.pt.world < 1) p.pt.world = 1;
@@ -641,16 +845,12 @@ void launch_dw(const DwArgs& a, cudaStream_t st) {
     p.mhalves = (a.H + 127) / 128;
     p.stream_h = a.K > 256 ? 1 : 0;
     p.g = a.g;
-    p.aw = a.w; p.am = a.m; p.av = a.v;
-    p.g_extra = a.g_extra; p.touched = a.touched;
-    p.adam = a.adam;
-    p.shadow = a.w != nullptr ? a.shadow : nullptr;
     p.ld = a.ld > 0 ? a.ld : a.H;
     p.col0 = a.col0;
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
     const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
     const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
-    k_dw_adam<<<grid, kDwThreads, kSmemItemTile, st>>>(tmDz, tmH, p);
+    k_dw<<<grid, kDwThreads, kSmemItemTile, st>>>(tmDz, tmH, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -810,11 +1010,13 @@ void preload_gemm() {
     cudaFuncAttributes a;
     cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_itemtile<MODE_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
-    cudaFuncSetAttribute(k_dw_adam, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_dw_adam_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused);
     cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
     cudaFuncGetAttributes(&a, k_itemtile<MODE_TRAIN>);
     cudaFuncGetAttributes(&a, k_itemtile<MODE_PREDICT>);
-    cudaFuncGetAttributes(&a, k_dw_adam);
+    cudaFuncGetAttributes(&a, k_dw);
+    cudaFuncGetAttributes(&a, k_dw_adam_fused);
     cudaFuncGetAttributes(&a, k_dh);
     (void)cudaGetLastError();
 }

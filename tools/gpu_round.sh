@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 if [ -z "$SKIP_TESTS" ]; then
-  echo "== pytest -m gpu"; timeout 1500 python -m pytest tests/ -x -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+  echo "== pytest -m gpu"; timeout 1500 python -m pytest ${PYTEST_ARGS:-tests/} -x -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_gpu.log
   echo "== smoke"; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/smoke.log
 fi
 echo "== bench"; timeout 600 python bench.py ${BENCH_ARGS} > gpurun_out/bench_round.json 2> gpurun_out/bench_round.err; echo "rc=$?"
