@@ -137,7 +137,8 @@ int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
  * (buffer "g_dec") and bit 1: the sparse-row dW_enc scatter ("g_enc", "touched") -- both otherwise
  * happen inside dae_model_apply_adam, after the step's second barrier.  bit 2: apply_adam forms dW_dec
  * in HBM and runs the decoder's Adam update as a second kernel, instead of the default fused kernel
- * that applies Adam to the dW tile while it is still in tensor memory. */
+ * that applies Adam to the dW tile while it is still in tensor memory.  bit 3: dae_model_train_step_staged keeps
+ * the decoder update on the main stream instead of overlapping it with the sparse / encoder tail of the step. */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row

@@ -156,6 +156,9 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     if (cfg->stream) { m->st = reinterpret_cast<cudaStream_t>(cfg->stream); }
     else { CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)); m->own_stream = true; }
     CK(cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&m->st3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&m->ev_dh, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_dec, cudaEventDisableTiming));
     m->rows_alloc = m->Bmax <= kMaxBpad ? round_up(m->Bmax, 64) : round_up(m->Bmax, kMaxBpad);
     m->max_nnz = m->Bmax * 1024;
     const int tiles_total = (m->N + kTileItems - 1) / kTileItems;
@@ -192,6 +195,7 @@ extern "C" void dae_model_destroy(dae_model* m) {
     if (!m) return;
     cudaStreamSynchronize(m->st);
     cudaStreamSynchronize(m->st2);
+    if (m->st3) cudaStreamSynchronize(m->st3);
     for (int r = 0; r < kMaxWorld; ++r) if (m->ipc_opened[r]) cudaIpcCloseMemHandle(m->ipc_opened[r]);
     if (m->arena.base) cudaFree(m->arena.base);
     for (void* p : m->host_allocs) cudaFreeHost(p);
@@ -208,6 +212,9 @@ extern "C" void dae_model_destroy(dae_model* m) {
     if (m->ph_ev[0]) for (int i = 0; i < 2 * PH_COUNT; ++i) cudaEventDestroy(m->ph_ev[i]);
     for (int i = 0; i < 2; ++i) if (m->ev_cost[i]) cudaEventDestroy(m->ev_cost[i]);
     cudaStreamDestroy(m->st2);
+    if (m->st3) cudaStreamDestroy(m->st3);
+    if (m->ev_dh) cudaEventDestroy(m->ev_dh);
+    if (m->ev_dec) cudaEventDestroy(m->ev_dec);
     if (m->own_stream) cudaStreamDestroy(m->st);
     delete m;
 }
@@ -502,6 +509,36 @@ static DwArgs dw_args(dae_model* m, int bpad) {
     return w;
 }
 
+// Decoder update of the rows this rank owns.  Default: ONE kernel, dW_dec tile in tensor memory + dense TF1 Adam + bf16
+// operand refresh (the gradient never exists in HBM).  debug bit 2: two kernels, dW_dec through HBM (buffer "g_dec").
+static void run_decoder_update(dae_model* m, int bpad, cudaStream_t st) {
+    const AdamArgs a0 = adam_args(m);
+    DwArgs w = dw_args(m, bpad);
+    if (!(m->debug & 4)) {
+        w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
+        w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
+        w.adam = AdamConst{a0.alpha, a0.one_minus_b1, a0.one_minus_b2, a0.eps, a0.lambda};
+        w.shadow = m->shadow;
+        ph_begin(m, PH_DW, st);
+        launch_dw(w, st);
+        ph_end(m, PH_DW, st);
+        m->launches += 1;
+    } else {
+        AdamArgs a = a0;
+        w.g = m->g_dec;
+        ph_begin(m, PH_DW, st);
+        launch_dw(w, st);
+        ph_end(m, PH_DW, st);
+        a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.row_touched = m->tied ? m->touched : nullptr;
+        a.n = (long long)m->n_local * m->H; a.row_len = m->H;
+        ph_begin(m, PH_ADAM_DEC, st);
+        launch_adam_rows(a, m->tied ? m->g_enc : nullptr, m->shadow, st);
+        ph_end(m, PH_ADAM_DEC, st);
+        m->launches += 2;
+    }
+    m->full_stale = true;
+}
+
 // Forward + backward of one step up to the gradients of the batch side (da, db_enc, db_dec, cost).  Three
 // cross-GPU barriers order the exchanges (none when world == 1):
 //   A  the previous step is over on every rank (its Adam wrote W_enc rows this step gathers; nobody still reads the
@@ -565,6 +602,17 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
             m->launches += 2;
         }
     }
+    // The decoder update needs only dz and h_d^T, both final now (and the l2 term above has read W_dec).  In a whole step (dae_model_train_step_staged) of an
+    // untied model it starts here on its own stream and streams w / m / v through HBM while the main stream runs the
+    // latency-bound tail (split-K sums, da, sparse scatter) and the encoder's Adam; apply_adam joins the two.  Not while
+    // profiling: the per-phase times (bench.py roofline) are taken with the kernels running alone.
+    if (m->overlap_dec && !m->tied && !m->profiling && !(m->debug & (1 | 2 | 8))) {
+        CK(cudaEventRecord(m->ev_dh, m->st));
+        CK(cudaStreamWaitEvent(m->st3, m->ev_dh, 0));
+        run_decoder_update(m, bpad, m->st3);
+        CK(cudaEventRecord(m->ev_dec, m->st3));
+        m->dec_inflight = true;
+    }
     launch_reduce_loss2(m->loss_partial, m->n_loss_partial, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost_part, m->st);
     m->launches += 1;
 
@@ -607,29 +655,13 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (!m->scatter_done) run_scatter(m, B, bpad);
     m->scatter_done = false;
 
-    DwArgs w = dw_args(m, bpad);
-    if (!(m->debug & 4)) {   // default: Adam applied to the dW tile while it is in tensor memory (gradient never in HBM)
-        w.w = m->W_dec; w.m = m->mW_dec; w.v = m->vW_dec;
-        w.g_extra = m->tied ? m->g_enc : nullptr; w.touched = m->tied ? m->touched : nullptr;
-        w.adam = AdamConst{a.alpha, a.one_minus_b1, a.one_minus_b2, a.eps, a.lambda};
-        w.shadow = m->shadow;
-        ph_begin(m, PH_DW);
-        launch_dw(w, m->st);
-        ph_end(m, PH_DW);
-        m->launches += 1;
-    } else {                 // debug bit 2: two kernels, the gradient goes through HBM (buffer "g_dec")
-        w.g = m->g_dec;
-        ph_begin(m, PH_DW);
-        launch_dw(w, m->st);
-        ph_end(m, PH_DW);
-        a.w = m->W_dec; a.m = m->mW_dec; a.v = m->vW_dec; a.g = m->g_dec; a.row_touched = m->tied ? m->touched : nullptr;
-        a.n = (long long)m->n_local * H; a.row_len = H;
-        ph_begin(m, PH_ADAM_DEC);
-        launch_adam_rows(a, m->tied ? m->g_enc : nullptr, m->shadow, m->st);
-        ph_end(m, PH_ADAM_DEC);
-        m->launches += 2;
+    if (!m->dec_inflight) run_decoder_update(m, bpad, m->st);
+    else {
+        // join before the encoder's Adam: two HBM-bound streams running together lose bandwidth (measured: 0.950 vs
+        // 0.934 ms / step), so only the latency-bound tail above (split-K sums, da, scatter) overlaps the decoder update
+        CK(cudaStreamWaitEvent(m->st, m->ev_dec, 0));
+        m->dec_inflight = false;
     }
-    m->full_stale = true;
 
     ph_begin(m, PH_ADAM_ENC);
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
@@ -658,7 +690,10 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
 }
 
 extern "C" int32_t dae_model_train_step_staged(dae_model* m, int32_t slot, float keep_prob, float input_keep_prob) {
-    TRY(dae_model_backward_staged(m, slot, keep_prob, input_keep_prob, 0, 0));
+    if (m) m->overlap_dec = true;
+    const int rc = dae_model_backward_staged(m, slot, keep_prob, input_keep_prob, 0, 0);
+    if (m) m->overlap_dec = false;
+    if (rc) return rc;
     return dae_model_apply_adam(m);
 }
 

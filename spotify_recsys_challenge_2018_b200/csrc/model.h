@@ -62,6 +62,10 @@ struct dae_model {
     bool tied = false, trainable = true, needs_y = true, own_stream = false, attached = false;
     cudaStream_t st = nullptr;      // main stream: the step
     cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
+    cudaStream_t st3 = nullptr;     // decoder-update stream: k_dw_adam_fused overlaps the sparse / encoder tail of the step
+    cudaEvent_t ev_dh = nullptr, ev_dec = nullptr;
+    bool overlap_dec = false;       // set by dae_model_train_step_staged: launch the decoder update as soon as dz is final
+    bool dec_inflight = false;      // this step's decoder update is already running on st3
     int cur = 0;                    // slot used by the last step (dae_model_buffer)
     Arena arena;
     PeerTable pt{};
