@@ -159,6 +159,10 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     CK(cudaStreamCreateWithFlags(&m->st3, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&m->ev_dh, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_dec, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_y, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_da, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_bias, cudaEventDisableTiming));
     m->rows_alloc = m->Bmax <= kMaxBpad ? round_up(m->Bmax, 64) : round_up(m->Bmax, kMaxBpad);
     m->max_nnz = m->Bmax * 1024;
     const int tiles_total = (m->N + kTileItems - 1) / kTileItems;
@@ -215,6 +219,10 @@ extern "C" void dae_model_destroy(dae_model* m) {
     if (m->st3) cudaStreamDestroy(m->st3);
     if (m->ev_dh) cudaEventDestroy(m->ev_dh);
     if (m->ev_dec) cudaEventDestroy(m->ev_dec);
+    if (m->ev_a) cudaEventDestroy(m->ev_a);
+    if (m->ev_y) cudaEventDestroy(m->ev_y);
+    if (m->ev_da) cudaEventDestroy(m->ev_da);
+    if (m->ev_bias) cudaEventDestroy(m->ev_bias);
     if (m->own_stream) cudaStreamDestroy(m->st);
     delete m;
 }
@@ -472,14 +480,15 @@ void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float 
 }
 
 // target bitmask of the global batch over this rank's item rows, from every rank's slot CSR
-void build_ybits(dae_model* m, int slot, int B, int bpad) {
+void build_ybits(dae_model* m, int slot, int B, int bpad, cudaStream_t st) {
     const Slot& s = m->slots[slot];
+    if (!st) st = m->st;
     YbitsArgs y{};
     y.y = s.yw; y.ybits = m->ybits; y.n_local = m->n_local; y.ywords = m->world * bpad / 32; y.B = B; y.bpad = bpad;
     y.err = m->err; y.pt = m->pt;
-    ph_begin(m, PH_YBITS);
-    launch_ybits_shard(y, m->st);
-    ph_end(m, PH_YBITS);
+    ph_begin(m, PH_YBITS, st);
+    launch_ybits_shard(y, st);
+    ph_end(m, PH_YBITS, st);
     m->launches += 1;
 }
 
@@ -565,8 +574,19 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     ph_begin(m, PH_BARRIER);
     barrier(m);                                                               // A
     ph_end(m, PH_BARRIER);
+    // whole-step calls fork the work that is off the critical path onto st3: the target bitmask (next to the encode), the
+    // decoder update (next to the sparse tail) and the bias updates (next to the encoder's Adam).  Not while profiling:
+    // the per-phase times are taken with every kernel running alone.
+    m->par_step = m->overlap_dec && !m->profiling && !(m->debug & (1 | 2 | 8));
+    if (m->par_step) {
+        CK(cudaEventRecord(m->ev_a, m->st));
+        CK(cudaStreamWaitEvent(m->st3, m->ev_a, 0));
+        build_ybits(m, slot, B, bpad, m->st3);
+        CK(cudaEventRecord(m->ev_y, m->st3));
+    }
     run_encode(m, slot, bpad, bpad, keep_prob, input_keep_prob, row_offset, true);
-    build_ybits(m, slot, B, bpad);
+    if (m->par_step) CK(cudaStreamWaitEvent(m->st, m->ev_y, 0));
+    else build_ybits(m, slot, B, bpad);
     barrier(m);                                                               // B1
     CK(cudaEventRecord(s.consumed, m->st));                 // every rank has read this slot: it may be re-prepared
 
@@ -606,7 +626,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     // untied model it starts here on its own stream and streams w / m / v through HBM while the main stream runs the
     // latency-bound tail (split-K sums, da, sparse scatter) and the encoder's Adam; apply_adam joins the two.  Not while
     // profiling: the per-phase times (bench.py roofline) are taken with the kernels running alone.
-    if (m->overlap_dec && !m->tied && !m->profiling && !(m->debug & (1 | 2 | 8))) {
+    if (m->par_step && !m->tied) {
         CK(cudaEventRecord(m->ev_dh, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_dh, 0));
         run_decoder_update(m, bpad, m->st3);
@@ -631,6 +651,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
         m->launches += 2;
     }
     ph_end(m, PH_DA);
+    if (m->par_step) CK(cudaEventRecord(m->ev_da, m->st));    // every bias gradient is final
 
     if (m->debug & 1) {    // parity tests: form dW_dec / dW_enc now, where they can be inspected before Adam consumes them
         DwArgs w = dw_args(m, bpad);
@@ -663,6 +684,21 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
         m->dec_inflight = false;
     }
 
+    cudaStream_t sb = m->st;
+    if (m->par_step) {              // bias updates behind the decoder update on st3, next to the encoder's Adam
+        sb = m->st3;
+        CK(cudaStreamWaitEvent(sb, m->ev_da, 0));
+    }
+    ph_begin(m, PH_ADAM_BIAS, sb);
+    a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
+    a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = H;
+    launch_adam(a, sb);
+    a.w = m->b_dec; a.m = m->mb_dec; a.v = m->vb_dec; a.g = m->g_b_dec; a.n = N;
+    launch_adam(a, sb);
+    m->launches += 2 + (N % 4 ? 1 : 0);
+    ph_end(m, PH_ADAM_BIAS, sb);
+    if (m->par_step) CK(cudaEventRecord(m->ev_bias, sb));
+
     ph_begin(m, PH_ADAM_ENC);
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
         a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
@@ -673,15 +709,10 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     launch_clear_flagged(m->n_local, H, m->g_enc, m->touched, m->st);
     m->launches += 1;
     ph_end(m, PH_ADAM_ENC);
-
-    ph_begin(m, PH_ADAM_BIAS);
-    a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
-    a.w = m->b_enc; a.m = m->mb_enc; a.v = m->vb_enc; a.g = m->g_b_enc; a.n = H;
-    launch_adam(a, m->st);
-    a.w = m->b_dec; a.m = m->mb_dec; a.v = m->vb_dec; a.g = m->g_b_dec; a.n = N;
-    launch_adam(a, m->st);
-    m->launches += 2 + (N % 4 ? 1 : 0);
-    ph_end(m, PH_ADAM_BIAS);
+    if (m->par_step) {
+        CK(cudaStreamWaitEvent(m->st, m->ev_bias, 0));
+        m->par_step = false;
+    }
     ph_collect(m);
     m->b1_pow *= kBeta1;
     m->b2_pow *= kBeta2;

@@ -63,7 +63,8 @@ struct dae_model {
     cudaStream_t st = nullptr;      // main stream: the step
     cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
     cudaStream_t st3 = nullptr;     // decoder-update stream: k_dw_adam_fused overlaps the sparse / encoder tail of the step
-    cudaEvent_t ev_dh = nullptr, ev_dec = nullptr;
+    cudaEvent_t ev_dh = nullptr, ev_dec = nullptr, ev_a = nullptr, ev_y = nullptr, ev_da = nullptr, ev_bias = nullptr;
+    bool par_step = false;          // this step forks work onto st3 (whole-step call, not profiling, debug bit 3 clear)
     bool overlap_dec = false;       // set by dae_model_train_step_staged: launch the decoder update as soon as dz is final
     bool dec_inflight = false;      // this step's decoder update is already running on st3
     int cur = 0;                    // slot used by the last step (dae_model_buffer)
@@ -135,4 +136,4 @@ int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_
                const int64_t* y_pos, const float* y_val, int64_t nnz_y, int32_t batch, bool with_y);
 int check_device_flag(dae_model* m);
 void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset, bool train);
-void build_ybits(dae_model* m, int slot, int B, int bpad);
+void build_ybits(dae_model* m, int slot, int B, int bpad, cudaStream_t st = nullptr);
