@@ -33,7 +33,7 @@ enum { MODE_TRAIN = 0, MODE_PREDICT = 1 };
 
 constexpr int kStages = 6;
 constexpr int kStagesStreamB = 4;                    // G2, K > 256: stages of (16 KB item chunk + 32 KB second-operand chunk)
-constexpr int kEpiWarps = 8;                         // 2 warps per TMEM lane quadrant: each takes half the columns
+constexpr int kEpiWarps = 16;                        // 4 warps per TMEM lane quadrant, 32-column chunks dealt round-robin
 constexpr int kItemThreads = 64 + 32 * kEpiWarps;
 constexpr int kABytes = kTileItems * 128;           // one K-chunk of the streamed operand: 128 rows x 128 B
 constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the resident operand: <=256 rows x 128 B
@@ -70,18 +70,19 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// G1 TRAIN epilogue on 32 accumulator values of one item row (32 batch columns): p = sigmoid(z), the weighted BCE
+// G1 TRAIN epilogue on 16 accumulator values of one item row (16 batch columns): p = sigmoid(z), the weighted BCE
 // term (DAEs.py:98-99), d cost / d z packed to bf16.  `yw` bit j = y[b0 + j, item].  The hot loop keeps
 // the cheap gradient form ratio = (1-p | p), which equals p(1-p)/((p | 1-p) + 1e-10) to fp32 rounding unless the
 // denominator is tiny; `minden` tells the caller when train_chunk_exact has to redo the chunk.  MASKED: columns
 // >= n_valid are padding of the batch tile.
+constexpr int kCw = 16;     // accumulator columns an epilogue warp handles per tcgen05.ld (keeps the live set under 96 registers)
 template <bool MASKED>
-__device__ __forceinline__ void train_chunk(const uint32_t (&r)[32], uint32_t yw, float c1, float c2, float wl_pos,
+__device__ __forceinline__ void train_chunk(const uint32_t (&r)[kCw], uint32_t yw, float c1, float c2, float wl_pos,
                                             float wl_neg, float c_pos, float c_neg, int n_valid, float& loss,
-                                            float& db, float& minden, uint32_t (&packed)[16]) {
+                                            float& db, float& minden, uint32_t (&packed)[kCw / 2]) {
     float md = 1.f;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < kCw; j += 2) {
         float dzv[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -109,10 +110,10 @@ __device__ __forceinline__ void train_chunk(const uint32_t (&r)[32], uint32_t yw
 }
 
 // the exact gradient form near saturation (p == 1.0f in fp32 -> p(1-p) == 0 -> dz == 0, as TF computes it)
-__device__ __forceinline__ void train_chunk_exact(const uint32_t (&r)[32], uint32_t yw, float c1, float c2, float c_pos,
-                                               float c_neg, int n_valid, float& db, uint32_t (&packed)[16]) {
+__device__ __forceinline__ void train_chunk_exact(const uint32_t (&r)[kCw], uint32_t yw, float c1, float c2, float c_pos,
+                                               float c_neg, int n_valid, float& db, uint32_t (&packed)[kCw / 2]) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {        // static register indices: the arrays must stay in registers
+    for (int j = 0; j < kCw; j += 2) {        // static register indices: the arrays must stay in registers
         float dzv[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -129,6 +130,42 @@ __device__ __forceinline__ void train_chunk_exact(const uint32_t (&r)[32], uint3
         }
         packed[j >> 1] = pack_bf16x2(dzv[0], dzv[1]);
     }
+}
+
+// min of three (sm_100 FMNMX3)
+__device__ __forceinline__ float min3(float a, float b, float c) { float y; asm("min.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
+
+// G1 TRAIN epilogue, the common case: 16 full columns treated as y = 0 (targets are ~5e-4 dense; the few y = 1
+// cells are patched afterwards from tensor memory).  Per element: t = -z log2e (bias folded, FFMA), e = 2^t (MUFU),
+// u = (1 + e) / c_neg (FFMA), dz = 1 / u = p * c_neg (MUFU: the reciprocal IS the gradient), 1 - p = 1 - dz / c_neg
+// (FFMA), and the loss term log2(1 - p) is taken once per EIGHT elements on their product (1 - p >= 2e-3 or the
+// caller redoes the chunk exactly, so the product cannot underflow): 2.125 MUFU + ~6.5 other instructions per
+// element instead of 3 + 19.  Returns sum(log2(1 - p)), sum(dz), min(1 - p).
+__device__ __forceinline__ void train_chunk_y0(const uint32_t (&r)[kCw], float c1, float c2, float ic, float& lg_sum,
+                                               float& dz_sum, float& minden, uint32_t (&packed)[kCw / 2]) {
+    float md = 1.f, ls = 0.f, sd = 0.f;
+    const float nic = -ic;
+#pragma unroll
+    for (int j0 = 0; j0 < kCw; j0 += 8) {
+        float prod = 1.f;
+#pragma unroll
+        for (int j = j0; j < j0 + 8; j += 2) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), c1, c2));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), c1, c2));
+            const float d0 = rcp_approx(fmaf(e0, ic, ic));
+            const float d1 = rcp_approx(fmaf(e1, ic, ic));
+            const float o0 = fmaf(d0, nic, 1.f);
+            const float o1 = fmaf(d1, nic, 1.f);
+            md = min3(md, o0, o1);
+            prod *= o0;
+            prod *= o1;
+            sd += d0;
+            sd += d1;
+            packed[j >> 1] = pack_bf16x2(d0, d1);
+        }
+        ls += lg2_approx(prod);
+    }
+    lg_sum = ls; dz_sum = sd; minden = md;
 }
 
 // blockIdx.y = batch tile: TRAIN decodes this rank's item rows against every rank's rows of the global batch
@@ -231,57 +268,103 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;          // which half of the accumulator columns this warp owns
+        const int part = (warp - 2) >> 2;          // chunks part, part + 4, ... of the accumulator columns are this warp's
         const int row_in_tile = q * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         int acc = 0;
         uint32_t acc_phase = 0;
         float loss_acc = 0.f;
         const int nchunks = p.n_cols >> 5;
-        const int c_lo = half * (nchunks >> 1), c_hi = c_lo + (nchunks >> 1);
         const int yword0 = bt * (p.n_cols >> 5);   // this batch tile's words inside a row of the target bitmask
+        // e^-z = 2^(acc * c1 + c2) with the bias folded in; -w ln(den) = wl * lg2(den); dz = ratio * (c_pos | c_neg)
+        const float c1 = -1.4426950408889634f;
+        const float wl_pos = -0.6931471805599453f, wl_neg = kNegWeight * wl_pos;
+        const float c_pos = -p.inv_batch, c_neg = kNegWeight * p.inv_batch;
+        const float ic = 1.f / c_neg;
+        // per-tile scalars of this lane's item row (bias, target words of the warp's two chunks) are fetched ONE TILE
+        // AHEAD: they come from HBM (~1 us) and would otherwise stall the warp at the top of every tile
+        float bz_nx = 0.f;
+        uint32_t ya_nx = 0, yb_nx = 0;
+        auto prefetch_row = [&](int tile) {
+            const int row = tile * kTileItems + row_in_tile;
+            const int item = MODE == MODE_TRAIN ? item_global(row, p.world, p.rank) : row;
+            bz_nx = 0.f; ya_nx = 0; yb_nx = 0;
+            if (tile < p.tiles && row < p.n_rows && item < p.n_global) {
+                bz_nx = __ldg(p.bias + item);
+                if (MODE == MODE_TRAIN) {
+                    const uint32_t* yrow = p.ybits + (size_t)row * p.ywords + yword0;
+                    if (part < nchunks) ya_nx = __ldg(yrow + part);
+                    if (part + 4 < nchunks) yb_nx = __ldg(yrow + part + 4);
+                }
+            }
+        };
+        prefetch_row(blockIdx.x);
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int row = tile * kTileItems + row_in_tile;                                   // row of the streamed operand
             const int item = MODE == MODE_TRAIN ? item_global(row, p.world, p.rank) : row;     // catalogue id
             const bool item_ok = row < p.n_rows && item < p.n_global;
-            float bz = 0.f;
-            uint32_t yw_next = 0;
-            const uint32_t* yrow = nullptr;
-            if (item_ok) bz = __ldg(p.bias + item);
-            if (MODE == MODE_TRAIN) {
-                if (item_ok) {
-                    yrow = p.ybits + (size_t)row * p.ywords + yword0;
-                    yw_next = __ldg(yrow + c_lo);
-                }
-            }
+            const float bz = bz_nx;
+            const uint32_t yw_a = ya_nx, yw_b = yb_nx;
+            prefetch_row(tile + gridDim.x);
             float db = 0.f, lt = 0.f;
-            // e^-z = 2^(acc * c1 + c2) with the bias folded in; -w ln(den) = wl * lg2(den); dz = ratio * (c_pos | c_neg)
-            const float c1 = -1.4426950408889634f, c2 = bz * c1;
-            const float wl_pos = -0.6931471805599453f, wl_neg = kNegWeight * wl_pos;
-            const float c_pos = -p.inv_batch, c_neg = kNegWeight * p.inv_batch;
+            const float c2 = bz * c1;
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
 #pragma unroll 1
-            for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t r[32];
-                tmem_ld32(t_addr + c * 32, r);
-                tmem_ld_wait();
+            for (int c = part; c < nchunks; c += 4) {
                 if (MODE == MODE_TRAIN) {
-                    const uint32_t w = yw_next;
-                    if (item_ok && c + 1 < c_hi) yw_next = __ldg(yrow + c + 1);
-                    uint32_t packed[16];
-                    float minden;
-                    if ((c + 1) * 32 <= p.batch) train_chunk<false>(r, w, c1, c2, wl_pos, wl_neg, c_pos, c_neg, 0, lt, db, minden, packed);
-                    else train_chunk<true>(r, w, c1, c2, wl_pos, wl_neg, c_pos, c_neg, p.batch - c * 32, lt, db, minden, packed);
-                    if (minden < 2e-3f)     // some p (or 1-p) is within reach of the 1e-10 inside the logs: exact gradient form
-                        train_chunk_exact(r, w, c1, c2, c_pos, c_neg, p.batch - c * 32, db, packed);
-                    if (item_ok) {
-                        __nv_bfloat16* dst = p.dzT + (size_t)row * p.ld_dz + bt * p.n_cols + c * 32;   // 64 B: two full sectors
-                        st_global_v8(dst, packed);
-                        st_global_v8(dst + 16, packed + 8);
+                    const uint32_t w32 = c == part ? yw_a : yw_b;
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int col0 = c * 32 + hh * kCw;            // first batch column of this half chunk
+                        uint32_t r[kCw];
+                        tmem_ld16(t_addr + col0, r);
+                        tmem_ld_wait();
+                        const uint32_t w = (w32 >> (hh * kCw)) & 0xffffu;
+                        uint32_t packed[kCw / 2];
+                        uint32_t pend = 0;             // y = 1 cells of this lane still to be patched
+                        bool general = col0 + kCw > p.batch;           // partial half chunk (batch padding): warp-uniform
+                        if (!general) {
+                            float ls, sd, md;
+                            train_chunk_y0(r, c1, c2, ic, ls, sd, md, packed);
+                            if (md < 2e-3f) general = true;            // some 1 - p is within reach of the 1e-10 inside the logs
+                            else { lt = fmaf(wl_neg, ls, lt); db += sd; pend = w; }
+                        }
+                        if (general) {
+                            float minden;
+                            if (col0 + kCw <= p.batch) train_chunk<false>(r, w, c1, c2, wl_pos, wl_neg, c_pos, c_neg, 0, lt, db, minden, packed);
+                            else train_chunk<true>(r, w, c1, c2, wl_pos, wl_neg, c_pos, c_neg, p.batch - col0, lt, db, minden, packed);
+                            if (minden < 2e-3f)     // exact gradient form near saturation
+                                train_chunk_exact(r, w, c1, c2, c_pos, c_neg, p.batch - col0, db, packed);
+                        }
+                        __nv_bfloat16* dst = p.dzT + (size_t)row * p.ld_dz + bt * p.n_cols + col0;     // 32 B: one full sector
+                        if (item_ok) st_global_v8(dst, packed);
+                        // patch the y = 1 cells: re-read the accumulator column (warp-uniform address), redo the cell with
+                        // its target, replace its bf16 gradient (same thread, later store wins) and correct the sums
+                        uint32_t um = __reduce_or_sync(0xffffffffu, item_ok ? pend : 0u);
+                        while (um != 0) {
+                            const int k = __ffs(um) - 1;
+                            um &= um - 1;
+                            const float zacc = __uint_as_float(tmem_ld1(t_addr + col0 + k));
+                            tmem_ld_wait();
+                            if (item_ok && ((pend >> k) & 1u)) {
+                                const float e = ex2_approx(fmaf(zacc, c1, c2));
+                                const float pr = rcp_approx(1.f + e);
+                                const float omp = 1.f - pr;
+                                const float den = pr + kEpsLog;
+                                lt = fmaf(wl_pos, lg2_approx(den), lt);
+                                lt = fmaf(-wl_neg, lg2_approx(omp), lt);
+                                const float dz1 = (den < 2e-3f ? __fdividef(pr * omp, den) : omp) * c_pos;
+                                db += dz1 - pr * c_neg;
+                                dst[k] = __float2bfloat16_rn(dz1);
+                            }
+                        }
                     }
                 } else {
+                    uint32_t r[32];
+                    tmem_ld32(t_addr + c * 32, r);
+                    tmem_ld_wait();
                     const bool col_ok = item < p.n_out;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
