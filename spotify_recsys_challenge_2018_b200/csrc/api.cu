@@ -600,14 +600,6 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     launch_decode_train(d, m->st);
     ph_end(m, PH_DECODE_LOSS);
 
-    DhArgs q{}; q.dzT = m->dz_all; q.W = m->shadow; q.partial = m->dh_partial; q.N = m->n_local; q.H = H; q.bpad = bpad;
-    q.nsplit = m->nsplit; q.n_batch_tiles = R; q.ld_dz = R * bpad;
-    ph_begin(m, PH_DH);
-    launch_dh(q, m->st);
-    launch_reduce_splits(m->dh_partial, m->nsplit, bpad, H, R, m->dh_sum, m->st);
-    ph_end(m, PH_DH);
-    m->launches += 3 + 2;
-
     int n_sq = 0;
     const float lam = m->cfg.reg_lambda;
     if (lam != 0.f) {      // l2 term (DAEs.py:79-82, :147-150): own rows of the matrices; the replicated biases once (rank 0)
@@ -622,6 +614,10 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
             m->launches += 2;
         }
     }
+    DhArgs q{}; q.dzT = m->dz_all; q.W = m->shadow; q.partial = m->dh_partial; q.N = m->n_local; q.H = H; q.bpad = bpad;
+    q.nsplit = m->nsplit; q.n_batch_tiles = R; q.ld_dz = R * bpad;
+    ph_begin(m, PH_DH);
+    launch_dh(q, m->st);
     // The decoder update needs only dz and h_d^T, both final now (and the l2 term above has read W_dec).  In a whole step (dae_model_train_step_staged) of an
     // untied model it starts here on its own stream and streams w / m / v through HBM while the main stream runs the
     // latency-bound tail (split-K sums, da, sparse scatter) and the encoder's Adam; apply_adam joins the two.  Not while
@@ -633,6 +629,10 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
         CK(cudaEventRecord(m->ev_dec, m->st3));
         m->dec_inflight = true;
     }
+    launch_reduce_splits(m->dh_partial, m->nsplit, bpad, H, R, m->dh_sum, m->st);
+    ph_end(m, PH_DH);
+    m->launches += 3 + 2;
+
     launch_reduce_loss2(m->loss_partial, m->n_loss_partial, m->sq_partial, n_sq, lam, 1.0f / (float)gb, m->cost_part, m->st);
     m->launches += 1;
 

@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(256)
 k_adam_rows_vec4(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v, const float4* __restrict__ g,
                  const float4* __restrict__ g_sparse, __nv_bfloat16* __restrict__ shadow,
                  const unsigned char* __restrict__ touched, unsigned int n4,
-                 unsigned int row_len4, const AdamConst c) {
+                 unsigned int row_len4, int row_shift, const AdamConst c) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const unsigned int lrow = i / row_len4;
+        const unsigned int lrow = row_shift >= 0 ? (i >> row_shift) : i / row_len4;   // H/4 is a power of two for H = 64, 128, 256
         // gradient = dense part (dW_dec) + sparse rows (dW_enc, read only where the step touched the row)
         float4 gv = g != nullptr ? __ldcs(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (g_sparse != nullptr && touched[lrow] != 0) {
@@ -83,9 +83,12 @@ void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* s
     long long blocks = (n4 + 255) / 256;
     const long long cap = 148LL * 16;
     if (blocks > cap) blocks = cap;
+    const unsigned int rl4 = (unsigned int)(a.row_len / 4);
+    int shift = -1;
+    if (rl4 != 0 && (rl4 & (rl4 - 1)) == 0) { shift = 0; while ((1u << shift) < rl4) ++shift; }
     k_adam_rows_vec4<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(a.w), reinterpret_cast<float4*>(a.m),
                                                   reinterpret_cast<float4*>(a.v), reinterpret_cast<const float4*>(a.g),
-                                                  reinterpret_cast<const float4*>(g_sparse), shadow, a.row_touched, (unsigned int)n4, (unsigned int)(a.row_len / 4), c);
+                                                  reinterpret_cast<const float4*>(g_sparse), shadow, a.row_touched, (unsigned int)n4, rl4, shift, c);
 }
 
 __global__ void k_adam_scalar(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,

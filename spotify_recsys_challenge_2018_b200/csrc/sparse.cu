@@ -156,7 +156,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
     return t;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const int* __restrict__ row_ptr,
              const int* __restrict__ row_len, const int* __restrict__ col, const float* __restrict__ val,
              const __grid_constant__ PubInput pub, float* __restrict__ rowsum, float* __restrict__ h, __nv_bfloat16* __restrict__ h_d,
@@ -164,7 +164,7 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
              float kp_in, unsigned long long seed, unsigned long long step, int row_offset, const __grid_constant__ PeerTable pt) {
     __shared__ __align__(16) float s_x[kMaxRowNnz];
     __shared__ int s_c[kMaxRowNnz];
-    __shared__ float s_red[8];
+    __shared__ float s_red[16];
     const int r = blockIdx.x;
     const int k = threadIdx.x;
     const int world = pt.world;
@@ -213,7 +213,8 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     __syncthreads();
     // a4: a = sum_j x_n[j] * W_enc[col_j, :].  Thread (g, t): row group g takes entries j = g (mod G),
     // lane t owns columns [4t, 4t+4) as one float4 -> every gathered row is a run of coalesced 16 B loads
-    // and up to 4*G rows are in flight per CTA.  Groups are combined through smem in a fixed order.
+    // and up to 8*G rows (64 at H = 256) are in flight per CTA: the kernel lasts as long as its longest playlist
+    // (250 entries), i.e. ceil(250 / 64) round trips to HBM.  Groups are combined through smem in a fixed order.
     // Rows live on their owner GPU (tile-cyclic); remote rows are plain loads over NVLink.
     const int tpr = H >> 2;                      // threads per row
     const int G = blockDim.x / tpr;              // concurrent row groups
@@ -225,16 +226,16 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     };
     if (g < G) {
         int i = g;
-        for (; i + 3 * G < n; i += 4 * G) {
-            float x[4];
-            float4 w[4];
+        for (; i + 7 * G < n; i += 8 * G) {
+            float x[8];
+            float4 w[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 x[u] = s_x[i + u * G];
                 w[u] = x[u] != 0.f ? __ldg(row_of(s_c[i + u * G])) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 acc.x = fmaf(x[u], w[u].x, acc.x); acc.y = fmaf(x[u], w[u].y, acc.y);
                 acc.z = fmaf(x[u], w[u].z, acc.z); acc.w = fmaf(x[u], w[u].w, acc.w);
             }
@@ -268,7 +269,7 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
 }
 
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st) {
-    const int threads = 256;                      // G = 1024 / H row groups of H/4 threads
+    const int threads = 512;                      // G = 2048 / H row groups of H/4 threads
     k_encode_fwd<<<a.bpad, threads, 0, st>>>(a.W_enc, a.b_enc, a.x.row_ptr, a.x.row_len, a.x.col, a.x.val, a.pub,
                                              a.rowsum, a.h, a.h_d, a.h_dT, a.B, a.bpad, a.H, a.K, a.row0, a.bcast,
                                              a.kp, a.kp_in, a.seed, a.step, a.row_offset, a.pt);
