@@ -1,0 +1,91 @@
+"""End-to-end parity of the metric the reference reports (BASELINE north_star): r-precision@500 after
+E epochs of `main.py --pretrain`-style training on synthetic MPD-shaped data (tools/synth_mpd.py, the reference's
+JSON schema read by the reader mirror), CUDA path vs the oracle on the SAME batch stream, parameters, seeds and
+dropout masks.  Bar: |delta r-precision| <= 0.001 per test file.
+
+Ranking ties and near-ties: the two paths differ by fp32 summation order / MUFU approximations / the scatter's atomic
+order, so individual candidates may swap; the metric is an average over 200 playlists x ~30 answers."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import dae_oracle as O
+from oracle import ranking
+from spotify_recsys_challenge_2018_b200.models.DAEs import DAE, DAE_tied
+from spotify_recsys_challenge_2018_b200.utils import data_reader as rdr
+from spotify_recsys_challenge_2018_b200.utils import metrics as met
+from tests.gpu_util import Conf
+from tools.synth_mpd import write_dataset
+
+pytestmark = pytest.mark.gpu
+
+R_PRECISION_TOL = 0.001     # BASELINE.json north_star: "r-precision@500 within +-0.001"
+
+
+def run_rprecision_parity(data_dir, tied, H, B, epochs, lr, tests=("test-5", "test-10", "test-25"), n_test=200):
+    random.seed(0)
+    np.random.seed(0)
+    reader = rdr.data_reader(data_dir, "train", B)
+    N, T = reader.num_items, reader.num_tracks
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=lr, reg_lambda=0.0, seed=3)
+    ora = O.DAEOracle(N, H, lr, tied=tied, seed=1, mode="b200")
+    m = (DAE_tied if tied else DAE)(conf).fit()
+    m.set_params(ora.params())
+    steps = epochs * (len(reader.playlists) // B + 1)
+    costs = []
+    for s in range(steps):
+        trk, art, y, titles, tv, av = reader.next_batch()
+        x, xv = (trk, tv) if s % 2 == 0 else (art, av)                 # hide-and-seek (main_train.py:202-213)
+        x = np.asarray(x, np.int64); xv = np.asarray(xv, np.float32)
+        y = np.asarray(y, np.int64); yv = np.ones(len(y), np.float32)
+        c_gpu = m.train_step(x, xv, y, yv, 0.8, 0.75)
+        c_ora = ora.train_step(x, xv, y, yv, B, 0.8, 0.75, seed=conf.seed)
+        costs.append((c_gpu, c_ora))
+    out = {}
+    for name in tests:
+        t = rdr.data_reader_test(data_dir, name, 100, n_test)
+        tot_g = tot_o = 0.0
+        n = 0
+        overlap = 0.0
+        while True:
+            x, seeds, answers, titles, ones = t.next_batch_test()
+            x = np.asarray(x, np.int64).reshape(-1, 2); ones = np.asarray(ones, np.float32)
+            cand_g = m.recommend(x, ones, seeds, k=500)
+            p = ora.predict(x, ones, len(seeds))[:, :T]
+            for i in range(len(seeds)):
+                cand_o = ranking.topk_excluding_seeds(p[i], seeds[i], 500)
+                g = [int(v) for v in cand_g[i] if v >= 0]
+                tot_g += met.get_r_precision(answers[i], g)
+                tot_o += met.get_r_precision(answers[i], [int(v) for v in cand_o])
+                overlap += len(set(g) & set(int(v) for v in cand_o)) / 500.0
+                n += 1
+            if t.test_idx == 0:
+                break
+        out[name] = (tot_g / n, tot_o / n, overlap / n, n)
+    m.close()
+    return costs, out
+
+
+@pytest.mark.parametrize("tied,H,B,epochs", [(True, 64, 128, 10), (False, 64, 128, 6)])
+def test_rprecision_parity_cfg1(tmp_path, tied, H, B, epochs):
+    """cfg1 (BASELINE configs[0]): 1k playlists x 5k tracks (+1k artists), latent 64, batch 128."""
+    write_dataset(str(tmp_path), n_tracks=5000, n_artists=1000, n_train=1000, n_test=200, n_challenge=4, n_clusters=16)
+    costs, out = run_rprecision_parity(str(tmp_path), tied, H, B, epochs, lr=0.005)
+    c_gpu, c_ora = costs[-1]
+    # the measured values travel back from the GPU box (gpurun_out/) so that they can be quoted in profiles/
+    rep = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(rep):
+        with open(os.path.join(rep, "rprecision_%s.json" % ("tied" if tied else "untied")), "w") as f:
+            json.dump({"config": {"tied": tied, "hidden": H, "batch": B, "epochs": epochs, "n_train": 1000, "n_tracks": 5000,
+                                  "n_artists": 1000, "test_playlists": 200, "k": 500},
+                       "last_cost": {"gpu": c_gpu, "oracle": c_ora},
+                       "r_precision": {k: {"gpu": v[0], "oracle": v[1], "top500_overlap": v[2]} for k, v in out.items()}}, f, indent=1)
+    assert abs(c_gpu - c_ora) <= 1e-2 * abs(c_ora), costs[-5:]
+    for name, (rp_gpu, rp_ora, overlap, n) in out.items():
+        assert n == 200
+        assert rp_ora > 0.05, (name, rp_ora)                               # the model has learnt the planted clusters
+        assert abs(rp_gpu - rp_ora) <= R_PRECISION_TOL, (name, rp_gpu, rp_ora)
+        assert overlap > 0.97, (name, overlap)                             # top-500 sets agree except near the cut
