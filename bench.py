@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -201,8 +201,8 @@ def aux_workload(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=5)
@@ -282,13 +282,15 @@ def main():
             torch.cuda.synchronize()
 
         # ---- device-timed throughput, inputs resident in HBM ------------------------------
+        # clocks / throttle reasons are sampled under load: from the warm-up through the timed region and the
+        # end-to-end loop (the timed region alone lasts ~50 ms, too short for nvidia-smi's sampling period)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         for i in range(args.warmup):
             step(i)
         model.sync_cost()
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         l0 = model.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -299,7 +301,6 @@ def main():
         launches = model.launch_count() - l0
         ms = e0.elapsed_time(e1)
         cost = model.sync_cost()
-        clocks = sampler.stop() if rank == 0 else None
         t = torch.tensor([ms], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -345,6 +346,7 @@ def main():
                    "api": "models.DAEs.DAE.train_step_async on every rank (world = N model attached with dp.DataParallelDAE): "
                           "per-rank host COO in, per-step cost back"}
 
+        clocks = sampler.stop() if rank == 0 else None
         # ---- per-phase device times (profiled steps; not part of `value`) -----------------------
         model.set_profiling(True)
         for i in range(min(args.steps, 20)):
