@@ -91,6 +91,15 @@ int32_t dae_model_train_flush(dae_model* m, float* cost_out, int32_t* has_cost);
 int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
                             const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t* out_idx,
                             float* out_score);
+/* The same ranking restricted to the catalogue range [item_lo, item_hi) (clipped to the tracks): global ids, seeds
+ * removed.  Item-sharded challenge inference gives every GPU one range and merges the per-shard lists with
+ * dae_topk_merge_device; the merged list is exactly the unsharded one.  Ranges of >= 131072 items (and debug bit 4)
+ * run the fused decode + top-K (threshold-filtered candidate lists, the [batch, T] score matrix never exists; batch
+ * up to max_batch rows in 256-row tiles); smaller ranges, or a candidate list that overflowed, take the dense path.
+ *                                                   main_challenge.py:80-90 (y_pred[:, :n_tracks] + cand_generate) */
+int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
+                                  const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t item_lo,
+                                  int32_t item_hi, int32_t* out_idx, float* out_score);
 
 /* ---- device-resident / asynchronous variants (bench `value`, data-parallel training) ---------- */
 
@@ -138,7 +147,8 @@ int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
  * happen inside dae_model_apply_adam, after the step's second barrier.  bit 2: apply_adam forms dW_dec
  * in HBM and runs the decoder's Adam update as a second kernel, instead of the default fused kernel
  * that applies Adam to the dW tile while it is still in tensor memory.  bit 3: dae_model_train_step_staged keeps
- * the decoder update on the main stream instead of overlapping it with the sparse / encoder tail of the step. */
+ * the decoder update on the main stream instead of overlapping it with the sparse / encoder tail of the step.
+ * bit 4: dae_model_recommend[_range] always takes the fused decode + top-K path, bit 5: never. */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row
@@ -210,6 +220,9 @@ int32_t dae_title_buffer(dae_title* t, const char* name, void** dev_ptr, int64_t
 int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t batch, int32_t n_tracks, int32_t k,
                         const int32_t* seed_ptr_dev, const int32_t* seed_idx_dev, int32_t idx_base,
                         int32_t* out_idx_dev, float* out_score_dev, void* stream);
+/* merge of per-shard top-k lists: row r = n (score, global id) pairs, -inf / -1 padded -> first k by (score desc, id asc) */
+int32_t dae_topk_merge_device(const float* scores_dev, const int32_t* idx_dev, int32_t n, int32_t batch, int32_t k,
+                              int32_t* out_idx_dev, float* out_score_dev, void* stream);
 /* ApplyAdam on one variable.                                         DAEs.py:102 [TF1] */
 int32_t dae_adam_device(float* w_dev, float* m_dev, float* v_dev, const float* g_dev, uint16_t* w_bf16_dev,
                         int64_t n, float lr, float beta1_power, float beta2_power, float reg_lambda, void* stream);

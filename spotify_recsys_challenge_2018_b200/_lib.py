@@ -46,6 +46,7 @@ SIGNATURES = {
     "dae_model_train_flush": (_I32, [_P, C.POINTER(_F), C.POINTER(_I32)]),
     "dae_model_predict": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P]),
     "dae_model_recommend": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _I32, _P, _P]),
+    "dae_model_recommend_range": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P]),
     "dae_model_stage_batch": (_I32, [_P, _I32, _P, _P, _I64, _P, _P, _I64, _I32]),
     "dae_model_restage": (_I32, [_P, _I32]),
     "dae_model_backward_staged": (_I32, [_P, _I32, _F, _F, _I32, _I32]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "dae_title_launch_count": (_I64, [_P]),
     "dae_title_buffer": (_I32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
     "dae_topk_device": (_I32, [_P, _I64, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P]),
+    "dae_topk_merge_device": (_I32, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "dae_adam_device": (_I32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P]),
     "dae_coo_to_csr_device": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "dae_dh_nsplit": (_I32, [_I32]),

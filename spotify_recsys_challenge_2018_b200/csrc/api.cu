@@ -1,6 +1,7 @@
 // C-ABI of libdae_b200.so (include/dae_b200.h): the model object (parameters, TF1-Adam state,
 // workspaces, staging) and the orchestration of one train / predict / recommend step.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -208,6 +209,8 @@ extern "C" void dae_model_destroy(dae_model* m) {
     if (m->topk_score) cudaFree(m->topk_score);
     if (m->seed_ptr) cudaFree(m->seed_ptr);
     if (m->seed_idx) cudaFree(m->seed_idx);
+    cudaFree(m->cand_val); cudaFree(m->cand_idx); cudaFree(m->cand_cnt); cudaFree(m->cand_thr);
+    cudaFree(m->cand_tk_idx); cudaFree(m->cand_tk_score);
     for (int s = 0; s < 2; ++s) {
         if (m->slots[s].h2d_done) cudaEventDestroy(m->slots[s].h2d_done);
         if (m->slots[s].prepared) cudaEventDestroy(m->slots[s].prepared);
@@ -854,37 +857,162 @@ static int ensure_buf(T** p, size_t* have, size_t need, cudaStream_t st) {
     return 0;
 }
 
-extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
-                                       int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
-                                       int32_t* out_idx, float* out_score) {
+// ---- fused decode + top-K (SURVEY 8d "challenge decode + top-K": T.H.s_w bytes, not B.T scores) ----------------------
+// The [B, T] score matrix is never materialised.  Three filter passes over growing prefixes of the item range
+// ([lo, lo+M1) c [lo, lo+M2) c [lo, hi)): a pass appends every logit >= the playlist's threshold to its candidate list,
+// an exact top-(k + max #seeds) of the list gives the threshold of the next pass.  The kp-th largest logit of a SUBSET is
+// a lower bound of the kp-th largest of the whole range, so no member of the final top-k can be filtered out; with
+// M2 / M1 = 16 and T / M2 = 8 the lists hold ~kp x 16 and ~kp x 8 entries for exchangeable scores (popularity-ranked ids
+// make the prefix bound tighter still).  A list that overflows its capacity is detected and the call falls back to the
+// tiled dense path, so the result is exact in every case.  Total decode work: (M1 + M2 + T) / T = 1.13x.
+constexpr int kCandCap = 16384;
+constexpr int kFusedMinItems = 131072;     // smaller ranges: dense scores + k_topk
+
+static int ensure_cand(dae_model* m, size_t rows, int kp) {
+    if (m->cand_rows >= rows) return 0;
+    CK(cudaStreamSynchronize(m->st));
+    cudaFree(m->cand_val); cudaFree(m->cand_idx); cudaFree(m->cand_cnt); cudaFree(m->cand_thr);
+    cudaFree(m->cand_tk_idx); cudaFree(m->cand_tk_score);
+    m->cand_rows = 0;
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->cand_val), rows * kCandCap * sizeof(float)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->cand_idx), rows * kCandCap * sizeof(int)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->cand_cnt), rows * 3 * sizeof(int)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->cand_thr), rows * sizeof(float)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->cand_tk_idx), rows * 1024 * sizeof(int)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&m->cand_tk_score), rows * 1024 * sizeof(float)));
+    if (!m->cand_cnt_host) TRY(halloc(m, &m->cand_cnt_host, 4));
+    m->cand_rows = rows;
+    (void)kp;
+    return 0;
+}
+
+// max over rows and passes of the candidate counts -> one int for the host
+__global__ void k_max_int(const int* __restrict__ v, int n, int* __restrict__ out) {
+    int mx = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mx = max(mx, v[i]);
+    atomicMax(out, mx);
+}
+
+// top-k of the item range [lo, hi) for the batch staged in slot 0 -> m->topk_idx / m->topk_score (global ids, sigmoid
+// scores).  *overflow_out = 1 when a candidate list overflowed (the caller redoes the range densely).
+static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* sp, const int* si, int max_seeds) {
+    const Slot& s = m->slots[0];
+    const int B = s.batch;
+    int bpad, nbt;
+    if (B <= kMaxBpad) { bpad = round_up(B, 64); nbt = 1; }
+    else { bpad = kMaxBpad; nbt = (B + kMaxBpad - 1) / kMaxBpad; }
+    if (!m->attached) return fail("world = %d but the peers are not attached (dae_model_attach_ipc)", m->world);
+    if (m->world > 1 && m->full_stale) {
+        launch_gather_rows_bf16(m->shadow, m->shadow_full, m->N, m->H, m->pt, m->st);
+        m->launches += 1;
+    }
+    m->full_stale = false;
+    const int rows = bpad * nbt, Tn = hi - lo, kp = k + max_seeds;
+    TRY(ensure_cand(m, (size_t)rows, kp));
+    CK(cudaStreamWaitEvent(m->st, s.prepared, 0));
+    run_encode(m, 0, bpad, rows, 1.0f, 1.0f, 0, false);
+    CK(cudaEventRecord(s.consumed, m->st));
+
+    const int M1 = std::min(Tn, std::min(kCandCap - 128, std::max(round_up(Tn / 128, kTileItems), 2048)));
+    const int M2 = std::min(Tn, std::max(round_up(Tn / 8, kTileItems), M1));
+    CK(cudaMemsetAsync(m->cand_cnt, 0, sizeof(int) * 3 * rows, m->st));
+    launch_thr_from_topk(nullptr, nullptr, kp, B, rows, m->cand_thr, m->st);          // pass A keeps everything
+    DecodeArgs d{};
+    d.W = m->shadow_full; d.h_d = m->h_d; d.bias = m->b_dec; d.N = m->N; d.H = m->H; d.batch = B; d.bpad = bpad;
+    d.n_batch_tiles = nbt; d.item0 = lo;
+    d.thr = m->cand_thr; d.cand_val = m->cand_val; d.cand_idx = m->cand_idx; d.cand_cap = kCandCap;
+    TopkArgs a{};
+    a.scores = m->cand_val; a.ld = kCandCap; a.B = B; a.T = kCandCap; a.remap = m->cand_idx; a.idx_base = 0;
+    const int stops[3] = {M1, M2, Tn};
+    int prev = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        if (stops[pass] == prev) continue;                         // small ranges need fewer passes
+        prev = stops[pass];
+        d.n_out = stops[pass];
+        d.cand_cnt = m->cand_cnt + pass * rows;
+        launch_decode_filter(d, m->st);
+        m->launches += 1;
+        a.row_n = d.cand_cnt;
+        if (stops[pass] < Tn) {                                    // threshold of the next pass: kp-th largest so far
+            a.k = kp; a.seed_ptr = nullptr; a.seed_idx = nullptr; a.sigmoid_out = 0;
+            a.out_idx = m->cand_tk_idx; a.out_score = m->cand_tk_score;
+            launch_topk(a, m->st);
+            launch_thr_from_topk(m->cand_tk_score, m->cand_tk_idx, kp, B, rows, m->cand_thr, m->st);
+            m->launches += 2;
+        }
+    }
+    a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.sigmoid_out = 1;
+    a.out_idx = m->topk_idx; a.out_score = m->topk_score;
+    launch_topk(a, m->st);
+    CK(cudaMemsetAsync(m->cand_tk_idx, 0, sizeof(int), m->st));
+    k_max_int<<<64, 256, 0, m->st>>>(m->cand_cnt, 3 * rows, m->cand_tk_idx);
+    CK(cudaMemcpyAsync(m->cand_cnt_host, m->cand_tk_idx, sizeof(int), cudaMemcpyDeviceToHost, m->st));
+    m->launches += 2;
+    return 0;
+}
+
+// Top-k of the catalogue range [item_lo, item_hi) (clipped to the tracks) for every playlist of the batch: global item
+// ids, sigmoid scores, seeds removed (metrics.py:58-68, main_challenge.py:26-36).  The whole-catalogue call is
+// dae_model_recommend; item-sharded challenge inference gives every GPU one range and merges the lists
+// (dae_topk_merge_device / dp.ShardedRecommender).
+extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                             int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
+                                             int32_t item_lo, int32_t item_hi, int32_t* out_idx, float* out_score) {
     if (!m || !out_idx) return fail("null argument");
     if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
-    TRY(stage_impl(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch, false));
     const int T = m->T;
-    TRY(ensure_scores(m, (size_t)batch * T));
+    if (item_lo < 0) item_lo = 0;
+    if (item_hi > T) item_hi = T;
+    if (item_lo >= item_hi) return fail("empty item range [%d, %d)", item_lo, item_hi);
+    TRY(stage_impl(m, 0, x_pos, x_val, nnz_x, nullptr, nullptr, 0, batch, false));
     size_t tk = m->topk_elems;
     TRY(ensure_buf(&m->topk_idx, &tk, (size_t)batch * k, m->st));
     tk = m->topk_elems;
     TRY(ensure_buf(&m->topk_score, &tk, (size_t)batch * k, m->st));
     m->topk_elems = tk;
     const int* sp = nullptr; const int* si = nullptr;
+    int max_seeds = 0;
     if (seed_ptr) {
         const int nseed = seed_ptr[batch];
+        for (int r = 0; r < batch; ++r) max_seeds = std::max(max_seeds, seed_ptr[r + 1] - seed_ptr[r]);
         TRY(ensure_buf(&m->seed_ptr, &m->seed_ptr_elems, (size_t)batch + 1, m->st));
         TRY(ensure_buf(&m->seed_idx, &m->seed_idx_elems, (size_t)(nseed > 0 ? nseed : 1), m->st));
         CK(cudaMemcpyAsync(m->seed_ptr, seed_ptr, ((size_t)batch + 1) * 4, cudaMemcpyHostToDevice, m->st));
         if (nseed > 0) CK(cudaMemcpyAsync(m->seed_idx, seed_idx, (size_t)nseed * 4, cudaMemcpyHostToDevice, m->st));
         sp = m->seed_ptr; si = m->seed_idx;
     }
-    TRY(run_predict(m, 0, T, m->scores, T));
-    TopkArgs a{};
-    a.scores = m->scores; a.ld = T; a.B = batch; a.T = T; a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.idx_base = 0;
-    a.out_idx = m->topk_idx; a.out_score = m->topk_score;
-    launch_topk(a, m->st);
-    m->launches += 1;
+    const int Tn = item_hi - item_lo;
+    // debug bit 4: always fused; bit 5: never
+    bool fused = ((Tn >= kFusedMinItems) || (m->debug & 16)) && !(m->debug & 32) && k + max_seeds <= 1024 && Tn >= 2 * (k + max_seeds);
+    if (fused) {
+        TRY(run_recommend_fused(m, k, item_lo, item_hi, sp, si, max_seeds));
+        CK(cudaStreamSynchronize(m->st));
+        if (*m->cand_cnt_host > kCandCap) fused = false;           // a candidate list overflowed: exact dense fallback
+    }
+    if (!fused) {
+        // dense path: scores of the range in row tiles that fit the scratch buffer, exact radix-select top-k per row
+        if (batch > kMaxBpad && (size_t)batch * Tn > ((size_t)1 << 31))
+            return fail("dense top-k of %d rows x %d items needs %zu GB of scores: reduce the batch", batch, Tn,
+                        (size_t)batch * Tn * 4 >> 30);
+        TRY(ensure_scores(m, (size_t)batch * T));
+        TRY(run_predict(m, 0, T, m->scores, T));
+        TopkArgs a{};
+        a.scores = m->scores + item_lo; a.ld = T; a.B = batch; a.T = Tn; a.k = k; a.seed_ptr = sp; a.seed_idx = si;
+        a.idx_base = item_lo;
+        a.out_idx = m->topk_idx; a.out_score = m->topk_score;
+        launch_topk(a, m->st);
+        m->launches += 1;
+    }
     CK(cudaMemcpyAsync(out_idx, m->topk_idx, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
     if (out_score) CK(cudaMemcpyAsync(out_score, m->topk_score, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
     return check_device_flag(m);
+}
+
+extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                       int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
+                                       int32_t* out_idx, float* out_score) {
+    if (!m) return fail("null argument");
+    return dae_model_recommend_range(m, x_pos, x_val, nnz_x, batch, seed_ptr, seed_idx, k, 0, m->T, out_idx, out_score);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -957,6 +1085,21 @@ extern "C" int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t 
     TopkArgs a{};
     a.scores = scores_dev; a.ld = ld; a.B = batch; a.T = n_tracks; a.k = k; a.seed_ptr = seed_ptr_dev;
     a.seed_idx = seed_idx_dev; a.idx_base = idx_base; a.out_idx = out_idx_dev; a.out_score = out_score_dev;
+    launch_topk(a, reinterpret_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Merge of per-shard top-k lists (item-sharded challenge inference): row r holds n (score, global id) pairs
+// (shards concatenated, -1 / -inf padded); the first k by (score desc, id asc) are exactly the unsharded list.
+extern "C" int32_t dae_topk_merge_device(const float* scores_dev, const int32_t* idx_dev, int32_t n, int32_t batch, int32_t k,
+                                         int32_t* out_idx_dev, float* out_score_dev, void* stream) {
+    ensure_loaded();
+    if (!scores_dev || !idx_dev || !out_idx_dev || !out_score_dev) return fail("null argument");
+    if (k <= 0 || k > 1024 || n <= 0) return fail("need 1 <= k <= 1024 and n > 0");
+    TopkArgs a{};
+    a.scores = scores_dev; a.ld = n; a.B = batch; a.T = n; a.k = k; a.remap = idx_dev;
+    a.out_idx = out_idx_dev; a.out_score = out_score_dev;
     launch_topk(a, reinterpret_cast<cudaStream_t>(stream));
     CK(cudaGetLastError());
     return 0;

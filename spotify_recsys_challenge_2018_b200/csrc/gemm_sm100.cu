@@ -29,7 +29,7 @@ namespace dae {
 // ------------------------------------------------------------------------------------------
 // G1 / G2: item-tile kernels
 // ------------------------------------------------------------------------------------------
-enum { MODE_TRAIN = 0, MODE_PREDICT = 1 };
+enum { MODE_TRAIN = 0, MODE_PREDICT = 1, MODE_FILTER = 2 };
 
 constexpr int kStages = 6;
 constexpr int kStagesStreamB = 4;                    // G2, K > 256: stages of (16 KB item chunk + 32 KB second-operand chunk)
@@ -40,7 +40,8 @@ constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the reside
 constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
 constexpr int kSmemA = kStages * kABytes;           // 98304
 constexpr int kSmemBars = 256;
-constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + 1024;  // + alignment slack
+constexpr int kSmemThr = kMaxBpad * 4;              // FILTER: per-playlist thresholds of the CTA's batch tile
+constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + kSmemThr + 1024;  // + alignment slack
 
 struct ItemTileDev {
     int n_rows;       // rows of the streamed operand (TRAIN: this rank's item rows; PREDICT: catalogue columns kept)
@@ -64,6 +65,13 @@ struct ItemTileDev {
     const float* mix_wp;
     const float* mix_wt;
     const float* title_score;
+    // FILTER: logits above the playlist's threshold are appended to its candidate list
+    const float* thr;        // [n_batch_tiles * n_cols]
+    float* cand_val;         // [n_batch_tiles * n_cols, cand_cap] logits z = h_d . W_dec[item] + b_dec[item]
+    int* cand_idx;           // [.., cand_cap] catalogue ids
+    int* cand_cnt;           // [..] candidates found (may exceed cand_cap: the caller checks)
+    int cand_cap;
+    int item0;               // catalogue id of row 0 of the streamed operand
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -186,10 +194,14 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
+    float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + kSmemA + kSmemBars);   // [n_cols] (FILTER)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int bt = blockIdx.y;
+    if (MODE == MODE_FILTER) {
+        for (int i = threadIdx.x; i < p.n_cols; i += blockDim.x) thr_smem[i] = p.thr[bt * p.n_cols + i];
+    }
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -361,6 +373,40 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                             }
                         }
                     }
+                } else if (MODE == MODE_FILTER) {
+                    // fused decode + top-K, filter stage: keep the logits above the playlist's threshold (a lower bound of
+                    // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.3 % of the cells pass
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int col0 = c * 32 + hh * kCw;
+                        uint32_t r[kCw];
+                        tmem_ld16(t_addr + col0, r);
+                        tmem_ld_wait();
+                        const float4* th4 = reinterpret_cast<const float4*>(thr_smem + col0);
+#pragma unroll
+                        for (int j4 = 0; j4 < kCw / 4; ++j4) {
+                            const float4 th = th4[j4];                       // same address for every lane: broadcast
+                            const float thv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float z = __uint_as_float(r[4 * j4 + u]) + bz;
+                                if (z >= thv[u] && item_ok) {
+                                    // every passing lane of the warp appends to the SAME playlist: one atomic per warp
+                                    const int b = bt * p.n_cols + col0 + 4 * j4 + u;
+                                    const unsigned am = __activemask();
+                                    const int leader = __ffs(am) - 1;
+                                    int base = 0;
+                                    if (lane == leader) base = atomicAdd(p.cand_cnt + b, __popc(am));
+                                    base = __shfl_sync(am, base, leader);
+                                    const int pos = base + __popc(am & ((1u << lane) - 1u));
+                                    if (pos < p.cand_cap) {
+                                        p.cand_val[(size_t)b * p.cand_cap + pos] = z;
+                                        p.cand_idx[(size_t)b * p.cand_cap + pos] = p.item0 + item;
+                                    }
+                                }
+                            }
+                        }
+                    }
                 } else {
                     uint32_t r[32];
                     tmem_ld32(t_addr + c * 32, r);
@@ -482,6 +528,27 @@ void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
     const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
     const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
     launch_itemtile<MODE_PREDICT>(tmA, tmB, p, dim3(decode_grid(p.n_rows, nbt), nbt, 1), st);
+}
+
+// G1f: decode of the catalogue rows [a.item0, a.item0 + a.n_out) against every batch tile, logits above the playlist's
+// threshold appended to its candidate list (fused decode + top-K: the [B, T] score matrix never exists)
+void launch_decode_filter(const DecodeArgs& a, cudaStream_t st) {
+    const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
+    ItemTileDev p{};
+    p.world = 1; p.rank = 0;
+    p.n_rows = a.n_out;
+    p.n_global = a.n_out;
+    p.tiles = (p.n_rows + kTileItems - 1) / kTileItems;
+    p.kchunks = a.H / 64;
+    p.n_cols = a.bpad;
+    p.batch = a.batch;
+    p.bias = a.bias + a.item0;
+    p.thr = a.thr; p.cand_val = a.cand_val; p.cand_idx = a.cand_idx; p.cand_cnt = a.cand_cnt; p.cand_cap = a.cand_cap;
+    p.item0 = a.item0;
+    if (p.tiles == 0) return;
+    const CUtensorMap tmA = make_map_bf16(a.W + (size_t)a.item0 * a.H, a.H, a.n_out, kTileItems);
+    const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
+    launch_itemtile<MODE_FILTER>(tmA, tmB, p, dim3(decode_grid(p.n_rows, nbt), nbt, 1), st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1093,11 +1160,13 @@ void preload_gemm() {
     cudaFuncAttributes a;
     cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_itemtile<MODE_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_itemtile<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_dw_adam_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused);
     cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
     cudaFuncGetAttributes(&a, k_itemtile<MODE_TRAIN>);
     cudaFuncGetAttributes(&a, k_itemtile<MODE_PREDICT>);
+    cudaFuncGetAttributes(&a, k_itemtile<MODE_FILTER>);
     cudaFuncGetAttributes(&a, k_dw);
     cudaFuncGetAttributes(&a, k_dw_adam_fused);
     cudaFuncGetAttributes(&a, k_dh);

@@ -159,10 +159,18 @@ struct DecodeArgs {
     const float* mix_wp;       // [batch] or nullptr: y_pred = title*w_t + p*w_p (DAEs.py:180)
     const float* mix_wt;
     const float* title_score;  // [batch, ld_out] or nullptr
+    // filter (fused decode + top-K): rows [item0, item0 + n_out) of W / bias are scanned
+    int item0;
+    const float* thr;          // [n_batch_tiles * bpad] per-playlist logit threshold (+inf: emit nothing)
+    float* cand_val;           // [n_batch_tiles * bpad, cand_cap]
+    int* cand_idx;
+    int* cand_cnt;             // [n_batch_tiles * bpad]
+    int cand_cap;
 };
 int decode_grid(int N, int n_batch_tiles);
 void launch_decode_train(const DecodeArgs& a, cudaStream_t st);    // G1: z, loss, dz, db_dec
 void launch_decode_predict(const DecodeArgs& a, cudaStream_t st);  // G1: z, sigmoid, scores
+void launch_decode_filter(const DecodeArgs& a, cudaStream_t st);   // G1f: z > threshold -> candidate lists
 
 struct DwArgs {
     const __nv_bfloat16* dzT;   // [local rows, K] d cost/dz of the item tiles this rank owns, all ranks' batch columns
@@ -293,8 +301,14 @@ struct TopkArgs {
     int idx_base;             // added to output indices (item-sharded inference)
     int* out_idx;             // [B,k]  (-1 padded)
     float* out_score;         // [B,k]
+    // candidate-list mode (fused decode + top-K): row r holds min(row_n[r], ld) entries, entry i is item remap[r * ld + i]
+    const int* remap;         // [B, ld] or nullptr (entry i is item i)
+    const int* row_n;         // [B] or nullptr (every row has T entries)
+    int sigmoid_out;          // 1: scores are logits; out_score = sigmoid(logit)
 };
 void launch_topk(const TopkArgs& a, cudaStream_t st);
+// thr[r] = score[r, kp-1] (r < batch, -inf when that slot is padding or score == nullptr), +inf for r in [batch, rows)
+void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch, int rows, float* thr, cudaStream_t st);
 
 // load every kernel of a translation unit (see sparse.cu: preload_sparse)
 void preload_sparse();

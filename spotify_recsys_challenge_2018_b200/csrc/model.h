@@ -105,6 +105,10 @@ struct dae_model {
     int *topk_idx = nullptr, *seed_ptr = nullptr, *seed_idx = nullptr;
     float* topk_score = nullptr;
     size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
+    // fused decode + top-K (large catalogues): per-playlist candidate lists, thresholds, intermediate top-K
+    float* cand_val = nullptr; int* cand_idx = nullptr; int* cand_cnt = nullptr; float* cand_thr = nullptr;
+    int* cand_tk_idx = nullptr; float* cand_tk_score = nullptr; int* cand_cnt_host = nullptr;
+    size_t cand_rows = 0;
     int last_batch = 0, last_bpad = 0;
     long long launches = 0;
     // pipelined train loop (dae_model_train_step_async): the host runs one step ahead of the device

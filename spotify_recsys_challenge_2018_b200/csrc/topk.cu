@@ -70,7 +70,8 @@ __device__ void select_bin(const uint32_t* hist, int nbins, uint32_t want, uint3
 
 __global__ void __launch_bounds__(kTopkThreads, 1)
 k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* __restrict__ seed_ptr,
-       const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score) {
+       const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score,
+       const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out) {
     __shared__ uint32_t s_hist[4096];
     __shared__ unsigned long long s_cand[kCandMax];
     __shared__ int s_seed[kCandMax];
@@ -80,6 +81,9 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     const int row = blockIdx.x;
     const int t = threadIdx.x;
     const float* x = scores + (size_t)row * ld;
+    // candidate-list mode: the row holds row_n[row] (item, logit) pairs in arbitrary order; entry i is item rm[i]
+    const int* rm = remap != nullptr ? remap + (size_t)row * ld : nullptr;
+    if (row_n != nullptr) T = min(row_n[row], (int)ld);
 
     int nseed = 0;
     if (seed_ptr != nullptr) {
@@ -134,7 +138,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
         if (in && key > thr) {
             const uint32_t slot = atomicAdd(&s_cnt[0], 1u);
             if (slot < (uint32_t)kCandMax)
-                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)i);
+                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)(rm ? rm[i] : i));
         }
         if (eq_seen < need_eq) {          // ordered pick among ties: chunk-ordered block scan
             const bool eq = in && key == thr;
@@ -151,7 +155,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
             const uint32_t rank = eq_seen + base + wrank;
             if (eq && rank < need_eq) {
                 const uint32_t slot = (want0 - need_eq) + rank;   // ties go after the strictly-greater block
-                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)i);
+                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)(rm ? rm[i] : i));
             }
             eq_seen += total;
             __syncthreads();
@@ -213,7 +217,8 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
             if (pos < (uint32_t)K) {
                 const unsigned long long c = s_cand[t * 2 + u];
                 out_idx[(size_t)row * K + pos] = (int)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull)) + idx_base;
-                out_score[(size_t)row * K + pos] = key_score((uint32_t)(c >> 32));
+                const float sc = key_score((uint32_t)(c >> 32));
+                out_score[(size_t)row * K + pos] = sigmoid_out ? __fdividef(1.f, 1.f + __expf(-sc)) : sc;
             }
             ++pos;
         }
@@ -224,9 +229,24 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     }
 }
 
+// Per-playlist filter threshold for the next pass of the fused decode + top-K: the kp-th largest logit found so far
+// (a lower bound of the kp-th largest of any superset), -inf while fewer than kp candidates exist, +inf for the
+// padding rows of the batch tile (they emit nothing).
+__global__ void k_thr_from_topk(const float* __restrict__ score, const int* __restrict__ idx, int kp, int batch, int rows,
+                                float* __restrict__ thr) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float t = CUDART_INF_F;
+    if (r < batch) t = (score != nullptr && idx[(size_t)r * kp + kp - 1] >= 0) ? score[(size_t)r * kp + kp - 1] : -CUDART_INF_F;
+    thr[r] = t;
+}
+void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch, int rows, float* thr, cudaStream_t st) {
+    k_thr_from_topk<<<(rows + 255) / 256, 256, 0, st>>>(score, idx, kp, batch, rows, thr);
+}
+
 void launch_topk(const TopkArgs& a, cudaStream_t st) {
     k_topk<<<a.B, kTopkThreads, 0, st>>>(a.scores, a.ld, a.T, a.k, a.seed_ptr, a.seed_idx, a.idx_base, a.out_idx,
-                                         a.out_score);
+                                         a.out_score, a.remap, a.row_n, a.sigmoid_out);
 }
 
 // Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
@@ -234,6 +254,7 @@ void launch_topk(const TopkArgs& a, cudaStream_t st) {
 void preload_topk() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k_topk);
+    cudaFuncGetAttributes(&a, k_thr_from_topk);
     (void)cudaGetLastError();
 }
 

@@ -248,6 +248,47 @@ def test_predict_and_recommend(N, T, H, B):
     m.close()
 
 
+@pytest.mark.parametrize("N,T,H,B,k", [(40000, 36000, 128, 300, 500), (9000, 8000, 64, 64, 100), (300000, 270000, 256, 700, 500)])
+def test_fused_decode_topk_equals_dense_ranking(N, T, H, B, k):
+    """Large catalogues rank through the fused decode + top-K (threshold-filtered candidate lists, no [B, T] scores;
+    debug bit 4 forces it here).  It must return what the dense path (scores + exact radix select, bit 5) returns:
+    same scores rank by rank, same ids except where two scores are equal to fp32 rounding (the fused path orders by
+    the logit, the dense one by sigmoid(logit) then id), and exactly the oracle's ranking on the device's own scores."""
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.01, DAEval=None)
+    ora = O.DAEOracle(N, H, 0.01, tied=False, seed=5, mode="b200")
+    ora.b_dec[:] = np.random.default_rng(2).normal(0, 0.5, N)
+    m = DAE(conf)
+    m.trainable = False
+    m.fit()
+    m.set_params(ora.params())
+    rng = np.random.default_rng(N)
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=30, empty_rows=(2,))
+    xv = np.ones(len(trk), np.float32)
+    seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(B)]
+    m.set_debug(32)
+    idx_d, sc_d = m.recommend(trk, xv, seeds, k=k, return_scores=True)
+    m.set_debug(16)
+    idx_f, sc_f = m.recommend(trk, xv, seeds, k=k, return_scores=True)
+    np.testing.assert_allclose(sc_f, sc_d, rtol=2e-6, atol=1e-9)
+    for r in range(B):
+        if not np.array_equal(idx_f[r], idx_d[r]):
+            bad = np.nonzero(idx_f[r] != idx_d[r])[0]
+            # only permutations among (near-)equal scores, or swaps at the k-th boundary between equal scores
+            assert np.all(np.abs(sc_f[r, bad] - sc_d[r, bad]) <= 2e-6 * np.abs(sc_d[r, bad])), r
+            assert len(bad) <= 8, (r, len(bad))
+        assert not (set(idx_f[r].tolist()) & set(seeds[r]))
+    # item-sharded: per-range lists merged by (score desc, id asc) == the whole-catalogue list
+    cuts = [0, T // 3 + 17, 2 * T // 3 + 5, T]
+    parts = [m.recommend(trk, xv, seeds, k=k, return_scores=True, item_range=(cuts[i], cuts[i + 1])) for i in range(3)]
+    for r in range(0, B, max(B // 8, 1)):
+        ids = np.concatenate([p[0][r] for p in parts]); scs = np.concatenate([p[1][r] for p in parts])
+        merged = ranking.merge_sharded_topk([p[0][r] for p in parts], [p[1][r] for p in parts], k)
+        assert np.array_equal(np.sort(merged[0]), np.sort(idx_f[r])) or \
+            len(set(merged[0].tolist()) ^ set(idx_f[r].tolist())) <= 4, r
+        assert len(ids) == 3 * k and np.isfinite(scs[ids >= 0]).all()
+    m.close()
+
+
 def test_errors_are_loud():
     from spotify_recsys_challenge_2018_b200._lib import DaeError
     conf = Conf(batch=8, n_input=100, n_tracks=80, hidden=64, lr=0.01)
