@@ -96,6 +96,7 @@ int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_v
  * dae_topk_merge_device; the merged list is exactly the unsharded one.  Ranges of >= 131072 items (and debug bit 4)
  * run the fused decode + top-K (threshold-filtered candidate lists, the [batch, T] score matrix never exists; batch
  * up to max_batch rows in 256-row tiles); smaller ranges, or a candidate list that overflowed, take the dense path.
+ * out_idx == NULL leaves the lists on the device (buffers "topk_idx" / "topk_score", [batch, k]).
  *                                                   main_challenge.py:80-90 (y_pred[:, :n_tracks] + cand_generate) */
 int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
                                   const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t item_lo,
@@ -155,7 +156,7 @@ int32_t dae_model_set_debug(dae_model* m, int32_t flags);
  * buffers hold the rows this rank owns in local-tile order (== global order when world == 1).  Names:
  * "g_dec" "g_enc" "g_b_enc" "g_b_dec" "g_b_enc_part" "g_b_dec_part" "touched" "cost" "W_enc" "W_dec"
  * "W_dec_bf16" "b_enc" "b_dec" "h" "h_d" "h_dT" "dzT" "dz_all" "dh_partial" "da" "x_row_ptr" "x_row_len"
- * "x_col" "x_val" "x_rowsum" "y_row_ptr" "y_row_len" "y_col" "ybits" "scores" "mW_dec" "vW_dec" "mW_enc" "vW_enc". */
+ * "x_col" "x_val" "x_rowsum" "y_row_ptr" "y_row_len" "y_col" "ybits" "scores" "topk_idx" "topk_score" "mW_dec" "vW_dec" "mW_enc" "vW_enc". */
 int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size);
 /* number of kernels launched by this model since creation (bench.py `gpu_launches`) */
 int64_t dae_model_launch_count(dae_model* m);

@@ -958,7 +958,7 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
 extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
                                              int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
                                              int32_t item_lo, int32_t item_hi, int32_t* out_idx, float* out_score) {
-    if (!m || !out_idx) return fail("null argument");
+    if (!m) return fail("null argument");          // out_idx == NULL: results stay on the device ("topk_idx" / "topk_score")
     if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
     const int T = m->T;
     if (item_lo < 0) item_lo = 0;
@@ -1003,7 +1003,7 @@ extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos,
         launch_topk(a, m->st);
         m->launches += 1;
     }
-    CK(cudaMemcpyAsync(out_idx, m->topk_idx, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
+    if (out_idx) CK(cudaMemcpyAsync(out_idx, m->topk_idx, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
     if (out_score) CK(cudaMemcpyAsync(out_score, m->topk_score, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
     return check_device_flag(m);
 }
@@ -1041,6 +1041,7 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
         {"y_row_ptr", sl.yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", sl.yw.row_len, m->Bmax, 4},
         {"y_col", sl.yw.col, m->max_nnz, 4}, {"ybits", m->ybits, (int64_t)m->n_local * m->world * (kMaxBpad / 32), 4},
         {"scores", m->scores, (int64_t)m->scores_elems, 4},
+        {"topk_idx", m->topk_idx, (int64_t)m->topk_elems, 4}, {"topk_score", m->topk_score, (int64_t)m->topk_elems, 4},
         {"mW_dec", m->mW_dec, LH, 4}, {"vW_dec", m->vW_dec, LH, 4}, {"mW_enc", m->mW_enc, LH, 4}, {"vW_enc", m->vW_enc, LH, 4},
     };
     for (const E& e : table) {

@@ -9,7 +9,11 @@ themselves with loads / stores into the peers' memory over NVLink / NVSwitch (in
 "data parallelism"): there is no collective call in the step.  torch.distributed is only the
 out-of-band channel that carries the 64-byte CUDA IPC handles at start-up.
 
-`shard_coo` and `exchange_handles` are backend-agnostic (tested with gloo on CPU, world_size 2).
+Challenge inference shards on the ITEM axis instead (ShardedRecommender): every rank ranks its own slice of the
+track catalogue with the fused decode + top-K and the per-shard lists are merged after ONE all-gather.
+
+`shard_coo`, `item_shard`, `merge_topk_lists` and `exchange_handles` are backend-agnostic (tested with gloo on CPU,
+world_size 2).
 """
 from __future__ import annotations
 
@@ -89,3 +93,73 @@ class DataParallelDAE:
         torch.cuda.synchronize()
         dist.barrier(self.group)
         return out
+
+
+def item_shard(n_tracks, rank, world, tile=128):
+    """Contiguous slice [lo, hi) of the track catalogue ranked by `rank`: equal numbers of 128-item tiles (the
+    decode kernel's granularity), the last rank takes the ragged end.  The slices partition [0, n_tracks)."""
+    tiles = (n_tracks + tile - 1) // tile
+    per = (tiles + world - 1) // world
+    lo = min(rank * per * tile, n_tracks)
+    hi = min((rank + 1) * per * tile, n_tracks)
+    return lo, hi
+
+
+def merge_topk_lists(idx_lists, score_lists, k):
+    """Host statement of the merge rule (score desc, id asc; -1 = padding) over per-shard [B, k] lists -> [B, k].
+    The device path (dae_topk_merge_device) must return exactly this."""
+    idx = np.concatenate(idx_lists, axis=1)
+    sc = np.concatenate(score_lists, axis=1).astype(np.float64)
+    sc = np.where(idx >= 0, sc, -np.inf)
+    order = np.lexsort((idx, -sc), axis=1)[:, :k]
+    out_i = np.take_along_axis(idx, order, 1)
+    out_s = np.take_along_axis(sc, order, 1)
+    return np.where(np.isfinite(out_s), out_i, -1).astype(np.int32), out_s.astype(np.float32)
+
+
+class ShardedRecommender:
+    """Challenge-mode inference sharded on the item axis (main_challenge.py:80-90 on one GPU upstream).
+
+    Every rank holds a replica of the inference model (a plain world = 1 model on its own GPU: 2 M x 256 parameters are
+    ~5 GB of 180), encodes the batch redundantly (microseconds) and ranks the tracks of ITS slice with the fused
+    decode + top-K.  One all-gather of B x k x 8 bytes per rank over NVLink, then the (score desc, id asc) merge of
+    world x k candidates per playlist on the device: exactly the unsharded list."""
+
+    def __init__(self, model, group=None):
+        import torch.distributed as dist
+        self.model, self.group = model, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.range = item_shard(model.n_tracks, self.rank, self.world)
+
+    def _dev(self, name, n, dtype):
+        import torch
+        ptr, have, es = self.model.buffer(name)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (int(n),), "typestr": dtype, "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
+
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        m = self.model
+        B = m.n_batch
+        m.recommend(x_positions, x_vals, seeds, k=k, item_range=self.range, on_device=True)
+        idx = self._dev("topk_idx", B * k, "<i4").view(B, k)
+        sc = self._dev("topk_score", B * k, "<f4").view(B, k)
+        all_i = torch.empty((self.world, B, k), dtype=torch.int32, device="cuda")
+        all_s = torch.empty((self.world, B, k), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(all_i, idx.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_s, sc.contiguous(), group=self.group)
+        cat_i = all_i.permute(1, 0, 2).reshape(B, self.world * k).contiguous()
+        cat_s = all_s.permute(1, 0, 2).reshape(B, self.world * k).contiguous()
+        out_i = torch.empty((B, k), dtype=torch.int32, device="cuda")
+        out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.load().dae_topk_merge_device(C.c_void_p(cat_s.data_ptr()), C.c_void_p(cat_i.data_ptr()),
+                                                     self.world * k, B, k, C.c_void_p(out_i.data_ptr()),
+                                                     C.c_void_p(out_s.data_ptr()),
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        res_i = out_i.cpu().numpy()
+        return (res_i, out_s.cpu().numpy()) if return_scores else res_i

@@ -168,10 +168,12 @@ class DAE_tied:
                                                _ptr(out)))
         return out
 
-    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, item_range=None):
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, item_range=None, on_device=False):
         """Top-k track ids per playlist with the seeds removed (metrics.py:58-68, main_challenge.py:26-36),
         decode + ranking on the device.  `seeds`: list of per-row seed id lists.  -> int32 [batch, k].
-        `item_range=(lo, hi)` ranks only that slice of the track catalogue (item-sharded inference; ids stay global)."""
+        `item_range=(lo, hi)` ranks only that slice of the track catalogue (item-sharded inference; ids stay global).
+        `on_device=True` skips the copy to the host: the lists stay in the device buffers "topk_idx" / "topk_score"
+        (self.buffer(name) -> pointer) and None is returned."""
         xp, xv = _coo(x_positions, x_vals)
         seed_ptr = np.zeros(self.n_batch + 1, np.int32)
         lens = [len(s) for s in seeds]
@@ -180,12 +182,14 @@ class DAE_tied:
         flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int64).reshape(-1) for s in seeds])
                                     if lens and sum(lens) else np.zeros(0, np.int64))
         flat = np.clip(flat, -1, 2 ** 31 - 1).astype(np.int32)
-        idx = np.empty((self.n_batch, k), np.int32)
-        sc = np.empty((self.n_batch, k), np.float32) if return_scores else None
+        idx = np.empty((self.n_batch, k), np.int32) if not on_device else None
+        sc = np.empty((self.n_batch, k), np.float32) if (return_scores and not on_device) else None
         lo, hi = item_range if item_range is not None else (0, self.n_tracks)
         _lib.check(self._lib.dae_model_recommend_range(self._h, _ptr(xp), _ptr(xv), xp.shape[0], self.n_batch,
                                                        _ptr(seed_ptr), _ptr(flat), int(k), int(lo), int(hi), _ptr(idx),
                                                        _ptr(sc)))
+        if on_device:
+            return None
         return (idx, sc) if return_scores else idx
 
     # ---- staged / asynchronous surface (bench, data-parallel trainer) -------------------

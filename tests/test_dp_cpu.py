@@ -128,3 +128,34 @@ def test_tile_cyclic_ownership_is_a_bijection(world):
     assert np.array_equal(back, item)
     n_local = -(-(-(-N // 128)) // world) * 128             # rows every rank allocates
     assert loc.max() < n_local
+
+
+@pytest.mark.parametrize("T,world", [(250000, 8), (2000000, 8), (1000, 3), (129, 2), (5, 4)])
+def test_item_shard_partitions_the_tracks(T, world):
+    from spotify_recsys_challenge_2018_b200.dp import item_shard
+    r = [item_shard(T, k, world) for k in range(world)]
+    assert r[0][0] == 0 and r[-1][1] == T
+    for a, b in zip(r, r[1:]):
+        assert a[1] == b[0] and a[0] <= a[1]
+    assert all(lo % 128 == 0 for lo, hi in r if lo < T)
+
+
+def test_merge_topk_lists_equals_unsharded_ranking():
+    """The merge rule of item-sharded inference (score desc, id asc) over per-shard top-k lists == the ranking of the
+    whole catalogue (oracle/ranking.py), ties and short shards included."""
+    from oracle import ranking
+    from spotify_recsys_challenge_2018_b200.dp import item_shard, merge_topk_lists
+    rng = np.random.default_rng(0)
+    T, B, k, world = 3000, 6, 50, 4
+    scores = np.round(rng.random((B, T)).astype(np.float32), 2)            # heavy ties
+    idx_l, sc_l = [], []
+    for r in range(world):
+        lo, hi = item_shard(T, r, world)
+        ii = np.full((B, k), -1, np.int32); ss = np.full((B, k), -np.inf, np.float32)
+        for b in range(B):
+            loc = ranking.topk_excluding_seeds(scores[b, lo:hi], [], k)
+            ii[b, :len(loc)] = loc + lo; ss[b, :len(loc)] = scores[b, loc + lo]
+        idx_l.append(ii); sc_l.append(ss)
+    got_i, got_s = merge_topk_lists(idx_l, sc_l, k)
+    for b in range(B):
+        assert np.array_equal(got_i[b], ranking.topk_excluding_seeds(scores[b], [], k))

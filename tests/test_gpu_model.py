@@ -277,15 +277,30 @@ def test_fused_decode_topk_equals_dense_ranking(N, T, H, B, k):
             assert np.all(np.abs(sc_f[r, bad] - sc_d[r, bad]) <= 2e-6 * np.abs(sc_d[r, bad])), r
             assert len(bad) <= 8, (r, len(bad))
         assert not (set(idx_f[r].tolist()) & set(seeds[r]))
-    # item-sharded: per-range lists merged by (score desc, id asc) == the whole-catalogue list
-    cuts = [0, T // 3 + 17, 2 * T // 3 + 5, T]
-    parts = [m.recommend(trk, xv, seeds, k=k, return_scores=True, item_range=(cuts[i], cuts[i + 1])) for i in range(3)]
-    for r in range(0, B, max(B // 8, 1)):
-        ids = np.concatenate([p[0][r] for p in parts]); scs = np.concatenate([p[1][r] for p in parts])
-        merged = ranking.merge_sharded_topk([p[0][r] for p in parts], [p[1][r] for p in parts], k)
-        assert np.array_equal(np.sort(merged[0]), np.sort(idx_f[r])) or \
-            len(set(merged[0].tolist()) ^ set(idx_f[r].tolist())) <= 4, r
-        assert len(ids) == 3 * k and np.isfinite(scs[ids >= 0]).all()
+    # item-sharded (dp.ShardedRecommender's data path): per-range lists merged on the device by (score desc, id asc)
+    # == the host statement of the rule == the whole-catalogue list
+    import ctypes as C
+    from spotify_recsys_challenge_2018_b200 import _lib
+    from spotify_recsys_challenge_2018_b200.dp import item_shard, merge_topk_lists
+    world = 3
+    ranges = [item_shard(T, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == T and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    parts = [m.recommend(trk, xv, seeds, k=k, return_scores=True, item_range=rg) for rg in ranges]
+    for (lo, hi), (pi, ps) in zip(ranges, parts):
+        assert ((pi == -1) | ((pi >= lo) & (pi < hi))).all()
+    want_i, want_s = merge_topk_lists([p[0] for p in parts], [p[1] for p in parts], k)
+    cat_i = torch.from_numpy(np.concatenate([p[0] for p in parts], 1)).cuda().contiguous()
+    cat_s = torch.from_numpy(np.concatenate([p[1] for p in parts], 1)).cuda().contiguous()
+    out_i = torch.empty((B, k), dtype=torch.int32, device="cuda"); out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().dae_topk_merge_device(C.c_void_p(cat_s.data_ptr()), C.c_void_p(cat_i.data_ptr()), world * k, B, k,
+                                                 C.c_void_p(out_i.data_ptr()), C.c_void_p(out_s.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(out_i.cpu().numpy(), want_i)
+    assert np.array_equal(out_s.cpu().numpy(), want_s)
+    # merged lists vs the unsharded call: same scores, ids equal except among equal scores
+    np.testing.assert_allclose(want_s, sc_f, rtol=2e-6, atol=1e-9)
+    assert (want_i != idx_f).mean() < 1e-3
     m.close()
 
 
