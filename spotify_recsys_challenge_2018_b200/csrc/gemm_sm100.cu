@@ -41,6 +41,7 @@ constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
 constexpr int kSmemA = kStages * kABytes;           // 98304
 constexpr int kSmemBars = 256;
 constexpr int kSmemThr = kMaxBpad * 4;              // FILTER: per-playlist thresholds of the CTA's batch tile
+constexpr int kWStg = kABytes / 8 / 16;             // FILTER: candidates staged per epilogue warp (128) in one ring stage's worth of smem
 constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + kSmemThr + 1024;  // + alignment slack
 
 struct ItemTileDev {
@@ -176,6 +177,25 @@ __device__ __forceinline__ void train_chunk_y0(const uint32_t (&r)[kCw], float c
     lg_sum = ls; dz_sum = sd; minden = md;
 }
 
+struct CandOut {
+    float* val; int* idx; int* cnt; int cap; int item0; int b0;    // b0: first playlist of the CTA's batch tile
+};
+// One warp moves its staged candidates (column | item << 8, logit) to the playlists' global lists: the returned global
+// atomics of 32 entries are in flight together, instead of one per hit stalling the scan.
+__device__ __noinline__ void flush_candidates(const uint2* seg, int n, const CandOut o) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32) {
+        const uint2 e = seg[i];
+        const int b = o.b0 + (int)(e.x & 255u);
+        const int gp = atomicAdd(o.cnt + b, 1);
+        if (gp < o.cap) {
+            o.val[(size_t)b * o.cap + gp] = __uint_as_float(e.y);
+            o.idx[(size_t)b * o.cap + gp] = o.item0 + (int)(e.x >> 8);
+        }
+    }
+    __syncwarp();
+}
+
 // blockIdx.y = batch tile: TRAIN decodes this rank's item rows against every rank's rows of the global batch
 // (tile bt = rank bt's playlists), PREDICT tiles an inference batch of more than 256 rows.
 template <int MODE>
@@ -195,6 +215,9 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
     float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + kSmemA + kSmemBars);   // [n_cols] (FILTER)
+    // FILTER gives the last ring stage (16 KB) to the candidate staging buffer
+    constexpr int NST = MODE == MODE_FILTER ? kStages - 1 : kStages;
+    uint2* stg = reinterpret_cast<uint2*>(sA + NST * kABytes);                       // [kEpiWarps][kWStg] (column | item << 8, logit)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -240,7 +263,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     // several batch tiles re-read the same item tile: keep it in L2 then, stream it otherwise
                     tma_load_2d_hint(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
                                      gridDim.y > 1 ? pol_keep : pol_stream);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -270,7 +293,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);
                 acc ^= 1;
@@ -293,6 +316,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const float wl_pos = -0.6931471805599453f, wl_neg = kNegWeight * wl_pos;
         const float c_pos = -p.inv_batch, c_neg = kNegWeight * p.inv_batch;
         const float ic = 1.f / c_neg;
+        // FILTER: this warp's staging segment, entries staged (warp-uniform), where they go
+        uint2* seg = stg + (warp - 2) * kWStg;
+        int wn = 0;
+        const unsigned ltmask = (1u << lane) - 1u;
+        const CandOut cout{p.cand_val, p.cand_idx, p.cand_cnt, p.cand_cap, p.item0, bt * p.n_cols};
         // per-tile scalars of this lane's item row (bias, target words of the warp's two chunks) are fetched ONE TILE
         // AHEAD: they come from HBM (~1 us) and would otherwise stall the warp at the top of every tile
         float bz_nx = 0.f;
@@ -374,8 +402,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         }
                     }
                 } else if (MODE == MODE_FILTER) {
-                    // fused decode + top-K, filter stage: keep the logits above the playlist's threshold (a lower bound of
-                    // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.3 % of the cells pass
+                    // fused decode + top-K, filter stage: keep the logits >= the playlist's threshold (a lower bound of
+                    // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.3 % of the cells pass in
+                    // the full-range pass.  Per cell: FADD, FSETP, ballot, uniform branch.  Hits go to the warp's PRIVATE
+                    // staging segment (position from the ballot, count in a warp-uniform register: no atomics, no block
+                    // barriers) and from there to the global lists 100+ at a time.
 #pragma unroll 1
                     for (int hh = 0; hh < 2; ++hh) {
                         const int col0 = c * 32 + hh * kCw;
@@ -390,19 +421,12 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const float z = __uint_as_float(r[4 * j4 + u]) + bz;
-                                if (z >= thv[u] && item_ok) {
-                                    // every passing lane of the warp appends to the SAME playlist: one atomic per warp
-                                    const int b = bt * p.n_cols + col0 + 4 * j4 + u;
-                                    const unsigned am = __activemask();
-                                    const int leader = __ffs(am) - 1;
-                                    int base = 0;
-                                    if (lane == leader) base = atomicAdd(p.cand_cnt + b, __popc(am));
-                                    base = __shfl_sync(am, base, leader);
-                                    const int pos = base + __popc(am & ((1u << lane) - 1u));
-                                    if (pos < p.cand_cap) {
-                                        p.cand_val[(size_t)b * p.cand_cap + pos] = z;
-                                        p.cand_idx[(size_t)b * p.cand_cap + pos] = p.item0 + item;
-                                    }
+                                const bool hit = item_ok && z >= thv[u];
+                                const unsigned am = __ballot_sync(0xffffffffu, hit);
+                                if (am != 0) {
+                                    if (wn + 32 > kWStg) { flush_candidates(seg, wn, cout); wn = 0; }
+                                    if (hit) seg[wn + __popc(am & ltmask)] = make_uint2((uint32_t)(col0 + 4 * j4 + u) | ((uint32_t)item << 8), __float_as_uint(z));
+                                    wn += __popc(am);
                                 }
                             }
                         }
@@ -439,6 +463,9 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (lane == 0) mbar_arrive(&tempty[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
+        }
+        if (MODE == MODE_FILTER) {
+            if (wn > 0) flush_candidates(seg, wn, cout);
         }
         if (MODE == MODE_TRAIN) {
 #pragma unroll
