@@ -171,12 +171,18 @@ def aux_workload(args, wl, rank=0, world=1):
         trk = np.ascontiguousarray(trk); tv = tv.astype(np.float32)
         order = np.argsort(trk[:, 0], kind="stable")
         bounds = np.searchsorted(trk[order, 0], np.arange(B + 1))
-        seeds = [trk[order[bounds[r]:bounds[r + 1]], 1].tolist() for r in range(B)]
+        seeds = (bounds.astype(np.int32), trk[order, 1].astype(np.int32))     # CSR of the seed tracks (= the input tracks)
         rec = m
         if world > 1:
             from spotify_recsys_challenge_2018_b200.dp import ShardedRecommender
             rec = ShardedRecommender(m)
         run = lambda i: rec.recommend(trk, tv, seeds, k=500)
+        if world > 1:
+            # the merged per-shard lists must be the unsharded list (checked once, outside the timed region)
+            got = rec.recommend(trk, tv, seeds, k=500, return_scores=True)
+            want = m.recommend(trk, tv, seeds, k=500, return_scores=True)
+            if not np.allclose(got[1], want[1], rtol=2e-6, atol=1e-9) or (got[0] != want[0]).mean() > 1e-3:
+                raise SystemExit("bench.py: item-sharded top-k differs from the unsharded list")
         h2d = int(trk.nbytes + tv.nbytes + 4 * (B + 1) + 4 * len(trk))
         d2h, units, metric = B * 500 * 4, B, "dae_challenge_topk_playlists_per_sec"
         desc = ("cfg5: challenge inference, top-500 over a %d-item decoder, batch %d in one call (fused decode + top-K, "

@@ -925,6 +925,21 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
     a.scores = m->cand_val; a.ld = kCandCap; a.B = B; a.T = kCandCap; a.remap = m->cand_idx; a.idx_base = 0;
     const int stops[3] = {M1, M2, Tn};
     int prev = 0;
+    if (M1 < Tn) {
+        // pass A keeps everything: dense logits of the first M1 items + the dense radix select, instead of M1 list appends
+        // per playlist
+        TRY(ensure_scores(m, (size_t)B * M1));
+        DecodeArgs da = d;
+        da.n_out = M1; da.out = m->scores; da.ld_out = M1; da.raw_logits = 1;
+        launch_decode_predict(da, m->st);
+        TopkArgs ta{};
+        ta.scores = m->scores; ta.ld = M1; ta.B = B; ta.T = M1; ta.k = kp; ta.idx_base = 0;
+        ta.out_idx = m->cand_tk_idx; ta.out_score = m->cand_tk_score;
+        launch_topk(ta, m->st);
+        launch_thr_from_topk(m->cand_tk_score, m->cand_tk_idx, kp, B, rows, m->cand_thr, m->st);
+        m->launches += 3;
+        prev = M1;
+    }
     for (int pass = 0; pass < 3; ++pass) {
         if (stops[pass] == prev) continue;                         // small ranges need fewer passes
         prev = stops[pass];

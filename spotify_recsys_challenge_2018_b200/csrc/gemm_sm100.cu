@@ -73,6 +73,7 @@ struct ItemTileDev {
     int* cand_cnt;           // [..] candidates found (may exceed cand_cap: the caller checks)
     int cand_cap;
     int item0;               // catalogue id of row 0 of the streamed operand
+    int raw_logits;          // PREDICT: write z instead of sigmoid(z)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -348,6 +349,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             prefetch_row(tile + gridDim.x);
             float db = 0.f, lt = 0.f;
             const float c2 = bz * c1;
+            const float bzf = item_ok ? bz : __int_as_float(0x7fc00000);   // FILTER: rows past the range compare false (NaN)
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
@@ -414,19 +416,28 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         tmem_ld16(t_addr + col0, r);
                         tmem_ld_wait();
                         const float4* th4 = reinterpret_cast<const float4*>(thr_smem + col0);
+                        // all 16 ballots first (independent: they pipeline), then the rare hits column by column
+                        unsigned am[kCw];
 #pragma unroll
                         for (int j4 = 0; j4 < kCw / 4; ++j4) {
                             const float4 th = th4[j4];                       // same address for every lane: broadcast
-                            const float thv[4] = {th.x, th.y, th.z, th.w};
+                            am[4 * j4 + 0] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 0]) + bzf >= th.x);
+                            am[4 * j4 + 1] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 1]) + bzf >= th.y);
+                            am[4 * j4 + 2] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 2]) + bzf >= th.z);
+                            am[4 * j4 + 3] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 3]) + bzf >= th.w);
+                        }
+                        unsigned any = 0;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float z = __uint_as_float(r[4 * j4 + u]) + bz;
-                                const bool hit = item_ok && z >= thv[u];
-                                const unsigned am = __ballot_sync(0xffffffffu, hit);
-                                if (am != 0) {
+                        for (int k = 0; k < kCw; ++k) any |= am[k];
+                        if (any != 0) {
+#pragma unroll
+                            for (int k = 0; k < kCw; ++k) {
+                                if (am[k] != 0) {
                                     if (wn + 32 > kWStg) { flush_candidates(seg, wn, cout); wn = 0; }
-                                    if (hit) seg[wn + __popc(am & ltmask)] = make_uint2((uint32_t)(col0 + 4 * j4 + u) | ((uint32_t)item << 8), __float_as_uint(z));
-                                    wn += __popc(am);
+                                    if ((am[k] >> lane) & 1u)
+                                        seg[wn + __popc(am[k] & ltmask)] = make_uint2((uint32_t)(col0 + k) | ((uint32_t)item << 8),
+                                                                                      __float_as_uint(__uint_as_float(r[k]) + bzf));
+                                    wn += __popc(am[k]);
                                 }
                             }
                         }
@@ -440,7 +451,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     for (int j = 0; j < 32; ++j) {
                         const int b = bt * p.n_cols + c * 32 + j;
                         const float z = __uint_as_float(r[j]) + bz;
-                        float pr = __fdividef(1.f, 1.f + __expf(-z));
+                        float pr = p.raw_logits ? z : __fdividef(1.f, 1.f + __expf(-z));
                         if (b < p.batch && col_ok && item_ok) {
                             const size_t o = (size_t)b * p.ld_out + item;
                             if (p.mix_wp != nullptr) {
@@ -543,16 +554,17 @@ void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
     const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
     ItemTileDev p{};
     p.world = 1; p.rank = 0;
-    p.n_rows = a.n_out < a.N ? a.n_out : a.N;       // only the columns that are kept (tracks) are scored
-    p.n_global = a.N;
+    p.n_rows = a.n_out < a.N - a.item0 ? a.n_out : a.N - a.item0;   // only the columns that are kept (tracks) are scored
+    p.n_global = a.N - a.item0;
     p.tiles = (p.n_rows + kTileItems - 1) / kTileItems;
     p.kchunks = a.H / 64;
     p.n_cols = a.bpad;
     p.batch = a.batch;
-    p.bias = a.bias;
+    p.bias = a.bias + a.item0;                      // rows [item0, item0 + n_out) of the catalogue -> output columns [0, n_out)
     p.out = a.out; p.ld_out = a.ld_out; p.n_out = a.n_out;
     p.mix_wp = a.mix_wp; p.mix_wt = a.mix_wt; p.title_score = a.title_score;
-    const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.N, kTileItems);
+    p.raw_logits = a.raw_logits;
+    const CUtensorMap tmA = make_map_bf16(a.W + (size_t)a.item0 * a.H, a.H, a.N - a.item0, kTileItems);
     const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
     launch_itemtile<MODE_PREDICT>(tmA, tmB, p, dim3(decode_grid(p.n_rows, nbt), nbt, 1), st);
 }

@@ -159,7 +159,8 @@ struct DecodeArgs {
     const float* mix_wp;       // [batch] or nullptr: y_pred = title*w_t + p*w_p (DAEs.py:180)
     const float* mix_wt;
     const float* title_score;  // [batch, ld_out] or nullptr
-    // filter (fused decode + top-K): rows [item0, item0 + n_out) of W / bias are scanned
+    int raw_logits;            // predict: write the logits z instead of sigmoid(z) (no title mix)
+    // predict / filter (fused decode + top-K): rows [item0, item0 + n_out) of W / bias are scored
     int item0;
     const float* thr;          // [n_batch_tiles * bpad] per-playlist logit threshold (+inf: emit nothing)
     float* cand_val;           // [n_batch_tiles * bpad, cand_cap]

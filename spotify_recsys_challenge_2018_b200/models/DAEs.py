@@ -170,18 +170,26 @@ class DAE_tied:
 
     def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, item_range=None, on_device=False):
         """Top-k track ids per playlist with the seeds removed (metrics.py:58-68, main_challenge.py:26-36),
-        decode + ranking on the device.  `seeds`: list of per-row seed id lists.  -> int32 [batch, k].
+        decode + ranking on the device.  `seeds`: list of per-row seed id lists, or the CSR pair (seed_ptr, seed_idx).
+        -> int32 [batch, k].
         `item_range=(lo, hi)` ranks only that slice of the track catalogue (item-sharded inference; ids stay global).
         `on_device=True` skips the copy to the host: the lists stay in the device buffers "topk_idx" / "topk_score"
         (self.buffer(name) -> pointer) and None is returned."""
         xp, xv = _coo(x_positions, x_vals)
-        seed_ptr = np.zeros(self.n_batch + 1, np.int32)
-        lens = [len(s) for s in seeds]
-        seed_ptr[1:len(lens) + 1] = np.cumsum(lens)
-        seed_ptr[len(lens) + 1:] = seed_ptr[len(lens)]
-        flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int64).reshape(-1) for s in seeds])
-                                    if lens and sum(lens) else np.zeros(0, np.int64))
-        flat = np.clip(flat, -1, 2 ** 31 - 1).astype(np.int32)
+        if isinstance(seeds, tuple):
+            # already CSR: (seed_ptr int32 [batch + 1], seed_idx int32 [nnz]) -- large batches skip the Python list walk
+            seed_ptr = np.ascontiguousarray(seeds[0], dtype=np.int32)
+            flat = np.ascontiguousarray(seeds[1], dtype=np.int32)
+            if seed_ptr.shape[0] != self.n_batch + 1:
+                raise ValueError("seed_ptr must have batch + 1 = %d entries" % (self.n_batch + 1))
+        else:
+            seed_ptr = np.zeros(self.n_batch + 1, np.int32)
+            lens = [len(s) for s in seeds]
+            seed_ptr[1:len(lens) + 1] = np.cumsum(lens)
+            seed_ptr[len(lens) + 1:] = seed_ptr[len(lens)]
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int64).reshape(-1) for s in seeds])
+                                        if lens and sum(lens) else np.zeros(0, np.int64))
+            flat = np.clip(flat, -1, 2 ** 31 - 1).astype(np.int32)
         idx = np.empty((self.n_batch, k), np.int32) if not on_device else None
         sc = np.empty((self.n_batch, k), np.float32) if (return_scores and not on_device) else None
         lo, hi = item_range if item_range is not None else (0, self.n_tracks)
