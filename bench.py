@@ -181,8 +181,13 @@ def aux_workload(args, wl, rank=0, world=1):
             # the merged per-shard lists must be the unsharded list (checked once, outside the timed region)
             got = rec.recommend(trk, tv, seeds, k=500, return_scores=True)
             want = m.recommend(trk, tv, seeds, k=500, return_scores=True)
-            if not np.allclose(got[1], want[1], rtol=2e-6, atol=1e-9) or (got[0] != want[0]).mean() > 1e-3:
-                raise SystemExit("bench.py: item-sharded top-k differs from the unsharded list")
+            if not (np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])):
+                bad = np.nonzero((got[0] != want[0]).any(1))[0]
+                raise SystemExit("bench.py: item-sharded top-k differs from the unsharded list (rank %d, range %s): %d rows differ, "
+                                 "idx mismatch %.4f, first bad row %d: got %s / %s want %s / %s"
+                                 % (rank, rec.range, len(bad), (got[0] != want[0]).mean(), bad[0] if len(bad) else -1,
+                                    got[0][bad[0]][:6] if len(bad) else "", got[1][bad[0]][:6] if len(bad) else "",
+                                    want[0][bad[0]][:6] if len(bad) else "", want[1][bad[0]][:6] if len(bad) else ""))
         h2d = int(trk.nbytes + tv.nbytes + 4 * (B + 1) + 4 * len(trk))
         d2h, units, metric = B * 500 * 4, B, "dae_challenge_topk_playlists_per_sec"
         desc = ("cfg5: challenge inference, top-500 over a %d-item decoder, batch %d in one call (fused decode + top-K, "

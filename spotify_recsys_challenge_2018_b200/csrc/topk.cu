@@ -26,6 +26,14 @@ __device__ __forceinline__ float key_score(uint32_t k) {
     return __uint_as_float(u);
 }
 
+// sigmoid_out: the row holds logits and is ranked by p = sigmoid(z) in fp32 -- the SAME expression as the decode
+// epilogue (gemm_sm100.cu), so that the fused decode + top-K orders exactly like the dense path / the reference
+// (distinct logits may round to the same p; ties then go by index)
+__device__ __forceinline__ float load_score(const float* __restrict__ x, int i, int sigmoid_out) {
+    const float v = x[i];
+    return sigmoid_out ? __fdividef(1.f, 1.f + __expf(-v)) : v;
+}
+
 // histogram increment with warp aggregation (scores cluster in a few bins -> avoid same-address atomics)
 __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t digit, bool active) {
     const uint32_t amask = __ballot_sync(0xffffffffu, active);
@@ -110,7 +118,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
         for (int i = t; i < Tround; i += kTopkThreads) {
             bool act = i < T;
             uint32_t key = 0;
-            if (act) key = score_key(x[i]);
+            if (act) key = score_key(load_score(x, i, sigmoid_out));
             if (pass == 1) act = act && ((key >> 20) == prefix);
             if (pass == 2) act = act && ((key >> 8) == prefix);
             hist_add(s_hist, (key >> sh) & masks[pass], act);
@@ -134,7 +142,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     for (int i = t; i < Tround; i += kTopkThreads) {
         uint32_t key = 0;
         const bool in = i < T;
-        if (in) key = score_key(x[i]);
+        if (in) key = score_key(load_score(x, i, sigmoid_out));
         if (in && key > thr) {
             const uint32_t slot = atomicAdd(&s_cnt[0], 1u);
             if (slot < (uint32_t)kCandMax)
@@ -217,8 +225,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
             if (pos < (uint32_t)K) {
                 const unsigned long long c = s_cand[t * 2 + u];
                 out_idx[(size_t)row * K + pos] = (int)(0xFFFFFFFFu - (uint32_t)(c & 0xFFFFFFFFull)) + idx_base;
-                const float sc = key_score((uint32_t)(c >> 32));
-                out_score[(size_t)row * K + pos] = sigmoid_out ? __fdividef(1.f, 1.f + __expf(-sc)) : sc;
+                out_score[(size_t)row * K + pos] = key_score((uint32_t)(c >> 32));
             }
             ++pos;
         }

@@ -186,3 +186,31 @@ def test_dp_ipc_two_gpus_equals_single():
     for a, b, name in zip(got, want, ("W_enc", "W_dec", "b_enc", "b_dec")):
         d = np.abs(a - b)
         assert (d > 1e-6).mean() < 2e-3, (name, d.max())
+
+
+def test_sharded_recommender_single_rank_group():
+    """dp.ShardedRecommender's device path (lists left on the device, all-gather, device merge) on a 1-rank NCCL group:
+    must return exactly what the plain recommend call returns."""
+    import torch.distributed as dist
+    from spotify_recsys_challenge_2018_b200.dp import ShardedRecommender
+    N, T, H, B, k = 40000, 36000, 128, 300, 500
+    port = _free_port()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, world_size=1, rank=0,
+                            device_id=torch.device("cuda", 0))
+    try:
+        conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.01, DAEval=None)
+        m = DAE(conf)
+        m.trainable = False
+        m.fit()
+        rng = np.random.default_rng(5)
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=30)
+        xv = np.ones(len(trk), np.float32)
+        seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(B)]
+        for flags in (32, 16):                       # dense ranking, fused decode + top-K
+            m.set_debug(flags)
+            want_i, want_s = m.recommend(trk, xv, seeds, k=k, return_scores=True)
+            got_i, got_s = ShardedRecommender(m).recommend(trk, xv, seeds, k=k, return_scores=True)
+            assert np.array_equal(got_i, want_i) and np.array_equal(got_s, want_s), flags
+        m.close()
+    finally:
+        dist.destroy_process_group()
