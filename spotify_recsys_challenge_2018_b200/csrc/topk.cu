@@ -76,7 +76,7 @@ __device__ void select_bin(const uint32_t* hist, int nbins, uint32_t want, uint3
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kTopkThreads, 1)
+__global__ void __launch_bounds__(kTopkThreads, 2)     // 2 CTAs / SM: the kernel is latency-bound (block scans between passes)
 k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* __restrict__ seed_ptr,
        const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score,
        const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out) {
