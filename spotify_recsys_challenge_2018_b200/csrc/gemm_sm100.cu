@@ -786,16 +786,17 @@ k_dw(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
 // through the two TMEM accumulators, and is ~10x shorter than it.
 constexpr int kFuItems = 8;                                    // rows of w / m / v per staging stage
 constexpr int kFuSub = kTileItems / kFuItems;                  // 16 row groups per tile
-constexpr int kFuStages = 5;
-constexpr int kFuMmaStages = 2;
+constexpr int kFuStages = 5;                                   // max staging stages  (K <= 512: 5 staging + 2 MMA stages;
+constexpr int kFuMmaStages = 3;                                // max MMA operand stages  K > 512: 3 + 3 -- the K loop is longer)
 constexpr int kFuMmaStageBytes = kABytes + kBChunkBytes;       // 16 KB dz chunk + 32 KB h_d^T chunk
 constexpr int kFuStageBytes = 3 * kFuItems * 256 * 4;          // 24 KB at H = 256
 constexpr int kFuEpiWarps = 16;
 constexpr int kFuThreads = 128 + 32 * kFuEpiWarps;             // producer, MMA, I/O, (idle), 16 epilogue warps
-constexpr int kSmemFused = kFuMmaStages * kFuMmaStageBytes + kFuStages * kFuStageBytes + 256 + 1024;
+constexpr int kSmemFused = 2 * kFuMmaStageBytes + 5 * kFuStageBytes + 256 + 1024;   // == 3 * 48 KB + 3 * 24 KB + ...
 
 struct FusedDev {
     int tiles, kchunks, H, mhalves, n_global, world, rank;
+    int n_mma, n_stg;                      // ring depths: (2, 5) or (3, 3)
     float* w; float* m; float* v;          // [local rows, H]
     const float* g_extra;                  // tied: sparse-row dW_enc, added where touched
     const unsigned char* touched;
@@ -809,8 +810,9 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
-    uint8_t* sS = smem + kFuMmaStages * kFuMmaStageBytes;            // optimizer-state staging ring
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + kFuStages * kFuStageBytes);
+    const int NM = p.n_mma, NS = p.n_stg;
+    uint8_t* sS = smem + NM * kFuMmaStageBytes;                      // optimizer-state staging ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFuMmaStageBytes + 5 * kFuStageBytes);   // fixed: end of either layout
     uint64_t* full = bars;                         // [2] MMA operand stage loaded
     uint64_t* empty = full + kFuMmaStages;         // [2] MMA operand stage consumed
     uint64_t* tfull = empty + kFuMmaStages;        // [2] accumulator complete
@@ -863,7 +865,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                     uint8_t* dst = smem + stage * kFuMmaStageBytes;
                     tma_load_2d_hint(dst, &tmDz, &full[stage], kc * 64, tile * kTileItems, pol_stream);
                     tma_load_2d_hint(dst + kABytes, &tmH, &full[stage], kc * 64, 0, pol_keep);
-                    if (++stage == kFuMmaStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == NM) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -892,7 +894,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                         }
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == kFuMmaStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == NM) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);
             }
@@ -908,7 +910,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                 return ((size_t)tile * kTileItems + (size_t)(i % kFuSub) * kFuItems) * p.H;
             };
             auto issue_load = [&](int i) {
-                const int s = i % kFuStages;
+                const int s = i % NS;
                 uint8_t* dst = sS + s * kFuStageBytes;
                 const size_t off = elem_off(i);
                 mbar_expect_tx(&ld_full[s], 3u * abytes);
@@ -916,10 +918,10 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                 bulk_load_hint(dst + abytes, p.m + off, abytes, &ld_full[s], pol);
                 bulk_load_hint(dst + 2 * abytes, p.v + off, abytes, &ld_full[s], pol);
             };
-            for (int i = 0; i < kFuStages && i < total; ++i) issue_load(i);
+            for (int i = 0; i < NS && i < total; ++i) issue_load(i);
             for (int i = 0; i < total; ++i) {
-                const int s = i % kFuStages;
-                mbar_wait(&done[s], static_cast<uint32_t>((i / kFuStages) & 1));
+                const int s = i % NS;
+                mbar_wait(&done[s], static_cast<uint32_t>((i / NS) & 1));
                 const uint8_t* src = sS + s * kFuStageBytes;
                 const size_t off = elem_off(i);
                 bulk_store_hint(p.w + off, src, abytes, pol);
@@ -928,7 +930,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                 bulk_commit_group();
                 if (i >= 1) {
                     bulk_wait_group_read<1>();           // the store of row group i-1 no longer reads its stage
-                    if (i - 1 + kFuStages < total) issue_load(i - 1 + kFuStages);
+                    if (i - 1 + NS < total) issue_load(i - 1 + NS);
                 }
             }
             bulk_wait_group<0>();
@@ -952,11 +954,11 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
 #pragma unroll 1
             for (int sub = grp; sub < kFuSub; sub += 2) {
                 const int i = t * kFuSub + sub;
-                const int s = i % kFuStages;
+                const int s = i % NS;
                 uint32_t r[8];
                 __syncwarp();                                                    // tcgen05.ld is warp-collective
                 tmem_ld8(t_addr + sub * kFuItems, r);
-                mbar_wait(&ld_full[s], static_cast<uint32_t>((i / kFuStages) & 1));
+                mbar_wait(&ld_full[s], static_cast<uint32_t>((i / NS) & 1));
                 tmem_ld_wait();
                 const int item0 = tile * kTileItems + sub * kFuItems;            // local row of column 0 of the group
                 const int gitem0 = item_global(item0, p.world, p.rank);          // 8 consecutive catalogue ids
@@ -1010,6 +1012,9 @@ void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
     p.g_extra = a.g_extra; p.touched = a.touched;
     p.shadow = a.shadow;
     p.adam = a.adam;
+    // K = ranks x batch tile: a long contraction (K > 512: 4+ ranks) needs the deeper operand ring more than staging depth
+    p.n_mma = a.K > 512 ? 3 : 2;
+    p.n_stg = a.K > 512 ? 3 : 5;
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
     const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
     const int grid = p.tiles < sm_count() ? p.tiles : sm_count();

@@ -93,9 +93,11 @@ def test_dp_local_equals_single(tied, world, N, T, H, b_local, lam):
         m.close()
 
 
-def test_dp_streamed_operand_vs_oracle():
-    """world x bpad = 512 batch columns: the dW contraction streams BOTH operands (K > 256)."""
-    world, N, T, H, b_local = 4, 6007, 5000, 256, 128
+@pytest.mark.parametrize("world,b_local", [(4, 128), (3, 256)])
+def test_dp_streamed_operand_vs_oracle(world, b_local):
+    """world x bpad = 512 / 768 batch columns: the dW contraction streams BOTH operands (K > 256); K > 512 switches the
+    fused dW + Adam kernel to its 3 + 3 ring layout."""
+    N, T, H = 6007, 5000, 256
     B = world * b_local
     ora = O.DAEOracle(N, H, 0.005, tied=False, seed=5, mode="b200")
     ora.b_dec[:] = np.random.default_rng(2).normal(0, 0.1, N)
