@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-flags", type=int, default=0, help="extra dae_model_set_debug bits (include/dae_b200.h)")
     ap.add_argument("--no-overlap", action="store_true", help="decoder update on the main stream (no overlap with the encoder tail)")
     ap.add_argument("--two-kernel", action="store_true", help="decoder dW and Adam as two kernels (gradient through HBM)")
     args = ap.parse_args()
@@ -293,8 +294,8 @@ def main():
     conf.stream = stream.cuda_stream
     with torch.cuda.stream(stream):
         model = (DAE_tied if tied else DAE)(conf).fit()
-        if args.two_kernel or args.no_overlap:
-            model.set_debug((4 if args.two_kernel else 0) | (8 if args.no_overlap else 0))
+        if args.two_kernel or args.no_overlap or args.debug_flags:
+            model.set_debug((4 if args.two_kernel else 0) | (8 if args.no_overlap else 0) | args.debug_flags)
         trainer = DataParallelDAE(model) if world > 1 else None
         batches = make_batches(wl, 8, seed=7, rank=rank)
         model.stage_batch(0, *batches[0])

@@ -581,14 +581,15 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     // decoder update (next to the sparse tail) and the bias updates (next to the encoder's Adam).  Not while profiling:
     // the per-phase times are taken with every kernel running alone.
     m->par_step = m->overlap_dec && !m->profiling && !(m->debug & (1 | 2 | 8));
-    if (m->par_step) {
+    const bool fork_y = m->par_step && !(m->debug & 64);
+    if (fork_y) {
         CK(cudaEventRecord(m->ev_a, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_a, 0));
         build_ybits(m, slot, B, bpad, m->st3);
         CK(cudaEventRecord(m->ev_y, m->st3));
     }
     run_encode(m, slot, bpad, bpad, keep_prob, input_keep_prob, row_offset, true);
-    if (m->par_step) CK(cudaStreamWaitEvent(m->st, m->ev_y, 0));
+    if (fork_y) CK(cudaStreamWaitEvent(m->st, m->ev_y, 0));
     else build_ybits(m, slot, B, bpad);
     barrier(m);                                                               // B1
     CK(cudaEventRecord(s.consumed, m->st));                 // every rank has read this slot: it may be re-prepared
@@ -625,7 +626,10 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     // untied model it starts here on its own stream and streams w / m / v through HBM while the main stream runs the
     // latency-bound tail (split-K sums, da, sparse scatter) and the encoder's Adam; apply_adam joins the two.  Not while
     // profiling: the per-phase times (bench.py roofline) are taken with the kernels running alone.
-    if (m->par_step && !m->tied) {
+    // Single-GPU only for now: with 4+ ranks the forked decoder update ends in a launch failure within a few steps
+    // (bisected on 4 GPUs: the target-bitmask and bias forks are fine, this one is not; 2 ranks pass) -- not understood yet,
+    // so the multi-GPU step keeps the decoder update on the main stream (debug bit 9 forces the fork for investigation).
+    if (m->par_step && !m->tied && !(m->debug & 128) && (m->world == 1 || (m->debug & 512))) {
         CK(cudaEventRecord(m->ev_dh, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_dh, 0));
         run_decoder_update(m, bpad, m->st3);
@@ -688,7 +692,8 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     }
 
     cudaStream_t sb = m->st;
-    if (m->par_step) {              // bias updates behind the decoder update on st3, next to the encoder's Adam
+    const bool fork_b = m->par_step && !(m->debug & 256);
+    if (fork_b) {                   // bias updates behind the decoder update on st3, next to the encoder's Adam
         sb = m->st3;
         CK(cudaStreamWaitEvent(sb, m->ev_da, 0));
     }
@@ -700,7 +705,7 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     launch_adam(a, sb);
     m->launches += 2 + (N % 4 ? 1 : 0);
     ph_end(m, PH_ADAM_BIAS, sb);
-    if (m->par_step) CK(cudaEventRecord(m->ev_bias, sb));
+    if (fork_b) CK(cudaEventRecord(m->ev_bias, sb));
 
     ph_begin(m, PH_ADAM_ENC);
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
@@ -712,10 +717,8 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     launch_clear_flagged(m->n_local, H, m->g_enc, m->touched, m->st);
     m->launches += 1;
     ph_end(m, PH_ADAM_ENC);
-    if (m->par_step) {
-        CK(cudaStreamWaitEvent(m->st, m->ev_bias, 0));
-        m->par_step = false;
-    }
+    if (fork_b) CK(cudaStreamWaitEvent(m->st, m->ev_bias, 0));
+    m->par_step = false;
     ph_collect(m);
     m->b1_pow *= kBeta1;
     m->b2_pow *= kBeta2;
