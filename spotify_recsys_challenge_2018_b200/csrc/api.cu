@@ -15,18 +15,40 @@
 
 static thread_local std::string g_err;
 std::string& dae_err() { return g_err; }
+static unsigned int* g_trap_host = nullptr;      // mapped pinned: where a bounded device-side spin gave up (umma.cuh)
 int fail(const char* fmt, ...) {
-    char buf[512];
+    char buf[768];
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
+    int n = vsnprintf(buf, 512, fmt, ap);
     va_end(ap);
+    if (g_trap_host != nullptr && g_trap_host[0] == 0xDAE0DEADu && n > 0 && n < 512) {
+        volatile unsigned int* l = g_trap_host;
+        if (l[1] == 0xBA221E2u)
+            snprintf(buf + n, sizeof(buf) - n, " [device trap: cross-GPU barrier timed out on rank %u waiting for rank %u, epoch %u, seen %u]",
+                     l[2], l[3], l[4], l[5]);
+        else
+            snprintf(buf + n, sizeof(buf) - n, " [device trap: mbarrier wait timed out: blockDim %u block (%u,%u) thread %u barrier smem 0x%x parity %u]",
+                     l[1], l[2], l[3], l[4], l[5], l[6]);
+    }
     g_err = buf;
     return 1;
 }
 void ensure_loaded() {
     static bool done = false;
-    if (!done) { preload_sparse(); preload_optim(); preload_gemm(); preload_topk(); preload_title(); done = true; }
+    if (done) return;
+    preload_sparse(); preload_optim(); preload_gemm(); preload_topk(); preload_title();
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+        memset(g_trap_host, 0, 64);
+        unsigned int* dptr = nullptr;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_trap_host, 0) == cudaSuccess) {
+            set_trap_log_gemm(dptr); set_trap_log_title_gemm(dptr); set_trap_log_sparse(dptr);
+        }
+    } else {
+        g_trap_host = nullptr;
+    }
+    (void)cudaGetLastError();
+    done = true;
 }
 
 static void layout_csr(Arena& A, CsrWork* w, int B, int max_nnz) {

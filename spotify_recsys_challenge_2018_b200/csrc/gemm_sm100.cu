@@ -1015,6 +1015,10 @@ void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
     // K = ranks x batch tile: a long contraction (K > 512: 4+ ranks) needs the deeper operand ring more than staging depth
     p.n_mma = a.K > 512 ? 3 : 2;
     p.n_stg = a.K > 512 ? 3 : 5;
+    if (const char* e = getenv("DAE_FUSED_RINGS")) {          // investigation knob: "25" or "33"
+        if (e[0] == '2') { p.n_mma = 2; p.n_stg = 5; }
+        if (e[0] == '3') { p.n_mma = 3; p.n_stg = 3; }
+    }
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
     const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
     const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
@@ -1215,6 +1219,10 @@ void preload_gemm() {
     cudaFuncGetAttributes(&a, k_dw_adam_fused);
     cudaFuncGetAttributes(&a, k_dh);
     (void)cudaGetLastError();
+}
+
+void set_trap_log_gemm(unsigned int* host_mapped) {
+    cudaMemcpyToSymbol(g_trap_log, &host_mapped, sizeof(host_mapped));
 }
 
 }  // namespace dae

@@ -311,6 +311,10 @@ void launch_topk(const TopkArgs& a, cudaStream_t st);
 // thr[r] = score[r, kp-1] (r < batch, -inf when that slot is padding or score == nullptr), +inf for r in [batch, rows)
 void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch, int rows, float* thr, cudaStream_t st);
 
+// bounded-spin diagnostics: 8 words of mapped pinned host memory written before a trap (umma.cuh trap_report, k_barrier)
+void set_trap_log_gemm(unsigned int* host_mapped);
+void set_trap_log_title_gemm(unsigned int* host_mapped);
+void set_trap_log_sparse(unsigned int* host_mapped);
 // load every kernel of a translation unit (see sparse.cu: preload_sparse)
 void preload_sparse();
 void preload_optim();

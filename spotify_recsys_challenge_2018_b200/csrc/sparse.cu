@@ -448,6 +448,10 @@ void launch_sum_partials(const float* part_local, float* out, int n, const PeerT
 // enqueued before it have completed (stream order), so their NVLink stores are visible to the peers
 // that observe the flag.  Bounded spin: a lost peer traps instead of hanging the box.
 // ------------------------------------------------------------------------------------------
+static __device__ unsigned int* g_trap_log_sparse = nullptr;
+void set_trap_log_sparse(unsigned int* host_mapped) {
+    cudaMemcpyToSymbol(g_trap_log_sparse, &host_mapped, sizeof(host_mapped));
+}
 __global__ void k_barrier(unsigned int* flags_local, unsigned int epoch, const __grid_constant__ PeerTable pt) {
     const int t = threadIdx.x;
     if (t >= pt.world) return;
@@ -460,6 +464,11 @@ __global__ void k_barrier(unsigned int* flags_local, unsigned int epoch, const _
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
         if ((int)(seen - epoch) >= 0) return;
         __nanosleep(64);
+    }
+    unsigned int* l = g_trap_log_sparse;      // {magic, 0xBA221E2 = cross-GPU barrier, rank, peer, epoch, seen}
+    if (l != nullptr && atomicCAS(l, 0u, 0xDAE0DEADu) == 0u) {
+        l[1] = 0xBA221E2u; l[2] = pt.rank; l[3] = t; l[4] = epoch; l[5] = seen;
+        __threadfence_system();
     }
     __trap();
 }

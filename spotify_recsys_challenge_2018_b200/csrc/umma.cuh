@@ -33,6 +33,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Where a bounded spin gave up: 8 words in MAPPED PINNED HOST memory (it survives the launch failure that follows the
+// trap): {magic, blockDim.x, blockIdx.x, blockIdx.y, threadIdx.x, barrier smem address, parity, spins}.  One copy of the
+// pointer per translation unit (set_trap_log_* in the .cu files); nullptr: no log.
+static __device__ unsigned int* g_trap_log = nullptr;
+static __device__ __noinline__ void trap_report(uint32_t a, uint32_t b) {
+    unsigned int* l = g_trap_log;
+    if (l != nullptr && atomicCAS(l, 0u, 0xDAE0DEADu) == 0u) {
+        l[1] = blockDim.x; l[2] = blockIdx.x; l[3] = blockIdx.y; l[4] = threadIdx.x; l[5] = a; l[6] = b;
+        __threadfence_system();
+    }
+    __trap();
+}
 // Bounded spin: a protocol bug traps (-> launch error on the host) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -48,7 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (done) return;
     }
-    __trap();
+    trap_report(addr, parity);
 }
 
 // ---------------------------------------------------------------- TMA
