@@ -28,8 +28,8 @@ int fail(const char* fmt, ...) {
             snprintf(buf + n, sizeof(buf) - n, " [device trap: cross-GPU barrier timed out on rank %u waiting for rank %u, epoch %u, seen %u]",
                      l[2], l[3], l[4], l[5]);
         else
-            snprintf(buf + n, sizeof(buf) - n, " [device trap: mbarrier wait timed out: blockDim %u block (%u,%u) thread %u barrier smem 0x%x parity %u]",
-                     l[1], l[2], l[3], l[4], l[5], l[6]);
+            snprintf(buf + n, sizeof(buf) - n, " [device trap: mbarrier wait timed out: blockDim %u block (%u,%u) thread %u barrier smem 0x%x parity %u; odd-phase mask 0x%x of the barriers at 0x%x]",
+                     l[1], l[2], l[3], l[4], l[5], l[6], l[7], l[8]);
     }
     g_err = buf;
     return 1;

@@ -860,7 +860,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
             for (int t = 0; t < n_my; ++t) {
                 const int tile = blockIdx.x + t * gridDim.x;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_wait(&empty[stage], phase ^ 1u, bars, 20);
                     mbar_expect_tx(&full[stage], tx);
                     uint8_t* dst = smem + stage * kFuMmaStageBytes;
                     tma_load_2d_hint(dst, &tmDz, &full[stage], kc * 64, tile * kTileItems, pol_stream);
@@ -877,11 +877,11 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
             uint32_t phase = 0;
             for (int t = 0; t < n_my; ++t) {
                 const int acc = t & 1;
-                mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1u);
+                mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1u, bars, 20);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&full[stage], phase, bars, 20);
                     tc_fence_after();
                     const uint32_t dz_addr = smem_u32(smem + stage * kFuMmaStageBytes);
                     const uint32_t h_addr = dz_addr + kABytes;
@@ -921,7 +921,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
             for (int i = 0; i < NS && i < total; ++i) issue_load(i);
             for (int i = 0; i < total; ++i) {
                 const int s = i % NS;
-                mbar_wait(&done[s], static_cast<uint32_t>((i / NS) & 1));
+                mbar_wait(&done[s], static_cast<uint32_t>((i / NS) & 1), bars, 20);
                 const uint8_t* src = sS + s * kFuStageBytes;
                 const size_t off = elem_off(i);
                 bulk_store_hint(p.w + off, src, abytes, pol);
@@ -948,7 +948,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
         for (int t = 0; t < n_my; ++t) {
             const int tile = blockIdx.x + t * gridDim.x;
             const int acc = t & 1;
-            mbar_wait(&tfull[acc], static_cast<uint32_t>((t >> 1) & 1));
+            mbar_wait(&tfull[acc], static_cast<uint32_t>((t >> 1) & 1), bars, 20);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256 + mh * kTileItems);
 #pragma unroll 1
@@ -958,7 +958,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                 uint32_t r[8];
                 __syncwarp();                                                    // tcgen05.ld is warp-collective
                 tmem_ld8(t_addr + sub * kFuItems, r);
-                mbar_wait(&ld_full[s], static_cast<uint32_t>((i / NS) & 1));
+                mbar_wait(&ld_full[s], static_cast<uint32_t>((i / NS) & 1), bars, 20);
                 tmem_ld_wait();
                 const int item0 = tile * kTileItems + sub * kFuItems;            // local row of column 0 of the group
                 const int gitem0 = item_global(item0, p.world, p.rank);          // 8 consecutive catalogue ids

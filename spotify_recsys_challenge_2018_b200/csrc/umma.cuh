@@ -37,16 +37,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // trap): {magic, blockDim.x, blockIdx.x, blockIdx.y, threadIdx.x, barrier smem address, parity, spins}.  One copy of the
 // pointer per translation unit (set_trap_log_* in the .cu files); nullptr: no log.
 static __device__ unsigned int* g_trap_log = nullptr;
-static __device__ __noinline__ void trap_report(uint32_t a, uint32_t b) {
+// `dump` (optional): the CTA's mbarrier array; word 7 of the record gets one bit per barrier: "the phase with parity 0
+// has completed" (mbarrier.test_wait.parity 0), i.e. which of them sit in an odd phase -- enough to see who is behind.
+static __device__ __noinline__ void trap_report(uint32_t a, uint32_t b, const uint64_t* dump = nullptr, int ndump = 0) {
     unsigned int* l = g_trap_log;
     if (l != nullptr && atomicCAS(l, 0u, 0xDAE0DEADu) == 0u) {
         l[1] = blockDim.x; l[2] = blockIdx.x; l[3] = blockIdx.y; l[4] = threadIdx.x; l[5] = a; l[6] = b;
+        unsigned int mask = 0;
+        for (int k = 0; k < ndump && k < 32; ++k) {
+            uint32_t ok = 0;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(dump + k)) : "memory");
+            mask |= ok << k;
+        }
+        l[7] = mask;
+        l[8] = smem_u32(dump);
         __threadfence_system();
     }
     __trap();
 }
 // Bounded spin: a protocol bug traps (-> launch error on the host) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const uint64_t* dump = nullptr, int ndump = 0) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
 #pragma unroll 1
@@ -60,7 +71,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
         if (done) return;
     }
-    trap_report(addr, parity);
+    trap_report(addr, parity, dump, ndump);
 }
 
 // ---------------------------------------------------------------- TMA
