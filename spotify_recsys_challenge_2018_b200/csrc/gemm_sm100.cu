@@ -775,7 +775,7 @@ k_dw(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
 // ------------------------------------------------------------------------------------------
 // Same W^T orientation as k_dw (TMEM lane = hidden unit, column = item).  The optimizer state never passes
 // through registers as global loads: one I/O thread streams 8-item row groups of w / m / v (8 x H fp32 = 8 KB
-// each, contiguous in the item-major layout) into a 5-stage shared-memory ring with 1-D bulk copies
+// each, contiguous in the item-major layout) into a 6- (or 4-) stage shared-memory ring with 1-D bulk copies
 // (cp.async.bulk, mbarrier complete_tx), the 16 epilogue warps (two groups of 8, alternating row groups)
 // read their accumulator columns with tcgen05.ld, update the stage IN PLACE (conflict-free: lanes =
 // consecutive h), and the I/O thread writes the stage back with bulk stores (bulk async-groups; a stage is
@@ -786,17 +786,28 @@ k_dw(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
 // through the two TMEM accumulators, and is ~10x shorter than it.
 constexpr int kFuItems = 8;                                    // rows of w / m / v per staging stage
 constexpr int kFuSub = kTileItems / kFuItems;                  // 16 row groups per tile
-constexpr int kFuStages = 5;                                   // max staging stages  (K <= 512: 5 staging + 2 MMA stages;
-constexpr int kFuMmaStages = 3;                                // max MMA operand stages  K > 512: 3 + 3 -- the K loop is longer)
+// Ring depths.  The staging depth MUST be even: row group i is handled by epilogue group i % 2 and uses stage i % NS, so
+// with NS even a stage (and its ld_full barrier) always belongs to the SAME group, whose warps then wait for consecutive
+// phases of that barrier.  With NS odd the two groups alternate on a barrier and a warp can be TWO phases ahead of it: a
+// parity wait cannot tell "phase k completed" from "phase k+2 completed", the warp passes early, updates a stage whose
+// rows have not landed and the pipeline derails (seen as a rare mbarrier time-out on one GPU, within a few steps with
+// 4+ ranks or other kernels sharing the SMs) -- round-1 bug of the 5- and 3-stage layouts.
+// Two layouts of the same 192 KB: K <= 256 (one GPU): 1 MMA operand stage + 6 staging stages (the 4 K-chunks of a tile
+// load back to back, ~8 us, under the ~21 us epilogue of the previous tile; 144 KB of optimizer state in flight);
+// K > 256 (data parallel, longer contraction): 2 + 4.
+constexpr int kFuStages = 6;                                   // max staging stages (8 rows x w, m, v each)
+constexpr int kFuMmaStages = 2;                                // max MMA operand stages (16 KB dz chunk + 32 KB h_d^T chunk)
 constexpr int kFuMmaStageBytes = kABytes + kBChunkBytes;       // 16 KB dz chunk + 32 KB h_d^T chunk
 constexpr int kFuStageBytes = 3 * kFuItems * 256 * 4;          // 24 KB at H = 256
 constexpr int kFuEpiWarps = 16;
 constexpr int kFuThreads = 128 + 32 * kFuEpiWarps;             // producer, MMA, I/O, (idle), 16 epilogue warps
-constexpr int kSmemFused = 2 * kFuMmaStageBytes + 5 * kFuStageBytes + 256 + 1024;   // == 3 * 48 KB + 3 * 24 KB + ...
+constexpr int kFuDataBytes = 1 * kFuMmaStageBytes + 6 * kFuStageBytes;              // == 2 * 48 KB + 4 * 24 KB
+static_assert(kFuDataBytes == 2 * kFuMmaStageBytes + 4 * kFuStageBytes, "both layouts fill the same bytes");
+constexpr int kSmemFused = kFuDataBytes + 256 + 1024;
 
 struct FusedDev {
     int tiles, kchunks, H, mhalves, n_global, world, rank;
-    int n_mma, n_stg;                      // ring depths: (2, 5) or (3, 3)
+    int n_mma, n_stg;                      // ring depths (kFuMmaStages, kFuStages)
     float* w; float* m; float* v;          // [local rows, H]
     const float* g_extra;                  // tied: sparse-row dW_enc, added where touched
     const unsigned char* touched;
@@ -812,7 +823,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
     uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
     const int NM = p.n_mma, NS = p.n_stg;
     uint8_t* sS = smem + NM * kFuMmaStageBytes;                      // optimizer-state staging ring
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kFuMmaStageBytes + 5 * kFuStageBytes);   // fixed: end of either layout
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFuDataBytes);
     uint64_t* full = bars;                         // [2] MMA operand stage loaded
     uint64_t* empty = full + kFuMmaStages;         // [2] MMA operand stage consumed
     uint64_t* tfull = empty + kFuMmaStages;        // [2] accumulator complete
@@ -1012,13 +1023,8 @@ void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
     p.g_extra = a.g_extra; p.touched = a.touched;
     p.shadow = a.shadow;
     p.adam = a.adam;
-    // K = ranks x batch tile: a long contraction (K > 512: 4+ ranks) needs the deeper operand ring more than staging depth
-    p.n_mma = a.K > 512 ? 3 : 2;
-    p.n_stg = a.K > 512 ? 3 : 5;
-    if (const char* e = getenv("DAE_FUSED_RINGS")) {          // investigation knob: "25" or "33"
-        if (e[0] == '2') { p.n_mma = 2; p.n_stg = 5; }
-        if (e[0] == '3') { p.n_mma = 3; p.n_stg = 3; }
-    }
+    p.n_mma = a.K <= 256 ? 1 : 2;
+    p.n_stg = a.K <= 256 ? 6 : 4;          // even, always (see kFuStages)
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
     const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
     const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
