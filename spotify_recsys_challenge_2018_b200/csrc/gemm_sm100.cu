@@ -786,24 +786,23 @@ k_dw(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
 // through the two TMEM accumulators, and is ~10x shorter than it.
 constexpr int kFuItems = 8;                                    // rows of w / m / v per staging stage
 constexpr int kFuSub = kTileItems / kFuItems;                  // 16 row groups per tile
-// Ring depths.  The staging depth MUST be even: row group i is handled by epilogue group i % 2 and uses stage i % NS, so
-// with NS even a stage (and its ld_full barrier) always belongs to the SAME group, whose warps then wait for consecutive
-// phases of that barrier.  With NS odd the two groups alternate on a barrier and a warp can be TWO phases ahead of it: a
-// parity wait cannot tell "phase k completed" from "phase k+2 completed", the warp passes early, updates a stage whose
-// rows have not landed and the pipeline derails (seen as a rare mbarrier time-out on one GPU, within a few steps with
-// 4+ ranks or other kernels sharing the SMs) -- round-1 bug of the 5- and 3-stage layouts.
-// Two layouts of the same 192 KB: K <= 256 (one GPU): 1 MMA operand stage + 6 staging stages (the 4 K-chunks of a tile
-// load back to back, ~8 us, under the ~21 us epilogue of the previous tile; 144 KB of optimizer state in flight);
-// K > 256 (data parallel, longer contraction): 2 + 4.
-constexpr int kFuStages = 6;                                   // max staging stages (8 rows x w, m, v each)
-constexpr int kFuMmaStages = 2;                                // max MMA operand stages (16 KB dz chunk + 32 KB h_d^T chunk)
+// Ring depths: K <= 512: 2 MMA operand stages + 5 staging stages; K > 512 (4+ ranks, longer contraction): 3 + 3.
+// Row group i is handled by epilogue group i % 2 and uses stage i % NS.  With NS odd the two groups ALTERNATE on a stage,
+// so every stage has one "rows have landed" barrier PER GROUP (ld_full[stage][group]): the warps of a group then wait for
+// consecutive phases of their own barrier.  (Round-1 bug: with one barrier per stage a warp could be two phases ahead of
+// it; a parity wait cannot tell "phase k completed" from "phase k+2 completed", the warp passed early, updated a stage
+// whose rows had not landed and the pipeline derailed -- a rare mbarrier time-out on one GPU, within a few steps with 4+
+// ranks or other kernels sharing the SMs.  Even depths (each stage owned by one group) are also correct but measured
+// 9 % slower: 0.381 vs 0.349 ms.)
+constexpr int kFuStages = 5;                                   // max staging stages (8 rows x w, m, v each)
+constexpr int kFuMmaStages = 3;                                // max MMA operand stages (16 KB dz chunk + 32 KB h_d^T chunk)
 constexpr int kFuMmaStageBytes = kABytes + kBChunkBytes;       // 16 KB dz chunk + 32 KB h_d^T chunk
 constexpr int kFuStageBytes = 3 * kFuItems * 256 * 4;          // 24 KB at H = 256
 constexpr int kFuEpiWarps = 16;
 constexpr int kFuThreads = 128 + 32 * kFuEpiWarps;             // producer, MMA, I/O, (idle), 16 epilogue warps
-constexpr int kFuDataBytes = 1 * kFuMmaStageBytes + 6 * kFuStageBytes;              // == 2 * 48 KB + 4 * 24 KB
-static_assert(kFuDataBytes == 2 * kFuMmaStageBytes + 4 * kFuStageBytes, "both layouts fill the same bytes");
-constexpr int kSmemFused = kFuDataBytes + 256 + 1024;
+constexpr int kFuDataBytes = 2 * kFuMmaStageBytes + 5 * kFuStageBytes;              // == 3 * 48 KB + 3 * 24 KB
+static_assert(kFuDataBytes == 3 * kFuMmaStageBytes + 3 * kFuStageBytes, "both layouts fill the same bytes");
+constexpr int kSmemFused = kFuDataBytes + 256 + 1024;       // data, barriers (25 x 8 B), alignment slack
 
 struct FusedDev {
     int tiles, kchunks, H, mhalves, n_global, world, rank;
@@ -828,8 +827,8 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
     uint64_t* empty = full + kFuMmaStages;         // [2] MMA operand stage consumed
     uint64_t* tfull = empty + kFuMmaStages;        // [2] accumulator complete
     uint64_t* tempty = tfull + 2;                  // [2] accumulator drained
-    uint64_t* ld_full = tempty + 2;                // [5] w / m / v rows of the stage have landed
-    uint64_t* done = ld_full + kFuStages;          // [5] the stage holds the updated rows
+    uint64_t* ld_full = tempty + 2;                // [5][2] w / m / v rows of the stage have landed, per consuming group
+    uint64_t* done = ld_full + 2 * kFuStages;      // [5] the stage holds the updated rows
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + kFuStages);
 
     const int warp = threadIdx.x >> 5;
@@ -849,7 +848,8 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
             mbar_init(&tempty[a], kFuEpiWarps);
         }
         for (int s = 0; s < kFuStages; ++s) {
-            mbar_init(&ld_full[s], 1);
+            mbar_init(&ld_full[2 * s], 1);
+            mbar_init(&ld_full[2 * s + 1], 1);
             mbar_init(&done[s], kFuEpiWarps / 2);
         }
         fence_barrier_init();
@@ -871,7 +871,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
             for (int t = 0; t < n_my; ++t) {
                 const int tile = blockIdx.x + t * gridDim.x;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&empty[stage], phase ^ 1u, bars, 20);
+                    mbar_wait(&empty[stage], phase ^ 1u, bars, 25);
                     mbar_expect_tx(&full[stage], tx);
                     uint8_t* dst = smem + stage * kFuMmaStageBytes;
                     tma_load_2d_hint(dst, &tmDz, &full[stage], kc * 64, tile * kTileItems, pol_stream);
@@ -888,11 +888,11 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
             uint32_t phase = 0;
             for (int t = 0; t < n_my; ++t) {
                 const int acc = t & 1;
-                mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1u, bars, 20);
+                mbar_wait(&tempty[acc], ((t >> 1) & 1) ^ 1u, bars, 25);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&full[stage], phase, bars, 20);
+                    mbar_wait(&full[stage], phase, bars, 25);
                     tc_fence_after();
                     const uint32_t dz_addr = smem_u32(smem + stage * kFuMmaStageBytes);
                     const uint32_t h_addr = dz_addr + kABytes;
@@ -924,15 +924,16 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                 const int s = i % NS;
                 uint8_t* dst = sS + s * kFuStageBytes;
                 const size_t off = elem_off(i);
-                mbar_expect_tx(&ld_full[s], 3u * abytes);
-                bulk_load_hint(dst, p.w + off, abytes, &ld_full[s], pol);
-                bulk_load_hint(dst + abytes, p.m + off, abytes, &ld_full[s], pol);
-                bulk_load_hint(dst + 2 * abytes, p.v + off, abytes, &ld_full[s], pol);
+                uint64_t* lf = &ld_full[2 * s + (i & 1)];       // the barrier of the group that consumes row group i
+                mbar_expect_tx(lf, 3u * abytes);
+                bulk_load_hint(dst, p.w + off, abytes, lf, pol);
+                bulk_load_hint(dst + abytes, p.m + off, abytes, lf, pol);
+                bulk_load_hint(dst + 2 * abytes, p.v + off, abytes, lf, pol);
             };
             for (int i = 0; i < NS && i < total; ++i) issue_load(i);
             for (int i = 0; i < total; ++i) {
                 const int s = i % NS;
-                mbar_wait(&done[s], static_cast<uint32_t>((i / NS) & 1), bars, 20);
+                mbar_wait(&done[s], static_cast<uint32_t>((i / NS) & 1), bars, 25);
                 const uint8_t* src = sS + s * kFuStageBytes;
                 const size_t off = elem_off(i);
                 bulk_store_hint(p.w + off, src, abytes, pol);
@@ -959,17 +960,18 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
         for (int t = 0; t < n_my; ++t) {
             const int tile = blockIdx.x + t * gridDim.x;
             const int acc = t & 1;
-            mbar_wait(&tfull[acc], static_cast<uint32_t>((t >> 1) & 1), bars, 20);
+            mbar_wait(&tfull[acc], static_cast<uint32_t>((t >> 1) & 1), bars, 25);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256 + mh * kTileItems);
 #pragma unroll 1
             for (int sub = grp; sub < kFuSub; sub += 2) {
                 const int i = t * kFuSub + sub;
                 const int s = i % NS;
-                uint32_t r[8];
+                uint32_t r[kFuItems];
                 __syncwarp();                                                    // tcgen05.ld is warp-collective
                 tmem_ld8(t_addr + sub * kFuItems, r);
-                mbar_wait(&ld_full[s], static_cast<uint32_t>((i / NS) & 1), bars, 20);
+                // this group's barrier of the stage: with NS odd the group uses the stage every 2 * NS row groups
+                mbar_wait(&ld_full[2 * s + grp], static_cast<uint32_t>((i / (2 * NS)) & 1), bars, 25);
                 tmem_ld_wait();
                 const int item0 = tile * kTileItems + sub * kFuItems;            // local row of column 0 of the group
                 const int gitem0 = item_global(item0, p.world, p.rank);          // 8 consecutive catalogue ids
@@ -1023,8 +1025,8 @@ void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
     p.g_extra = a.g_extra; p.touched = a.touched;
     p.shadow = a.shadow;
     p.adam = a.adam;
-    p.n_mma = a.K <= 256 ? 1 : 2;
-    p.n_stg = a.K <= 256 ? 6 : 4;          // even, always (see kFuStages)
+    p.n_mma = a.K > 512 ? 3 : 2;
+    p.n_stg = a.K > 512 ? 3 : 5;           // ODD: the per-group barrier phase in the epilogue is (i / (2 * NS)) & 1
     const CUtensorMap tmDz = make_map_bf16(a.dzT, a.K, a.n_local, kTileItems);
     const CUtensorMap tmH = make_map_bf16(a.h_dT, a.K, a.H, p.mhalves * 128);   // rows >= H: out-of-bounds zero fill
     const int grid = p.tiles < sm_count() ? p.tiles : sm_count();
