@@ -151,7 +151,7 @@ int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
  * the decoder update on the main stream instead of overlapping it with the sparse / encoder tail of the step.
  * bit 4: dae_model_recommend[_range] always takes the fused decode + top-K path, bit 5: never.
  * bits 6 / 7 / 8: keep the target bitmask / the decoder update / the bias updates on the main stream (bisecting the
- * three forks of the whole-step call); bit 9: fork the decoder update also when world > 1 (off by default, see api.cu). */
+ * three forks of the whole-step call). */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row

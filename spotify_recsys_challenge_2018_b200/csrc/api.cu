@@ -648,10 +648,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     // untied model it starts here on its own stream and streams w / m / v through HBM while the main stream runs the
     // latency-bound tail (split-K sums, da, sparse scatter) and the encoder's Adam; apply_adam joins the two.  Not while
     // profiling: the per-phase times (bench.py roofline) are taken with the kernels running alone.
-    // Single-GPU only for now: with 4+ ranks the forked decoder update ends in a launch failure within a few steps
-    // (bisected on 4 GPUs: the target-bitmask and bias forks are fine, this one is not; 2 ranks pass) -- not understood yet,
-    // so the multi-GPU step keeps the decoder update on the main stream (debug bit 9 forces the fork for investigation).
-    if (m->par_step && !m->tied && !(m->debug & 128) && (m->world == 1 || (m->debug & 512))) {
+    if (m->par_step && !m->tied && !(m->debug & 128)) {
         CK(cudaEventRecord(m->ev_dh, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_dh, 0));
         run_decoder_update(m, bpad, m->st3);
