@@ -33,8 +33,43 @@ def _load(data_dir, filename):
         return json.load(f)
 
 
+def _ragged(lists, dtype=np.int32):
+    """list of id lists -> (flat [total], ptr [n + 1])"""
+    lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+    ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    flat = np.fromiter((v for x in lists for v in x), dtype=dtype, count=int(ptr[-1]))
+    return flat, ptr
+
+
+def _gather_rows(flat, ptr, ids):
+    """The rows `ids` of a ragged array, concatenated: -> (values int64 [total], lens int64 [len(ids)])."""
+    beg = ptr[ids]
+    lens = ptr[ids + 1] - beg
+    total = int(lens.sum())
+    if total == 0:
+        return np.empty(0, np.int64), lens
+    starts = np.cumsum(lens) - lens
+    idx = np.arange(total, dtype=np.int64) + np.repeat(beg - starts, lens)
+    return flat[idx].astype(np.int64), lens
+
+
+def _coo_block(vals, lens):
+    """int64 [nnz, 2]: column 0 = row in the batch, column 1 = item id, playlist order."""
+    out = np.empty((len(vals), 2), dtype=np.int64)
+    out[:, 0] = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
+    out[:, 1] = vals
+    return out
+
+
 class data_reader:
-    """Whole-playlist reader (reference utils/data_reader.py:7-54)."""
+    """Whole-playlist reader (reference utils/data_reader.py:7-54).
+
+    Same batches, same Python-`random` consumption and the same epoch rule as the reference (a batch may straddle the
+    wrap: the list is reshuffled the moment its last playlist has been consumed, data_reader.py:43-46) -- but assembled
+    from a flat CSR copy of the playlists with a handful of NumPy calls instead of a per-playlist Python loop
+    (at < 1 ms per device step the reference's loop would be the bottleneck).  The value vectors come back
+    as float32 arrays (the reference returns Python lists of 1); `titles` is an int64 [batch, max_title_len] array."""
 
     def __init__(self, data_dir, filename, batch_size):
         d = _load(data_dir, filename)
@@ -42,33 +77,64 @@ class data_reader:
         self.num_items = self.num_tracks + len(d["artist_uri2id"])
         self.max_title_len = d["max_title_len"]
         self.num_char = d["num_char"]
-        self.playlists = d["playlists"]
+        pls = d["playlists"]
         self.class_divpnt = d.get("class_divpnt", [])
         self.batch_size = batch_size
         self.train_idx = 0
+        self._n = len(pls)
+        self._trk, self._trk_ptr = _ragged([p[0] for p in pls])
+        self._art, self._art_ptr = _ragged([p[1] for p in pls])
+        L = self.max_title_len
+        self._titles = np.full((self._n, L), -1, dtype=np.int64)
+        for i, p in enumerate(pls):
+            t = p[2][:L]
+            self._titles[i, :len(t)] = t
+        # current order of the playlist list; random.shuffle on a list of the same length consumes the RNG exactly as the
+        # reference's shuffle of the playlists themselves and yields the same permutation
+        self._order_list = list(range(self._n))
+        self._order = np.arange(self._n, dtype=np.int64)
 
-    def _advance(self):
-        self.train_idx += 1
-        if self.train_idx == len(self.playlists):          # data_reader.py:44-46
-            self.train_idx = 0
-            random.shuffle(self.playlists)
+    @property
+    def playlists(self):
+        """The playlists in their current order, as the reference keeps them: [[tracks], [artists], [title ids]]."""
+        out = []
+        for i in self._order_list:
+            out.append([self._trk[self._trk_ptr[i]:self._trk_ptr[i + 1]].tolist(),
+                        self._art[self._art_ptr[i]:self._art_ptr[i + 1]].tolist(), self._titles[i].tolist()])
+        return out
+
+    def __len__(self):
+        return self._n
+
+    def _take(self, count):
+        """ids of the next `count` playlists, with the reference's wrap + reshuffle rule (data_reader.py:43-46)."""
+        parts, need = [], count
+        while need > 0:
+            k = min(need, self._n - self.train_idx)
+            parts.append(self._order[self.train_idx:self.train_idx + k])
+            self.train_idx += k
+            need -= k
+            if self.train_idx == self._n:
+                self.train_idx = 0
+                random.shuffle(self._order_list)
+                self._order = np.asarray(self._order_list, dtype=np.int64)
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
     def next_batch(self):
-        trk, art, titles = [], [], []
-        for i in range(self.batch_size):
-            t, a, title = self.playlists[self.train_idx]
-            trk.append((i, t)); art.append((i, a)); titles.append(title)
-            self._advance()
-        trk_positions = _block(trk)
-        art_positions = _block(art)
+        ids = self._take(self.batch_size)
+        trk, trk_lens = _gather_rows(self._trk, self._trk_ptr, ids)
+        art, art_lens = _gather_rows(self._art, self._art_ptr, ids)
+        trk_positions = _coo_block(trk, trk_lens)
+        art_positions = _coo_block(art, art_lens)
         y_positions = np.concatenate((trk_positions, art_positions), 0)       # data_reader.py:50
-        return (trk_positions, art_positions, y_positions, titles,
-                [1] * len(trk_positions), [1] * len(art_positions))
+        return (trk_positions, art_positions, y_positions, self._titles[ids],
+                np.ones(len(trk_positions), np.float32), np.ones(len(art_positions), np.float32))
 
 
 class data_reader_firstN(data_reader):
     """Reader that marks only the first `given_num` entries of each modality as input
-    (value 1, the rest 0; reference utils/data_reader.py:57-128)."""
+    (value 1, the rest 0; reference utils/data_reader.py:57-128).  `given_num` is drawn with the reference's own
+    `random.randrange` calls, in the reference's order (tracks then artists, per playlist)."""
 
     def __init__(self, data_dir, filename, batch_size, from_to):
         data_reader.__init__(self, data_dir, filename, batch_size)
@@ -85,25 +151,67 @@ class data_reader_firstN(data_reader):
             m = int(max(n_items * f1, 1))
         return random.randrange(n, m + 1)                      # data_reader.py:91
 
+    def _bounds(self, n_items):
+        """Vector form of _given's range: -> (n, width = m + 1 - n), width 0 where the modality is empty."""
+        f0, f1 = self.from_to[0], self.from_to[1]
+        n_items = np.asarray(n_items, dtype=np.int64)
+        if f0 >= 1:
+            m = np.minimum(n_items.astype(np.float64), float(f1)).astype(np.int64)
+            n = np.minimum(int(f0), m)
+        else:
+            n = np.maximum(n_items * float(f0), 1.0).astype(np.int64)
+            m = np.maximum(n_items * float(f1), 1.0).astype(np.int64)
+        width = np.where(n_items != 0, m + 1 - n, 0)
+        return n, width
+
     def next_batch(self):
-        trk, art, titles = [], [], []
-        trk_val, art_val = [], []
-        for i in range(self.batch_size):
-            t, a, title = self.playlists[self.train_idx]
-            if len(t) != 0:
-                g = self._given(len(t))
-                trk.append((i, t))
-                trk_val += [1] * g + [0] * (len(t) - g)
-            if len(a) != 0:
-                g = self._given(len(a))
-                art.append((i, a))
-                art_val += [1] * g + [0] * (len(a) - g)
-            titles.append(title)
-            self._advance()
-        trk_positions = _block(trk)
-        art_positions = _block(art)
+        # the draws must interleave with the epoch reshuffle exactly as in the reference (both use `random`): walk the
+        # batch in runs that do not cross the wrap
+        id_parts, gt_parts, ga_parts = [], [], []
+        need = self.batch_size
+        while need > 0:
+            k = min(need, self._n - self.train_idx)
+            ids = self._order[self.train_idx:self.train_idx + k]
+            tl = self._trk_ptr[ids + 1] - self._trk_ptr[ids]
+            al = self._art_ptr[ids + 1] - self._art_ptr[ids]
+            # [n, m] of every draw at once (same float arithmetic as _given), then the draws themselves in the reference's
+            # order with random.randrange's own algorithm (CPython _randbelow_with_getrandbits) on random.getrandbits
+            lo_t, w_t = self._bounds(tl)
+            lo_a, w_a = self._bounds(al)
+            lo = np.stack([lo_t, lo_a], 1).reshape(-1).tolist()
+            wd = np.stack([w_t, w_a], 1).reshape(-1).tolist()          # 0: empty modality, no draw
+            g = [0] * (2 * k)
+            getrandbits = random.getrandbits
+            for j in range(2 * k):
+                w = wd[j]
+                if w > 0:
+                    nb = w.bit_length()
+                    r = getrandbits(nb)
+                    while r >= w:
+                        r = getrandbits(nb)
+                    g[j] = lo[j] + r
+            gt, ga = g[0::2], g[1::2]
+            id_parts.append(ids); gt_parts.append(gt); ga_parts.append(ga)
+            self.train_idx += k
+            need -= k
+            if self.train_idx == self._n:
+                self.train_idx = 0
+                random.shuffle(self._order_list)
+                self._order = np.asarray(self._order_list, dtype=np.int64)
+        ids = id_parts[0] if len(id_parts) == 1 else np.concatenate(id_parts)
+        gt = np.asarray([g for part in gt_parts for g in part], dtype=np.int64)
+        ga = np.asarray([g for part in ga_parts for g in part], dtype=np.int64)
+        trk, trk_lens = _gather_rows(self._trk, self._trk_ptr, ids)
+        art, art_lens = _gather_rows(self._art, self._art_ptr, ids)
+        trk_positions = _coo_block(trk, trk_lens)
+        art_positions = _coo_block(art, art_lens)
         y_positions = np.concatenate((trk_positions, art_positions), 0)
-        return trk_positions, art_positions, y_positions, titles, trk_val, art_val
+
+        def first_n(lens, given):          # 1 for the first given[r] entries of row r, 0 for the rest
+            within = np.arange(int(lens.sum()), dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+            return (within < np.repeat(given, lens)).astype(np.float32)
+        return (trk_positions, art_positions, y_positions, self._titles[ids],
+                first_n(trk_lens, gt), first_n(art_lens, ga))
 
 
 class data_reader_test:

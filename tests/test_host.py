@@ -22,9 +22,11 @@ DATA = os.path.join(GOLDEN, "data")
 
 def _pack(out):
     res = []
-    for o in out:
-        if isinstance(o, np.ndarray):
+    for k, o in enumerate(out):
+        if isinstance(o, np.ndarray) and k < 3 and o.ndim == 2 and o.shape[1] == 2:      # COO positions
             res.append(np.asarray(o).reshape(-1, 2).astype(np.int64).tolist())
+        elif isinstance(o, np.ndarray):                       # titles [batch, L] / value vectors (arrays here, lists upstream)
+            res.append(o.tolist())
         else:
             res.append(json.loads(json.dumps(o)))
     return res
@@ -73,6 +75,48 @@ def test_data_reader_challenge_matches_reference(golden):
     # the >50-seed in-order rule (data_reader.py:288-291) is exercised by the fixture
     flat = [v for b in golden["challenge"] for v in b[5]]
     assert 0.15 in flat and 0.5 in flat
+
+
+@pytest.mark.parametrize("ft", [[0.0, 0.3], [0.2, 0.9], [1.0, 4.0], [5.0, 100.0], [0.0, 1.0]])
+def test_firstN_fast_draws_equal_reference_randrange(ft):
+    """The vectorised reader draws `given_num` with random.getrandbits + CPython's _randbelow loop; it must consume the
+    Mersenne Twister exactly like the reference's random.randrange(n, m + 1) (data_reader.py:85-91)."""
+    r = rdr.data_reader_firstN.__new__(rdr.data_reader_firstN)
+    r.from_to = ft
+    lens = np.array(list(range(1, 260)) + [1, 2, 3, 250], dtype=np.int64)
+    lo, w = r._bounds(lens)
+    random.seed(5)
+    want = [r._given(int(n)) for n in lens]
+    random.seed(5)
+    got = []
+    for l, ww in zip(lo.tolist(), w.tolist()):
+        nb = ww.bit_length()
+        x = random.getrandbits(nb)
+        while x >= ww:
+            x = random.getrandbits(nb)
+        got.append(l + x)
+    assert got == want
+    assert r._bounds(np.array([0, 3]))[1][0] == 0           # empty modality: no draw
+
+
+def test_reader_batch_larger_than_dataset_wraps_and_reshuffles():
+    random.seed(9)
+    r = rdr.data_reader(DATA, "train", 60)                   # 23 playlists: two wraps inside one batch
+    ref_order = list(range(23))
+    trk, art, y, titles, tv, av = r.next_batch()
+    rows = trk[:, 0]
+    assert rows.max() == 59 and len(titles) == 60 and r.train_idx == 60 - 2 * 23
+    random.seed(9)
+    expect = list(ref_order); ids = []
+    idx = 0
+    for _ in range(60):
+        ids.append(expect[idx]); idx += 1
+        if idx == 23:
+            idx = 0
+            random.shuffle(expect)
+    want_lens = [len(json.load(open(os.path.join(DATA, "train")))["playlists"][i][0]) for i in ids]
+    assert np.bincount(rows, minlength=60).tolist() == want_lens
+    assert isinstance(r.playlists, list) and len(r.playlists) == 23 == len(r)
 
 
 def test_positions_are_int64_even_with_empty_rows():
