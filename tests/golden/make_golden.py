@@ -13,6 +13,9 @@ Everything pure-Python/NumPy on the hot path's host side is executed from
                         next_batch outputs on tests/golden/data (np.int -> int shim for numpy>=1.24)
   conf_golden.json      main.Conf parsed from the four shipped config.ini files (main_runner stubbed)
 
+  merge_results_golden.csv / merge_results_input.pkl   the reference's merge_results.py run (subprocess, cwd = a temp
+                        dir) on one small challenge pickle: `python tests/golden/make_golden.py --merge`
+
 TensorFlow-1 arithmetic (models/DAEs.py) cannot be executed here; see oracle/__init__.py.
 """
 import json
@@ -37,8 +40,28 @@ def _stub(name, **attrs):
     return m
 
 
+def make_merge_golden():
+    """results.csv of the reference's own merge_results.py for one small challenge pickle."""
+    import pickle
+    import shutil
+    import subprocess
+    import tempfile
+    d = tempfile.mkdtemp()
+    os.makedirs(os.path.join(d, "challenge_results"))
+    rows = [[1000000 + i] + ["spotify:track:t%d" % ((i * 7 + j) % 900) for j in range(500)] for i in range(3)]
+    with open(os.path.join(d, "challenge_results", "result_a"), "wb") as f:
+        pickle.dump(rows, f)
+    subprocess.run([sys.executable, os.path.join(REF, "merge_results.py")], cwd=d, check=True, capture_output=True)
+    shutil.copy(os.path.join(d, "results.csv"), os.path.join(HERE, "merge_results_golden.csv"))
+    with open(os.path.join(HERE, "merge_results_input.pkl"), "wb") as f:
+        pickle.dump(rows, f)
+
+
 def main():
     assert os.path.isdir(REF), "reference not mounted"
+    if "--merge" in sys.argv:
+        make_merge_golden()
+        return
     if not hasattr(np, "int"):
         np.int = int                                      # SURVEY D8
     sys.path.insert(0, REF)

@@ -189,6 +189,22 @@ def test_host_metrics_match_reference():
         assert met.get_rsc(c["answer"], c["cand"]) == c["rsc"]
 
 
+def test_merge_results_matches_reference(tmp_path):
+    """results.csv written by the merger mirror == the file the reference's merge_results.py wrote for the same pickle
+    (tests/golden/merge_results_golden.csv; one result file, so os.listdir order does not matter)."""
+    import pickle
+    import shutil
+    from spotify_recsys_challenge_2018_b200.merge_results import merge
+    d = tmp_path / "challenge_results"
+    d.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "merge_results_input.pkl"), d / "result_a")
+    out = tmp_path / "results.csv"
+    assert merge(str(d), str(out), verbose=False) == 3
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "merge_results_golden.csv"), "rb").read()
+    rows = pickle.load(open(d / "result_a", "rb"))
+    assert len(rows[0]) == 501
+
+
 # ---------------------------------------------------------------- synthetic generator -> readers
 def test_synth_dataset_roundtrip(tmp_path):
     from tools.synth_mpd import write_dataset
