@@ -1,20 +1,28 @@
 // Tensor-core kernels of the DAE step for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
 //
-//   G1  k_itemtile<TRAIN|PREDICT>   Z[item, b] = W_dec[item,:] . h_d[b,:]      (DAEs.py:75 / :143)
-//         TRAIN   epilogue: +b_dec, sigmoid, weighted BCE (DAEs.py:98-99), d cost/dz (bf16, item-major),
-//                           db_dec = sum_b dz, per-CTA loss partial.  The [B,N] score matrix is never written.
-//         PREDICT epilogue: +b_dec, sigmoid (, title mix DAEs.py:180) -> y_pred[b, item] fp32
-//   G2  k_itemtile<DW>              dW_dec[item, :] = sum_b dz[item,b] h_d[b,:]  (autodiff of DAEs.py:75)
-//   G3  k_dh                        dh_d[b,:] = sum_item dz[item,b] W_dec[item,:]  (split-K over items,
-//                                   both operands MN-major straight from their item-major layouts)
+//   G1    k_itemtile<TRAIN|PREDICT|FILTER>   Z[item, b] = W_dec[item,:] . h_d[b,:]      (DAEs.py:75 / :143)
+//           TRAIN   epilogue: +b_dec, sigmoid, weighted BCE (DAEs.py:98-99), d cost/dz (bf16, item-major),
+//                             db_dec = sum_b dz, per-CTA loss partial.  The [B,N] score matrix is never written.
+//           PREDICT epilogue: +b_dec, sigmoid (, title mix DAEs.py:180) -> y_pred[b, item] fp32 (or the raw logits)
+//           FILTER  epilogue: logits >= the playlist's threshold -> its candidate list (fused decode + top-K)
+//   G2    k_dw              dW_dec^T tile = h_d^T . dz^T -> g_dec (parity tests, title head, two-kernel path)
+//   G2+K5 k_dw_adam_fused   the same tile kept in tensor memory, dense TF1 Adam applied from there; w / m / v staged
+//                           through shared memory with 1-D bulk copies (the default decoder update)
+//   G3    k_dh              dh_d[b,:] = sum_item dz[item,b] W_dec[item,:]  (split-K over items,
+//                           both operands MN-major straight from their item-major layouts)
 //
-// Shape of every kernel: persistent, 1 CTA / SM, 192 threads =
-//   warp 0  TMA producer (one elected lane)      -> smem ring, mbarrier full/empty
+// Shape of every kernel: persistent, 1 CTA / SM,
+//   warp 0  TMA producer (one elected lane)        -> smem ring, mbarrier full/empty
 //   warp 1  TMEM allocator + MMA issuer (one lane) -> 2 x 256-column fp32 accumulators, tcgen05.commit
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns per warp, lane == item row (G1/G2) or batch row (G3)
-// The small operand (h_d, 128 KB at B=256,H=256) stays resident in shared memory for the CTA's
-// lifetime; only the catalogue-sized operand streams through the ring, so W / dz are read from
-// HBM exactly once per kernel.
+//   (warp 2 of k_dw_adam_fused: the optimizer-state I/O thread)
+//   4 (k_dh) or 16 epilogue warps: tcgen05.ld 32 lanes x 16/32 columns per warp; lane == item row (G1), hidden unit
+//   (G2) or batch row (G3)
+// The small operand (h_d, 128 KB at B=256,H=256) stays resident in shared memory for the CTA's lifetime where it
+// fits; only the catalogue-sized operand streams through the ring, so W / dz are read from HBM exactly once per kernel.
+//
+// Synchronisation rule that every kernel here obeys (learnt the hard way, see k_dw_adam_fused): an mbarrier parity wait
+// is only meaningful if the waiter has observed the PREVIOUS phase of that barrier -- every waiter must see
+// consecutive phases of every barrier it waits on.  tests/test_sync_protocol.py models it.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
