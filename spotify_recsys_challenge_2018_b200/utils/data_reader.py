@@ -17,17 +17,6 @@ import random
 import numpy as np
 
 
-def _block(rows_ids):
-    """[(row, ids), ...] -> int64 [nnz, 2] in order."""
-    lens = np.fromiter((len(ids) for _, ids in rows_ids), dtype=np.int64, count=len(rows_ids))
-    total = int(lens.sum())
-    out = np.empty((total, 2), dtype=np.int64)
-    if total:
-        out[:, 0] = np.repeat(np.fromiter((r for r, _ in rows_ids), dtype=np.int64, count=len(rows_ids)), lens)
-        out[:, 1] = np.concatenate([np.asarray(ids, dtype=np.int64).reshape(-1) for _, ids in rows_ids])
-    return out
-
-
 def _load(data_dir, filename):
     with open(os.path.join(data_dir, filename)) as f:
         return json.load(f)
@@ -217,13 +206,21 @@ class data_reader_firstN(data_reader):
 class data_reader_test:
     """Held-out reader (reference utils/data_reader.py:131-254).  Records are the writer's
     [seed_trks, seed_arts, title_ixs, answers] (spotify_reader.py:286); the 5-tuple form the committed
-    reader unpacks (seed, seed_art, answer, seed_cls, answer_cls; data_reader.py:158) is accepted too."""
+    reader unpacks (seed, seed_art, answer, seed_cls, answer_cls; data_reader.py:158) is accepted too.
+    The COO blocks come from a flat CSR copy of the seeds (as in data_reader); seeds / answers / titles are handed out
+    as the stored lists, which is what metrics.single_eval and the rankers take."""
 
     def __init__(self, data_dir, filename, batch_size, test_num):
         d = _load(data_dir, filename)
         self.playlists = d["playlists"][:test_num]
         self.batch_size = batch_size
         self.test_idx = 0
+        recs = [self._unpack(r) for r in self.playlists]
+        self._seeds = [r[0] for r in recs]
+        self._answers = [r[3] for r in recs]
+        self._titles = [r[2] for r in recs]
+        self._trk, self._trk_ptr = _ragged(self._seeds)
+        self._art, self._art_ptr = _ragged([r[1] for r in recs])
 
     @staticmethod
     def _unpack(rec):
@@ -237,26 +234,25 @@ class data_reader_test:
     def next_batch_test(self, with_artists=False):
         """-> (x_positions, seeds, answers, titles, x_vals): the signature the eval loop unpacks
         (main_train.py:64).  Seed tracks weigh 1; with_artists adds the seed artists at 0.5
-        (data_reader.py:251-254)."""
-        trk, art, seeds, answers, titles = [], [], [], [], []
-        for i in range(self.batch_size):
-            seed, seed_art, title, answer = self._unpack(self.playlists[self.test_idx])
-            trk.append((i, seed)); art.append((i, seed_art))
-            seeds.append(seed); answers.append(answer); titles.append(title)
-            self.test_idx += 1
-            if self.test_idx == len(self.playlists):           # data_reader.py:186-188
-                self.test_idx = 0
-                break
-        trk_positions = _block(trk)
+        (data_reader.py:251-254).  The last batch of a file is short (data_reader.py:186-188)."""
+        lo = self.test_idx
+        hi = min(lo + self.batch_size, len(self.playlists))
+        ids = np.arange(lo, hi, dtype=np.int64)
+        self.test_idx = 0 if hi == len(self.playlists) else hi
+        trk, trk_lens = _gather_rows(self._trk, self._trk_ptr, ids)
+        trk_positions = _coo_block(trk, trk_lens)
+        seeds, answers, titles = self._seeds[lo:hi], self._answers[lo:hi], self._titles[lo:hi]
         if not with_artists:
-            return trk_positions, seeds, answers, titles, [1] * len(trk_positions)
-        art_positions = _block(art)
+            return trk_positions, seeds, answers, titles, np.ones(len(trk_positions), np.float32)
+        art, art_lens = _gather_rows(self._art, self._art_ptr, ids)
+        art_positions = _coo_block(art, art_lens)
         x_positions = np.concatenate((trk_positions, art_positions), 0)
-        return x_positions, seeds, answers, titles, [1] * len(trk_positions) + [0.5] * len(art_positions)
+        x_vals = np.concatenate((np.ones(len(trk_positions), np.float32), np.full(len(art_positions), 0.5, np.float32)))
+        return x_positions, seeds, answers, titles, x_vals
 
 
 class data_reader_challenge:
-    """Challenge-set reader (reference utils/data_reader.py:257-319)."""
+    """Challenge-set reader (reference utils/data_reader.py:257-319), COO blocks from a flat CSR copy of the seeds."""
 
     def __init__(self, data_dir, filename, batch_size):
         d = _load(data_dir, filename)
@@ -269,26 +265,26 @@ class data_reader_challenge:
         self.num_char = d["num_char"]
         self.batch_size = batch_size
         self.ch_idx = 0
+        self._trk, self._trk_ptr = _ragged([p[0] for p in self.playlists])
+        self._art, self._art_ptr = _ragged([p[1] for p in self.playlists])
 
     def next_batch(self):
-        trk, art = [], []
-        trk_ones = []
-        ch_seed, ch_titles, ch_titles_exist, ch_pid = [], [], [], []
-        for i in range(self.batch_size):
-            seed, seed_art, title, title_exist, pid = self.playlists[self.ch_idx]
-            n = len(seed)
-            if n > 50 and self.is_in_order:                    # data_reader.py:288-291
-                trk_ones += [0.15] * (n - 15) + [1.0] * 15
-            else:
-                trk_ones += [1.0] * n
-            trk.append((i, seed)); art.append((i, seed_art))
-            ch_seed.append(seed); ch_titles.append(title); ch_titles_exist.append(title_exist); ch_pid.append(pid)
-            self.ch_idx += 1
-            if self.ch_idx == len(self.playlists):             # data_reader.py:309-311
-                self.ch_idx = 0
-                break
-        trk_positions = _block(trk)
-        art_positions = _block(art)
+        lo = self.ch_idx
+        hi = min(lo + self.batch_size, len(self.playlists))
+        ids = np.arange(lo, hi, dtype=np.int64)
+        self.ch_idx = 0 if hi == len(self.playlists) else hi                  # data_reader.py:309-311
+        trk, trk_lens = _gather_rows(self._trk, self._trk_ptr, ids)
+        art, art_lens = _gather_rows(self._art, self._art_ptr, ids)
+        trk_positions = _coo_block(trk, trk_lens)
+        art_positions = _coo_block(art, art_lens)
+        # in-order playlists with more than 50 seeds: the last 15 tracks weigh 1.0, the earlier ones 0.15 (data_reader.py:288-291)
+        trk_ones = np.ones(len(trk), np.float64)          # float64: 0.15 exactly as the reference's Python floats
+        if self.is_in_order and len(trk):
+            within = np.arange(len(trk), dtype=np.int64) - np.repeat(np.cumsum(trk_lens) - trk_lens, trk_lens)
+            n_row = np.repeat(trk_lens, trk_lens)
+            trk_ones[(n_row > 50) & (within < n_row - 15)] = 0.15
+        recs = self.playlists[lo:hi]
         x_positions = np.concatenate((trk_positions, art_positions), 0)
-        x_ones = trk_ones + [0.5] * len(art_positions)         # data_reader.py:317
-        return x_positions, ch_seed, ch_titles, ch_titles_exist, ch_pid, x_ones
+        x_ones = np.concatenate((trk_ones, np.full(len(art_positions), 0.5, np.float64)))   # data_reader.py:317
+        return (x_positions, [p[0] for p in recs], [p[2] for p in recs], [p[3] for p in recs], [p[4] for p in recs],
+                x_ones)

@@ -136,12 +136,12 @@ def test_test_reader_both_record_forms(tmp_path):
             json.dump({"playlists": recs, "class_divpnt": []}, f)
         r = rdr.data_reader_test(str(tmp_path), name, 8, 100)
         x, seeds, answers, titles, ones = r.next_batch_test()
-        assert x.tolist() == [[0, 1], [0, 2], [1, 3]] and ones == [1, 1, 1]
+        assert x.tolist() == [[0, 1], [0, 2], [1, 3]] and list(ones) == [1, 1, 1]
         assert seeds == [[1, 2], [3]] and answers == [[5, 6, -1], [7]]
         assert r.test_idx == 0
         x, _, _, _, ones = r.next_batch_test(with_artists=True)
         assert x.tolist() == [[0, 1], [0, 2], [1, 3], [0, 61], [1, 62], [1, 62]]
-        assert ones == [1, 1, 1, 0.5, 0.5, 0.5]
+        assert list(ones) == [1, 1, 1, 0.5, 0.5, 0.5]
 
 
 # ---------------------------------------------------------------- Conf vs reference main.Conf
