@@ -189,6 +189,25 @@ def test_host_metrics_match_reference():
         assert met.get_rsc(c["answer"], c["cand"]) == c["rsc"]
 
 
+@pytest.mark.parametrize("mode", ["--pretrain", "--dae", "--title", "--challenge"])
+def test_cli_host_side_reaches_the_device_boundary(tmp_path, monkeypatch, mode):
+    """Without a GPU every entry point must get through its host side (config, readers, log) and then fail LOUDLY at
+    model creation -- there is no CPU fallback to fall into."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the CLI is exercised end to end by tests/test_gpu_zz_cli.py")
+    from spotify_recsys_challenge_2018_b200 import main as cli
+    from tools.synth_mpd import write_dataset
+    ini = open(os.path.join(ROOT, "tests", "test_gpu_zz_cli.py")).read().split('INI = """')[1].split('"""')[0]
+    write_dataset(str(tmp_path / "data"), n_tracks=300, n_artists=40, n_train=80, n_test=8, n_challenge=6, n_clusters=4)
+    (tmp_path / "run1").mkdir()
+    (tmp_path / "run1" / "config.ini").write_text(ini.format(data=str(tmp_path / "data"), res=str(tmp_path / "res")))
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(_lib.DaeError, match="no CUDA device"):
+        cli.main(["--dir", "run1", mode])
+    assert "mode]" in (tmp_path / "run1" / "log.txt").read_text()
+
+
 def test_merge_results_matches_reference(tmp_path):
     """results.csv written by the merger mirror == the file the reference's merge_results.py wrote for the same pickle
     (tests/golden/merge_results_golden.csv; one result file, so os.listdir order does not matter)."""
