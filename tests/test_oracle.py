@@ -294,3 +294,38 @@ def test_title_training_lowers_cost():
     m = TO.DAETitleOracle(dae, cnn, 0.02)
     costs = [m.train_step(x, xv, y, yv, titles, np.ones(B, np.float32), B, 1.0, 1.0, 1.0) for _ in range(15)]
     assert costs[-1] < costs[0]
+
+
+def test_decode_epilogue_fast_path_algebra():
+    """The G1 TRAIN epilogue (csrc/gemm_sm100.cu: train_chunk_y0) does not evaluate the reference's formulas literally:
+    for y = 0 cells it takes dz = rcp((1 + e) / c_neg) with e = 2^(-z log2 e) (the reciprocal IS the gradient
+    0.55 p / B), 1 - p = 1 - dz / c_neg, and the loss term log(1 - p) once per EIGHT cells on their product, skipping
+    the 1e-10 inside the log unless some 1 - p < 2e-3 (then the exact path redoes the chunk).  This restates that
+    arithmetic in fp32 NumPy and checks it against the oracle's literal formulas: gradients within one bf16 ulp (they
+    are stored as bf16), the loss of every 8-cell group within 2e-5 relative (the worst case sits next to the 2e-3
+    saturation cut, where 1 - p itself carries 3e-5 of fp32 rounding in any evaluation order; the contract on the cost is
+    1e-3) -- for logits over the whole range the fast path accepts."""
+    rng = np.random.default_rng(0)
+    B = 256
+    inv_b = np.float32(1.0 / B)
+    z = rng.uniform(-14.0, 6.0, size=(4096, 8)).astype(np.float32)          # 1 - sigmoid(6) = 2.5e-3 > 2e-3
+    y = np.zeros_like(z)
+    p = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
+    want_dz = O.bce_dz(p, y, inv_b)
+    # fast path, fp32 throughout
+    c1 = np.float32(-1.4426950408889634)
+    c_neg = np.float32(0.55) * inv_b
+    ic = np.float32(1.0) / c_neg
+    e = np.exp2((z * c1).astype(np.float32)).astype(np.float32)
+    dz = (np.float32(1.0) / (e * ic + ic).astype(np.float32)).astype(np.float32)
+    omp = (np.float32(1.0) - dz * ic).astype(np.float32)
+    assert omp.min() >= 2e-3                                                # the fast path's own precondition
+    prod = np.prod(omp, axis=1, dtype=np.float32)                           # 8 cells -> one log2
+    assert prod.min() > 1e-30                                               # no underflow: (2e-3)^8 = 2.6e-22
+    loss_fast = np.float32(-0.6931471805599453 * 0.55) * np.log2(prod).astype(np.float32)
+    loss_exact = -(0.55 * np.log(1.0 - p.astype(np.float64) + 1e-10)).sum(axis=1)
+    np.testing.assert_allclose(loss_fast, loss_exact, rtol=2e-5, atol=1e-7)
+    assert abs(loss_fast.sum(dtype=np.float64) - loss_exact.sum()) <= 2e-6 * loss_exact.sum()      # and it averages out
+    ulp = np.abs(O.bf16_round(want_dz)) * 2.0 ** -7 + 1e-30
+    assert (np.abs(O.bf16_round(dz) - O.bf16_round(want_dz)) <= ulp).all()
+    np.testing.assert_allclose(dz, want_dz, rtol=3e-6, atol=1e-12)
