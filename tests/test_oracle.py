@@ -329,3 +329,29 @@ def test_decode_epilogue_fast_path_algebra():
     ulp = np.abs(O.bf16_round(want_dz)) * 2.0 ** -7 + 1e-30
     assert (np.abs(O.bf16_round(dz) - O.bf16_round(want_dz)) <= ulp).all()
     np.testing.assert_allclose(dz, want_dz, rtol=3e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_threshold_pass_topk_is_exact(ties):
+    """The fused decode + top-K never loses a member of the top-k: thresholds taken from a prefix are lower bounds.
+    Random logits (optionally quantised: heavy ties, the case where '>=' rather than '>' matters), random seeds, random
+    prefix lengths, popularity-skewed and adversarial (best items last) orders -> identical to ranking the whole range."""
+    rng = np.random.default_rng(7 + ties)
+    for trial in range(60):
+        T = int(rng.integers(300, 4000))
+        k = int(rng.integers(5, 120))
+        z = rng.normal(0, 2, T).astype(np.float32)
+        if trial % 3 == 1:
+            z = np.sort(z)                                        # adversarial: the best items come last
+        if trial % 3 == 2:
+            z = np.sort(z)[::-1].copy()                           # popularity-ranked ids: the prefix bound is tight
+        if ties:
+            z = np.round(z * 4) / 4
+        seeds = rng.choice(T, int(rng.integers(0, 40)), replace=False).tolist()
+        m1 = int(rng.integers(1, T // 2))
+        m2 = int(rng.integers(m1, T))
+        got, counts, _ = ranking.topk_by_threshold_passes(z, seeds, k, [m1, m2, T])
+        p = (1.0 / (1.0 + np.exp(-z, dtype=np.float32))).astype(np.float32)
+        want = ranking.topk_excluding_seeds(p, seeds, k)
+        assert np.array_equal(got, want), (trial, T, k, m1, m2)
+        assert counts[-1] >= min(T, k + len(seeds)) or counts[-1] == T
