@@ -34,21 +34,42 @@ int fail(const char* fmt, ...) {
     g_err = buf;
     return 1;
 }
+__global__ void k_max_int(const int* __restrict__ v, int n, int* __restrict__ out);
+__global__ void k_stamp(unsigned long long* t);
 void ensure_loaded() {
     static bool done = false;
     if (done) return;
     preload_sparse(); preload_optim(); preload_gemm(); preload_topk(); preload_title();
+    {
+        cudaFuncAttributes a;
+        PRELOAD_KERNEL(k_stamp);
+        PRELOAD_KERNEL(k_max_int);
+    }
     if (cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
         memset(g_trap_host, 0, 64);
         unsigned int* dptr = nullptr;
         if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_trap_host, 0) == cudaSuccess) {
-            set_trap_log_gemm(dptr); set_trap_log_title_gemm(dptr); set_trap_log_sparse(dptr);
+            set_trap_log_gemm(dptr); set_trap_log_title_gemm(dptr); set_trap_log_sparse(dptr); set_trap_log_optim(dptr);
         }
     } else {
         g_trap_host = nullptr;
     }
     (void)cudaGetLastError();
     done = true;
+}
+
+// debug bit 13: device-side time stamps (%globaltimer) of the step's fork / join points, one tiny kernel each, into the
+// "trace" buffer -- the only way to see how the streams of a step overlap without a timeline profiler (tools/gpu_trace.py)
+__global__ void k_stamp(unsigned long long* t) {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    *t = v;
+}
+enum { TR_START = 0, TR_ENCODE, TR_YBITS, TR_DECODE, TR_DH, TR_DEC_BEGIN, TR_DEC_END, TR_BG_BEGIN, TR_BG_END, TR_TAIL, TR_REST_BEGIN,
+       TR_REST_END, TR_G1_FIRST, TR_G1_LAST, TR_STEP_END, TR_PREPARED, TR_COUNT };
+// two records of 16 stamps, alternating by step parity: the last two steps of a pipelined run can be read side by side
+static inline void stamp(dae_model* m, cudaStream_t s, int id) {
+    if (m->debug & 8192) k_stamp<<<1, 1, 0, s>>>(m->trace + 16 * (m->step & 1) + id);
 }
 
 static void layout_csr(Arena& A, CsrWork* w, int B, int max_nnz) {
@@ -84,8 +105,12 @@ static void layout(dae_model* m) {
         m->g_dec = A.take<float>(LH);
         m->g_enc = A.take<float>(LH);
         m->touched = A.take<unsigned char>(m->n_local);
+        m->touch_cnt = A.take<int>(m->n_local);
+        m->hot_list = A.take<int>((size_t)m->n_local + 1);
+        m->touched_list = A.take<int>((size_t)m->n_local + 1);
         m->g_b_enc = A.take<float>(H);
         m->g_b_dec_sh = A.take<float>(m->n_local);
+        m->g_b_dec_parts = A.take<float>((size_t)4 * m->world * m->n_local);
         m->g_b_dec = m->world > 1 ? A.take<float>(N) : m->g_b_dec_sh;
         m->da = A.take<float>((size_t)K * H);
         m->dz_all = A.take<__nv_bfloat16>((size_t)m->n_local * K);
@@ -104,10 +129,15 @@ static void layout(dae_model* m) {
     m->h = A.take<float>((size_t)rows_h * H);
     m->h_d = A.take<__nv_bfloat16>((size_t)rows_h * H);
     m->h_dT = A.take<__nv_bfloat16>((size_t)H * rows_h);
-    m->pub.row_ptr = A.take<int>(m->Bmax);
-    m->pub.row_len = A.take<int>(m->Bmax);
-    m->pub.col = A.take<int>(m->max_nnz);
-    m->pub.xn = A.take<float>(m->max_nnz);
+    // published input of the global batch: training keeps every rank's segment on every rank (k_encode_fwd)
+    const int n_seg = m->trainable ? m->world : 1;
+    m->pub.seg_rows = m->Bmax; m->pub.seg_nnz = m->max_nnz;
+    m->pub.row_ptr = A.take<int>((size_t)n_seg * m->Bmax);
+    m->pub.row_len = A.take<int>((size_t)n_seg * m->Bmax);
+    m->pub.col = A.take<int>((size_t)n_seg * m->max_nnz);
+    m->pub.xn = A.take<float>((size_t)n_seg * m->max_nnz);
+    if (m->trainable) m->bg.ctl = A.take<unsigned int>(kBgCtlWords);
+    m->trace = A.take<unsigned long long>(32);
     for (int s = 0; s < 2; ++s) {
         Slot& sl = m->slots[s];
         layout_csr(A, &sl.xw, m->Bmax, m->max_nnz);
@@ -122,17 +152,17 @@ static void layout(dae_model* m) {
     A.off = (A.off + 1023) & ~size_t(1023);
 }
 
-enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_YBITS, PH_DECODE_LOSS, PH_DH, PH_DA, PH_BARRIER, PH_SCATTER, PH_DW, PH_ADAM_DEC,
-             PH_ADAM_ENC, PH_ADAM_BIAS, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"prepare_csr", "encode_fwd", "ybits", "decode_loss_dz", "dh", "da_all",
-                                            "barriers", "scatter_dw_enc", "dw_dec", "adam_dec", "adam_enc", "adam_bias"};
-static inline void ph_begin(dae_model* m, int k, cudaStream_t s = nullptr) {
+                                            "barriers", "scatter_dw_enc", "dw_dec", "adam_dec", "adam_enc", "adam_bias",
+                                            "rec_dense_prefix", "rec_filter_mid", "rec_filter_full", "rec_select",
+                                            "title_fwd_loss", "title_dw_adam", "title_dfeat", "title_cnn_bwd", "title_adam_small"};
+void ph_begin(dae_model* m, int k, cudaStream_t s) {
     if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k], s ? s : m->st); }
 }
-static inline void ph_end(dae_model* m, int k, cudaStream_t s = nullptr) {
+void ph_end(dae_model* m, int k, cudaStream_t s) {
     if (m->profiling) { cudaEventRecord(m->ph_ev[2 * k + 1], s ? s : m->st); m->ph_used[k] = true; }
 }
-static void ph_collect(dae_model* m) {
+void ph_collect(dae_model* m) {
     if (!m->profiling) return;
     cudaStreamSynchronize(m->st2);
     cudaStreamSynchronize(m->st);
@@ -180,6 +210,15 @@ extern "C" int32_t dae_model_create(const dae_config* cfg, dae_model** out) {
     else { CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking)); m->own_stream = true; }
     CK(cudaStreamCreateWithFlags(&m->st2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&m->st3, cudaStreamNonBlocking));
+    {   // the background streamer's blocks must be on the SMs BEFORE the encode's (one per SM, see k_adam_bg): its stream
+        // has the highest priority, and the encode is released by the same event as the streamer
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&m->st4, cudaStreamNonBlocking, hi));
+    }
+    CK(cudaEventCreateWithFlags(&m->ev_pre, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_touch, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_bg, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_dh, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_dec, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->ev_a, cudaEventDisableTiming));
@@ -223,6 +262,7 @@ extern "C" void dae_model_destroy(dae_model* m) {
     cudaStreamSynchronize(m->st);
     cudaStreamSynchronize(m->st2);
     if (m->st3) cudaStreamSynchronize(m->st3);
+    if (m->st4) cudaStreamSynchronize(m->st4);
     for (int r = 0; r < kMaxWorld; ++r) if (m->ipc_opened[r]) cudaIpcCloseMemHandle(m->ipc_opened[r]);
     if (m->arena.base) cudaFree(m->arena.base);
     for (void* p : m->host_allocs) cudaFreeHost(p);
@@ -242,6 +282,10 @@ extern "C" void dae_model_destroy(dae_model* m) {
     for (int i = 0; i < 2; ++i) if (m->ev_cost[i]) cudaEventDestroy(m->ev_cost[i]);
     cudaStreamDestroy(m->st2);
     if (m->st3) cudaStreamDestroy(m->st3);
+    if (m->st4) cudaStreamDestroy(m->st4);
+    if (m->ev_touch) cudaEventDestroy(m->ev_touch);
+    if (m->ev_bg) cudaEventDestroy(m->ev_bg);
+    if (m->ev_pre) cudaEventDestroy(m->ev_pre);
     if (m->ev_dh) cudaEventDestroy(m->ev_dh);
     if (m->ev_dec) cudaEventDestroy(m->ev_dec);
     if (m->ev_a) cudaEventDestroy(m->ev_a);
@@ -420,6 +464,7 @@ static int prepare_slot(dae_model* m, int slot) {
         m->launches += s.nnz_y > 0 ? 4 : 2;
     }
     ph_end(m, PH_PREPARE, m->st2);
+    if (m->trainable) stamp(m, m->st2, TR_PREPARED);          // (lands in the record of the step being enqueued next)
     CK(cudaEventRecord(s.prepared, m->st2));
     return 0;
 }
@@ -528,12 +573,17 @@ static AdamArgs adam_args(dae_model* m) {
 // sparse-row dW_enc of the rows this rank owns, from every rank's batch
 static void run_scatter(dae_model* m, int B, int bpad) {
     ScatterArgs sc{};
-    sc.pub = m->pub; sc.da = m->da; sc.g_enc = m->g_enc; sc.touched = m->touched; sc.B = B; sc.bpad = bpad; sc.H = m->H;
+    sc.pub = m->pub; sc.da = m->da; sc.g_enc = m->g_enc; sc.touch_cnt = m->touch_cnt; sc.hot_list = m->hot_list; sc.n_local = m->n_local;
+    sc.B = B; sc.bpad = bpad; sc.H = m->H;
+    // one GPU: the gather form (fixed summation order, bit-reproducible; it runs under the decoder update anyway).
+    // Several GPUs: the sparse tail is on the critical path and the fp32 red.add form is the shorter one.
+    // debug bit 11 forces the atomic form, bit 12 the deterministic one.
+    sc.deterministic = ((m->world == 1 && !(m->debug & 2048)) || (m->debug & 4096)) ? 1 : 0;
     sc.pt = m->pt;
     ph_begin(m, PH_SCATTER);
     launch_scatter_shard(sc, m->st);
     ph_end(m, PH_SCATTER);
-    m->launches += 1;
+    m->launches += 1 + sc.deterministic;
 }
 
 static DwArgs dw_args(dae_model* m, int bpad) {
@@ -592,6 +642,21 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     // the loss is a mean over the GLOBAL batch (DAEs.py:100); dropout is keyed by the global row
     const int gb = global_batch > 0 ? global_batch : B * R;
     if (global_batch <= 0) row_offset = m->rank * B;
+    // the hidden-dropout mask of the backward (k_da_all) is keyed like the forward's: rank s's rows start at row_offset0 + s * B
+    if (R > 1 && row_offset != m->rank * B)
+        return fail("world = %d: row_offset must be rank * batch = %d (got %d): the ranks' rows are consecutive blocks of the global batch",
+                    R, m->rank * B, row_offset);
+    m->row_offset0 = row_offset - m->rank * B;
+    if (m->last_bpad != 0 && m->last_bpad != bpad) {
+        if (R > 1) return fail("world = %d: the padded batch size may not change between steps (%d -> %d)", R, m->last_bpad, bpad);
+        // the padding columns / rows of these buffers are only ever written as zeros for ONE padded batch size: a C caller
+        // that changes the batch between steps gets them re-zeroed (the Python wrappers always pass conf.batch)
+        CK(cudaMemsetAsync(m->dz_all, 0, sizeof(__nv_bfloat16) * (size_t)m->n_local * R * kMaxBpad, m->st));
+        CK(cudaMemsetAsync(m->h_d, 0, sizeof(__nv_bfloat16) * (size_t)R * kMaxBpad * H, m->st));
+        CK(cudaMemsetAsync(m->h_dT, 0, sizeof(__nv_bfloat16) * (size_t)R * kMaxBpad * H, m->st));
+        CK(cudaMemsetAsync(m->h, 0, sizeof(float) * (size_t)R * kMaxBpad * H, m->st));
+        CK(cudaMemsetAsync(m->da, 0, sizeof(float) * (size_t)R * kMaxBpad * H, m->st));
+    }
     m->last_batch = B; m->last_bpad = bpad;
     if (!s.has_y) return fail("slot %d was staged without targets", slot);
 
@@ -599,18 +664,49 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     ph_begin(m, PH_BARRIER);
     barrier(m);                                                               // A
     ph_end(m, PH_BARRIER);
-    // whole-step calls fork the work that is off the critical path onto st3: the target bitmask (next to the encode), the
-    // decoder update (next to the sparse tail) and the bias updates (next to the encoder's Adam).  Not while profiling:
-    // the per-phase times are taken with every kernel running alone.
+    stamp(m, m->st, TR_START);
+    // whole-step calls fork the work that is off the critical path onto st3 / st4: the touched-row flags and the target
+    // bitmask (next to the encode), the encoder's Adam on the rows no playlist touches (st4, co-resident with the encode,
+    // the decode and dh), the decoder update (next to the sparse tail) and the bias updates (next to the encoder's Adam).
+    // Not while profiling: the per-phase times are taken with every kernel running alone.
     m->par_step = m->overlap_dec && !m->profiling && !(m->debug & (1 | 2 | 8));
     const bool fork_y = m->par_step && !(m->debug & 64);
+    m->bg_inflight = false;
     if (fork_y) {
         CK(cudaEventRecord(m->ev_a, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_a, 0));
+        launch_touch_shard(s.xw, m->touched, m->touch_cnt, m->hot_list, m->touched_list, B, m->pt, m->st3);
+        m->launches += 1;
+        // (not with an l2 term: the cost's sum of squares reads ALL of W_enc as it is BEFORE this step's update).
+        // OFF by default (debug bit 10 turns it on): measured on B200 it moves 7-18 % of the encoder rows under the front
+        // but costs more than it saves -- see DESIGN.md section 4 "background encoder Adam".
+        if (!m->tied && m->cfg.reg_lambda == 0.f && (m->debug & 1024)) {
+            // encoder rows outside `touched` have g == 0 this step: their dense Adam update starts NOW and streams through
+            // HBM while the compute-bound front of the step runs; it stops when the decoder update is about to start
+            CK(cudaEventRecord(m->ev_touch, m->st3));
+            CK(cudaStreamWaitEvent(m->st4, m->ev_touch, 0));
+            CK(cudaMemsetAsync(m->bg.ctl, 0, sizeof(unsigned int) * kBgCtlWords, m->st4));
+            CK(cudaEventRecord(m->ev_pre, m->st4));
+            CK(cudaStreamWaitEvent(m->st, m->ev_pre, 0));      // encode and streamer become runnable together: priority decides
+            AdamArgs a = adam_args(m);
+            a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.row_touched = m->touched;
+            a.n = (long long)m->n_local * H; a.row_len = H;
+            stamp(m, m->st4, TR_BG_BEGIN);
+            launch_adam_bg(a, m->bg, m->st4);
+            stamp(m, m->st4, TR_BG_END);
+            CK(cudaEventRecord(m->ev_bg, m->st4));
+            m->bg_inflight = true;
+            m->launches += 1;
+        }
         build_ybits(m, slot, B, bpad, m->st3);
+        stamp(m, m->st3, TR_YBITS);
         CK(cudaEventRecord(m->ev_y, m->st3));
+    } else {
+        launch_touch_shard(s.xw, m->touched, m->touch_cnt, m->hot_list, m->touched_list, B, m->pt, m->st);
+        m->launches += 1;
     }
     run_encode(m, slot, bpad, bpad, keep_prob, input_keep_prob, row_offset, true);
+    stamp(m, m->st, TR_ENCODE);
     if (fork_y) CK(cudaStreamWaitEvent(m->st, m->ev_y, 0));
     else build_ybits(m, slot, B, bpad);
     barrier(m);                                                               // B1
@@ -620,11 +716,17 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     d.W = m->shadow; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;
     d.n_batch_tiles = R; d.n_local = m->n_local; d.pt = m->pt;
     d.ybits = m->ybits; d.ywords = R * bpad / 32; d.dzT = m->dz_all;
-    d.db_dec = m->g_b_dec_sh;
+    d.db_dec = m->g_b_dec_sh; d.db_parts = m->g_b_dec_parts;
     d.loss_partial = m->loss_partial; d.inv_batch = 1.0f / (float)gb;
+    if (m->debug & 8192) {
+        d.trace = m->trace + 16 * (m->step & 1) + TR_G1_FIRST;
+        CK(cudaMemsetAsync(d.trace, 0xff, 8, m->st));
+        CK(cudaMemsetAsync(d.trace + 1, 0, 8, m->st));
+    }
     ph_begin(m, PH_DECODE_LOSS);
     launch_decode_train(d, m->st);
     ph_end(m, PH_DECODE_LOSS);
+    stamp(m, m->st, TR_DECODE);
 
     int n_sq = 0;
     const float lam = m->cfg.reg_lambda;
@@ -644,6 +746,8 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     q.nsplit = m->nsplit; q.n_batch_tiles = R; q.ld_dz = R * bpad;
     ph_begin(m, PH_DH);
     launch_dh(q, m->st);
+    if (m->bg_inflight) { launch_bg_stop(m->bg, m->st); m->launches += 1; }   // the decoder update needs the SMs and the bandwidth now
+    stamp(m, m->st, TR_DH);
     // The decoder update needs only dz and h_d^T, both final now (and the l2 term above has read W_dec).  In a whole step (dae_model_train_step_staged) of an
     // untied model it starts here on its own stream and streams w / m / v through HBM while the main stream runs the
     // latency-bound tail (split-K sums, da, sparse scatter) and the encoder's Adam; apply_adam joins the two.  Not while
@@ -651,7 +755,24 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     if (m->par_step && !m->tied && !(m->debug & 128)) {
         CK(cudaEventRecord(m->ev_dh, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_dh, 0));
+        stamp(m, m->st3, TR_DEC_BEGIN);
         run_decoder_update(m, bpad, m->st3);
+        stamp(m, m->st3, TR_DEC_END);
+        // The encoder rows no playlist lists have g == 0 whatever the sparse tail (da, scatter) computes: their dense Adam
+        // pass follows the decoder update directly on ITS stream (two HBM-bound kernels back to back), so the latency-
+        // bound tail -- slow while it shares the SMs with them -- has both kernels' duration to finish; only the pass over
+        // the listed rows (a few thousand) waits for it.
+        {
+            AdamArgs a = adam_args(m);
+            a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
+            a.n = (long long)m->n_local * H; a.row_len = H; a.touch_mode = 1;
+            if (m->bg_inflight) CK(cudaStreamWaitEvent(m->st3, m->ev_bg, 0));
+            stamp(m, m->st3, TR_REST_BEGIN);
+            launch_adam_rows(a, nullptr, nullptr, m->st3, m->bg_inflight ? &m->bg : nullptr);
+            stamp(m, m->st3, TR_REST_END);
+            m->launches += 1;
+            m->enc_split = true;
+        }
         CK(cudaEventRecord(m->ev_dec, m->st3));
         m->dec_inflight = true;
     }
@@ -667,7 +788,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     ph_end(m, PH_BARRIER);
     DaArgs da{};
     da.dh_sum = m->dh_sum; da.h = m->h; da.da = m->da; da.db_enc = m->g_b_enc; da.B = B; da.bpad = bpad; da.H = H;
-    da.kp = keep_prob; da.seed = m->cfg.seed; da.step = (unsigned long long)m->step; da.pt = m->pt;
+    da.kp = keep_prob; da.seed = m->cfg.seed; da.step = (unsigned long long)m->step; da.row_offset0 = m->row_offset0; da.pt = m->pt;
     ph_begin(m, PH_DA);
     launch_da_all(da, m->st);
     m->launches += 2;
@@ -701,6 +822,7 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     AdamArgs a = adam_args(m);
     if (!m->scatter_done) run_scatter(m, B, bpad);
     m->scatter_done = false;
+    stamp(m, m->st, TR_TAIL);
 
     if (!m->dec_inflight) run_decoder_update(m, bpad, m->st);
     else {
@@ -730,10 +852,18 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
         a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
         a.n = (long long)m->n_local * H; a.row_len = H;
-        launch_adam_rows(a, m->g_enc, nullptr, m->st);
+        if (m->enc_split) {
+            launch_adam_listed(a, m->g_enc, m->touched_list, m->st);   // the rows a playlist lists, with their gradient: all that is left
+        } else {
+            // what the background streamer has not done: the rows it never claimed, and every touched row (with its gradient)
+            if (m->bg_inflight) CK(cudaStreamWaitEvent(m->st, m->ev_bg, 0));
+            launch_adam_rows(a, m->g_enc, nullptr, m->st, m->bg_inflight ? &m->bg : nullptr);
+        }
+        m->bg_inflight = false; m->enc_split = false;
         m->launches += 1;
     }
-    launch_clear_flagged(m->n_local, H, m->g_enc, m->touched, m->st);
+    launch_clear_listed(H, m->g_enc, m->touched, m->touch_cnt, m->touched_list, m->st);
+    stamp(m, m->st, TR_STEP_END);
     m->launches += 1;
     ph_end(m, PH_ADAM_ENC);
     if (fork_b) CK(cudaStreamWaitEvent(m->st, m->ev_bias, 0));
@@ -951,6 +1081,7 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         // pass A keeps everything: dense logits of the first M1 items + the dense radix select, instead of M1 list appends
         // per playlist
         TRY(ensure_scores(m, (size_t)B * M1));
+        ph_begin(m, PH_REC_A);
         DecodeArgs da = d;
         da.n_out = M1; da.out = m->scores; da.ld_out = M1; da.raw_logits = 1;
         launch_decode_predict(da, m->st);
@@ -959,6 +1090,7 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         ta.out_idx = m->cand_tk_idx; ta.out_score = m->cand_tk_score;
         launch_topk(ta, m->st);
         launch_thr_from_topk(m->cand_tk_score, m->cand_tk_idx, kp, B, rows, m->cand_thr, m->st);
+        ph_end(m, PH_REC_A);
         m->launches += 3;
         prev = M1;
     }
@@ -967,7 +1099,10 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         prev = stops[pass];
         d.n_out = stops[pass];
         d.cand_cnt = m->cand_cnt + pass * rows;
+        const int ph = stops[pass] == Tn ? PH_REC_C : PH_REC_B;     // the full-range pass is the tensor-bound one
+        ph_begin(m, ph);
         launch_decode_filter(d, m->st);
+        ph_end(m, ph);
         m->launches += 1;
         a.row_n = d.cand_cnt;
         if (stops[pass] < Tn) {                                    // threshold of the next pass: kp-th largest so far
@@ -980,7 +1115,9 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
     }
     a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.sigmoid_out = 1;
     a.out_idx = m->topk_idx; a.out_score = m->topk_score;
+    ph_begin(m, PH_REC_SELECT);
     launch_topk(a, m->st);
+    ph_end(m, PH_REC_SELECT);
     CK(cudaMemsetAsync(m->cand_tk_idx, 0, sizeof(int), m->st));
     k_max_int<<<64, 256, 0, m->st>>>(m->cand_cnt, 3 * rows, m->cand_tk_idx);
     CK(cudaMemcpyAsync(m->cand_cnt_host, m->cand_tk_idx, sizeof(int), cudaMemcpyDeviceToHost, m->st));
@@ -1024,6 +1161,7 @@ extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos,
     if (fused) {
         TRY(run_recommend_fused(m, k, item_lo, item_hi, sp, si, max_seeds));
         CK(cudaStreamSynchronize(m->st));
+        ph_collect(m);
         if (*m->cand_cnt_host > kCandCap) fused = false;           // a candidate list overflowed: exact dense fallback
     }
     if (!fused) {
@@ -1074,11 +1212,13 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
         {"dh_partial", m->dh_partial, (int64_t)m->world * m->nsplit * kMaxBpad * m->H, 4}, {"dh_sum", m->dh_sum, KH, 4},
         {"da", m->da, KH, 4},
         {"x_row_ptr", sl.xw.row_ptr, m->Bmax + 1, 4}, {"x_row_len", sl.xw.row_len, m->Bmax, 4},
-        {"x_col", sl.xw.col, m->max_nnz, 4}, {"x_val", m->pub.xn, m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
+        {"x_col", sl.xw.col, m->max_nnz, 4},
+        {"x_val", m->pub.xn + (m->trainable ? (size_t)m->rank * m->max_nnz : 0), m->max_nnz, 4}, {"x_rowsum", m->rowsum, m->Bmax, 4},
         {"y_row_ptr", sl.yw.row_ptr, m->Bmax + 1, 4}, {"y_row_len", sl.yw.row_len, m->Bmax, 4},
         {"y_col", sl.yw.col, m->max_nnz, 4}, {"ybits", m->ybits, (int64_t)m->n_local * m->world * (kMaxBpad / 32), 4},
         {"scores", m->scores, (int64_t)m->scores_elems, 4},
         {"topk_idx", m->topk_idx, (int64_t)m->topk_elems, 4}, {"topk_score", m->topk_score, (int64_t)m->topk_elems, 4},
+        {"bg_ctl", m->bg.ctl, kBgCtlWords, 4}, {"trace", m->trace, 32, 8},
         {"mW_dec", m->mW_dec, LH, 4}, {"vW_dec", m->vW_dec, LH, 4}, {"mW_enc", m->mW_enc, LH, 4}, {"vW_enc", m->vW_enc, LH, 4},
     };
     for (const E& e : table) {

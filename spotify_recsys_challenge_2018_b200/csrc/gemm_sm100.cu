@@ -51,6 +51,10 @@ constexpr int kSmemBars = 256;
 constexpr int kSmemThr = kMaxBpad * 4;              // FILTER: per-playlist thresholds of the CTA's batch tile
 constexpr int kWStg = kABytes / 8 / 16;             // FILTER: candidates staged per epilogue warp (128) in one ring stage's worth of smem
 constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + kSmemThr + 1024;  // + alignment slack
+// TRAIN runs a 4-stage ring: the epilogue paces the kernel (one tile = 4 chunks is ahead of the MMA at any time), and
+// the 32 KB it gives up is what lets the background optimizer streamer (optim.cu: k_adam_bg, 31 KB) share the SM
+constexpr int kStagesTrain = 4;
+constexpr int kSmemItemTileTrain = kSmemB + kStagesTrain * kABytes + kSmemBars + 1024;
 
 struct ItemTileDev {
     int n_rows;       // rows of the streamed operand (TRAIN: this rank's item rows; PREDICT: catalogue columns kept)
@@ -82,6 +86,7 @@ struct ItemTileDev {
     int cand_cap;
     int item0;               // catalogue id of row 0 of the streamed operand
     int raw_logits;          // PREDICT: write z instead of sigmoid(z)
+    unsigned long long* trace;   // debug: %globaltimer when the first / last CTA of the grid started
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -213,9 +218,13 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+    // ring stages that exist in shared memory (TRAIN: 4, see kStagesTrain) and that carry W chunks (FILTER gives the
+    // last one, 16 KB, to the candidate staging buffer)
+    constexpr int RING = MODE == MODE_TRAIN ? kStagesTrain : kStages;
+    constexpr int NST = MODE == MODE_FILTER ? kStages - 1 : RING;
     uint8_t* sB = smem;
     uint8_t* sA = smem + kSmemB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemB + kSmemA);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemB + RING * kABytes);
     uint64_t* full = bars;                 // [kStages]
     uint64_t* empty = bars + kStages;      // [kStages]
     uint64_t* bfull = bars + 2 * kStages;  // [1]
@@ -223,14 +232,18 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
-    float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + kSmemA + kSmemBars);   // [n_cols] (FILTER)
-    // FILTER gives the last ring stage (16 KB) to the candidate staging buffer
-    constexpr int NST = MODE == MODE_FILTER ? kStages - 1 : kStages;
+    float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + RING * kABytes + kSmemBars);   // [n_cols] (FILTER)
     uint2* stg = reinterpret_cast<uint2*>(sA + NST * kABytes);                       // [kEpiWarps][kWStg] (column | item << 8, logit)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int bt = blockIdx.y;
+    if (MODE == MODE_TRAIN && p.trace != nullptr && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(p.trace, now);
+        atomicMax(p.trace + 1, now);
+    }
     if (MODE == MODE_FILTER) {
         for (int i = threadIdx.x; i < p.n_cols; i += blockDim.x) thr_smem[i] = p.thr[bt * p.n_cols + i];
     }
@@ -473,7 +486,9 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
             if (MODE == MODE_TRAIN) {
                 if (item_ok) {
-                    atomicAdd(p.db_dec + row, db);            // 2 column halves x batch tiles addends per item
+                    // this warp's share of the row's bias gradient (its column chunks of this batch tile): stored, not
+                    // atomically added -- k_sum_db_parts adds the 4 x batch-tile shares in a fixed order (deterministic)
+                    p.db_dec[(size_t)(bt * 4 + part) * p.n_rows + row] = db;
                     loss_acc += lt;
                 }
             }
@@ -506,6 +521,17 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// db_dec[row] = sum of the epilogue warps' shares (4 column parts x batch tiles), fixed order; rows of tiles no CTA
+// processed (beyond the catalogue) are zero
+__global__ void k_sum_db_parts(const float* __restrict__ parts, int n_parts, int n_rows, int rows_done, float* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    float t = 0.f;
+    if (r < rows_done)
+        for (int k = 0; k < n_parts; ++k) t += parts[(size_t)k * n_rows + r];
+    out[r] = t;
+}
+
 static int sm_count() {
     static int n = [] {
         int dev = 0, v = 148;
@@ -526,12 +552,11 @@ int decode_grid(int N, int n_batch_tiles) {
 template <int MODE>
 static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, const ItemTileDev& p, dim3 grid,
                             cudaStream_t st) {
-    k_itemtile<MODE><<<grid, kItemThreads, kSmemItemTile, st>>>(tmA, tmB, p);
+    k_itemtile<MODE><<<grid, kItemThreads, MODE == MODE_TRAIN ? kSmemItemTileTrain : kSmemItemTile, st>>>(tmA, tmB, p);
 }
 
 void launch_decode_train(const DecodeArgs& a, cudaStream_t st) {
     const int nbt = a.n_batch_tiles > 0 ? a.n_batch_tiles : 1;
-    cudaMemsetAsync(a.db_dec, 0, sizeof(float) * a.n_local, st);   // the epilogue accumulates column halves / batch tiles
     ItemTileDev p{};
     p.world = a.pt.world > 0 ? a.pt.world : 1;
     p.rank = a.pt.rank;
@@ -546,16 +571,19 @@ void launch_decode_train(const DecodeArgs& a, cudaStream_t st) {
     p.bias = a.bias;
     p.ybits = a.ybits; p.ywords = a.ywords;
     p.dzT = a.dzT; p.ld_dz = nbt * a.bpad;
-    p.db_dec = a.db_dec; p.loss_partial = a.loss_partial; p.inv_batch = a.inv_batch;
+    p.db_dec = a.db_parts; p.loss_partial = a.loss_partial; p.inv_batch = a.inv_batch;
+    p.trace = a.trace;
     const int gx = decode_grid(p.tiles * kTileItems, nbt);
     if (p.tiles == 0) {                                             // a rank may own no tile of a tiny catalogue
         cudaMemsetAsync(a.loss_partial, 0, sizeof(float) * 2 * 148, st);
+        cudaMemsetAsync(a.db_dec, 0, sizeof(float) * a.n_local, st);
         return;
     }
     cudaMemsetAsync(a.loss_partial, 0, sizeof(float) * 2 * 148, st);
     const CUtensorMap tmA = make_map_bf16(a.W, a.H, a.n_local, kTileItems);
     const CUtensorMap tmB = make_map_bf16(a.h_d, a.H, (uint64_t)a.bpad * nbt, a.bpad);
     launch_itemtile<MODE_TRAIN>(tmA, tmB, p, dim3(gx, nbt, 1), st);
+    k_sum_db_parts<<<(a.n_local + 255) / 256, 256, 0, st>>>(a.db_parts, 4 * nbt, a.n_local, p.tiles * kTileItems, a.db_dec);
 }
 
 void launch_decode_predict(const DecodeArgs& a, cudaStream_t st) {
@@ -1097,7 +1125,8 @@ k_dh(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorM
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // this CTA's slice of the contraction dimension (64-item chunks)
+    // this CTA's slice of the contraction dimension (64-item chunks), contiguous.  (A reverse wavefront over the whole
+    // catalogue -- to start where G1 has just left dz and W in L2 -- was measured: 6 us SLOWER alone, no gain in the step.)
     const int per = (p.kchunks_total + gridDim.x - 1) / gridDim.x;
     const int kc0 = blockIdx.x * per;
     const int kc1 = min(kc0 + per, p.kchunks_total);
@@ -1222,18 +1251,19 @@ void launch_dh(const DhArgs& a, cudaStream_t st) {
 
 void preload_gemm() {
     cudaFuncAttributes a;
-    cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
+    cudaFuncSetAttribute(k_itemtile<MODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTileTrain);
     cudaFuncSetAttribute(k_itemtile<MODE_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_itemtile<MODE_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemItemTile);
     cudaFuncSetAttribute(k_dw_adam_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFused);
     cudaFuncSetAttribute(k_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemDh);
-    cudaFuncGetAttributes(&a, k_itemtile<MODE_TRAIN>);
-    cudaFuncGetAttributes(&a, k_itemtile<MODE_PREDICT>);
-    cudaFuncGetAttributes(&a, k_itemtile<MODE_FILTER>);
-    cudaFuncGetAttributes(&a, k_dw);
-    cudaFuncGetAttributes(&a, k_dw_adam_fused);
-    cudaFuncGetAttributes(&a, k_dh);
+    PRELOAD_KERNEL(k_itemtile<MODE_TRAIN>);
+    PRELOAD_KERNEL(k_itemtile<MODE_PREDICT>);
+    PRELOAD_KERNEL(k_itemtile<MODE_FILTER>);
+    PRELOAD_KERNEL(k_dw);
+    PRELOAD_KERNEL(k_dw_adam_fused);
+    PRELOAD_KERNEL(k_dh);
+    PRELOAD_KERNEL(k_sum_db_parts);
     (void)cudaGetLastError();
 }
 

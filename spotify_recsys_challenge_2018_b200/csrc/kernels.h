@@ -61,12 +61,14 @@ void launch_coo_to_csr(const long long* pos, const float* val, int nnz, int B, i
                        cudaStream_t st);
 
 // The normalised input of the step in flight, published for the sparse-row scatter of every rank
-// (same offsets as the slot's CSR): x_n = x_d / (s + 1e-10) per kept entry.
+// (same offsets as the slot's CSR): x_n = x_d / (s + 1e-10) per kept entry.  Training keeps the WHOLE global
+// batch on every rank: segment s (seg_rows rows, seg_nnz entries) is written by rank s's encode into every copy.
 struct PubInput {
-    int* row_ptr;       // [B]
-    int* row_len;       // [B]
-    int* col;           // [max_nnz]
-    float* xn;          // [max_nnz]
+    int* row_ptr;       // [world][seg_rows]
+    int* row_len;       // [world][seg_rows]
+    int* col;           // [world][seg_nnz]
+    float* xn;          // [world][seg_nnz]
+    int seg_rows, seg_nnz;
 };
 
 struct EncodeArgs {
@@ -110,19 +112,26 @@ struct DaArgs {               // da = dh * (keep/kp) * h(1-h) for EVERY row of t
     int B, bpad, H;           // rows per rank, padded rows per rank
     float kp;
     unsigned long long seed, step;
+    int row_offset0;          // global row of rank 0's first playlist in the dropout keys (the forward uses row_offset0 + rank * B)
     PeerTable pt;
 };
 void launch_da_all(const DaArgs& a, cudaStream_t st);
 
-struct ScatterArgs {          // dW_enc rows owned by this rank, from every rank's published input and the local da
-    PubInput pub;             // local pointers; peers through pt
-    const float* da;          // [K, H] (local)
-    float* g_enc;             // [local rows, H]
-    unsigned char* touched;   // [local rows]
-    int B, bpad, H;
+struct ScatterArgs {          // dW_enc rows owned by this rank, from the published input of the global batch and da (both local)
+    PubInput pub;
+    const float* da;          // [K, H]
+    float* g_enc;             // [local rows, H], zero outside the touched rows
+    const int* touch_cnt;     // [local rows] playlists of the global batch listing the row (launch_touch_shard)
+    const int* hot_list;      // [1 + local rows] count, then the rows listed by three or more playlists
+    int n_local, B, bpad, H;
+    int deterministic;        // 1: rows with > 2 contributors are gathered in a fixed order (bit-reproducible), 0: fp32 red.add only
     PeerTable pt;
 };
 void launch_scatter_shard(const ScatterArgs& a, cudaStream_t st);
+// touched[local row] = 1 for every catalogue row this rank owns that occurs in the input CSR of any rank's slot
+// hot_list / touched_list: [1 + local rows]: count, then the rows listed by >= 3 playlists / by any playlist (arbitrary order)
+void launch_touch_shard(const CsrWork& x, unsigned char* touched, int* touch_cnt, int* hot_list, int* touched_list, int B,
+                        const PeerTable& pt, cudaStream_t st);
 
 // out[global item] = src_of_owner[local item] for every catalogue item (fp32 vector / bf16 rows of H)
 void launch_gather_items_f32(const float* src_local, float* out, int N, const PeerTable& pt, cudaStream_t st);
@@ -150,6 +159,8 @@ struct DecodeArgs {
     int ywords;
     __nv_bfloat16* dzT;        // [local rows, n_batch_tiles * bpad]
     float* db_dec;             // [local rows]
+    float* db_parts;           // [4 * n_batch_tiles, local rows] workspace: the epilogue warps' shares of db_dec
+    unsigned long long* trace; // debug: [2] %globaltimer of the first / last CTA start (nullptr: off)
     float* loss_partial;       // [grid.x * grid.y]
     float inv_batch;
     // predict
@@ -212,18 +223,34 @@ struct AdamArgs {
     long long n;                      // elements
     int row_len;                      // H for matrices (row = idx / row_len), 1 for vectors
     float alpha, one_minus_b1, one_minus_b2, eps, lambda;
+    int touch_mode;                   // launch_adam_rows: 0 every row, 1 only rows with row_touched == 0, 2 only rows with row_touched != 0
 };
 void launch_adam(const AdamArgs& a, cudaStream_t st);
 // matrices: a.w/m/v are [rows, row_len] (row_len % 4 == 0); gradient = a.g (dense, or nullptr) + g_sparse rows where
 // a.row_touched != 0 (or nullptr); shadow: bf16 copy of the same rows (same indexing), or nullptr
-void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, cudaStream_t st);
+// background streamer of the encoder's untouched rows (optim.cu: k_adam_bg): control words in device memory
+struct BgAdam {
+    unsigned int* ctl;                // [kBgCtlWords], zeroed before every launch of launch_adam_bg
+};
+constexpr int kBgCtlWords = 2 + 256;
+void launch_adam_rows(const AdamArgs& a, const float* g_sparse, __nv_bfloat16* shadow, cudaStream_t st,
+                      const BgAdam* bg = nullptr);
+// a.w / m / v [rows, row_len] with a.row_touched: dense TF1 Adam (g = 0) of the untouched rows, claimed chunk by chunk from
+// the top of the row range until launch_bg_stop; launch_adam_rows(..., &bg) afterwards does everything that is left
+void launch_adam_bg(const AdamArgs& a, const BgAdam& bg, cudaStream_t st);
+void launch_bg_stop(const BgAdam& bg, cudaStream_t st);
+void set_trap_log_optim(unsigned int* host_mapped);
 // U(-limit, limit) keyed by the GLOBAL element index; w: this rank's rows in local-tile order
 void launch_xavier_init(float* w, int n_local_rows, int N, int H, float limit, unsigned long long seed,
                         unsigned stream_id, int world, int rank, cudaStream_t st);
 void launch_sumsq(const float* x, long long n, float* partial, int nblocks, cudaStream_t st);
 void launch_reduce_loss2(const float* partial, int n, const float* sumsq_partial, int n_sq, float lambda,
                          float inv_batch, float* loss_out, cudaStream_t st);
-void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, cudaStream_t st);
+void launch_clear_flagged(int N, int H, float* g_enc, unsigned char* touched, int* touch_cnt, cudaStream_t st);
+// the same two jobs over a LIST of rows (list[0] = count): dense TF1 Adam of the listed rows of w / m / v [rows, row_len] with
+// their gradient rows g_sparse; zeroing of the listed gradient rows, flags and counts
+void launch_adam_listed(const AdamArgs& a, const float* g_sparse, const int* list, cudaStream_t st);
+void launch_clear_listed(int H, float* g_enc, unsigned char* touched, int* touch_cnt, const int* list, cudaStream_t st);
 
 // ---- title.cu / title_sm100.cu: the title branch (Char_CNN.py:16-75, DAEs.py:153-201) ----------
 constexpr int kTitleFpad = 512;    // feature columns of the output layer's operands (D = filters x widths <= 512, zero padded)
@@ -315,6 +342,10 @@ void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch,
 void set_trap_log_gemm(unsigned int* host_mapped);
 void set_trap_log_title_gemm(unsigned int* host_mapped);
 void set_trap_log_sparse(unsigned int* host_mapped);
+// Load a kernel now: CUDA's lazy loading would otherwise synchronise the context at its first launch, against a
+// cross-GPU flag barrier that may already be spinning.  (Asking every kernel for the largest shared-memory carveout was
+// tried and reverted: the streaming optimizer kernels lose 30 % of their bandwidth with a minimal L1.)
+#define PRELOAD_KERNEL(k) cudaFuncGetAttributes(&a, k)
 // load every kernel of a translation unit (see sparse.cu: preload_sparse)
 void preload_sparse();
 void preload_optim();

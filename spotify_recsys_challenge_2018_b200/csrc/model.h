@@ -24,6 +24,15 @@ int fail(const char* fmt, ...);               // records the message, returns 1
 
 void ensure_loaded();                         // load every kernel once per process (kernels.h: preload_*)
 
+// per-phase device timing (dae_model_set_profiling): events around each phase of a step / call
+enum Phase { PH_PREPARE = 0, PH_ENCODE, PH_YBITS, PH_DECODE_LOSS, PH_DH, PH_DA, PH_BARRIER, PH_SCATTER, PH_DW, PH_ADAM_DEC,
+             PH_ADAM_ENC, PH_ADAM_BIAS, PH_REC_A, PH_REC_B, PH_REC_C, PH_REC_SELECT,
+             PH_T_FWD, PH_T_DW_ADAM, PH_T_DFEAT, PH_T_CNN_BWD, PH_T_ADAM_SMALL, PH_COUNT };
+struct dae_model;
+void ph_begin(dae_model* m, int k, cudaStream_t s = nullptr);
+void ph_end(dae_model* m, int k, cudaStream_t s = nullptr);
+void ph_collect(dae_model* m);
+
 constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;   // [TF1] AdamOptimizer defaults (DAEs.py:102)
 constexpr int kSqBlocks = 256;
 
@@ -63,6 +72,13 @@ struct dae_model {
     cudaStream_t st = nullptr;      // main stream: the step
     cudaStream_t st2 = nullptr;     // side stream: H2D + COO->CSR + ybits of the NEXT batch, overlapped with the step
     cudaStream_t st3 = nullptr;     // decoder-update stream: k_dw_adam_fused overlaps the sparse / encoder tail of the step
+    cudaStream_t st4 = nullptr;     // background stream: encoder Adam of the untouched rows under the compute-bound front of the step
+    cudaEvent_t ev_touch = nullptr, ev_bg = nullptr, ev_pre = nullptr;
+    BgAdam bg{};
+    unsigned long long* trace = nullptr;   // debug bit 13: %globaltimer stamps of the step's fork / join points
+    bool enc_split = false;         // this step's encoder Adam of the unlisted rows already follows the decoder update on st3
+    bool bg_inflight = false;       // this step launched the background streamer (the dense encoder pass must account for it)
+    int row_offset0 = 0;            // global row of rank 0's first playlist in the dropout keys of the step in flight
     cudaEvent_t ev_dh = nullptr, ev_dec = nullptr, ev_a = nullptr, ev_y = nullptr, ev_da = nullptr, ev_bias = nullptr;
     bool par_step = false;          // this step forks work onto st3 (whole-step call, not profiling, debug bit 3 clear)
     bool overlap_dec = false;       // set by dae_model_train_step_staged: launch the decoder update as soon as dz is final
@@ -82,7 +98,10 @@ struct dae_model {
     long long step = 0;
     float *g_enc = nullptr;                          // sparse-row dW_enc of the rows this rank owns
     unsigned char* touched = nullptr;
-    float *g_b_enc = nullptr, *g_b_dec_sh = nullptr, *g_b_dec = nullptr;
+    int* touched_list = nullptr;                     // [1 + rows]: rows listed by any playlist of the global batch
+    int* hot_list = nullptr;                         // [1 + rows]: rows listed by >= 3 playlists (ordered gather of dW_enc)
+    int* touch_cnt = nullptr;                        // playlists of the global batch that list each owned row
+    float *g_b_enc = nullptr, *g_b_dec_sh = nullptr, *g_b_dec = nullptr, *g_b_dec_parts = nullptr;
     uint32_t* ybits = nullptr;                       // targets of the global batch over this rank's item rows
     float* g_dec = nullptr;                          // dW_dec of the rows this rank owns
     int debug = 0;
@@ -119,10 +138,10 @@ struct dae_model {
     int* err_ring = nullptr;         // pinned [2]
     // optional per-phase device timing (bench.py roofline): events around each phase of a step
     bool profiling = false;
-    cudaEvent_t ph_ev[2 * 16] = {};
-    bool ph_used[16] = {};
-    double ph_ms[16] = {};
-    long long ph_n[16] = {};
+    cudaEvent_t ph_ev[2 * PH_COUNT] = {};
+    bool ph_used[PH_COUNT] = {};
+    double ph_ms[PH_COUNT] = {};
+    long long ph_n[PH_COUNT] = {};
     std::vector<void*> host_allocs;
 };
 

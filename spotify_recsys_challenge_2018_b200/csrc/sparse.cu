@@ -199,16 +199,24 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     }
     const float s = block_sum(part, s_red);
     __syncthreads();
+    // x_n and its column are re-read by the sparse-row scatter of EVERY rank: each rank keeps a copy of the whole global
+    // batch's published input (segment = producing rank), so the scatter reads local memory only
+    const size_t seg_e = (size_t)(bcast ? pt.rank : 0) * pub.seg_nnz + beg;
+    const int seg_r = (bcast ? pt.rank : 0) * pub.seg_rows + r;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float xn = __fdiv_rn(s_x[i], s + kEpsLog);
         s_x[i] = xn;
-        pub.xn[beg + i] = xn;         // x_n and its column are re-read by the sparse-row scatter of every rank
-        pub.col[beg + i] = s_c[i];
+        for (int d = 0; d < n_dst; ++d) {
+            (bcast ? peer_ptr(pt, d, pub.xn) : pub.xn)[seg_e + i] = xn;
+            (bcast ? peer_ptr(pt, d, pub.col) : pub.col)[seg_e + i] = s_c[i];
+        }
     }
     if (threadIdx.x == 0) {
         rowsum[r] = s;
-        pub.row_ptr[r] = beg;
-        pub.row_len[r] = n;
+        for (int d = 0; d < n_dst; ++d) {
+            (bcast ? peer_ptr(pt, d, pub.row_ptr) : pub.row_ptr)[seg_r] = beg;
+            (bcast ? peer_ptr(pt, d, pub.row_len) : pub.row_len)[seg_r] = n;
+        }
     }
     __syncthreads();
     // a4: a = sum_j x_n[j] * W_enc[col_j, :].  Thread (g, t): row group g takes entries j = g (mod G),
@@ -304,6 +312,39 @@ void launch_ybits_shard(const YbitsArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Rows of W_enc this rank owns that ANY playlist of the global batch lists in its input (before dropout): the only
+// rows whose dW_enc can be non-zero and the only rows the encode gathers.  Known as soon as the slot CSRs are (barrier
+// A), long before the backward: every other row's dense Adam update (g == 0) may start right away (optim.cu: k_adam_bg).
+// ------------------------------------------------------------------------------------------
+__global__ void k_touch_shard(const int* __restrict__ row_ptr, const int* __restrict__ row_len, const int* __restrict__ col,
+                              unsigned char* __restrict__ touched, int* __restrict__ touch_cnt, int* __restrict__ hot_list,
+                              int* __restrict__ touched_list, const __grid_constant__ PeerTable pt) {
+    const int r = blockIdx.x, s = blockIdx.y;                  // row r of rank s's batch
+    const int world = pt.world;
+    const int* prow_ptr = world == 1 ? row_ptr : peer_ptr(pt, s, row_ptr);
+    const int* prow_len = world == 1 ? row_len : peer_ptr(pt, s, row_len);
+    const int* pcol = world == 1 ? col : peer_ptr(pt, s, col);
+    const int beg = prow_ptr[r], n = prow_len[r];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = pcol[beg + i];
+        if (world != 1 && item_owner(c, world) != pt.rank) continue;
+        const int lc = world == 1 ? c : item_local(c, world);
+        touched[lc] = 1;
+        // playlists of the global batch that list the row (integer atomics: order-independent).  The THIRD one puts the
+        // row on the hot list: hot_list[0] = number of entries, rows from hot_list[1] on (each exactly once)
+        const int before = atomicAdd(touch_cnt + lc, 1);
+        if (before == 0) touched_list[1 + atomicAdd(touched_list, 1)] = lc;      // every listed row, once (same layout)
+        if (before == 2) hot_list[1 + atomicAdd(hot_list, 1)] = lc;
+    }
+}
+void launch_touch_shard(const CsrWork& x, unsigned char* touched, int* touch_cnt, int* hot_list, int* touched_list, int B,
+                        const PeerTable& pt, cudaStream_t st) {
+    cudaMemsetAsync(hot_list, 0, sizeof(int), st);
+    cudaMemsetAsync(touched_list, 0, sizeof(int), st);
+    k_touch_shard<<<dim3(B, pt.world), 128, 0, st>>>(x.row_ptr, x.row_len, x.col, touched, touch_cnt, hot_list, touched_list, pt);
+}
+
+// ------------------------------------------------------------------------------------------
 // encode backward, part 1: dh -> da for the whole global batch
 // ------------------------------------------------------------------------------------------
 // fixed-order sum of the split-K partials [bt][split][bpad][H] -> dh_sum [bt * bpad + row][H]
@@ -331,7 +372,7 @@ void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, int
 // da = dh * (keep / kp) * h (1 - h).  Every rank computes every row (K x H values), so da itself never crosses NVLink.
 __global__ void __launch_bounds__(256)
 k_da_all(const float* __restrict__ dh_sum, const float* __restrict__ h, float* __restrict__ da_out, int B, int bpad, int H,
-         float kp, unsigned long long seed, unsigned long long step, const __grid_constant__ PeerTable pt) {
+         float kp, unsigned long long seed, unsigned long long step, int row_offset0, const __grid_constant__ PeerTable pt) {
     const int i = blockIdx.x, s = blockIdx.y;
     const int k = threadIdx.x;
     if (k >= H) return;
@@ -340,7 +381,8 @@ k_da_all(const float* __restrict__ dh_sum, const float* __restrict__ h, float* _
     float dh = 0.f;
     for (int q = 0; q < pt.world; ++q) dh += (pt.world == 1 ? dh_sum : peer_ptr(pt, q, dh_sum))[o];
     const float hv = h[o];
-    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(s * B + i), static_cast<uint32_t>(k), kp);
+    // the same key as the forward's mask (k_encode_fwd: local row + row_offset; rank s's offset is row_offset0 + s * B)
+    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(row_offset0 + s * B + i), static_cast<uint32_t>(k), kp);
     da_out[o] = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
 }
 
@@ -361,25 +403,24 @@ __global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __
 }
 
 void launch_da_all(const DaArgs& a, cudaStream_t st) {
-    k_da_all<<<dim3(a.bpad, a.pt.world), 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed, a.step, a.pt);
+    k_da_all<<<dim3(a.bpad, a.pt.world), 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed, a.step, a.row_offset0, a.pt);
     k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.bpad * a.pt.world, a.H, a.db_enc);
 }
 
 // ------------------------------------------------------------------------------------------
 // encode backward, part 2: sparse-row scatter-add dW_enc[col_j,:] += x_n[j] * da[row,:] into the rows
-// THIS rank owns.  Block (r, s) walks row r of rank s's published input (read over NVLink when
-// s != rank: ~70 entries) and keeps the entries whose item tile lives here; da is local.
+// THIS rank owns.  Every rank holds the published input (x_n, columns) of the whole global batch (k_encode_fwd
+// stores its rows into every copy), so block (r, s) walks row r of rank s's segment in LOCAL memory and keeps the
+// entries whose item tile lives here; da is local too.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_scatter_shard(const __grid_constant__ PubInput pub, const float* __restrict__ da, float* __restrict__ g_enc,
-                unsigned char* __restrict__ touched, int bpad, int H, const __grid_constant__ PeerTable pt) {
+                const int* __restrict__ touch_cnt, int max_cnt, int bpad, int H, const __grid_constant__ PeerTable pt) {
     __shared__ __align__(16) float s_da[256];
     const int r = blockIdx.x, s = blockIdx.y;
     const int world = pt.world;
-    const int* prow_ptr = world == 1 ? pub.row_ptr : peer_ptr(pt, s, pub.row_ptr);
-    const int* prow_len = world == 1 ? pub.row_len : peer_ptr(pt, s, pub.row_len);
-    const int* pcol = world == 1 ? pub.col : peer_ptr(pt, s, pub.col);
-    const float* pxn = world == 1 ? pub.xn : peer_ptr(pt, s, pub.xn);
+    const int* pcol = pub.col + (size_t)s * pub.seg_nnz;
+    const float* pxn = pub.xn + (size_t)s * pub.seg_nnz;
     if (threadIdx.x < H) s_da[threadIdx.x] = da[((size_t)s * bpad + r) * H + threadIdx.x];
     __syncthreads();
     // thread (g, t) takes entries j = g (mod G), lane t adds 4 columns with one 16-byte reduction
@@ -387,24 +428,119 @@ k_scatter_shard(const __grid_constant__ PubInput pub, const float* __restrict__ 
     const int g = threadIdx.x / tpr, t = threadIdx.x - g * tpr;
     if (g >= G) return;
     const float4 dav = *reinterpret_cast<const float4*>(s_da + 4 * t);
-    const int beg = prow_ptr[r], n = prow_len[r];
+    const int beg = pub.row_ptr[s * pub.seg_rows + r], n = pub.row_len[s * pub.seg_rows + r];
     for (int i = g; i < n; i += G) {
         const int c = pcol[beg + i];
         if (world != 1 && item_owner(c, world) != pt.rank) continue;
         const float x = pxn[beg + i];
         if (x != 0.f) {
             const int lc = world == 1 ? c : item_local(c, world);
+            if (touch_cnt != nullptr && touch_cnt[lc] > max_cnt) continue;     // deterministic mode: gathered by k_scatter_det
             float* dst = g_enc + (size_t)lc * H + 4 * t;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x * dav.x), "f"(x * dav.y),
                          "f"(x * dav.z), "f"(x * dav.w)
                          : "memory");
-            if (t == 0) touched[lc] = 1;
+        }
+    }
+}
+
+// Deterministic form ("determinism test for scatter-add").  fp32 addition commutes, so a row with at
+// most TWO contributing playlists is order-independent under the red.add form above (0 + a + b == 0 + b + a exactly);
+// only the rows listed by three or more playlists of the global batch (touch_cnt > 2: the popular head of the
+// catalogue, a few hundred rows) need a fixed order.  One warp per such row gathers its contributions: every lane
+// binary-searches the row's catalogue id in the (column-sorted, de-duplicated) input rows of 8 playlists at a time --
+// the 8 searches advance in lockstep, so 8 loads are in flight per lane instead of one dependent chain -- and the hits
+// are added in ascending global batch row.  dW_enc (and everything downstream of it) is then bit-identical run to run.
+// 128 threads x <= 64 registers: the blocks must fit NEXT to the decoder update's CTAs (148 x 640 threads x 64 registers,
+// 217 KB of shared memory), under which this kernel runs; the first version (256 x 97) only got on an SM once those had left.
+constexpr int kDetRows = 4;     // playlists per lane per sweep: 128 playlists of the global batch per warp sweep
+__global__ void __maxnreg__(64)
+k_scatter_det(const __grid_constant__ PubInput pub, const float* __restrict__ da, float* __restrict__ g_enc,
+              const int* __restrict__ hot_list, int B, int bpad, int H, const __grid_constant__ PeerTable pt) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int world = pt.world;
+    const int K = world * B;                                   // valid rows of the global batch (rank-major)
+    const int cpl = H >> 5;                                    // columns per lane: k = lane + 32 j
+    const int n_hot = hot_list[0];
+    {
+        // one warp per row of the hot list (the list's order is arbitrary; every row is independent of the others)
+        for (int hi_ = warp_global; hi_ < n_hot; hi_ += nwarps) {
+            const int lrow = hot_list[1 + hi_];
+            const int c = world == 1 ? lrow : item_global(lrow, world, pt.rank);
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            bool any = false;
+            for (int g0 = 0; g0 < K; g0 += 32 * kDetRows) {
+                // lane l searches playlists g0 + 32 u + l, u = 0..7, in lockstep
+                int lo[kDetRows], hi[kDetRows], len[kDetRows];
+                const int* pc[kDetRows];
+                const float* px[kDetRows];
+#pragma unroll
+                for (int u = 0; u < kDetRows; ++u) {
+                    const int gi = g0 + 32 * u + lane;
+                    lo[u] = 0; hi[u] = 0; len[u] = 0; pc[u] = pub.col; px[u] = pub.xn;
+                    if (gi < K) {
+                        const int s = gi / B, r = gi - s * B;
+                        const int beg = pub.row_ptr[s * pub.seg_rows + r];
+                        len[u] = hi[u] = pub.row_len[s * pub.seg_rows + r];
+                        pc[u] = pub.col + (size_t)s * pub.seg_nnz + beg;
+                        px[u] = pub.xn + (size_t)s * pub.seg_nnz + beg;
+                    }
+                }
+                bool more = true;
+                while (more) {                                 // lower bound of c in each row's sorted columns
+                    more = false;
+                    int v[kDetRows];
+#pragma unroll
+                    for (int u = 0; u < kDetRows; ++u) v[u] = lo[u] < hi[u] ? pc[u][(lo[u] + hi[u]) >> 1] : 0;
+#pragma unroll
+                    for (int u = 0; u < kDetRows; ++u) {
+                        if (lo[u] < hi[u]) {
+                            const int mid = (lo[u] + hi[u]) >> 1;
+                            if (v[u] < c) lo[u] = mid + 1; else hi[u] = mid;
+                            more |= lo[u] < hi[u];
+                        }
+                    }
+                }
+                float x[kDetRows];
+#pragma unroll
+                for (int u = 0; u < kDetRows; ++u) x[u] = (lo[u] < len[u] && pc[u][lo[u]] == c) ? px[u][lo[u]] : 0.f;
+#pragma unroll
+                for (int u = 0; u < kDetRows; ++u) {           // ascending global batch row
+                    unsigned hits = __ballot_sync(0xffffffffu, x[u] != 0.f);
+                    while (hits) {
+                        const int b = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float xb = __shfl_sync(0xffffffffu, x[u], b);
+                        const int gb = g0 + 32 * u + b;
+                        const int s = gb / B, r = gb - s * B;
+                        const float* drow = da + ((size_t)s * bpad + r) * H;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < cpl) acc[j] = __fadd_rn(acc[j], __fmul_rn(xb, drow[lane + 32 * j]));
+                        any = true;
+                    }
+                }
+            }
+            if (any) {
+                float* dst = g_enc + (size_t)lrow * H;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < cpl) dst[lane + 32 * j] = acc[j];   // these rows are zero between steps and untouched by the red.add form
+            }
         }
     }
 }
 
 void launch_scatter_shard(const ScatterArgs& a, cudaStream_t st) {
-    k_scatter_shard<<<dim3(a.B, a.pt.world), 256, 0, st>>>(a.pub, a.da, a.g_enc, a.touched, a.bpad, a.H, a.pt);
+    // deterministic: rows with <= 2 contributors through red.add (order-independent), the others gathered in a fixed order
+    k_scatter_shard<<<dim3(a.B, a.pt.world), 256, 0, st>>>(a.pub, a.da, a.g_enc, a.deterministic ? a.touch_cnt : nullptr, 2,
+                                                           a.bpad, a.H, a.pt);
+    if (a.deterministic)
+        k_scatter_det<<<148 * 4, 128, 0, st>>>(a.pub, a.da, a.g_enc, a.hot_list, a.B, a.bpad, a.H, a.pt);
 }
 
 // out[global item] = the owner's src[local item]
@@ -480,20 +616,22 @@ void launch_barrier(unsigned int* flags_local, unsigned int epoch, const PeerTab
 // synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
 void preload_sparse() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_coo_count);
-    cudaFuncGetAttributes(&a, k_row_scan);
-    cudaFuncGetAttributes(&a, k_coo_fill);
-    cudaFuncGetAttributes(&a, k_row_sort_dedup);
-    cudaFuncGetAttributes(&a, k_ybits_shard);
-    cudaFuncGetAttributes(&a, k_reduce_splits);
-    cudaFuncGetAttributes(&a, k_da_all);
-    cudaFuncGetAttributes(&a, k_gather_items_f32);
-    cudaFuncGetAttributes(&a, k_gather_rows_bf16);
-    cudaFuncGetAttributes(&a, k_encode_fwd);
-    cudaFuncGetAttributes(&a, k_colsum);
-    cudaFuncGetAttributes(&a, k_scatter_shard);
-    cudaFuncGetAttributes(&a, k_sum_partials);
-    cudaFuncGetAttributes(&a, k_barrier);
+    PRELOAD_KERNEL(k_coo_count);
+    PRELOAD_KERNEL(k_row_scan);
+    PRELOAD_KERNEL(k_coo_fill);
+    PRELOAD_KERNEL(k_row_sort_dedup);
+    PRELOAD_KERNEL(k_ybits_shard);
+    PRELOAD_KERNEL(k_reduce_splits);
+    PRELOAD_KERNEL(k_da_all);
+    PRELOAD_KERNEL(k_gather_items_f32);
+    PRELOAD_KERNEL(k_gather_rows_bf16);
+    PRELOAD_KERNEL(k_encode_fwd);
+    PRELOAD_KERNEL(k_colsum);
+    PRELOAD_KERNEL(k_scatter_shard);
+    PRELOAD_KERNEL(k_scatter_det);
+    PRELOAD_KERNEL(k_touch_shard);
+    PRELOAD_KERNEL(k_sum_partials);
+    PRELOAD_KERNEL(k_barrier);
     (void)cudaGetLastError();
 }
 

@@ -268,14 +268,14 @@ void launch_transpose_pad(const float* src, float* dst, int D, int N, int ld, in
 
 void preload_title_cnn() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_charcnn_fwd);
-    cudaFuncGetAttributes(&a, k_mix_weights);
-    cudaFuncGetAttributes(&a, k_title_dfeat);
-    cudaFuncGetAttributes(&a, k_charcnn_bwd_w);
-    cudaFuncGetAttributes(&a, k_charcnn_bwd_emb);
-    cudaFuncGetAttributes(&a, k_trunc_normal);
-    cudaFuncGetAttributes(&a, k_cast_bf16);
-    cudaFuncGetAttributes(&a, k_transpose_pad);
+    PRELOAD_KERNEL(k_charcnn_fwd);
+    PRELOAD_KERNEL(k_mix_weights);
+    PRELOAD_KERNEL(k_title_dfeat);
+    PRELOAD_KERNEL(k_charcnn_bwd_w);
+    PRELOAD_KERNEL(k_charcnn_bwd_emb);
+    PRELOAD_KERNEL(k_trunc_normal);
+    PRELOAD_KERNEL(k_cast_bf16);
+    PRELOAD_KERNEL(k_transpose_pad);
     (void)cudaGetLastError();
 }
 

@@ -243,8 +243,8 @@ void preload_title_gemm() {
     cudaFuncAttributes a;
     cudaFuncSetAttribute(k_title_tile<TMODE_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTitle);
     cudaFuncSetAttribute(k_title_tile<TMODE_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTitle);
-    cudaFuncGetAttributes(&a, k_title_tile<TMODE_TRAIN>);
-    cudaFuncGetAttributes(&a, k_title_tile<TMODE_PREDICT>);
+    PRELOAD_KERNEL(k_title_tile<TMODE_TRAIN>);
+    PRELOAD_KERNEL(k_title_tile<TMODE_PREDICT>);
     (void)cudaGetLastError();
 }
 

@@ -260,8 +260,8 @@ void launch_topk(const TopkArgs& a, cudaStream_t st) {
 // synchronise the context, which would deadlock against a cross-GPU flag barrier already spinning.
 void preload_topk() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_topk);
-    cudaFuncGetAttributes(&a, k_thr_from_topk);
+    PRELOAD_KERNEL(k_topk);
+    PRELOAD_KERNEL(k_thr_from_topk);
     (void)cudaGetLastError();
 }
 
