@@ -102,6 +102,15 @@ int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos, const floa
                                   const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t item_lo,
                                   int32_t item_hi, int32_t* out_idx, float* out_score);
 
+/* dae_model_recommend followed by met.single_eval of every playlist ON THE DEVICE: answers as a CSR (ans_ptr [batch+1],
+ * ans_idx; an answer list may contain -1 = a track outside the vocabulary: never matched, still counted), metrics_out
+ * [batch, 3] doubles = (r-precision, ndcg with the reference's own IDCG, recommended-songs clicks).  Replaces the
+ * runner's per-playlist Python loop over a [batch, 500] id matrix: 24 bytes per playlist come back instead of 2 KB.
+ *                                             main_train.py:62-100; metrics.py:20-27 (r-precision), :29-42, :44-49 */
+int32_t dae_model_evaluate(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
+                           const int32_t* seed_ptr, const int32_t* seed_idx, const int32_t* ans_ptr, const int32_t* ans_idx,
+                           int32_t k, double* metrics_out);
+
 /* ---- device-resident / asynchronous variants (bench `value`, data-parallel training) ---------- */
 
 /* Copy one batch (host COO) into device staging slot 0 or 1 and build its CSR / target bitmask, all
@@ -142,6 +151,24 @@ int32_t dae_model_ipc_handle(dae_model* m, void* handle_out64);
 int32_t dae_model_attach_ipc(dae_model* m, const void* handles, int32_t n_handles);
 int32_t dae_model_attach_local(dae_model* m, dae_model* const* peers, int32_t n_peers);
 int32_t dae_model_arena_bytes(dae_model* m, int64_t* bytes);
+
+/* ---- item-sharded challenge inference (main_challenge.py:80-90 on one GPU upstream) -------------------
+ * Every rank holds a replica of the inference model and ranks ITS slice of the track catalogue with
+ * dae_model_recommend_range(..., out_idx = NULL) (lists stay on the device: buffers "topk_idx" / "topk_score").  A
+ * dae_exchange merges the per-shard lists without a collective library: dae_exchange_merge_topk stores this rank's lists
+ * into every peer's merge buffer (plain stores over NVLink through the CUDA IPC mapping), one flag barrier, then the
+ * (score desc, id asc) merge of world x k candidates per playlist runs locally -- exactly the unsharded ranking, on every
+ * rank.  Create one per rank, exchange the 64-byte handles out of band (as for the models), attach, then call
+ * dae_exchange_merge_topk collectively (same batch and k on every rank). */
+typedef struct dae_exchange dae_exchange;
+int32_t dae_exchange_create(int32_t device, int32_t world, int32_t rank, int32_t max_batch, int32_t max_k, dae_exchange** out);
+void dae_exchange_destroy(dae_exchange* x);
+int32_t dae_exchange_ipc_handle(dae_exchange* x, void* handle_out64);
+int32_t dae_exchange_attach_ipc(dae_exchange* x, const void* handles, int32_t n_handles);
+int32_t dae_exchange_attach_local(dae_exchange* x, dae_exchange* const* peers, int32_t n_peers);
+int32_t dae_exchange_merge_topk(dae_exchange* x, const int32_t* idx_dev, const float* score_dev, int32_t batch, int32_t k,
+                                int32_t* out_idx, float* out_score, void* stream);
+int64_t dae_exchange_launch_count(dae_exchange* x);
 
 /* debug / tuning flags.  bit 0: dae_model_backward_staged also forms dW_dec of the rows this rank owns
  * (buffer "g_dec") and bit 1: the sparse-row dW_enc scatter ("g_enc", "touched") -- both otherwise
@@ -212,9 +239,15 @@ int32_t dae_title_predict(dae_title* t, const int64_t* x_pos, const float* x_val
 int32_t dae_title_recommend(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
                             const int64_t* titles, const float* titles_use, int32_t batch, const int32_t* seed_ptr,
                             const int32_t* seed_idx, int32_t k, int32_t* out_idx, float* out_score);
+/* dae_title_recommend + the metrics of every list on the device (see dae_model_evaluate).       main_train.py:69-100 */
+int32_t dae_title_evaluate(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x, const int64_t* titles,
+                           const float* titles_use, int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx,
+                           const int32_t* ans_ptr, const int32_t* ans_idx, int32_t k, double* metrics_out);
 int64_t dae_title_launch_count(dae_title* t);
-/* named device buffers for parity tests: "feat" "argpos" "feat_d" "w_t" "w_p" "dzT" "d" "g_emb" "g_conv_W"
- * "g_conv_b" "g_W_out" "g_b_out" "W_out" "W_out_bf16" */
+/* named device buffers for parity tests ("W_out", its moments and "g_W_out" are two dense column blocks, [Np, h0]
+ * followed by [Np, h1], Np = n_output rounded up to 128, h0 = min(256, D rounded up to 64), h1 = D - 256 rounded up to 64; the bf16 operand copy
+ * "W_out_bf16" is [n_output, 512]): "feat" "argpos" "feat_d" "w_t" "w_p" "dzT" "d" "g_emb" "g_conv_W"
+ * "g_conv_b" "g_W_out" (debug bit 14 only) "g_b_out" "W_out" "W_out_bf16" "m_W_out" "v_W_out" */
 int32_t dae_title_buffer(dae_title* t, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size);
 
 /* ---- kernel-level entry points on caller-owned DEVICE memory (parity tests, other hosts) ------- */
@@ -223,6 +256,10 @@ int32_t dae_title_buffer(dae_title* t, const char* name, void** dev_ptr, int64_t
 int32_t dae_topk_device(const float* scores_dev, int64_t ld, int32_t batch, int32_t n_tracks, int32_t k,
                         const int32_t* seed_ptr_dev, const int32_t* seed_idx_dev, int32_t idx_base,
                         int32_t* out_idx_dev, float* out_score_dev, void* stream);
+/* met.get_r_precision / get_ndcg / get_rsc of ranked lists already on the device: cand_dev [batch, ld] int32 (k ranks used,
+ * -1 padded), answers CSR on the device, out_dev [batch, 3] doubles.              metrics.py:20-27, :29-42, :44-49 */
+int32_t dae_metrics_device(const int32_t* cand_dev, int64_t ld, int32_t batch, int32_t k, const int32_t* ans_ptr_dev,
+                           const int32_t* ans_idx_dev, double* out_dev, void* stream);
 /* merge of per-shard top-k lists: row r = n (score, global id) pairs, -inf / -1 padded -> first k by (score desc, id asc) */
 int32_t dae_topk_merge_device(const float* scores_dev, const int32_t* idx_dev, int32_t n, int32_t batch, int32_t k,
                               int32_t* out_idx_dev, float* out_score_dev, void* stream);

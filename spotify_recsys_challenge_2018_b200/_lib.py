@@ -47,6 +47,7 @@ SIGNATURES = {
     "dae_model_predict": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P]),
     "dae_model_recommend": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _I32, _P, _P]),
     "dae_model_recommend_range": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "dae_model_evaluate": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _P, _P, _I32, _P]),
     "dae_model_stage_batch": (_I32, [_P, _I32, _P, _P, _I64, _P, _P, _I64, _I32]),
     "dae_model_restage": (_I32, [_P, _I32]),
     "dae_model_backward_staged": (_I32, [_P, _I32, _F, _F, _I32, _I32]),
@@ -74,9 +75,18 @@ SIGNATURES = {
     "dae_title_train_step": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _I32, _F, _F, _F, C.POINTER(_F)]),
     "dae_title_predict": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _I32, _P]),
     "dae_title_recommend": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P, _I32, _P, _P]),
+    "dae_title_evaluate": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _P]),
     "dae_title_launch_count": (_I64, [_P]),
     "dae_title_buffer": (_I32, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
+    "dae_exchange_create": (_I32, [_I32, _I32, _I32, _I32, _I32, C.POINTER(_P)]),
+    "dae_exchange_destroy": (None, [_P]),
+    "dae_exchange_ipc_handle": (_I32, [_P, _P]),
+    "dae_exchange_attach_ipc": (_I32, [_P, _P, _I32]),
+    "dae_exchange_attach_local": (_I32, [_P, C.POINTER(_P), _I32]),
+    "dae_exchange_merge_topk": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P]),
+    "dae_exchange_launch_count": (_I64, [_P]),
     "dae_topk_device": (_I32, [_P, _I64, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P]),
+    "dae_metrics_device": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "dae_topk_merge_device": (_I32, [_P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "dae_adam_device": (_I32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P]),
     "dae_coo_to_csr_device": (_I32, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),

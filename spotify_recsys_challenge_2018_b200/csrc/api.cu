@@ -271,6 +271,7 @@ extern "C" void dae_model_destroy(dae_model* m) {
     if (m->topk_score) cudaFree(m->topk_score);
     if (m->seed_ptr) cudaFree(m->seed_ptr);
     if (m->seed_idx) cudaFree(m->seed_idx);
+    cudaFree(m->ans_ptr); cudaFree(m->ans_idx); cudaFree(m->metrics);
     cudaFree(m->cand_val); cudaFree(m->cand_idx); cudaFree(m->cand_cnt); cudaFree(m->cand_thr);
     cudaFree(m->cand_tk_idx); cudaFree(m->cand_tk_score);
     for (int s = 0; s < 2; ++s) {
@@ -1183,6 +1184,37 @@ extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos,
     return check_device_flag(m);
 }
 
+// answers CSR (host) -> device; metrics of the lists in `idx_dev` [batch, k] -> out_host [batch, 3] doubles
+int run_metrics(dae_model* m, const int* idx_dev, int32_t batch, int32_t k, const int32_t* ans_ptr, const int32_t* ans_idx,
+                double* out_host) {
+    if (!ans_ptr || !out_host) return fail("null argument");
+    const int n_ans = ans_ptr[batch];
+    for (int r = 0; r < batch; ++r) {
+        const int a = ans_ptr[r + 1] - ans_ptr[r];
+        if (a <= 0) return fail("playlist %d has no answers: r-precision divides by len(answer) (metrics.py:26)", r);
+        if (a > 2048) return fail("playlist %d has %d answers (limit 2048)", r, a);
+    }
+    TRY(ensure_buf(&m->ans_ptr, &m->ans_ptr_elems, (size_t)batch + 1, m->st));
+    TRY(ensure_buf(&m->ans_idx, &m->ans_idx_elems, (size_t)(n_ans > 0 ? n_ans : 1), m->st));
+    TRY(ensure_buf(&m->metrics, &m->metrics_elems, (size_t)batch * 3, m->st));
+    CK(cudaMemcpyAsync(m->ans_ptr, ans_ptr, ((size_t)batch + 1) * 4, cudaMemcpyHostToDevice, m->st));
+    if (n_ans > 0) CK(cudaMemcpyAsync(m->ans_idx, ans_idx, (size_t)n_ans * 4, cudaMemcpyHostToDevice, m->st));
+    launch_metrics(idx_dev, k, batch, k, m->ans_ptr, m->ans_idx, m->metrics, m->st);
+    m->launches += 1;
+    CK(cudaMemcpyAsync(out_host, m->metrics, (size_t)batch * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->st));
+    return 0;
+}
+
+// recommend + met.single_eval on the device: only 3 doubles per playlist come back (main_train.py:62-100)
+extern "C" int32_t dae_model_evaluate(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x, int32_t batch,
+                                      const int32_t* seed_ptr, const int32_t* seed_idx, const int32_t* ans_ptr,
+                                      const int32_t* ans_idx, int32_t k, double* metrics_out) {
+    if (!m || !metrics_out) return fail("null argument");
+    TRY(dae_model_recommend_range(m, x_pos, x_val, nnz_x, batch, seed_ptr, seed_idx, k, 0, m->T, nullptr, nullptr));
+    TRY(run_metrics(m, m->topk_idx, batch, k, ans_ptr, ans_idx, metrics_out));
+    return check_device_flag(m);
+}
+
 extern "C" int32_t dae_model_recommend(dae_model* m, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
                                        int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
                                        int32_t* out_idx, float* out_score) {
@@ -1279,6 +1311,16 @@ extern "C" int32_t dae_topk_merge_device(const float* scores_dev, const int32_t*
     a.scores = scores_dev; a.ld = n; a.B = batch; a.T = n; a.k = k; a.remap = idx_dev;
     a.out_idx = out_idx_dev; a.out_score = out_score_dev;
     launch_topk(a, reinterpret_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t dae_metrics_device(const int32_t* cand_dev, int64_t ld, int32_t batch, int32_t k, const int32_t* ans_ptr_dev,
+                                      const int32_t* ans_idx_dev, double* out_dev, void* stream) {
+    ensure_loaded();
+    if (!cand_dev || !ans_ptr_dev || !ans_idx_dev || !out_dev) return fail("null argument");
+    if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
+    launch_metrics(cand_dev, ld, batch, k, ans_ptr_dev, ans_idx_dev, out_dev, reinterpret_cast<cudaStream_t>(stream));
     CK(cudaGetLastError());
     return 0;
 }

@@ -14,6 +14,12 @@ struct dae_title {
     dae_title_config cfg{};
     CnnShape shape{};
     int D = 0, N = 0, H = 0, Bmax = 0, n_conv_w = 0, nsplit = 0;
+    // The output layer's master / moments are kept as TWO DENSE column blocks, [N, h0] (feature columns 0..255) followed by
+    // [N, h1] (columns 256..D-1 rounded up to 64: D = 400 -> 256 + 192), block b at offset blk_off[b]: the fused dW + Adam
+    // kernel streams dense row groups with 1-D bulk copies and the dead columns of a [N, 512] layout are never touched.
+    // The bf16 tensor-core operand (W_out_bf16) stays [N, 512].
+    int hb[2] = {0, 0};
+    size_t blk_off[2] = {0, 0};
     bool trainable = true;
     cudaStream_t st = nullptr;
     // variables (fp32 masters), TF1-Adam moments, gradients
@@ -27,6 +33,7 @@ struct dae_title {
     // activations / workspaces
     long long *titles = nullptr, *h_titles = nullptr;
     float *titles_use = nullptr, *h_titles_use = nullptr;
+    float *dx = nullptr;
     float *feat = nullptr, *d = nullptr, *w_t = nullptr, *w_p = nullptr, *dh_partial = nullptr, *scratch = nullptr;
     unsigned char* argpos = nullptr;
     __nv_bfloat16 *feat_d = nullptr, *feat_dT = nullptr, *dzT = nullptr;
@@ -71,18 +78,24 @@ extern "C" int32_t dae_title_create(dae_model* dae, const dae_title_config* cfg,
         maxw = w > maxw ? w : maxw;
     }
     if (maxw * s.E > 512) { delete t; return fail("filter size x char_emb must be <= 512"); }
+    if (s.E > 128) { delete t; return fail("char_emb must be <= 128"); }
     t->n_conv_w = off;
     t->D = s.F * s.n_widths;
+    t->hb[0] = t->D >= 256 ? 256 : round_up(t->D, 64);
+    t->hb[1] = t->D > 256 ? round_up(t->D - 256, 64) : 0;
+    // (rows padded to whole 128-item tiles: the fused kernel moves the last tile's row groups as a whole)
+    t->blk_off[0] = 0; t->blk_off[1] = (size_t)round_up(dae->N, kTileItems) * t->hb[0];
     const size_t NF = (size_t)t->N * kTitleFpad;
+    const size_t NB = (size_t)round_up(t->N, kTileItems) * (t->hb[0] + t->hb[1]);       // the two dense column blocks
     const int B = t->Bmax, D = t->D, N = t->N;
     TRY(dalloc(t, &t->emb, (size_t)s.C * s.E)); TRY(dalloc(t, &t->conv_W, off)); TRY(dalloc(t, &t->conv_b, D));
-    TRY(dalloc(t, &t->W_out, NF)); TRY(dalloc(t, &t->b_out, N)); TRY(dalloc(t, &t->W_out_bf16, NF));
+    TRY(dalloc(t, &t->W_out, NB)); TRY(dalloc(t, &t->b_out, N)); TRY(dalloc(t, &t->W_out_bf16, NF));
     TRY(dalloc(t, &t->scratch, NF));                                  // [D, N] <-> [N, 512] transposes; dW_out during training
     if (t->trainable) {
         TRY(dalloc(t, &t->m_emb, (size_t)s.C * s.E)); TRY(dalloc(t, &t->v_emb, (size_t)s.C * s.E));
         TRY(dalloc(t, &t->m_conv_W, off)); TRY(dalloc(t, &t->v_conv_W, off));
         TRY(dalloc(t, &t->m_conv_b, D)); TRY(dalloc(t, &t->v_conv_b, D));
-        TRY(dalloc(t, &t->m_W_out, NF)); TRY(dalloc(t, &t->v_W_out, NF));
+        TRY(dalloc(t, &t->m_W_out, NB)); TRY(dalloc(t, &t->v_W_out, NB));
         TRY(dalloc(t, &t->m_b_out, N)); TRY(dalloc(t, &t->v_b_out, N));
         TRY(dalloc(t, &t->g_emb, (size_t)s.C * s.E)); TRY(dalloc(t, &t->g_conv_W, off)); TRY(dalloc(t, &t->g_conv_b, D));
         TRY(dalloc(t, &t->g_b_out, N));
@@ -91,6 +104,7 @@ extern "C" int32_t dae_title_create(dae_model* dae, const dae_title_config* cfg,
         t->nsplit = dh_nsplit(N);
         TRY(dalloc(t, &t->dh_partial, (size_t)2 * t->nsplit * kMaxBpad * 256));
         TRY(dalloc(t, &t->d, (size_t)B * D));
+        TRY(dalloc(t, &t->dx, (size_t)B * s.L * s.E));
         TRY(dalloc(t, &t->loss_partial, 148 * 2));
         TRY(dalloc(t, &t->cost, 1));
     }
@@ -131,8 +145,18 @@ extern "C" int32_t dae_title_param_size(dae_title* t, int32_t idx, int64_t* n_el
 }
 
 static void refresh_out_shadow(dae_title* t) {
-    launch_cast_bf16(t->W_out, t->W_out_bf16, (long long)t->N * kTitleFpad, t->st);
-    t->launches += 1;
+    for (int b = 0; b < 2; ++b)
+        launch_cast_block_bf16(t->W_out + t->blk_off[b], t->W_out_bf16, t->N, t->hb[b], kTitleFpad, 256 * b, t->st);
+    t->launches += 2;
+}
+// [D, N] host layout (Char_CNN.py:72) <-> the two dense column blocks
+static void out_layer_transpose(dae_title* t, float* dn, float* blocks, bool to_blocks) {
+    for (int b = 0; b < 2; ++b) {
+        if (t->hb[b] == 0) continue;
+        const int d_live = b == 0 ? (t->D < 256 ? t->D : 256) : t->D - 256;
+        if (to_blocks) launch_transpose_pad(dn + (size_t)256 * b * t->N, blocks + t->blk_off[b], d_live, t->N, t->hb[b], 1, t->st);
+        else launch_transpose_pad(blocks + t->blk_off[b], dn + (size_t)256 * b * t->N, d_live, t->N, t->hb[b], 0, t->st);
+    }
 }
 
 extern "C" int32_t dae_title_set_params(dae_title* t, const float* const* arrays) {
@@ -144,7 +168,7 @@ extern "C" int32_t dae_title_set_params(dae_title* t, const float* const* arrays
         CK(cudaMemcpyAsync(t->conv_b + i * s.F, arrays[2 + 2 * i], sizeof(float) * s.F, cudaMemcpyHostToDevice, t->st));
     }
     CK(cudaMemcpyAsync(t->scratch, arrays[1 + 2 * s.n_widths], sizeof(float) * (size_t)t->D * t->N, cudaMemcpyHostToDevice, t->st));
-    launch_transpose_pad(t->scratch, t->W_out, t->D, t->N, kTitleFpad, 1, t->st);
+    out_layer_transpose(t, t->scratch, t->W_out, true);
     CK(cudaMemcpyAsync(t->b_out, arrays[2 + 2 * s.n_widths], sizeof(float) * t->N, cudaMemcpyHostToDevice, t->st));
     refresh_out_shadow(t);
     CK(cudaStreamSynchronize(t->st));
@@ -159,7 +183,7 @@ extern "C" int32_t dae_title_get_params(dae_title* t, float* const* arrays) {
         CK(cudaMemcpyAsync(arrays[1 + 2 * i], t->conv_W + s.w_off[i], sizeof(float) * s.width[i] * s.E * s.F, cudaMemcpyDeviceToHost, t->st));
         CK(cudaMemcpyAsync(arrays[2 + 2 * i], t->conv_b + i * s.F, sizeof(float) * s.F, cudaMemcpyDeviceToHost, t->st));
     }
-    launch_transpose_pad(t->W_out, t->scratch, t->D, t->N, kTitleFpad, 0, t->st);
+    out_layer_transpose(t, t->scratch, t->W_out, false);
     CK(cudaMemcpyAsync(arrays[1 + 2 * s.n_widths], t->scratch, sizeof(float) * (size_t)t->D * t->N, cudaMemcpyDeviceToHost, t->st));
     CK(cudaMemcpyAsync(arrays[2 + 2 * s.n_widths], t->b_out, sizeof(float) * t->N, cudaMemcpyDeviceToHost, t->st));
     CK(cudaStreamSynchronize(t->st));
@@ -178,7 +202,12 @@ extern "C" int32_t dae_title_init(dae_title* t, uint64_t seed) {
         launch_trunc_normal(t->conv_W + s.w_off[i], (long long)s.width[i] * s.E, s.F, s.F, sd(rf, rf * s.F), seed, stream++, t->st);
         launch_trunc_normal(t->conv_b + i * s.F, 1, s.F, s.F, sd(s.F, s.F), seed, stream++, t->st);
     }
-    launch_trunc_normal(t->W_out, t->N, t->D, kTitleFpad, sd(t->D, t->N), seed, stream++, t->st);   // padding columns stay zero
+    for (int b = 0; b < 2; ++b) {                                                                  // padding columns stay zero
+        const int d_live = b == 0 ? (t->D < 256 ? t->D : 256) : t->D - 256;
+        if (t->hb[b] > 0)
+            launch_trunc_normal(t->W_out + t->blk_off[b], t->N, t->D, t->hb[b], sd(t->D, t->N), seed, stream, t->st, 256 * b, d_live);
+    }
+    ++stream;
     launch_trunc_normal(t->b_out, 1, t->N, t->N, sd(t->N, t->N), seed, stream++, t->st);
     refresh_out_shadow(t);
     t->launches += 3 + 2 * s.n_widths;
@@ -241,50 +270,82 @@ extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, cons
     TitleTileArgs a = tile_args(t, batch);
     a.ybits = m->ybits; a.ywords = bpad / 32; a.dzT = t->dzT; a.db_out = t->g_b_out; a.loss_partial = t->loss_partial;
     a.inv_batch = 1.0f / (float)batch;
+    ph_begin(m, PH_T_FWD, t->st);
     launch_title_train(a, t->st);
+    ph_end(m, PH_T_FWD, t->st);
     CK(cudaEventRecord(sl.consumed, t->st));
     launch_reduce_loss2(t->loss_partial, decode_grid(N, 1), nullptr, 0, 0.f, 1.0f / (float)batch, t->cost, t->st);   // no l2 term (DAEs.py:196)
     t->launches += 2;
-
-    // output layer: dW_out = dz_t^T . feat_d and d cost / d feat_d = dz_t . W_out, each as two 256-column halves
-    for (int half = 0; half < 2; ++half) {
-        DwArgs w{};
-        w.dzT = t->dzT; w.h_dT = t->feat_dT + (size_t)half * 256 * bpad; w.g = t->g_W_out; w.n_local = N; w.N = N; w.H = 256;
-        w.K = bpad; w.pt.world = 1; w.ld = kTitleFpad; w.col0 = half * 256;
-        launch_dw(w, t->st);
-        DhArgs q{};
-        q.dzT = t->dzT; q.W = t->W_out_bf16 + half * 256; q.ldW = kTitleFpad; q.N = N; q.H = 256; q.bpad = bpad;
-        q.nsplit = t->nsplit; q.partial = t->dh_partial + (size_t)half * t->nsplit * bpad * 256;
-        launch_dh(q, t->st);
-        t->launches += 2;
-    }
-    CnnBwdArgs b{};
-    b.titles = t->titles; b.emb = t->emb; b.conv_W = t->conv_W; b.shape = t->shape; b.dh_partial = t->dh_partial;
-    b.nsplit = t->nsplit; b.bpad = bpad; b.B = batch; b.feat = t->feat; b.argpos = t->argpos; b.kp_t = title_keep_prob;
-    b.seed = m->cfg.seed; b.step = (unsigned long long)t->step; b.row_offset = 0; b.d = t->d;
-    b.g_emb = t->g_emb; b.g_conv_W = t->g_conv_W; b.g_conv_b = t->g_conv_b;
-    launch_charcnn_bwd(b, t->st);
-    t->launches += 3;
 
     // dense TF1 Adam on every title variable (DAEs.py:198; the DAE's are constants)
     AdamArgs ad{};
     ad.alpha = t->cfg.lr * sqrtf(1.0f - t->b2_pow) / (1.0f - t->b1_pow);
     ad.one_minus_b1 = 1.0f - kBeta1; ad.one_minus_b2 = 1.0f - kBeta2; ad.eps = kAdamEps; ad.lambda = 0.f;
     ad.row_touched = nullptr; ad.w_bf16 = nullptr;
-    ad.w = t->W_out; ad.m = t->m_W_out; ad.v = t->v_W_out; ad.g = t->g_W_out; ad.n = (long long)N * kTitleFpad;
-    ad.row_len = kTitleFpad;
-    launch_adam_rows(ad, nullptr, t->W_out_bf16, t->st);
+
+    // d cost / d feat_d = dz_t . W_out FIRST (it reads the operand copy the update below rewrites), as two 256-column halves
+    ph_begin(m, PH_T_DFEAT, t->st);
+    for (int half = 0; half < 2; ++half) {
+        DhArgs q{};
+        q.dzT = t->dzT; q.W = t->W_out_bf16 + half * 256; q.ldW = kTitleFpad; q.N = N; q.H = 256; q.bpad = bpad;
+        q.nsplit = t->nsplit; q.partial = t->dh_partial + (size_t)half * t->nsplit * bpad * 256;
+        launch_dh(q, t->st);
+        t->launches += 1;
+    }
+    ph_end(m, PH_T_DFEAT, t->st);
+    // Output layer: dW_out = dz_t^T . feat_d per dense column block (feature columns [0, 256) and [256, 256 + hb[1])).
+    // Default: the block's dW tile stays in tensor memory and the dense TF1 Adam is applied from there (k_dw_adam_fused):
+    // dW_out never exists in HBM.  Debug bit 14: dW_out through HBM (buffer "g_W_out", same block layout) +
+    // k_adam_rows_vec4 + a cast of the blocks into the operand copy.
+    const bool two_kernel = (m->debug & 16384) != 0;
+    ph_begin(m, PH_T_DW_ADAM, t->st);
+    for (int half = 0; half < 2; ++half) {
+        const int hw = t->hb[half];
+        if (hw == 0) continue;
+        DwArgs w{};
+        w.dzT = t->dzT; w.h_dT = t->feat_dT + (size_t)half * 256 * bpad; w.n_local = N; w.N = N; w.H = hw;
+        w.K = bpad; w.pt.world = 1;
+        if (two_kernel) w.g = t->g_W_out + t->blk_off[half];
+        else {
+            w.w = t->W_out + t->blk_off[half]; w.m = t->m_W_out + t->blk_off[half]; w.v = t->v_W_out + t->blk_off[half];
+            w.shadow = t->W_out_bf16; w.shadow_ld = kTitleFpad; w.shadow_col0 = 256 * half;
+            w.adam = AdamConst{ad.alpha, ad.one_minus_b1, ad.one_minus_b2, ad.eps, ad.lambda};
+        }
+        launch_dw(w, t->st);
+        t->launches += 1;
+        if (two_kernel) {
+            ad.w = t->W_out + t->blk_off[half]; ad.m = t->m_W_out + t->blk_off[half]; ad.v = t->v_W_out + t->blk_off[half];
+            ad.g = t->g_W_out + t->blk_off[half]; ad.n = (long long)N * hw; ad.row_len = hw;
+            launch_adam_rows(ad, nullptr, nullptr, t->st);
+            t->launches += 1;
+        }
+    }
+    if (two_kernel) refresh_out_shadow(t);
+    ph_end(m, PH_T_DW_ADAM, t->st);
+    ph_begin(m, PH_T_CNN_BWD, t->st);
+    CnnBwdArgs b{};
+    b.titles = t->titles; b.emb = t->emb; b.conv_W = t->conv_W; b.shape = t->shape; b.dh_partial = t->dh_partial;
+    b.nsplit = t->nsplit; b.bpad = bpad; b.B = batch; b.feat = t->feat; b.argpos = t->argpos; b.kp_t = title_keep_prob;
+    b.seed = m->cfg.seed; b.step = (unsigned long long)t->step; b.row_offset = 0; b.d = t->d; b.dx = t->dx;
+    b.g_emb = t->g_emb; b.g_conv_W = t->g_conv_W; b.g_conv_b = t->g_conv_b;
+    launch_charcnn_bwd(b, t->st);
+    ph_end(m, PH_T_CNN_BWD, t->st);
+    t->launches += 3;
+
+    ph_begin(m, PH_T_ADAM_SMALL, t->st);
     ad.row_len = 1;
     const CnnShape& s = t->shape;
     ad.w = t->b_out; ad.m = t->m_b_out; ad.v = t->v_b_out; ad.g = t->g_b_out; ad.n = N; launch_adam(ad, t->st);
     ad.w = t->emb; ad.m = t->m_emb; ad.v = t->v_emb; ad.g = t->g_emb; ad.n = (long long)s.C * s.E; launch_adam(ad, t->st);
     ad.w = t->conv_W; ad.m = t->m_conv_W; ad.v = t->v_conv_W; ad.g = t->g_conv_W; ad.n = t->n_conv_w; launch_adam(ad, t->st);
     ad.w = t->conv_b; ad.m = t->m_conv_b; ad.v = t->v_conv_b; ad.g = t->g_conv_b; ad.n = t->D; launch_adam(ad, t->st);
-    t->launches += 5;
+    ph_end(m, PH_T_ADAM_SMALL, t->st);
+    t->launches += 4;
     t->b1_pow *= kBeta1; t->b2_pow *= kBeta2; t->step += 1;
 
     CK(cudaMemcpyAsync(t->cost_host, t->cost, sizeof(float), cudaMemcpyDeviceToHost, t->st));
     TRY(check_device_flag(m));
+    ph_collect(m);
     if (cost_out) *cost_out = *t->cost_host;
     return 0;
 }
@@ -319,11 +380,10 @@ extern "C" int32_t dae_title_predict(dae_title* t, const int64_t* x_pos, const f
 }
 
 // y_pred[:, :n_tracks] + cand_generate (argsort, seed removal, first k)           main_challenge.py:26-36, :87-90
-extern "C" int32_t dae_title_recommend(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
-                                       const int64_t* titles, const float* titles_use, int32_t batch,
-                                       const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t* out_idx,
-                                       float* out_score) {
-    if (!t || !out_idx) return fail("null argument");
+// (+ the metrics of the lists against the answers CSR when metrics_out != NULL: main_train.py:88-100 on the device)
+static int title_rank(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x, const int64_t* titles,
+                      const float* titles_use, int32_t batch, const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k,
+                      int32_t* out_idx, float* out_score, const int32_t* ans_ptr, const int32_t* ans_idx, double* metrics_out) {
     if (k <= 0 || k > 1024) return fail("k must be in [1,1024]");
     dae_model* m = t->dae;
     const int T = m->T;
@@ -344,12 +404,34 @@ extern "C" int32_t dae_title_recommend(dae_title* t, const int64_t* x_pos, const
     a.out_idx = d_idx; a.out_score = d_sc;
     launch_topk(a, t->st);
     t->launches += 1;
-    CK(cudaMemcpyAsync(out_idx, d_idx, sizeof(int) * batch * k, cudaMemcpyDeviceToHost, t->st));
+    int rc = 0;
+    if (metrics_out) { rc = run_metrics(m, d_idx, batch, k, ans_ptr, ans_idx, metrics_out); t->launches += 1; }
+    if (out_idx) CK(cudaMemcpyAsync(out_idx, d_idx, sizeof(int) * batch * k, cudaMemcpyDeviceToHost, t->st));
     if (out_score) CK(cudaMemcpyAsync(out_score, d_sc, sizeof(float) * batch * k, cudaMemcpyDeviceToHost, t->st));
     cudaFreeAsync(d_idx, t->st); cudaFreeAsync(d_sc, t->st);
     if (d_sp) cudaFreeAsync(d_sp, t->st);
     if (d_si) cudaFreeAsync(d_si, t->st);
+    if (rc) return rc;
     return check_device_flag(m);
+}
+
+extern "C" int32_t dae_title_recommend(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                       const int64_t* titles, const float* titles_use, int32_t batch,
+                                       const int32_t* seed_ptr, const int32_t* seed_idx, int32_t k, int32_t* out_idx,
+                                       float* out_score) {
+    if (!t || !out_idx) return fail("null argument");
+    return title_rank(t, x_pos, x_val, nnz_x, titles, titles_use, batch, seed_ptr, seed_idx, k, out_idx, out_score, nullptr,
+                      nullptr, nullptr);
+}
+
+// dae_title_recommend + met.single_eval of every playlist on the device -> [batch, 3] (r-precision, ndcg, clicks)
+extern "C" int32_t dae_title_evaluate(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                      const int64_t* titles, const float* titles_use, int32_t batch,
+                                      const int32_t* seed_ptr, const int32_t* seed_idx, const int32_t* ans_ptr,
+                                      const int32_t* ans_idx, int32_t k, double* metrics_out) {
+    if (!t || !metrics_out) return fail("null argument");
+    return title_rank(t, x_pos, x_val, nnz_x, titles, titles_use, batch, seed_ptr, seed_idx, k, nullptr, nullptr, ans_ptr,
+                      ans_idx, metrics_out);
 }
 
 extern "C" int64_t dae_title_launch_count(dae_title* t) { return t ? t->launches : 0; }
@@ -357,15 +439,15 @@ extern "C" int64_t dae_title_launch_count(dae_title* t) { return t ? t->launches
 extern "C" int32_t dae_title_buffer(dae_title* t, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size) {
     if (!t || !name || !dev_ptr) return fail("null argument");
     const CnnShape& s = t->shape;
-    const int64_t NF = (int64_t)t->N * kTitleFpad;
+    const int64_t NF = (int64_t)t->N * kTitleFpad, NB = (int64_t)round_up(t->N, kTileItems) * (t->hb[0] + t->hb[1]);
     struct E { const char* n; void* p; int64_t c; int32_t s; };
     const E table[] = {
         {"feat", t->feat, (int64_t)t->Bmax * t->D, 4}, {"argpos", t->argpos, (int64_t)t->Bmax * t->D, 1},
         {"feat_d", t->feat_d, (int64_t)kMaxBpad * kTitleFpad, 2}, {"w_t", t->w_t, kMaxBpad, 4}, {"w_p", t->w_p, kMaxBpad, 4},
         {"dzT", t->dzT, (int64_t)t->N * kMaxBpad, 2}, {"d", t->d, (int64_t)t->Bmax * t->D, 4},
         {"g_emb", t->g_emb, (int64_t)s.C * s.E, 4}, {"g_conv_W", t->g_conv_W, t->n_conv_w, 4},
-        {"g_conv_b", t->g_conv_b, t->D, 4}, {"g_W_out", t->g_W_out, NF, 4}, {"g_b_out", t->g_b_out, t->N, 4},
-        {"W_out", t->W_out, NF, 4}, {"W_out_bf16", t->W_out_bf16, NF, 2},
+        {"g_conv_b", t->g_conv_b, t->D, 4}, {"g_W_out", t->g_W_out, NB, 4}, {"g_b_out", t->g_b_out, t->N, 4},
+        {"W_out", t->W_out, NB, 4}, {"W_out_bf16", t->W_out_bf16, NF, 2}, {"m_W_out", t->m_W_out, NB, 4}, {"v_W_out", t->v_W_out, NB, 4},
     };
     for (const E& e : table) {
         if (strcmp(e.n, name) == 0) {

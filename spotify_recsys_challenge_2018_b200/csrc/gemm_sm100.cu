@@ -846,7 +846,8 @@ struct FusedDev {
     float* w; float* m; float* v;          // [local rows, H]
     const float* g_extra;                  // tied: sparse-row dW_enc, added where touched
     const unsigned char* touched;
-    __nv_bfloat16* shadow;                 // [local rows, H] or nullptr
+    __nv_bfloat16* shadow;                 // [local rows, shadow_ld] (+ shadow_col0) or nullptr
+    int shadow_ld, shadow_col0;
     AdamConst adam;
 };
 
@@ -1023,7 +1024,7 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
                             g = __fadd_rn(g, __ldcs(p.g_extra + (size_t)(item0 + j) * p.H + h));
                         adam_one(wv, mv, vv, g, p.adam);
                         pw[0] = wv; pw[astride] = mv; pw[2 * astride] = vv;
-                        if (p.shadow != nullptr) p.shadow[(size_t)(item0 + j) * p.H + h] = __float2bfloat16_rn(wv);
+                        if (p.shadow != nullptr) p.shadow[(size_t)(item0 + j) * p.shadow_ld + p.shadow_col0 + h] = __float2bfloat16_rn(wv);
                     }
                 }
                 fence_proxy_async_smem();              // the bulk store (async proxy) must see these writes
@@ -1043,6 +1044,9 @@ k_dw_adam_fused(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
 }
 
 void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
+    // w / m / v must be DENSE [rows, H] (8-row groups are contiguous 1-D bulk copies).  A column block of a wider matrix
+    // through 2-D tensor maps was tried for the title output layer ([N, 512]): 1 KB segments at a 2 KB pitch ran at
+    // 0.56 ms per 2 GB block instead of 0.35 ms -- the title head therefore keeps its output layer as dense column blocks.
     if ((a.ld != 0 && a.ld != a.H) || a.col0 != 0 || a.H % 64 != 0 || a.H > 256) {
         fprintf(stderr, "dae_b200: launch_dw_adam_fused needs dense [rows, H <= 256] state (ld=%d col0=%d H=%d)\n", a.ld, a.col0, a.H);
         abort();
@@ -1060,6 +1064,7 @@ void launch_dw_adam_fused(const DwArgs& a, cudaStream_t st) {
     p.w = a.w; p.m = a.m; p.v = a.v;
     p.g_extra = a.g_extra; p.touched = a.touched;
     p.shadow = a.shadow;
+    p.shadow_ld = a.shadow_ld != 0 ? a.shadow_ld : a.H; p.shadow_col0 = a.shadow_col0;   // the operand copy may be a column block
     p.adam = a.adam;
     p.n_mma = a.K > 512 ? 3 : 2;
     p.n_stg = a.K > 512 ? 3 : 5;           // ODD: the per-group barrier phase in the epilogue is (i / (2 * NS)) & 1

@@ -197,7 +197,8 @@ struct DwArgs {
     AdamConst adam;
     __nv_bfloat16* shadow;              // bf16 operand copy of the same rows (same indexing as w), or nullptr
     PeerTable pt;                       // world / rank: which catalogue rows the local tiles are
-    int ld, col0;                       // row stride (0: H) and first column of g / w / m / v / shadow (title head: two 256-column halves of [N, 512])
+    int ld, col0;                       // row stride (0: H) and first column of g / w / m / v (title head: column blocks of [N, 512])
+    int shadow_ld, shadow_col0;         // fused path: row stride (0: H) and first column of shadow (a column block of the title operand)
 };
 void launch_dw(const DwArgs& a, cudaStream_t st);                  // G2: dW_dec = dz^T . h_d (+ Adam)
 
@@ -289,12 +290,15 @@ struct CnnBwdArgs {
     unsigned long long seed, step;
     int row_offset;
     float* d;                            // [B, D] workspace: gradient at the arg-max positions
+    float* dx;                           // [B, L, E] workspace: gradient at the embedded characters, per title
     float* g_emb; float* g_conv_W; float* g_conv_b;
 };
 void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st);
+// columns [col0, col0 + ncols) (ncols <= 0: all) of a [rows, row_len] variable -> w[r * ld + (c - col0)]
 void launch_trunc_normal(float* w, long long rows, int row_len, int ld, float stddev, unsigned long long seed,
-                         unsigned stream_id, cudaStream_t st);
+                         unsigned stream_id, cudaStream_t st, int col0 = 0, int ncols = 0);
 void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
+void launch_cast_block_bf16(const float* src, __nv_bfloat16* dst, long long rows, int cols, int ld, int col0, cudaStream_t st);
 void launch_transpose_pad(const float* src, float* dst, int D, int N, int ld, int to_item_major, cudaStream_t st);
 
 struct TitleTileArgs {                   // y_pred = title_score * w_t + sigmoid(z_dae) * w_p over one batch tile  (DAEs.py:175-181)
@@ -337,6 +341,10 @@ struct TopkArgs {
 void launch_topk(const TopkArgs& a, cudaStream_t st);
 // thr[r] = score[r, kp-1] (r < batch, -inf when that slot is padding or score == nullptr), +inf for r in [batch, rows)
 void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch, int rows, float* thr, cudaStream_t st);
+
+// (r-precision, ndcg, clicks) per playlist from its ranked list [B, ld] (k ranks, -1 padded) and the answers CSR -> out [B, 3]
+void launch_metrics(const int* cand, long long ld, int B, int k, const int* ans_ptr, const int* ans_idx, double* out,
+                    cudaStream_t st);
 
 // bounded-spin diagnostics: 8 words of mapped pinned host memory written before a trap (umma.cuh trap_report, k_barrier)
 void set_trap_log_gemm(unsigned int* host_mapped);

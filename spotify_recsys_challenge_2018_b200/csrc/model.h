@@ -124,6 +124,9 @@ struct dae_model {
     int *topk_idx = nullptr, *seed_ptr = nullptr, *seed_idx = nullptr;
     float* topk_score = nullptr;
     size_t topk_elems = 0, seed_idx_elems = 0, seed_ptr_elems = 0;
+    int *ans_ptr = nullptr, *ans_idx = nullptr;     // answers CSR of the batch being evaluated (dae_model_evaluate)
+    double* metrics = nullptr;                      // [batch, 3] r-precision, ndcg, clicks
+    size_t ans_ptr_elems = 0, ans_idx_elems = 0, metrics_elems = 0;
     // fused decode + top-K (large catalogues): per-playlist candidate lists, thresholds, intermediate top-K
     float* cand_val = nullptr; int* cand_idx = nullptr; int* cand_cnt = nullptr; float* cand_thr = nullptr;
     int* cand_tk_idx = nullptr; float* cand_tk_score = nullptr; int* cand_cnt_host = nullptr;
@@ -160,3 +163,5 @@ int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_
 int check_device_flag(dae_model* m);
 void run_encode(dae_model* m, int slot, int bpad, int rows_pad, float kp, float kp_in, int row_offset, bool train);
 void build_ybits(dae_model* m, int slot, int B, int bpad, cudaStream_t st = nullptr);
+int run_metrics(dae_model* m, const int* idx_dev, int32_t batch, int32_t k, const int32_t* ans_ptr, const int32_t* ans_idx,
+                double* out_host);

@@ -161,7 +161,7 @@ k_charcnn_bwd_w(const long long* __restrict__ titles, const float* __restrict__ 
 // shared memory, then one atomic row add per (position, e).
 __global__ void __launch_bounds__(256)
 k_charcnn_bwd_emb(const long long* __restrict__ titles, const float* __restrict__ conv_W, const float* __restrict__ d,
-                  const unsigned char* __restrict__ argpos, const CnnShape s, float* __restrict__ g_emb) {
+                  const unsigned char* __restrict__ argpos, const CnnShape s, float* __restrict__ dx) {
     extern __shared__ float s_dx[];                // [L][E]
     const int b = blockIdx.x;
     const int D = s.F * s.n_widths;
@@ -180,12 +180,32 @@ k_charcnn_bwd_emb(const long long* __restrict__ titles, const float* __restrict_
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < s.L * s.E; i += blockDim.x) {
-        const int pos = i / s.E, e = i - pos * s.E;
-        const long long id = titles[(size_t)b * s.L + pos];
-        const float v = s_dx[i];
-        if (id >= 0 && id < s.C && v != 0.f) atomicAdd(g_emb + (size_t)id * s.E + e, v);
+    // d cost / d x[b, pos, :] of this title; k_charcnn_emb_reduce adds the positions of each character in a fixed order
+    for (int i = threadIdx.x; i < s.L * s.E; i += blockDim.x) dx[(size_t)b * s.L * s.E + i] = s_dx[i];
+}
+
+// g_emb[c, e] = sum over (b, pos) with title[b, pos] == c of dx[b, pos, e], in ascending (b, pos): no atomics, bit-reproducible.
+// One WARP per character: the lanes test 32 title positions at a time (ballot), the matches are added in order, lane e
+// (and e + 32, ...) owning its embedding columns.
+__global__ void __launch_bounds__(32)
+k_charcnn_emb_reduce(const long long* __restrict__ titles, const float* __restrict__ dx, int n_pos, int E,
+                     float* __restrict__ g_emb) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};           // E <= 128
+    for (int i0 = 0; i0 < n_pos; i0 += 32) {
+        const int i = i0 + lane;
+        unsigned hits = __ballot_sync(0xffffffffu, i < n_pos && titles[i] == (long long)c);
+        while (hits) {
+            const int j = i0 + __ffs(hits) - 1;
+            hits &= hits - 1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (lane + 32 * u < E) acc[u] += dx[(size_t)j * E + lane + 32 * u];
+        }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < E) g_emb[(size_t)c * E + lane + 32 * u] = acc[u];
 }
 
 void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st) {
@@ -196,18 +216,22 @@ void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st) {
     for (int i = 0; i < a.shape.n_widths; ++i) maxw = a.shape.width[i] > maxw ? a.shape.width[i] : maxw;
     k_charcnn_bwd_w<<<D, (maxw * a.shape.E + 31) / 32 * 32, 0, st>>>(a.titles, a.emb, a.d, a.argpos, a.shape, a.B, a.g_conv_W,
                                                                      a.g_conv_b);
-    cudaMemsetAsync(a.g_emb, 0, sizeof(float) * a.shape.C * a.shape.E, st);
-    k_charcnn_bwd_emb<<<a.B, 64, sizeof(float) * a.shape.L * a.shape.E, st>>>(a.titles, a.conv_W, a.d, a.argpos, a.shape, a.g_emb);
+    k_charcnn_bwd_emb<<<a.B, 64, sizeof(float) * a.shape.L * a.shape.E, st>>>(a.titles, a.conv_W, a.d, a.argpos, a.shape, a.dx);
+    k_charcnn_emb_reduce<<<a.shape.C, 32, 0, st>>>(a.titles, a.dx, a.B * a.shape.L, a.shape.E, a.g_emb);
 }
 
 // ------------------------------------------------------------------------------------------
 // tf.contrib.layers.xavier_initializer(uniform=False) [TF1]: truncated normal, stddev sqrt(2.6 / (fan_in + fan_out)),
 // samples beyond two standard deviations redrawn (Char_CNN.py:19, :45-47, :71-73).  Philox -> Box-Muller.
 // ------------------------------------------------------------------------------------------
-__global__ void k_trunc_normal(float* __restrict__ w, long long n, int row_len, int ld, float stddev,
+// Columns [col0, col0 + ncols) of a [rows, row_len] variable, stored at w[r * ld + (c - col0)]; keyed by the element's
+// index in the WHOLE variable (r * row_len + c): the values do not depend on how the variable is split into blocks.
+__global__ void k_trunc_normal(float* __restrict__ w, long long n, int row_len, int col0, int ncols, int ld, float stddev,
                                unsigned long long seed, unsigned stream_id) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const long long r = e / ncols, c = col0 + (e - r * ncols);
+        const long long i = r * row_len + c;
         float z = 0.f;
         for (unsigned long long attempt = 0; attempt < 64; ++attempt) {
             const float u1 = philox_uniform24(seed, stream_id, 2 * attempt, static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(i));
@@ -216,13 +240,13 @@ __global__ void k_trunc_normal(float* __restrict__ w, long long n, int row_len, 
             if (fabsf(z) <= 2.f) break;
             z = 0.f;
         }
-        const long long r = i / row_len, c = i - r * row_len;
-        w[r * ld + c] = z * stddev;
+        w[r * ld + (c - col0)] = z * stddev;
     }
 }
 void launch_trunc_normal(float* w, long long rows, int row_len, int ld, float stddev, unsigned long long seed,
-                         unsigned stream_id, cudaStream_t st) {
-    k_trunc_normal<<<1184, 256, 0, st>>>(w, rows * row_len, row_len, ld, stddev, seed, stream_id);
+                         unsigned stream_id, cudaStream_t st, int col0, int ncols) {
+    if (ncols <= 0) { col0 = 0; ncols = row_len; }
+    k_trunc_normal<<<1184, 256, 0, st>>>(w, rows * ncols, row_len, col0, ncols, ld, stddev, seed, stream_id);
 }
 
 // fp32 [rows, ld] -> bf16 [rows, ld] (operand copy of the output layer)
@@ -232,6 +256,17 @@ __global__ void k_cast_bf16(const float* __restrict__ src, __nv_bfloat16* __rest
 }
 void launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {
     k_cast_bf16<<<1184, 256, 0, st>>>(src, dst, n);
+}
+// dense fp32 block [rows, cols] -> columns [col0, col0 + cols) of the bf16 operand [rows, ld]
+__global__ void k_cast_block_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n, int cols, int ld, int col0) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long r = i / cols;
+        dst[r * ld + col0 + (i - r * cols)] = __float2bfloat16(src[i]);
+    }
+}
+void launch_cast_block_bf16(const float* src, __nv_bfloat16* dst, long long rows, int cols, int ld, int col0, cudaStream_t st) {
+    if (cols > 0) k_cast_block_bf16<<<1184, 256, 0, st>>>(src, dst, rows * cols, cols, ld, col0);
 }
 
 // [D, N] (the reference's Output_W layout, Char_CNN.py:72) <-> item-major [N, ld] with zero padding columns
@@ -273,8 +308,10 @@ void preload_title_cnn() {
     PRELOAD_KERNEL(k_title_dfeat);
     PRELOAD_KERNEL(k_charcnn_bwd_w);
     PRELOAD_KERNEL(k_charcnn_bwd_emb);
+    PRELOAD_KERNEL(k_charcnn_emb_reduce);
     PRELOAD_KERNEL(k_trunc_normal);
     PRELOAD_KERNEL(k_cast_bf16);
+    PRELOAD_KERNEL(k_cast_block_bf16);
     PRELOAD_KERNEL(k_transpose_pad);
     (void)cudaGetLastError();
 }

@@ -251,6 +251,71 @@ void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch,
     k_thr_from_topk<<<(rows + 255) / 256, 256, 0, st>>>(score, idx, kp, batch, rows, thr);
 }
 
+// ------------------------------------------------------------------------------------------
+// Challenge metrics of a ranked list (utils/metrics.py:20-49), one CTA per playlist:
+//   r-precision  |set(answer) & set(cand[:len(answer)])| / len(answer)      metrics.py:25-27  (answers may hold -1:
+//                never matched, still counted in the denominator)
+//   ndcg         dcg / idcg with the reference's own IDCG: 1 + sum_{j=2..1+h} 1/log2(j), h = hits found after rank 0
+//                (metrics.py:29-42)
+//   clicks       first hit index // 10, 51 when there is none                metrics.py:44-49
+// cand rows are -1 padded at the end (a list may be shorter than k).  Integer work is exact; the two quotients are
+// formed in double precision like the Python code, the sums in rank order by one thread (<= k terms).
+// ------------------------------------------------------------------------------------------
+constexpr int kMetricsMaxAns = 2048;
+__global__ void __launch_bounds__(128)
+k_metrics(const int* __restrict__ cand, long long ld, int k, const int* __restrict__ ans_ptr, const int* __restrict__ ans_idx,
+          double* __restrict__ out) {
+    __shared__ int s_ans[kMetricsMaxAns];
+    __shared__ unsigned int s_hit[32];                 // k <= 1024 ranks, one bit each
+    __shared__ unsigned int s_rep[32];                 // hit whose id already occurred at an earlier rank (set semantics of r-precision)
+    const int row = blockIdx.x, t = threadIdx.x;
+    const int a0 = ans_ptr[row], A = ans_ptr[row + 1] - a0;
+    const int An = A < kMetricsMaxAns ? A : kMetricsMaxAns;
+    for (int i = t; i < An; i += blockDim.x) s_ans[i] = ans_idx[a0 + i];
+    if (t < 32) { s_hit[t] = 0u; s_rep[t] = 0u; }
+    __syncthreads();
+    for (int i = t; i < k; i += blockDim.x) {
+        const int c = cand[(size_t)row * ld + i];
+        if (c < 0) continue;                           // padding (and -1 answers can never match a candidate)
+        bool hit = false;
+        for (int j = 0; j < An; ++j) hit |= (s_ans[j] == c);
+        if (hit) {
+            atomicOr(&s_hit[i >> 5], 1u << (i & 31));
+            // r-precision intersects SETS (metrics.py:25): a repeated id counts once.  (Ranked lists never repeat an id;
+            // the reference function is defined for any list.)
+            bool rep = false;
+            for (int j = 0; j < i; ++j) rep |= (cand[(size_t)row * ld + j] == c);
+            if (rep) atomicOr(&s_rep[i >> 5], 1u << (i & 31));
+        }
+    }
+    __syncthreads();
+    if (t != 0) return;
+    int n_cand = 0;
+    while (n_cand < k && cand[(size_t)row * ld + n_cand] >= 0) ++n_cand;
+    int r_hits = 0, first = -1, later = 0;
+    double dcg = 0.0;
+    for (int w = 0; w < (k + 31) / 32; ++w) {
+        unsigned int m = s_hit[w];
+        while (m) {
+            const int i = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            if (i < A && !((s_rep[w] >> (i & 31)) & 1u)) ++r_hits;
+            if (first < 0) first = i;
+            if (i == 0) dcg = 1.0;
+            else { dcg += 1.0 / (log((double)(i + 1)) / log(2.0)); ++later; }
+        }
+    }
+    double idcg = 1.0;
+    for (int j = 2; j < 2 + later; ++j) idcg += 1.0 / (log((double)j) / log(2.0));
+    out[(size_t)row * 3 + 0] = A > 0 ? (double)r_hits / (double)A : 0.0;
+    out[(size_t)row * 3 + 1] = n_cand > 0 ? dcg / idcg : 0.0;
+    out[(size_t)row * 3 + 2] = first >= 0 ? (double)(first / 10) : 51.0;
+}
+void launch_metrics(const int* cand, long long ld, int B, int k, const int* ans_ptr, const int* ans_idx, double* out,
+                    cudaStream_t st) {
+    k_metrics<<<B, 128, 0, st>>>(cand, ld, k, ans_ptr, ans_idx, out);
+}
+
 void launch_topk(const TopkArgs& a, cudaStream_t st) {
     k_topk<<<a.B, kTopkThreads, 0, st>>>(a.scores, a.ld, a.T, a.k, a.seed_ptr, a.seed_idx, a.idx_base, a.out_idx,
                                          a.out_score, a.remap, a.row_n, a.sigmoid_out);
@@ -262,6 +327,7 @@ void preload_topk() {
     cudaFuncAttributes a;
     PRELOAD_KERNEL(k_topk);
     PRELOAD_KERNEL(k_thr_from_topk);
+    PRELOAD_KERNEL(k_metrics);
     (void)cudaGetLastError();
 }
 

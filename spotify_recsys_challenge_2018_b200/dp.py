@@ -10,7 +10,8 @@ themselves with loads / stores into the peers' memory over NVLink / NVSwitch (in
 out-of-band channel that carries the 64-byte CUDA IPC handles at start-up.
 
 Challenge inference shards on the ITEM axis instead (ShardedRecommender): every rank ranks its own slice of the
-track catalogue with the fused decode + top-K and the per-shard lists are merged after ONE all-gather.
+track catalogue with the fused decode + top-K; the per-shard lists are stored into every peer's merge buffer over
+NVLink (no collective call either) and merged on the device.
 
 `shard_coo`, `item_shard`, `merge_topk_lists` and `exchange_handles` are backend-agnostic (tested with gloo on CPU,
 world_size 2).
@@ -61,8 +62,8 @@ def attach_peers(model, group=None):
 class DataParallelDAE:
     """A models.DAEs model created with conf.world / conf.rank on this rank's GPU, attached to its peers.
 
-    train_step_staged is the single-GPU call: the library enqueues the two cross-GPU flag barriers
-    of the step itself.  Every rank must stage batches of the same size and call in the same order."""
+    train_step_staged is the single-GPU call: the library enqueues the three cross-GPU flag barriers
+    of the step itself (include/dae_b200.h, "data parallelism").  Every rank must stage batches of the same size and call in the same order."""
 
     def __init__(self, model, group=None):
         import torch.distributed as dist
@@ -122,44 +123,82 @@ class ShardedRecommender:
 
     Every rank holds a replica of the inference model (a plain world = 1 model on its own GPU: 2 M x 256 parameters are
     ~5 GB of 180), encodes the batch redundantly (microseconds) and ranks the tracks of ITS slice with the fused
-    decode + top-K.  One all-gather of B x k x 8 bytes per rank over NVLink, then the (score desc, id asc) merge of
-    world x k candidates per playlist on the device: exactly the unsharded list."""
+    decode + top-K.  The per-shard lists never leave the devices and no collective library is involved: each rank's
+    final select is followed by plain stores of its B x k (id, score) pairs into every peer's merge buffer over NVLink
+    (`dae_exchange_*`, CUDA IPC mapping), one flag barrier, and the (score desc, id asc) merge of world x k candidates
+    per playlist on every rank: exactly the unsharded list.  torch.distributed only carries the 64-byte IPC handles at
+    construction.  `local_peers`: the exchanges of all ranks living in THIS process (tests on one GPU)."""
 
-    def __init__(self, model, group=None):
-        import torch.distributed as dist
-        self.model, self.group = model, group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.range = item_shard(model.n_tracks, self.rank, self.world)
-
-    def _dev(self, name, n, dtype):
-        import torch
-        ptr, have, es = self.model.buffer(name)
-
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (int(n),), "typestr": dtype, "data": (int(ptr), False), "version": 2}
-        return torch.as_tensor(_Arr(), device="cuda")
-
-    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False):
+    def __init__(self, model, group=None, rank=None, world=None, max_k=500):
         import ctypes as C
-        import torch
+        from . import _lib
+        self.model, self.group = model, group
+        explicit = rank is not None              # ranks of one process (tests): the caller attaches them with attach_local
+        if not explicit:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.rank, self.world = rank, world
+        self.range = item_shard(model.n_tracks, self.rank, self.world)
+        self._lib = _lib.load()
+        self._x = C.c_void_p()
+        _lib.check(self._lib.dae_exchange_create(model.device, world, rank, model.n_batch, int(max_k), C.byref(self._x)))
+        self.max_k = int(max_k)
+        if not explicit and world > 1:
+            self.attach_ipc(group)
+
+    def ipc_handle(self):
+        import ctypes as C
+        buf = C.create_string_buffer(64)
+        from . import _lib
+        _lib.check(self._lib.dae_exchange_ipc_handle(self._x, buf))
+        return buf.raw
+
+    def attach_ipc(self, group=None):
         import torch.distributed as dist
         from . import _lib
-        m = self.model
-        B = m.n_batch
-        m.recommend(x_positions, x_vals, seeds, k=k, item_range=self.range, on_device=True)
-        idx = self._dev("topk_idx", B * k, "<i4").view(B, k)
-        sc = self._dev("topk_score", B * k, "<f4").view(B, k)
-        all_i = torch.empty((self.world, B, k), dtype=torch.int32, device="cuda")
-        all_s = torch.empty((self.world, B, k), dtype=torch.float32, device="cuda")
-        dist.all_gather_into_tensor(all_i, idx.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_s, sc.contiguous(), group=self.group)
-        cat_i = all_i.permute(1, 0, 2).reshape(B, self.world * k).contiguous()
-        cat_s = all_s.permute(1, 0, 2).reshape(B, self.world * k).contiguous()
-        out_i = torch.empty((B, k), dtype=torch.int32, device="cuda")
-        out_s = torch.empty((B, k), dtype=torch.float32, device="cuda")
-        _lib.check(_lib.load().dae_topk_merge_device(C.c_void_p(cat_s.data_ptr()), C.c_void_p(cat_i.data_ptr()),
-                                                     self.world * k, B, k, C.c_void_p(out_i.data_ptr()),
-                                                     C.c_void_p(out_s.data_ptr()),
-                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        res_i = out_i.cpu().numpy()
-        return (res_i, out_s.cpu().numpy()) if return_scores else res_i
+        blob = b"".join(exchange_handles(self.ipc_handle(), group))
+        _lib.check(self._lib.dae_exchange_attach_ipc(self._x, blob, self.world))
+        dist.barrier(group)
+
+    def attach_local(self, recommenders):
+        import ctypes as C
+        from . import _lib
+        arr = (C.c_void_p * len(recommenders))(*[r._x for r in recommenders])
+        _lib.check(self._lib.dae_exchange_attach_local(self._x, arr, len(recommenders)))
+
+    def rank_shard(self, x_positions, x_vals, seeds, k=500):
+        """This rank's slice: lists stay on the device (model buffers "topk_idx" / "topk_score")."""
+        self.model.recommend(x_positions, x_vals, seeds, k=k, item_range=self.range, on_device=True)
+
+    def merge(self, k=500, return_scores=False):
+        """Collective: store this rank's lists into every peer's merge buffer, barrier, merge locally -> host arrays."""
+        import ctypes as C
+        from . import _lib
+        B = self.model.n_batch
+        pi, _, _ = self.model.buffer("topk_idx")
+        ps, _, _ = self.model.buffer("topk_score")
+        out_i = np.empty((B, k), np.int32)
+        out_s = np.empty((B, k), np.float32) if return_scores else None
+        _lib.check(self._lib.dae_exchange_merge_topk(self._x, C.c_void_p(pi), C.c_void_p(ps), B, int(k),
+                                                     out_i.ctypes.data_as(C.c_void_p),
+                                                     out_s.ctypes.data_as(C.c_void_p) if out_s is not None else None,
+                                                     C.c_void_p(self.model.stream) if self.model.stream else None))
+        return (out_i, out_s) if return_scores else out_i
+
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False):
+        self.rank_shard(x_positions, x_vals, seeds, k)
+        return self.merge(k, return_scores)
+
+    def launch_count(self):
+        return int(self._lib.dae_exchange_launch_count(self._x))
+
+    def close(self):
+        if self._x:
+            self._lib.dae_exchange_destroy(self._x)
+            self._x = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

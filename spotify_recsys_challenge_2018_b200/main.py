@@ -111,6 +111,9 @@ class Conf:
         os.makedirs(self.result_dir, exist_ok=True)
         self.apply("CHALLENGE")
         self.result = os.path.join(self.result_dir, self.ini.get("CHALLENGE", "result"))
+        # optional key (not in the reference's schema): rank with the DAE scores alone instead of failing when the
+        # title checkpoint is missing (main_runner/main_challenge.py)
+        self.challenge_dae_only = _flag(self.ini.get("CHALLENGE", "dae_only", fallback="False"))
 
     set_challenge_conf = set_challenge_oonf
 

@@ -31,7 +31,14 @@ def run(conf):
     info = "[challenge mode]"
     model_title = None
     title_ckpt = conf.save
-    if os.path.exists(title_ckpt):
+    # The reference restores the title checkpoint unconditionally and fails when it is missing (saver.restore,
+    # main_challenge.py:68-69).  Same here: a mistyped path must not silently produce a lower-quality submission.
+    # DAE-only ranking (titles_use = 0 for every playlist) is an explicit opt-in: [CHALLENGE] dae_only = True.
+    dae_only = bool(getattr(conf, "challenge_dae_only", False))
+    if not dae_only:
+        if not os.path.exists(title_ckpt):
+            raise FileNotFoundError("title checkpoint %r not found (main_challenge.py:69 restores it unconditionally); set "
+                                    "[CHALLENGE] dae_only = True to rank with the DAE scores alone" % title_ckpt)
         from ..models.title_get import get_model
         model_title = get_model(conf)
     model = DAE_title(conf, model_title)
@@ -43,7 +50,7 @@ def run(conf):
         model_title.fit(model)
         model_title.restore(title_ckpt)                                        # saver.restore (main_challenge.py:69)
     else:
-        log_write(conf, "no title checkpoint at %s: ranking by the DAE scores alone (titles_use = 0)" % title_ckpt)
+        log_write(conf, "[CHALLENGE] dae_only: ranking by the DAE scores alone (titles_use = 0)")
 
     total_cands = []
     while True:

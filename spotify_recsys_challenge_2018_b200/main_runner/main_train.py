@@ -42,12 +42,12 @@ def eval(reader_test, conf, model, model_title=None):
     test_size = len(reader_test.playlists)
     while True:
         x_positions, test_seed, test_answer, titles, x_ones = reader_test.next_batch_test()
+        # y_pred[:, :n_tracks] + met.single_eval of every playlist (main_train.py:66-90), ranked AND scored on the device
         if model_title is not None:
-            cand = model_title.recommend(model, x_positions, x_ones, titles, test_seed, titles_use=1.0)
+            res = model_title.evaluate(model, x_positions, x_ones, titles, test_seed, test_answer, titles_use=1.0)
         else:
-            cand = model.recommend(x_positions, x_ones, test_seed, k=500)    # y_pred[:, :n_tracks] + single_eval
-        for i in range(len(test_seed)):
-            total += met.single_eval(cand[i], test_answer[i])
+            res = model.evaluate(x_positions, x_ones, test_seed, test_answer, k=500)
+        total += res.sum(axis=0)
         if reader_test.test_idx == 0:                                         # main_train.py:97-98
             break
     total /= test_size

@@ -32,6 +32,20 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+def _csr(lists, n_rows, pad_value=None):
+    """Per-row id lists -> (ptr int32 [n_rows + 1], flat int32).  Rows past len(lists) (a short last batch) are empty, or hold
+    the single id `pad_value` when one is given (the metrics kernel divides by the row length)."""
+    lists = [np.asarray(s, dtype=np.int64).reshape(-1) for s in lists]
+    if pad_value is not None:
+        lists = lists + [np.asarray([pad_value], np.int64)] * (n_rows - len(lists))
+    ptr = np.zeros(n_rows + 1, np.int32)
+    lens = [len(s) for s in lists]
+    ptr[1:len(lens) + 1] = np.cumsum(lens)
+    ptr[len(lens) + 1:] = ptr[len(lens)]
+    flat = np.concatenate(lists) if lens and sum(lens) else np.zeros(0, np.int64)
+    return ptr, np.ascontiguousarray(np.clip(flat, -1, 2 ** 31 - 1).astype(np.int32))
+
+
 class DAE_tied:
     """Tied-weight DAE used by --pretrain (reference models/DAEs.py:13-111)."""
 
@@ -200,6 +214,18 @@ class DAE_tied:
             return None
         return (idx, sc) if return_scores else idx
 
+    def evaluate(self, x_positions, x_vals, seeds, answers, k=500):
+        """`recommend` + `met.single_eval` of every playlist on the device (main_train.py:62-100): float64 [n, 3] =
+        (r-precision, ndcg, recommended-songs clicks) for the n = len(answers) playlists of the batch; rows past n are
+        padding of a short last batch.  Only 24 bytes per playlist cross PCIe."""
+        xp, xv = _coo(x_positions, x_vals)
+        seed_ptr, flat = _csr(seeds, self.n_batch)
+        ans_ptr, ans = _csr(answers, self.n_batch, pad_value=-1)
+        out = np.empty((self.n_batch, 3), np.float64)
+        _lib.check(self._lib.dae_model_evaluate(self._h, _ptr(xp), _ptr(xv), xp.shape[0], self.n_batch, _ptr(seed_ptr),
+                                                _ptr(flat), _ptr(ans_ptr), _ptr(ans), int(k), _ptr(out)))
+        return out[:len(answers)]
+
     # ---- staged / asynchronous surface (bench, data-parallel trainer) -------------------
     def stage_batch(self, slot, x_positions, x_vals, y_positions, y_vals):
         xp, xv = _coo(x_positions, x_vals)
@@ -298,3 +324,8 @@ class DAE_title(DAE):
         if self.title_score is None or titles is None:
             return DAE.recommend(self, x_positions, x_vals, seeds, k, return_scores)
         return self.title_score.recommend(self, x_positions, x_vals, titles, seeds, titles_use, k, return_scores)
+
+    def evaluate(self, x_positions, x_vals, seeds, answers, titles=None, titles_use=1.0, k=500):
+        if self.title_score is None or titles is None:
+            return DAE.evaluate(self, x_positions, x_vals, seeds, answers, k)
+        return self.title_score.evaluate(self, x_positions, x_vals, titles, seeds, answers, titles_use, k)

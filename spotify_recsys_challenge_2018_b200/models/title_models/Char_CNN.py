@@ -14,7 +14,7 @@ import pickle
 import numpy as np
 
 from ... import _lib
-from ..DAEs import _coo, _ptr
+from ..DAEs import _coo, _csr, _ptr
 
 
 class Char_CNN:
@@ -151,6 +151,18 @@ class Char_CNN:
                                                  _ptr(seed_ptr), _ptr(flat), int(k), _ptr(idx), _ptr(sc)))
         return (idx, sc) if return_scores else idx
 
+    def evaluate(self, dae_model, x_positions, x_vals, titles, seeds, answers, titles_use=1.0, k=500):
+        """`recommend` + met.single_eval per playlist on the device -> float64 [len(answers), 3] (main_train.py:69-100)."""
+        xp, xv = _coo(x_positions, x_vals)
+        B = dae_model.n_batch
+        t, u = self._titles(titles, titles_use, B)
+        seed_ptr, flat = _csr(seeds, B)
+        ans_ptr, ans = _csr(answers, B, pad_value=-1)
+        out = np.empty((B, 3), np.float64)
+        _lib.check(self._lib.dae_title_evaluate(self._h, _ptr(xp), _ptr(xv), xp.shape[0], _ptr(t), _ptr(u), B, _ptr(seed_ptr),
+                                                _ptr(flat), _ptr(ans_ptr), _ptr(ans), int(k), _ptr(out)))
+        return out[:len(answers)]
+
     def buffer(self, name):
         p = C.c_void_p(); n = C.c_int64(); s = C.c_int32()
         _lib.check(self._lib.dae_title_buffer(self._h, name.encode(), C.byref(p), C.byref(n), C.byref(s)))
@@ -158,6 +170,13 @@ class Char_CNN:
 
     def launch_count(self):
         return int(self._lib.dae_title_launch_count(self._h))
+
+    def set_profiling(self, on):
+        """Per-phase device times of the title step are kept by the underlying DAE model object (phases "title_*")."""
+        self._dae.set_profiling(on)
+
+    def phase_times(self):
+        return self._dae.phase_times()
 
     def __str__(self):                                          # Char_CNN.py:77-83
         return "\n".join(["Wide CNN", "Embedding Size : " + str(self.embedding),

@@ -159,11 +159,15 @@ def _ipc_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_dp_ipc_two_gpus_equals_single():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_dp_ipc_n_gpus_equals_single(world):
+    """One PROCESS per GPU over CUDA IPC (the production path: peer stores through NVLink, three flag barriers per step):
+    `world` ranks x 128 rows must reproduce one rank x (world * 128)... rows -- at world = 2 against ONE world = 1 model fed the
+    whole batch (<= 256 rows fit a single training tile); at 4 and 8 against the same ranks run as `world` models in one
+    process on one GPU (attach_local: the same kernels and peer addressing, no NVLink, no IPC)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -181,7 +185,26 @@ def test_dp_ipc_two_gpus_equals_single():
     for i in range(4):
         trk, art, y = random_batch(rng, B, T, N - T, mean_len=25)
         batches.append((trk, np.ones(len(trk), np.float32), y, np.ones(len(y), np.float32)))
-    want, want_costs = _run_single(DAE, N, T, H, B, _params(N, H), batches)
+    if world == 2:
+        want, want_costs = _run_single(DAE, N, T, H, B, _params(N, H), batches)
+    else:
+        ms = [DAE(Conf(batch=b_local, n_input=N, n_tracks=T, hidden=H, lr=0.005, seed=11, world=world, rank=r)).fit()
+              for r in range(world)]
+        for mm in ms:
+            mm.attach_local(ms)
+            mm.set_params(_params(N, H))
+        want_costs = []
+        for x, xv, y, yv in batches:
+            for r, mm in enumerate(ms):
+                mm.stage_batch(0, *shard_coo(x, xv, r, b_local), *shard_coo(y, yv, r, b_local))
+            for mm in ms:
+                mm.backward_staged(0, 0.8, 0.75)
+            for mm in ms:
+                mm.apply_adam()
+            want_costs.append([mm.sync_cost() for mm in ms][0])
+        want = ms[0].get_params()
+        for mm in ms:
+            mm.close()
     for c, w in zip(costs, want_costs):
         assert abs(c - w) <= 1e-5 * abs(w)
     # (not bit-exact over several steps: the fp32 atomics of the dW_enc scatter commute differently per layout)
@@ -191,7 +214,7 @@ def test_dp_ipc_two_gpus_equals_single():
 
 
 def test_sharded_recommender_single_rank_group():
-    """dp.ShardedRecommender's device path (lists left on the device, all-gather, device merge) on a 1-rank NCCL group:
+    """dp.ShardedRecommender's device path (lists left on the device, peer stores, device merge) on a 1-rank group:
     must return exactly what the plain recommend call returns."""
     import torch.distributed as dist
     from spotify_recsys_challenge_2018_b200.dp import ShardedRecommender
@@ -216,3 +239,50 @@ def test_sharded_recommender_single_rank_group():
         m.close()
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N,T,H,B,k", [(3, 40000, 36000, 128, 300, 500), (8, 300000, 270000, 64, 256, 500)])
+def test_sharded_recommender_peer_store_merge_local(world, N, T, H, B, k):
+    """`world` ShardedRecommenders in ONE process on one GPU (dae_exchange_attach_local: the same kernels, peer addressing
+    and flag barrier as the one-process-per-GPU path): each rank ranks its item slice, stores its lists into every peer's
+    merge buffer, and every rank's merged list must be exactly the unsharded ranking (main_challenge.py:26-36)."""
+    from spotify_recsys_challenge_2018_b200.dp import ShardedRecommender
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.01, DAEval=None)
+    ms = []
+    for r in range(world):
+        m = DAE(conf)
+        m.trainable = False
+        m.fit()
+        ms.append(m)
+    params = ms[0].get_params()
+    for m in ms[1:]:
+        m.set_params(params)
+    recs = [ShardedRecommender(m, rank=r, world=world, max_k=k) for r, m in enumerate(ms)]
+    for rc in recs:
+        rc.attach_local(recs)
+    rng = np.random.default_rng(N)
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=30, empty_rows=(2,))
+    xv = np.ones(len(trk), np.float32)
+    seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(B)]
+    want_i, want_s = ms[0].recommend(trk, xv, seeds, k=k, return_scores=True)
+    # the call is collective (every rank's barrier kernel waits for all the others): ranks of one process call it from
+    # threads; several calls in a row exercise the call-parity double buffering of the merge buffer
+    import threading
+    res = [None] * world
+
+    def run(r):
+        for call in range(3):
+            recs[r].rank_shard(trk, xv, seeds, k)
+            res[r] = recs[r].merge(k, return_scores=True)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t_ in ts:
+        t_.start()
+    for t_ in ts:
+        t_.join(timeout=300)
+    for r in range(world):
+        got_i, got_s = res[r]
+        assert np.array_equal(got_i, want_i) and np.array_equal(got_s, want_s), r
+    for rc in recs:
+        rc.close()
+    for m in ms:
+        m.close()

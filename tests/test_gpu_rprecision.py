@@ -32,6 +32,9 @@ def run_rprecision_parity(data_dir, tied, H, B, epochs, lr, tests=("test-5", "te
     N, T = reader.num_items, reader.num_tracks
     conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=lr, reg_lambda=0.0, seed=3)
     ora = O.DAEOracle(N, H, lr, tied=tied, seed=1, mode="b200")
+    # the reference's own arithmetic: everything fp32, no bf16 rounding anywhere (oracle/dae_oracle.py "fp32" mode) --
+    # the bar of BASELINE.json's north_star is stated against THIS path
+    ora32 = O.DAEOracle(N, H, lr, tied=tied, seed=1, mode="fp32")
     m = (DAE_tied if tied else DAE)(conf).fit()
     m.set_params(ora.params())
     steps = epochs * (len(reader.playlists) // B + 1)
@@ -43,28 +46,33 @@ def run_rprecision_parity(data_dir, tied, H, B, epochs, lr, tests=("test-5", "te
         y = np.asarray(y, np.int64); yv = np.ones(len(y), np.float32)
         c_gpu = m.train_step(x, xv, y, yv, 0.8, 0.75)
         c_ora = ora.train_step(x, xv, y, yv, B, 0.8, 0.75, seed=conf.seed)
-        costs.append((c_gpu, c_ora))
+        c_o32 = ora32.train_step(x, xv, y, yv, B, 0.8, 0.75, seed=conf.seed)
+        costs.append((c_gpu, c_ora, c_o32))
     out = {}
     for name in tests:
         t = rdr.data_reader_test(data_dir, name, 100, n_test)
-        tot_g = tot_o = 0.0
+        tot_g = tot_o = tot_32 = 0.0
         n = 0
-        overlap = 0.0
+        overlap = overlap32 = 0.0
         while True:
             x, seeds, answers, titles, ones = t.next_batch_test()
             x = np.asarray(x, np.int64).reshape(-1, 2); ones = np.asarray(ones, np.float32)
             cand_g = m.recommend(x, ones, seeds, k=500)
             p = ora.predict(x, ones, len(seeds))[:, :T]
+            p32 = ora32.predict(x, ones, len(seeds))[:, :T]
             for i in range(len(seeds)):
                 cand_o = ranking.topk_excluding_seeds(p[i], seeds[i], 500)
+                cand_32 = ranking.topk_excluding_seeds(p32[i], seeds[i], 500)
                 g = [int(v) for v in cand_g[i] if v >= 0]
                 tot_g += met.get_r_precision(answers[i], g)
                 tot_o += met.get_r_precision(answers[i], [int(v) for v in cand_o])
+                tot_32 += met.get_r_precision(answers[i], [int(v) for v in cand_32])
                 overlap += len(set(g) & set(int(v) for v in cand_o)) / 500.0
+                overlap32 += len(set(g) & set(int(v) for v in cand_32)) / 500.0
                 n += 1
             if t.test_idx == 0:
                 break
-        out[name] = (tot_g / n, tot_o / n, overlap / n, n)
+        out[name] = (tot_g / n, tot_o / n, overlap / n, n, tot_32 / n, overlap32 / n)
     m.close()
     return costs, out
 
@@ -74,18 +82,23 @@ def test_rprecision_parity_cfg1(tmp_path, tied, H, B, epochs):
     """cfg1 (BASELINE configs[0]): 1k playlists x 5k tracks (+1k artists), latent 64, batch 128."""
     write_dataset(str(tmp_path), n_tracks=5000, n_artists=1000, n_train=1000, n_test=200, n_challenge=4, n_clusters=16)
     costs, out = run_rprecision_parity(str(tmp_path), tied, H, B, epochs, lr=0.005)
-    c_gpu, c_ora = costs[-1]
+    c_gpu, c_ora, c_o32 = costs[-1]
     # the measured values travel back from the GPU box (gpurun_out/) so that they can be quoted in profiles/
     rep = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(rep):
         with open(os.path.join(rep, "rprecision_%s.json" % ("tied" if tied else "untied")), "w") as f:
             json.dump({"config": {"tied": tied, "hidden": H, "batch": B, "epochs": epochs, "n_train": 1000, "n_tracks": 5000,
                                   "n_artists": 1000, "test_playlists": 200, "k": 500},
-                       "last_cost": {"gpu": c_gpu, "oracle": c_ora},
-                       "r_precision": {k: {"gpu": v[0], "oracle": v[1], "top500_overlap": v[2]} for k, v in out.items()}}, f, indent=1)
+                       "last_cost": {"gpu": c_gpu, "oracle_b200_rounding": c_ora, "oracle_fp32_reference": c_o32},
+                       "r_precision": {k: {"gpu": v[0], "oracle_b200_rounding": v[1], "top500_overlap_b200": v[2],
+                                           "oracle_fp32_reference": v[4], "top500_overlap_fp32": v[5]} for k, v in out.items()}}, f, indent=1)
     assert abs(c_gpu - c_ora) <= 1e-2 * abs(c_ora), costs[-5:]
-    for name, (rp_gpu, rp_ora, overlap, n) in out.items():
+    assert abs(c_gpu - c_o32) <= 1e-2 * abs(c_o32), costs[-5:]
+    for name, (rp_gpu, rp_ora, overlap, n, rp_32, overlap32) in out.items():
         assert n == 200
         assert rp_ora > 0.05, (name, rp_ora)                               # the model has learnt the planted clusters
         assert abs(rp_gpu - rp_ora) <= R_PRECISION_TOL, (name, rp_gpu, rp_ora)
         assert overlap > 0.97, (name, overlap)                             # top-500 sets agree except near the cut
+        # against the fp32 reference arithmetic (bf16 operands on the device side only): the north_star bar
+        assert abs(rp_gpu - rp_32) <= R_PRECISION_TOL, (name, rp_gpu, rp_32)
+        assert overlap32 > 0.95, (name, overlap32)

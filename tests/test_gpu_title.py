@@ -85,6 +85,7 @@ def test_title_train_step_stage_by_stage(N, T, H, B, fn, fs):
     ora = TO.DAETitleOracle(dae_o, cnn_o, 0.005)
     c_ora, grads, f = ora.loss_and_grads(y, yv, y, yv, titles, np.ones(B, np.float32), B, kp, kp_in, kp_t, seed=11, step=0)
     before = [p.copy() for p in cnn_o.params()]
+    m.set_debug(16384)                                  # dW_out through HBM ("g_W_out"); the default keeps it in tensor memory
     cost = tm.train_step(m, y, yv, titles, kp, kp_t, kp_in)
     assert abs(cost - c_ora) <= 1e-3 * abs(c_ora), (cost, c_ora)
     D = fn * len(fs)
@@ -109,9 +110,16 @@ def test_title_train_step_stage_by_stage(N, T, H, B, fn, fs):
     g_cb = _tbuf(tm, "g_conv_b", torch.float32).cpu().numpy().reshape(len(fs), fn)
     for i in range(len(fs)):
         np.testing.assert_allclose(g_cb[i], grads[2 + 2 * i], rtol=0, atol=3e-2 * np.abs(grads[2 + 2 * i]).max())
-    g_wo = _tbuf(tm, "g_W_out", torch.float32).cpu().numpy().reshape(N, 512)
-    assert np.all(g_wo[:, D:] == 0)
-    np.testing.assert_allclose(g_wo[:, :D].T, grads[-2], rtol=0, atol=2e-2 * np.abs(grads[-2]).max())
+    # dW_out: two dense column blocks [N, h0] ++ [N, h1] (include/dae_b200.h)
+    h0 = 256 if D >= 256 else (D + 63) // 64 * 64
+    h1 = (D - 256 + 63) // 64 * 64 if D > 256 else 0
+    g_raw = _tbuf(tm, "g_W_out", torch.float32).cpu().numpy()
+    Np = (N + 127) // 128 * 128
+    g_wo = np.concatenate([g_raw[:N * h0].reshape(N, h0), g_raw[Np * h0:Np * h0 + N * h1].reshape(N, h1)], 1)
+    live = np.r_[0:min(D, 256), h0:h0 + max(D - 256, 0)]
+    dead = np.setdiff1d(np.arange(h0 + h1), live)
+    assert np.all(g_wo[:, dead] == 0)
+    np.testing.assert_allclose(g_wo[:, live].T, grads[-2], rtol=0, atol=2e-2 * np.abs(grads[-2]).max())
     np.testing.assert_allclose(_tbuf(tm, "g_b_out", torch.float32).cpu().numpy(), grads[-1], rtol=5e-3,
                                atol=1e-3 * np.abs(grads[-1]).max())
     # Adam: first step moves every element by ~lr * sign(g)
@@ -125,6 +133,34 @@ def test_title_train_step_stage_by_stage(N, T, H, B, fn, fs):
     shadow = _tbuf(tm, "W_out_bf16", torch.bfloat16).float().cpu().numpy().reshape(N, 512)[:, :D]
     assert np.array_equal(shadow.T, O.bf16_round(got[-2]))
     tm.close(); m.close()
+
+
+@pytest.mark.parametrize("N,T,H,B,fn,fs", [(6007, 5000, 256, 250, 100, (3, 5, 7, 9)), (3001, 2500, 128, 150, 40, (3, 5, 7)),
+                                          (20000, 17000, 256, 256, 128, (3, 5, 7, 9))])
+def test_title_fused_dw_adam_equals_two_kernel_path(N, T, H, B, fn, fs):
+    """Default: the dW_out tile of each column block stays in tensor memory and the dense TF1 Adam is applied from there
+    (k_dw_adam_fused over 2-D TMA boxes of the [N, 512] layout; D = 400 -> blocks of 256 + 192 columns).  Debug bit 14:
+    dW_out through HBM + k_adam_rows_vec4.  Same MMA order, same rounded Adam ops: master, moments and the bf16 operand
+    copy agree bit for bit after several steps (Char_CNN.py:62-75 trained by DAEs.py:198)."""
+    rng = np.random.default_rng(N)
+    steps = []
+    for i in range(3):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=20, empty_rows=(1,))
+        steps.append((y, np.ones(len(y), np.float32), _titles(rng, B, 25, 41)))
+    out = []
+    for flags in (0, 16384):
+        conf, dae_o, cnn_o, m, tm = _setup(N, T, H, B, fn, fs)
+        m.set_debug(flags)
+        costs = [tm.train_step(m, y, yv, titles, 0.8, 0.7, 0.3) for y, yv, titles in steps]
+        snap = {k: _tbuf(tm, k, torch.bfloat16 if k == "W_out_bf16" else torch.float32).view(torch.int16 if k == "W_out_bf16" else torch.int32).clone()
+                for k in ("W_out", "m_W_out", "v_W_out", "W_out_bf16")}
+        out.append((costs, snap, [p.copy() for p in tm.get_params()]))
+        tm.close(); m.close()
+    assert out[0][0] == out[1][0]
+    for k in out[0][1]:
+        assert torch.equal(out[0][1][k], out[1][1][k]), k
+    for a, b in zip(out[0][2], out[1][2]):
+        assert np.array_equal(a, b)
 
 
 def test_title_training_trajectory_matches_oracle():

@@ -203,6 +203,12 @@ def test_cli_host_side_reaches_the_device_boundary(tmp_path, monkeypatch, mode):
     (tmp_path / "run1").mkdir()
     (tmp_path / "run1" / "config.ini").write_text(ini.format(data=str(tmp_path / "data"), res=str(tmp_path / "res")))
     monkeypatch.chdir(tmp_path)
+    if mode == "--challenge":
+        # no title checkpoint: fails like the reference's saver.restore (main_challenge.py:69), not a silent DAE-only run
+        with pytest.raises(FileNotFoundError, match="title checkpoint"):
+            cli.main(["--dir", "run1", mode])
+        cfg = tmp_path / "run1" / "config.ini"
+        cfg.write_text(cfg.read_text().replace("[CHALLENGE]", "[CHALLENGE]\ndae_only = True"))
     with pytest.raises(_lib.DaeError, match="no CUDA device"):
         cli.main(["--dir", "run1", mode])
     assert "mode]" in (tmp_path / "run1" / "log.txt").read_text()
