@@ -231,6 +231,13 @@ int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, const float* x_
                              const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
                              const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
                              float title_keep_prob, float* cost_out);
+/* The same step pipelined like dae_model_train_step_async: stages this batch while the previous step runs, returns the
+ * PREVIOUS step's cost (*has_prev = 0 on the first call); dae_title_train_flush returns the last pending one. */
+int32_t dae_title_train_step_async(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                   const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
+                                   const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
+                                   float title_keep_prob, float* prev_cost_out, int32_t* has_prev);
+int32_t dae_title_train_flush(dae_title* t, float* cost_out, int32_t* has_cost);
 /* sess.run(y_pred, {..., titles, titles_use, keep probabilities 1}) -> [batch, n_cols] fp32.
  *                                                                   main_train.py:69-79; main_challenge.py:80-85 */
 int32_t dae_title_predict(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x, const int64_t* titles,

@@ -73,6 +73,8 @@ SIGNATURES = {
     "dae_title_set_params": (_I32, [_P, C.POINTER(_P)]),
     "dae_title_get_params": (_I32, [_P, C.POINTER(_P)]),
     "dae_title_train_step": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _I32, _F, _F, _F, C.POINTER(_F)]),
+    "dae_title_train_step_async": (_I32, [_P, _P, _P, _I64, _P, _P, _I64, _P, _P, _I32, _F, _F, _F, C.POINTER(_F), C.POINTER(_I32)]),
+    "dae_title_train_flush": (_I32, [_P, C.POINTER(_F), C.POINTER(_I32)]),
     "dae_title_predict": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _I32, _P]),
     "dae_title_recommend": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P, _I32, _P, _P]),
     "dae_title_evaluate": (_I32, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _P]),

@@ -22,6 +22,8 @@ struct dae_title {
     size_t blk_off[2] = {0, 0};
     bool trainable = true;
     cudaStream_t st = nullptr;
+    cudaStream_t st_cnn = nullptr;     // the CNN's backward + small Adam updates run here, under the output layer's HBM-bound update
+    cudaEvent_t ev_dfeat = nullptr, ev_cnn = nullptr;
     // variables (fp32 masters), TF1-Adam moments, gradients
     float *emb = nullptr, *conv_W = nullptr, *conv_b = nullptr, *W_out = nullptr, *b_out = nullptr;
     float *m_emb = nullptr, *m_conv_W = nullptr, *m_conv_b = nullptr, *m_W_out = nullptr, *m_b_out = nullptr;
@@ -31,9 +33,17 @@ struct dae_title {
     float b1_pow = kBeta1, b2_pow = kBeta2;
     long long step = 0;
     // activations / workspaces
-    long long *titles = nullptr, *h_titles = nullptr;
+    long long *titles = nullptr, *h_titles = nullptr;      // slot of the call in flight (points into the pairs below)
     float *titles_use = nullptr, *h_titles_use = nullptr;
-    float *dx = nullptr;
+    long long *titles2[2] = {nullptr, nullptr}, *h_titles2[2] = {nullptr, nullptr};   // per staging slot
+    float *titles_use2[2] = {nullptr, nullptr}, *h_titles_use2[2] = {nullptr, nullptr};
+    cudaEvent_t ev_titles[2] = {nullptr, nullptr};        // the slot's pinned mirrors have been copied to the device
+    cudaEvent_t ev_cost[2] = {nullptr, nullptr};
+    float* cost_ring = nullptr;                            // pinned [2]
+    int* err_ring = nullptr;                               // pinned [2]
+    int async_slot = 1;
+    bool async_pending = false;
+    float *dx = nullptr, *conv_WT = nullptr;
     float *feat = nullptr, *d = nullptr, *w_t = nullptr, *w_p = nullptr, *dh_partial = nullptr, *scratch = nullptr;
     unsigned char* argpos = nullptr;
     __nv_bfloat16 *feat_d = nullptr, *feat_dT = nullptr, *dzT = nullptr;
@@ -65,6 +75,9 @@ extern "C" int32_t dae_title_create(dae_model* dae, const dae_title_config* cfg,
     ensure_loaded();
     dae_title* t = new dae_title();
     t->dae = dae; t->cfg = *cfg; t->st = dae->st;
+    CK(cudaStreamCreateWithFlags(&t->st_cnn, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&t->ev_dfeat, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&t->ev_cnn, cudaEventDisableTiming));
     t->N = dae->N; t->H = dae->H; t->Bmax = dae->Bmax;
     t->trainable = cfg->trainable != 0;
     if (t->trainable && !dae->needs_y) { delete t; return fail("training the title branch needs a DAE created with trainable = 2"); }
@@ -105,15 +118,23 @@ extern "C" int32_t dae_title_create(dae_model* dae, const dae_title_config* cfg,
         TRY(dalloc(t, &t->dh_partial, (size_t)2 * t->nsplit * kMaxBpad * 256));
         TRY(dalloc(t, &t->d, (size_t)B * D));
         TRY(dalloc(t, &t->dx, (size_t)B * s.L * s.E));
+        TRY(dalloc(t, &t->conv_WT, off));
         TRY(dalloc(t, &t->loss_partial, 148 * 2));
         TRY(dalloc(t, &t->cost, 1));
     }
-    TRY(dalloc(t, &t->titles, (size_t)B * s.L)); TRY(dalloc(t, &t->titles_use, B));
+    for (int k = 0; k < 2; ++k) {
+        TRY(dalloc(t, &t->titles2[k], (size_t)B * s.L)); TRY(dalloc(t, &t->titles_use2[k], B));
+        CK(cudaMallocHost(reinterpret_cast<void**>(&t->h_titles2[k]), sizeof(long long) * B * s.L)); t->host_allocs.push_back(t->h_titles2[k]);
+        CK(cudaMallocHost(reinterpret_cast<void**>(&t->h_titles_use2[k]), sizeof(float) * B)); t->host_allocs.push_back(t->h_titles_use2[k]);
+        CK(cudaEventCreateWithFlags(&t->ev_titles[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&t->ev_cost[k], cudaEventDisableTiming));
+    }
+    t->titles = t->titles2[0]; t->titles_use = t->titles_use2[0]; t->h_titles = t->h_titles2[0]; t->h_titles_use = t->h_titles_use2[0];
+    CK(cudaMallocHost(reinterpret_cast<void**>(&t->cost_ring), sizeof(float) * 2)); t->host_allocs.push_back(t->cost_ring);
+    CK(cudaMallocHost(reinterpret_cast<void**>(&t->err_ring), sizeof(int) * 2)); t->host_allocs.push_back(t->err_ring);
     TRY(dalloc(t, &t->feat, (size_t)B * D)); TRY(dalloc(t, &t->argpos, (size_t)B * D));
     TRY(dalloc(t, &t->feat_d, (size_t)kMaxBpad * kTitleFpad)); TRY(dalloc(t, &t->feat_dT, (size_t)kTitleFpad * kMaxBpad));
     TRY(dalloc(t, &t->w_t, kMaxBpad)); TRY(dalloc(t, &t->w_p, kMaxBpad));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&t->h_titles), sizeof(long long) * B * s.L)); t->host_allocs.push_back(t->h_titles);
-    CK(cudaMallocHost(reinterpret_cast<void**>(&t->h_titles_use), sizeof(float) * B)); t->host_allocs.push_back(t->h_titles_use);
     CK(cudaMallocHost(reinterpret_cast<void**>(&t->cost_host), sizeof(float))); t->host_allocs.push_back(t->cost_host);
     CK(cudaStreamSynchronize(t->st));
     *out = t;
@@ -123,6 +144,13 @@ extern "C" int32_t dae_title_create(dae_model* dae, const dae_title_config* cfg,
 extern "C" void dae_title_destroy(dae_title* t) {
     if (!t) return;
     cudaStreamSynchronize(t->st);
+    if (t->st_cnn) { cudaStreamSynchronize(t->st_cnn); cudaStreamDestroy(t->st_cnn); }
+    if (t->ev_dfeat) cudaEventDestroy(t->ev_dfeat);
+    if (t->ev_cnn) cudaEventDestroy(t->ev_cnn);
+    for (int k = 0; k < 2; ++k) {
+        if (t->ev_titles[k]) cudaEventDestroy(t->ev_titles[k]);
+        if (t->ev_cost[k]) cudaEventDestroy(t->ev_cost[k]);
+    }
     for (void* p : t->dev_allocs) cudaFree(p);
     for (void* p : t->host_allocs) cudaFreeHost(p);
     delete t;
@@ -171,6 +199,7 @@ extern "C" int32_t dae_title_set_params(dae_title* t, const float* const* arrays
     out_layer_transpose(t, t->scratch, t->W_out, true);
     CK(cudaMemcpyAsync(t->b_out, arrays[2 + 2 * s.n_widths], sizeof(float) * t->N, cudaMemcpyHostToDevice, t->st));
     refresh_out_shadow(t);
+    if (t->conv_WT) launch_conv_transpose(t->conv_W, t->conv_WT, t->shape, t->st);
     CK(cudaStreamSynchronize(t->st));
     return 0;
 }
@@ -210,6 +239,7 @@ extern "C" int32_t dae_title_init(dae_title* t, uint64_t seed) {
     ++stream;
     launch_trunc_normal(t->b_out, 1, t->N, t->N, sd(t->N, t->N), seed, stream++, t->st);
     refresh_out_shadow(t);
+    if (t->conv_WT) launch_conv_transpose(t->conv_W, t->conv_WT, t->shape, t->st);
     t->launches += 3 + 2 * s.n_widths;
     CK(cudaStreamSynchronize(t->st));
     return 0;
@@ -218,23 +248,31 @@ extern "C" int32_t dae_title_init(dae_title* t, uint64_t seed) {
 // stage the batch, run the constant DAE's encoder and the character CNN; leaves h_d, feat_d, w_t, w_p ready
 static int title_forward(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x, const int64_t* y_pos,
                          const float* y_val, int64_t nnz_y, const int64_t* titles, const float* titles_use, int32_t batch,
-                         float kp, float kp_in, float kp_t, bool with_y) {
+                         float kp, float kp_in, float kp_t, bool with_y, int slot = 0) {
     dae_model* m = t->dae;
     if (!titles || !titles_use) return fail("null titles");
     if (batch <= 0 || batch > t->Bmax) return fail("batch %d outside (0, %d]", batch, t->Bmax);
     if (!(kp > 0.f) || !(kp_in > 0.f) || !(kp_t > 0.f)) return fail("keep probabilities must be > 0");
-    TRY(stage_impl(m, 0, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch, with_y));
+    TRY(stage_impl(m, slot, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, batch, with_y));
     const CnnShape& s = t->shape;
-    CK(cudaStreamSynchronize(t->st));                     // the pinned title mirrors of the previous call are free
+    t->titles = t->titles2[slot]; t->titles_use = t->titles_use2[slot];
+    t->h_titles = t->h_titles2[slot]; t->h_titles_use = t->h_titles_use2[slot];
+    CK(cudaEventSynchronize(t->ev_titles[slot]));         // this slot's pinned title mirrors have left for the device
     memcpy(t->h_titles, titles, sizeof(long long) * batch * s.L);
     memcpy(t->h_titles_use, titles_use, sizeof(float) * batch);
+    // (on the main stream: the slot's device copies are only overwritten after the step that read them two calls ago)
     CK(cudaMemcpyAsync(t->titles, t->h_titles, sizeof(long long) * batch * s.L, cudaMemcpyHostToDevice, t->st));
     CK(cudaMemcpyAsync(t->titles_use, t->h_titles_use, sizeof(float) * batch, cudaMemcpyHostToDevice, t->st));
+    CK(cudaEventRecord(t->ev_titles[slot], t->st));
     const int bpad = round_up(batch, 64);
+    if (t->last_batch != batch) {                         // padding rows / columns of the operand copies must read zero
+        CK(cudaMemsetAsync(t->feat_d, 0, sizeof(__nv_bfloat16) * (size_t)kMaxBpad * kTitleFpad, t->st));
+        CK(cudaMemsetAsync(t->feat_dT, 0, sizeof(__nv_bfloat16) * (size_t)kTitleFpad * kMaxBpad, t->st));
+    }
     m->step = t->step;                                    // dropout masks are keyed by the title model's step
-    CK(cudaStreamWaitEvent(t->st, m->slots[0].prepared, 0));
-    run_encode(m, 0, bpad, bpad, kp, kp_in, 0, false);
-    if (with_y) build_ybits(m, 0, batch, bpad);
+    CK(cudaStreamWaitEvent(t->st, m->slots[slot].prepared, 0));
+    run_encode(m, slot, bpad, bpad, kp, kp_in, 0, false);
+    if (with_y) build_ybits(m, slot, batch, bpad);
     CnnFwdArgs c{};
     c.titles = t->titles; c.emb = t->emb; c.conv_W = t->conv_W; c.conv_b = t->conv_b; c.shape = s;
     c.feat = t->feat; c.argpos = t->argpos; c.feat_d = t->feat_d; c.feat_dT = t->feat_dT; c.B = batch; c.bpad = bpad;
@@ -257,16 +295,18 @@ static TitleTileArgs tile_args(dae_title* t, int batch) {
 
 // sess.run([model.optimizer, model.cost], {x, y, titles, keep_prob, title keep_prob, input_keep_prob, titles_use})
 //                                                                        main_train.py:214-221
-extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
-                                        const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
-                                        const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
-                                        float title_keep_prob, float* cost_out) {
-    if (!t || !t->trainable) return fail("title model is not trainable");
+extern "C" int32_t dae_title_train_flush(dae_title* t, float* cost_out, int32_t* has_cost);
+// one title-mode train step from staging slot `slot`; sync: wait for it and return its cost, else leave cost / error flag
+// in the slot's ring entries behind ev_cost[slot]
+static int title_train_impl(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                            const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
+                            const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
+                            float title_keep_prob, int slot, bool sync, float* cost_out) {
     dae_model* m = t->dae;
     TRY(title_forward(t, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, titles, titles_use, batch, keep_prob, input_keep_prob,
-                      title_keep_prob, true));
+                      title_keep_prob, true, slot));
     const int bpad = round_up(batch, 64), N = t->N;
-    const Slot& sl = m->slots[0];
+    const Slot& sl = m->slots[slot];
     TitleTileArgs a = tile_args(t, batch);
     a.ybits = m->ybits; a.ywords = bpad / 32; a.dzT = t->dzT; a.db_out = t->g_b_out; a.loss_partial = t->loss_partial;
     a.inv_batch = 1.0f / (float)batch;
@@ -293,6 +333,13 @@ extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, cons
         t->launches += 1;
     }
     ph_end(m, PH_T_DFEAT, t->st);
+    // fork: everything behind d cost / d feat_d (CNN backward, the small Adam updates) is latency-bound CUDA-core work that
+    // runs on its own stream UNDER the output layer's HBM-bound update; profiled steps keep it on the main stream
+    cudaStream_t sc = m->profiling ? t->st : t->st_cnn;
+    if (sc != t->st) {
+        CK(cudaEventRecord(t->ev_dfeat, t->st));
+        CK(cudaStreamWaitEvent(sc, t->ev_dfeat, 0));
+    }
     // Output layer: dW_out = dz_t^T . feat_d per dense column block (feature columns [0, 256) and [256, 256 + hb[1])).
     // Default: the block's dW tile stays in tensor memory and the dense TF1 Adam is applied from there (k_dw_adam_fused):
     // dW_out never exists in HBM.  Debug bit 14: dW_out through HBM (buffer "g_W_out", same block layout) +
@@ -322,32 +369,89 @@ extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, cons
     }
     if (two_kernel) refresh_out_shadow(t);
     ph_end(m, PH_T_DW_ADAM, t->st);
-    ph_begin(m, PH_T_CNN_BWD, t->st);
+    ph_begin(m, PH_T_CNN_BWD, sc);
     CnnBwdArgs b{};
     b.titles = t->titles; b.emb = t->emb; b.conv_W = t->conv_W; b.shape = t->shape; b.dh_partial = t->dh_partial;
     b.nsplit = t->nsplit; b.bpad = bpad; b.B = batch; b.feat = t->feat; b.argpos = t->argpos; b.kp_t = title_keep_prob;
-    b.seed = m->cfg.seed; b.step = (unsigned long long)t->step; b.row_offset = 0; b.d = t->d; b.dx = t->dx;
+    b.seed = m->cfg.seed; b.step = (unsigned long long)t->step; b.row_offset = 0; b.d = t->d; b.dx = t->dx; b.conv_WT = t->conv_WT;
     b.g_emb = t->g_emb; b.g_conv_W = t->g_conv_W; b.g_conv_b = t->g_conv_b;
-    launch_charcnn_bwd(b, t->st);
-    ph_end(m, PH_T_CNN_BWD, t->st);
-    t->launches += 3;
-
-    ph_begin(m, PH_T_ADAM_SMALL, t->st);
-    ad.row_len = 1;
-    const CnnShape& s = t->shape;
-    ad.w = t->b_out; ad.m = t->m_b_out; ad.v = t->v_b_out; ad.g = t->g_b_out; ad.n = N; launch_adam(ad, t->st);
-    ad.w = t->emb; ad.m = t->m_emb; ad.v = t->v_emb; ad.g = t->g_emb; ad.n = (long long)s.C * s.E; launch_adam(ad, t->st);
-    ad.w = t->conv_W; ad.m = t->m_conv_W; ad.v = t->v_conv_W; ad.g = t->g_conv_W; ad.n = t->n_conv_w; launch_adam(ad, t->st);
-    ad.w = t->conv_b; ad.m = t->m_conv_b; ad.v = t->v_conv_b; ad.g = t->g_conv_b; ad.n = t->D; launch_adam(ad, t->st);
-    ph_end(m, PH_T_ADAM_SMALL, t->st);
+    launch_charcnn_bwd(b, sc);
+    ph_end(m, PH_T_CNN_BWD, sc);
     t->launches += 4;
+
+    ph_begin(m, PH_T_ADAM_SMALL, sc);
+    ad.row_len = 1; ad.g = nullptr;
+    const CnnShape& s = t->shape;
+    ad.w = t->emb; ad.m = t->m_emb; ad.v = t->v_emb; ad.g = t->g_emb; ad.n = (long long)s.C * s.E; launch_adam(ad, sc);
+    ad.w = t->conv_W; ad.m = t->m_conv_W; ad.v = t->v_conv_W; ad.g = t->g_conv_W; ad.n = t->n_conv_w; launch_adam(ad, sc);
+    ad.w = t->conv_b; ad.m = t->m_conv_b; ad.v = t->v_conv_b; ad.g = t->g_conv_b; ad.n = t->D; launch_adam(ad, sc);
+    launch_conv_transpose(t->conv_W, t->conv_WT, t->shape, sc);
+    ph_end(m, PH_T_ADAM_SMALL, sc);
+    if (sc != t->st) CK(cudaEventRecord(t->ev_cnn, sc));
+    ad.w = t->b_out; ad.m = t->m_b_out; ad.v = t->v_b_out; ad.g = t->g_b_out; ad.n = N; launch_adam(ad, t->st);
+    if (sc != t->st) CK(cudaStreamWaitEvent(t->st, t->ev_cnn, 0));     // join: the next step's CNN forward reads the updated variables
+    t->launches += 5;
     t->b1_pow *= kBeta1; t->b2_pow *= kBeta2; t->step += 1;
 
+    if (!sync) {
+        CK(cudaMemcpyAsync(t->cost_ring + slot, t->cost, sizeof(float), cudaMemcpyDeviceToHost, t->st));
+        CK(cudaMemcpyAsync(t->err_ring + slot, m->err, sizeof(int), cudaMemcpyDeviceToHost, t->st));
+        CK(cudaEventRecord(t->ev_cost[slot], t->st));
+        return 0;
+    }
     CK(cudaMemcpyAsync(t->cost_host, t->cost, sizeof(float), cudaMemcpyDeviceToHost, t->st));
     TRY(check_device_flag(m));
     ph_collect(m);
     if (cost_out) *cost_out = *t->cost_host;
     return 0;
+}
+
+extern "C" int32_t dae_title_train_step(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                        const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
+                                        const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
+                                        float title_keep_prob, float* cost_out) {
+    if (!t || !t->trainable) return fail("title model is not trainable");
+    if (t->async_pending) TRY(dae_title_train_flush(t, nullptr, nullptr));       // drain a pipelined step first
+    return title_train_impl(t, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, titles, titles_use, batch, keep_prob, input_keep_prob,
+                            title_keep_prob, 0, true, cost_out);
+}
+
+static int title_collect(dae_title* t, int slot, float* cost_out) {
+    CK(cudaEventSynchronize(t->ev_cost[slot]));
+    const int e = t->err_ring[slot];
+    if (e != 0) {
+        cudaMemsetAsync(t->dae->err, 0, sizeof(int), t->st);
+        return fail("invalid sparse batch (flag %d)", e);
+    }
+    if (cost_out) *cost_out = t->cost_ring[slot];
+    return 0;
+}
+
+// The same step pipelined for the training loop (main_train.py:214-223 only accumulates the cost): the batch is staged into
+// the slot the device is not using while the previous step still runs, the step is enqueued, and the PREVIOUS step's cost
+// comes back (*has_prev = 0 on the first call).  dae_title_train_flush returns the last pending cost.
+extern "C" int32_t dae_title_train_step_async(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x,
+                                              const int64_t* y_pos, const float* y_val, int64_t nnz_y, const int64_t* titles,
+                                              const float* titles_use, int32_t batch, float keep_prob, float input_keep_prob,
+                                              float title_keep_prob, float* prev_cost_out, int32_t* has_prev) {
+    if (!t || !t->trainable) return fail("title model is not trainable");
+    const int slot = t->async_slot ^ 1;
+    TRY(title_train_impl(t, x_pos, x_val, nnz_x, y_pos, y_val, nnz_y, titles, titles_use, batch, keep_prob, input_keep_prob,
+                         title_keep_prob, slot, false, nullptr));
+    const bool had = t->async_pending;
+    t->async_slot = slot;
+    t->async_pending = true;
+    if (has_prev) *has_prev = had ? 1 : 0;
+    if (had) return title_collect(t, slot ^ 1, prev_cost_out);
+    return 0;
+}
+
+extern "C" int32_t dae_title_train_flush(dae_title* t, float* cost_out, int32_t* has_cost) {
+    if (!t) return fail("null model");
+    if (has_cost) *has_cost = t->async_pending ? 1 : 0;
+    if (!t->async_pending) return 0;
+    t->async_pending = false;
+    return title_collect(t, t->async_slot, cost_out);
 }
 
 static int title_scores(dae_title* t, const int64_t* x_pos, const float* x_val, int64_t nnz_x, const int64_t* titles,

@@ -282,6 +282,7 @@ void launch_mix_weights(const float* rowsum, const float* titles_use, float kp_i
 struct CnnBwdArgs {
     const long long* titles;
     const float* emb; const float* conv_W;
+    const float* conv_WT;                // conv_W with every width block transposed to [f][k][e] (launch_conv_transpose)
     CnnShape shape;
     const float* dh_partial;             // [2 halves][nsplit][bpad][256] split-K partials of d cost / d feat_d
     int nsplit, bpad, B;
@@ -294,6 +295,7 @@ struct CnnBwdArgs {
     float* g_emb; float* g_conv_W; float* g_conv_b;
 };
 void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st);
+void launch_conv_transpose(const float* W, float* WT, const CnnShape& s, cudaStream_t st);
 // columns [col0, col0 + ncols) (ncols <= 0: all) of a [rows, row_len] variable -> w[r * ld + (c - col0)]
 void launch_trunc_normal(float* w, long long rows, int row_len, int ld, float stddev, unsigned long long seed,
                          unsigned stream_id, cudaStream_t st, int col0 = 0, int ncols = 0);

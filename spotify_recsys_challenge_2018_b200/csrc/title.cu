@@ -81,8 +81,148 @@ k_charcnn_fwd(const long long* __restrict__ titles, const float* __restrict__ em
     }
 }
 
+// The same forward, register-tiled (one launch per filter width): CTA = 4 titles, thread = (filter f, position half).
+// A weight is loaded ONCE per thread (one step ahead of its use) and feeds 4 titles x NP positions; the embedded titles sit
+// in shared memory padded to float4 rows, so one 16-byte broadcast load feeds four FMAs.  NP = ceil(P / 2) is a template
+// parameter and the second half starts at P - NP (one position may be computed by both halves): no predicated-off
+// FMAs.  Same (k, e) summation order as the kernel above: bit-identical features.  92 M -> ~30 M warp instructions per
+// 256 titles of the shipped shape (the kernel is issue-bound).
+constexpr int kCnnG = 4;           // titles per CTA
+template <int NP>
+__global__ void __launch_bounds__(256)
+k_charcnn_fwd_tiled(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ conv_W,
+                    const float* __restrict__ conv_b, const CnnShape s, int wi, float* __restrict__ feat,
+                    unsigned char* __restrict__ argpos, __nv_bfloat16* __restrict__ feat_d, __nv_bfloat16* __restrict__ feat_dT,
+                    int B, int bpad, float kp_t, unsigned long long seed, unsigned long long step, int row_offset) {
+    extern __shared__ __align__(16) float s_x[];   // [kCnnG][L][Epad]: embedded titles, pad ids zero
+    const int Epad = (s.E + 3) & ~3;
+    const int b0 = blockIdx.x * kCnnG;
+    const int w = s.width[wi], P = s.L - w + 1, D = s.F * s.n_widths;
+    const int half = threadIdx.x >= s.F ? 1 : 0, f = threadIdx.x - half * s.F;     // threads [0, F) / [F, 2F)
+    const bool active = threadIdx.x < 2 * s.F;
+    float* s_best = s_x + kCnnG * s.L * Epad;                 // [kCnnG][F] best of the second half
+    int* s_bpos = reinterpret_cast<int*>(s_best + kCnnG * s.F);
+    for (int i = threadIdx.x; i < kCnnG * s.L * Epad; i += blockDim.x) {
+        const int g = i / (s.L * Epad), r = i - g * s.L * Epad;
+        const int pos = r / Epad, e = r - pos * Epad;
+        float v = 0.f;
+        if (b0 + g < B && e < s.E) {
+            const long long id = titles[(size_t)(b0 + g) * s.L + pos];
+            if (id >= 0 && id < s.C) v = emb[(size_t)id * s.E + e];              // pad id -1 -> zero vector
+        }
+        s_x[i] = v;
+    }
+    __syncthreads();
+    const int p0 = half ? P - NP : 0;                         // 2 * NP >= P: the halves may share one position
+    float acc[kCnnG][NP];
+#pragma unroll
+    for (int g = 0; g < kCnnG; ++g)
+#pragma unroll
+        for (int pi = 0; pi < NP; ++pi) acc[g][pi] = 0.f;
+    if (active) {
+        const float* W = conv_W + s.w_off[wi] + f;            // [k][e][f]: threads read consecutive f
+        // the weights of step (k, e4) are loaded one step ahead: their L2 latency hides under the previous step's FMAs
+        const int n_e4 = Epad >> 2, n_steps = w * n_e4;
+        float wn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wn[u] = u < s.E ? __ldg(W + (size_t)u * s.F) : 0.f;
+        for (int stp = 0; stp < n_steps; ++stp) {
+            const int k = stp / n_e4, e4 = (stp - k * n_e4) << 2;
+            float wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = wn[u];
+            if (stp + 1 < n_steps) {
+                const int k1 = (stp + 1) / n_e4, e1 = ((stp + 1) - k1 * n_e4) << 2;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) wn[u] = e1 + u < s.E ? __ldg(W + (size_t)(k1 * s.E + e1 + u) * s.F) : 0.f;
+            }
+            const float* xb = s_x + (p0 + k) * Epad + e4;
+#pragma unroll
+            for (int pi = 0; pi < NP; ++pi) {
+#pragma unroll
+                for (int g = 0; g < kCnnG; ++g) {
+                    const float4 x = *reinterpret_cast<const float4*>(xb + (g * s.L + pi) * Epad);
+                    acc[g][pi] = fmaf(x.x, wv[0], acc[g][pi]);
+                    acc[g][pi] = fmaf(x.y, wv[1], acc[g][pi]);
+                    acc[g][pi] = fmaf(x.z, wv[2], acc[g][pi]);
+                    acc[g][pi] = fmaf(x.w, wv[3], acc[g][pi]);
+                }
+            }
+        }
+    }
+    float best[kCnnG];
+    int bpos[kCnnG];
+    const float bias = active ? conv_b[wi * s.F + f] : 0.f;
+#pragma unroll
+    for (int g = 0; g < kCnnG; ++g) {
+        best[g] = -1.f;                                       // relu output >= 0: the first position always wins over -1
+        bpos[g] = p0;
+#pragma unroll
+        for (int pi = 0; pi < NP; ++pi) {
+            const float v = fmaxf(acc[g][pi] + bias, 0.f);                       // bias_add, relu, reduce_max (Char_CNN.py:50-58)
+            if (v > best[g]) { best[g] = v; bpos[g] = p0 + pi; }
+        }
+        if (active && half) { s_best[g * s.F + f] = best[g]; s_bpos[g * s.F + f] = bpos[g]; }
+    }
+    __syncthreads();
+    if (active && !half) {
+        const int j = wi * s.F + f;
+#pragma unroll
+        for (int g = 0; g < kCnnG; ++g) {
+            const int b = b0 + g;
+            if (b >= B) continue;
+            const float v1 = s_best[g * s.F + f];
+            if (v1 > best[g]) { best[g] = v1; bpos[g] = s_bpos[g * s.F + f]; }   // ties keep the earlier position, like a scan
+            feat[(size_t)b * D + j] = best[g];
+            argpos[(size_t)b * D + j] = static_cast<unsigned char>(bpos[g]);
+            // dropout (Char_CNN.py:67) and the bf16 operand copies [bpad, 512] / [512, bpad]
+            const bool keep = philox_keep(seed, kStreamTitle, step, static_cast<uint32_t>(b + row_offset),
+                                          static_cast<uint32_t>(j), kp_t);
+            const __nv_bfloat16 hb = __float2bfloat16(keep ? __fdiv_rn(best[g], kp_t) : 0.f);
+            feat_d[(size_t)b * kTitleFpad + j] = hb;
+            feat_dT[(size_t)j * bpad + b] = hb;
+        }
+    }
+}
+
+template <int NP>
+static void launch_fwd_tiled_np(const CnnFwdArgs& a, int wi, cudaStream_t st) {
+    const int Epad = (a.shape.E + 3) & ~3;
+    const size_t smem = sizeof(float) * (kCnnG * a.shape.L * Epad + kCnnG * a.shape.F) + sizeof(int) * kCnnG * a.shape.F;
+    k_charcnn_fwd_tiled<NP><<<(a.B + kCnnG - 1) / kCnnG, 256, smem, st>>>(
+        a.titles, a.emb, a.conv_W, a.conv_b, a.shape, wi, a.feat, a.argpos, a.feat_d, a.feat_dT, a.B, a.bpad, a.kp_t, a.seed,
+        a.step, a.row_offset);
+}
+
 void launch_charcnn_fwd(const CnnFwdArgs& a, cudaStream_t st) {
     const int D = a.shape.F * a.shape.n_widths;
+    bool tiled = a.shape.F <= 128;
+    for (int i = 0; i < a.shape.n_widths; ++i) {
+        const int np = (a.shape.L - a.shape.width[i] + 2) / 2;
+        tiled = tiled && np >= 1 && np <= 13;
+    }
+    if (tiled) {
+        // padding rows / columns of the operand copies are zero from allocation and never written (api_title.cu re-zeroes
+        // them when the batch size changes); widest filters first: their CTAs take longest
+        for (int i = a.shape.n_widths - 1; i >= 0; --i) {
+            switch ((a.shape.L - a.shape.width[i] + 2) / 2) {
+                case 1: launch_fwd_tiled_np<1>(a, i, st); break;
+                case 2: launch_fwd_tiled_np<2>(a, i, st); break;
+                case 3: launch_fwd_tiled_np<3>(a, i, st); break;
+                case 4: launch_fwd_tiled_np<4>(a, i, st); break;
+                case 5: launch_fwd_tiled_np<5>(a, i, st); break;
+                case 6: launch_fwd_tiled_np<6>(a, i, st); break;
+                case 7: launch_fwd_tiled_np<7>(a, i, st); break;
+                case 8: launch_fwd_tiled_np<8>(a, i, st); break;
+                case 9: launch_fwd_tiled_np<9>(a, i, st); break;
+                case 10: launch_fwd_tiled_np<10>(a, i, st); break;
+                case 11: launch_fwd_tiled_np<11>(a, i, st); break;
+                case 12: launch_fwd_tiled_np<12>(a, i, st); break;
+                default: launch_fwd_tiled_np<13>(a, i, st); break;
+            }
+        }
+        return;
+    }
     const int threads = ((D > kTitleFpad ? D : kTitleFpad) + 31) / 32 * 32;
     k_charcnn_fwd<<<a.bpad, threads, sizeof(float) * a.shape.L * a.shape.E, st>>>(
         a.titles, a.emb, a.conv_W, a.conv_b, a.shape, a.feat, a.argpos, a.feat_d, a.feat_dT, a.B, a.bpad, a.kp_t, a.seed,
@@ -133,68 +273,115 @@ __global__ void k_title_dfeat(const float* __restrict__ partial, int nsplit, int
 }
 
 // dW[k][e][f] = sum_b x[b, arg[b,f] + k, e] * d[b, f];  db[f] = sum_b d[b, f].  One CTA per feature: no atomics.
+// Everything the inner loop touches is staged in shared memory first (the feature's gradient column, the character ids
+// under its arg-max windows, the embedding table): the first version chased titles -> embedding through global memory
+// once per title and thread (124 us per step); summation order over b unchanged.
 __global__ void __launch_bounds__(512)
 k_charcnn_bwd_w(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ d,
                 const unsigned char* __restrict__ argpos, const CnnShape s, int B, float* __restrict__ g_W,
                 float* __restrict__ g_b) {
+    extern __shared__ __align__(16) float s_mem[];
+    float* s_emb = s_mem;                                       // [C][E]
+    float* s_d = s_emb + s.C * s.E;                             // [B]
+    short* s_id = reinterpret_cast<short*>(s_d + B);            // [B][w]
     const int j = blockIdx.x;
     const int D = s.F * s.n_widths;
     const int wi = j / s.F, f = j - wi * s.F;
     const int w = s.width[wi];
-    const int t = threadIdx.x;                     // (k, e) pair
-    const int k = t / s.E, e = t - k * s.E;
+    const int t = threadIdx.x;
+    for (int i = t; i < s.C * s.E; i += blockDim.x) s_emb[i] = emb[i];
+    for (int b = t; b < B; b += blockDim.x) s_d[b] = d[(size_t)b * D + j];
+    for (int i = t; i < B * w; i += blockDim.x) {
+        const int b = i / w, k = i - b * w;
+        const long long id = titles[(size_t)b * s.L + argpos[(size_t)b * D + j] + k];
+        s_id[i] = (id >= 0 && id < s.C) ? (short)id : (short)-1;
+    }
+    __syncthreads();
+    const int k = t / s.E, e = t - k * s.E;                     // (k, e) pair
     float acc = 0.f, accb = 0.f;
     for (int b = 0; b < B; ++b) {
-        const float dv = d[(size_t)b * D + j];
-        if (dv == 0.f) continue;                   // uniform over the CTA
+        const float dv = s_d[b];
+        if (dv == 0.f) continue;                                // uniform over the CTA
         accb += dv;
         if (k < w) {
-            const long long id = titles[(size_t)b * s.L + argpos[(size_t)b * D + j] + k];
-            if (id >= 0 && id < s.C) acc = fmaf(emb[(size_t)id * s.E + e], dv, acc);
+            const int id = s_id[b * w + k];
+            if (id >= 0) acc = fmaf(s_emb[id * s.E + e], dv, acc);
         }
     }
     if (k < w) g_W[s.w_off[wi] + (size_t)(k * s.E + e) * s.F + f] = acc;
     if (t == 0) g_b[wi * s.F + f] = accb;
 }
 
-// demb[c][e] += sum_{j, k : title[b, arg+k] == c} W[k][e][f] * d[b, j].  One CTA per title, positions accumulated in
-// shared memory, then one atomic row add per (position, e).
-__global__ void __launch_bounds__(256)
-k_charcnn_bwd_emb(const long long* __restrict__ titles, const float* __restrict__ conv_W, const float* __restrict__ d,
-                  const unsigned char* __restrict__ argpos, const CnnShape s, float* __restrict__ dx) {
-    extern __shared__ float s_dx[];                // [L][E]
+// conv_W [k][e][f] per width -> conv_WT [f][k][e] (e contiguous): the layout the embedding backward reads coalesced
+__global__ void k_conv_transpose(const float* __restrict__ W, float* __restrict__ WT, const CnnShape s) {
+    const int wi = blockIdx.y;
+    const int w = s.width[wi], n = w * s.E * s.F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int f = i / (w * s.E), ke = i - f * (w * s.E);
+        WT[s.w_off[wi] + i] = W[s.w_off[wi] + (size_t)ke * s.F + f];
+    }
+}
+void launch_conv_transpose(const float* W, float* WT, const CnnShape& s, cudaStream_t st) {
+    k_conv_transpose<<<dim3(32, s.n_widths), 256, 0, st>>>(W, WT, s);
+}
+
+// dx[b, pos, e] = sum_{j, k : arg[b,j] + k == pos} W[k][e][f] * d[b, j]: the gradient at the embedded characters of title b.
+// One CTA per title, 8 feature groups x 64 embedding lanes: group jg walks features jg, jg + 8, ... and accumulates into
+// ITS OWN [L][E] slab of shared memory (thread (jg, e) is the only writer of its column: no conflicts, no atomics); the
+// slabs are added in group order.  Weights come from the transposed copy (coalesced over e).
+constexpr int kEmbGroups = 8;
+__global__ void __launch_bounds__(512)
+k_charcnn_bwd_emb(const float* __restrict__ conv_WT, const float* __restrict__ d, const unsigned char* __restrict__ argpos,
+                  const CnnShape s, float* __restrict__ dx) {
+    extern __shared__ __align__(16) float s_mem[];
+    const int LE = s.L * s.E;
+    float* s_dx = s_mem;                                        // [kEmbGroups][L][E]
+    float* s_d = s_dx + kEmbGroups * LE;                        // [D]
     const int b = blockIdx.x;
     const int D = s.F * s.n_widths;
-    for (int i = threadIdx.x; i < s.L * s.E; i += blockDim.x) s_dx[i] = 0.f;
+    for (int i = threadIdx.x; i < kEmbGroups * LE; i += blockDim.x) s_dx[i] = 0.f;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) s_d[j] = d[(size_t)b * D + j];
     __syncthreads();
-    // thread -> embedding column e (strided); loop features: every thread adds its own e, so no smem conflicts
-    for (int e = threadIdx.x; e < s.E; e += blockDim.x) {
-        for (int j = 0; j < D; ++j) {
-            const float dv = d[(size_t)b * D + j];
-            if (dv == 0.f) continue;
+    const int e = threadIdx.x & 63, jg = threadIdx.x >> 6;
+    if (e < s.E) {
+        float* my = s_dx + jg * LE + e;
+        for (int j = jg; j < D; j += kEmbGroups) {
+            const float dv = s_d[j];
+            if (dv == 0.f) continue;                            // uniform over the group's two warps
             const int wi = j / s.F, f = j - wi * s.F;
             const int w = s.width[wi];
             const int p0 = argpos[(size_t)b * D + j];
-            const float* W = conv_W + s.w_off[wi] + f;
-            for (int k = 0; k < w; ++k) s_dx[(p0 + k) * s.E + e] = fmaf(__ldg(W + (size_t)(k * s.E + e) * s.F), dv, s_dx[(p0 + k) * s.E + e]);
+            const float* WT = conv_WT + s.w_off[wi] + (size_t)f * w * s.E + e;
+            for (int k = 0; k < w; ++k) my[(p0 + k) * s.E] = fmaf(__ldg(WT + k * s.E), dv, my[(p0 + k) * s.E]);
         }
     }
     __syncthreads();
-    // d cost / d x[b, pos, :] of this title; k_charcnn_emb_reduce adds the positions of each character in a fixed order
-    for (int i = threadIdx.x; i < s.L * s.E; i += blockDim.x) dx[(size_t)b * s.L * s.E + i] = s_dx[i];
+    for (int i = threadIdx.x; i < LE; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int g = 0; g < kEmbGroups; ++g) v += s_dx[g * LE + i];
+        dx[(size_t)b * LE + i] = v;
+    }
 }
 
-// g_emb[c, e] = sum over (b, pos) with title[b, pos] == c of dx[b, pos, e], in ascending (b, pos): no atomics, bit-reproducible.
-// One WARP per character: the lanes test 32 title positions at a time (ballot), the matches are added in order, lane e
-// (and e + 32, ...) owning its embedding columns.
-__global__ void __launch_bounds__(32)
+// g_emb[c, e] = sum over (b, pos) with title[b, pos] == c of dx[b, pos, e]: no atomics, bit-reproducible.  One CTA per
+// character: the ids are staged in shared memory, each of the 8 warps takes one contiguous eighth of the (b, pos) range
+// (ballot over 32 positions at a time, matches added in ascending order, lane e and e + 32, ... own the embedding columns),
+// and the 8 partial rows are added in warp order.
+__global__ void __launch_bounds__(256)
 k_charcnn_emb_reduce(const long long* __restrict__ titles, const float* __restrict__ dx, int n_pos, int E,
                      float* __restrict__ g_emb) {
-    const int c = blockIdx.x, lane = threadIdx.x;
+    extern __shared__ int s_ids[];                 // [n_pos] then [8][128] partial sums
+    float* s_part = reinterpret_cast<float*>(s_ids + ((n_pos + 31) & ~31));
+    const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < n_pos; i += blockDim.x) s_ids[i] = (int)titles[i];
+    __syncthreads();
+    const int seg = (((n_pos + 7) / 8) + 31) & ~31;
+    const int lo = warp * seg, hi = min(n_pos, lo + seg);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};           // E <= 128
-    for (int i0 = 0; i0 < n_pos; i0 += 32) {
+    for (int i0 = lo; i0 < hi; i0 += 32) {
         const int i = i0 + lane;
-        unsigned hits = __ballot_sync(0xffffffffu, i < n_pos && titles[i] == (long long)c);
+        unsigned hits = __ballot_sync(0xffffffffu, i < hi && s_ids[i] == c);
         while (hits) {
             const int j = i0 + __ffs(hits) - 1;
             hits &= hits - 1;
@@ -204,8 +391,14 @@ k_charcnn_emb_reduce(const long long* __restrict__ titles, const float* __restri
         }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-        if (lane + 32 * u < E) g_emb[(size_t)c * E + lane + 32 * u] = acc[u];
+    for (int u = 0; u < 4; ++u) s_part[warp * 128 + lane + 32 * u] = acc[u];
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) v += s_part[w8 * 128 + e];
+        g_emb[(size_t)c * E + e] = v;
+    }
 }
 
 void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st) {
@@ -214,10 +407,14 @@ void launch_charcnn_bwd(const CnnBwdArgs& a, cudaStream_t st) {
                                                       a.row_offset, a.d);
     int maxw = 0;
     for (int i = 0; i < a.shape.n_widths; ++i) maxw = a.shape.width[i] > maxw ? a.shape.width[i] : maxw;
-    k_charcnn_bwd_w<<<D, (maxw * a.shape.E + 31) / 32 * 32, 0, st>>>(a.titles, a.emb, a.d, a.argpos, a.shape, a.B, a.g_conv_W,
-                                                                     a.g_conv_b);
-    k_charcnn_bwd_emb<<<a.B, 64, sizeof(float) * a.shape.L * a.shape.E, st>>>(a.titles, a.conv_W, a.d, a.argpos, a.shape, a.dx);
-    k_charcnn_emb_reduce<<<a.shape.C, 32, 0, st>>>(a.titles, a.dx, a.B * a.shape.L, a.shape.E, a.g_emb);
+    const size_t smem_w = sizeof(float) * (a.shape.C * a.shape.E + a.B) + sizeof(short) * (size_t)a.B * maxw + 16;
+    k_charcnn_bwd_w<<<D, (maxw * a.shape.E + 31) / 32 * 32, smem_w, st>>>(a.titles, a.emb, a.d, a.argpos, a.shape, a.B, a.g_conv_W,
+                                                                          a.g_conv_b);
+    const size_t smem_e = sizeof(float) * (kEmbGroups * a.shape.L * a.shape.E + D);
+    k_charcnn_bwd_emb<<<a.B, 512, smem_e, st>>>(a.conv_WT, a.d, a.argpos, a.shape, a.dx);
+    const int n_pos = a.B * a.shape.L;
+    k_charcnn_emb_reduce<<<a.shape.C, 256, sizeof(int) * ((n_pos + 31) & ~31) + sizeof(float) * 8 * 128, st>>>(
+        a.titles, a.dx, n_pos, a.shape.E, a.g_emb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,6 +501,12 @@ void launch_transpose_pad(const float* src, float* dst, int D, int N, int ld, in
 void preload_title_cnn() {
     cudaFuncAttributes a;
     PRELOAD_KERNEL(k_charcnn_fwd);
+    PRELOAD_KERNEL(k_charcnn_fwd_tiled<9>);
+    PRELOAD_KERNEL(k_charcnn_fwd_tiled<10>);
+    PRELOAD_KERNEL(k_charcnn_fwd_tiled<11>);
+    PRELOAD_KERNEL(k_charcnn_fwd_tiled<12>);
+    PRELOAD_KERNEL(k_conv_transpose);
+    cudaFuncSetAttribute(k_charcnn_bwd_emb, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     PRELOAD_KERNEL(k_mix_weights);
     PRELOAD_KERNEL(k_title_dfeat);
     PRELOAD_KERNEL(k_charcnn_bwd_w);

@@ -123,15 +123,14 @@ def run(conf, only_testmode):
             else:
                 l = model.train_step_async(art_positions, art_val, y_positions, y_ones, conf.kp, input_kp)
         else:                                                                  # main_train.py:214-221
-            l = model_title.train_step(model, y_positions, np.ones(len(y_positions), np.float32), titles,
-                                       conf.kp, conf.title_kp, input_kp)
+            l = model_title.train_step_async(model, y_positions, np.ones(len(y_positions), np.float32), titles,
+                                             conf.kp, conf.title_kp, input_kp)            # pipelined like the DAE modes
         if l is not None:
             loss += l
         it += 1
         n_seen += conf.batch
         if start_idx > end_idx or end_idx == 0:                               # main_train.py:227
-            if conf.mode in ("pretrain", "dae"):
-                loss += model.flush() or 0.0                                  # the epoch's last step
+            loss += (model.flush() if conf.mode in ("pretrain", "dae") else model_title.flush()) or 0.0   # the epoch's last step
             epoch += 1
             loss = loss / it
             log_write(conf, "epoch " + str(epoch))

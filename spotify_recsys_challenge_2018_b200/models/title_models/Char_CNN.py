@@ -123,6 +123,26 @@ class Char_CNN:
                                                   float(title_keep_prob), C.byref(cost)))
         return float(cost.value)
 
+    def train_step_async(self, dae_model, x_positions, x_vals, titles, keep_prob, title_keep_prob, input_keep_prob,
+                         y_positions=None, y_vals=None, titles_use=1.0):
+        """The same step pipelined: returns the PREVIOUS step's cost (None on the first call) while this one runs;
+        `flush()` returns the last pending cost.  The runner only accumulates the cost (main_train.py:223)."""
+        xp, xv = _coo(x_positions, x_vals)
+        yp, yv = (xp, xv) if y_positions is None else _coo(y_positions, y_vals)
+        B = dae_model.n_batch
+        t, u = self._titles(titles, titles_use, B)
+        cost = C.c_float(); has = C.c_int32()
+        _lib.check(self._lib.dae_title_train_step_async(self._h, _ptr(xp), _ptr(xv), xp.shape[0], _ptr(yp), _ptr(yv),
+                                                        yp.shape[0], _ptr(t), _ptr(u), B, float(keep_prob),
+                                                        float(input_keep_prob), float(title_keep_prob), C.byref(cost),
+                                                        C.byref(has)))
+        return float(cost.value) if has.value else None
+
+    def flush(self):
+        cost = C.c_float(); has = C.c_int32()
+        _lib.check(self._lib.dae_title_train_flush(self._h, C.byref(cost), C.byref(has)))
+        return float(cost.value) if has.value else None
+
     def predict(self, dae_model, x_positions, x_vals, titles, titles_use=1.0, tracks_only=False):
         """`sess.run(y_pred)` with every keep probability 1 (main_train.py:69-79, main_challenge.py:80-85)."""
         xp, xv = _coo(x_positions, x_vals)

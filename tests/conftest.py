@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# several tests run `world` model objects in ONE process on one GPU (the cross-GPU kernels with local peers): give every one
+# of their streams its own hardware queue, or a rank's kernel can be queued behind a peer's spinning barrier kernel
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -177,3 +177,26 @@ def test_title_training_trajectory_matches_oracle():
         tol = 1e-3 if step < 3 else 1e-2
         assert abs(c_gpu - c_ora) <= tol * abs(c_ora), (step, c_gpu, c_ora)
     tm.close(); m.close()
+
+
+def test_title_pipelined_step_equals_synchronous_step():
+    """train_step_async (the runner's call in --title mode) returns the same costs as train_step, one call late, and leaves
+    the same parameters (the title step has no atomics: bit for bit)."""
+    N, T, H, B = 3000, 2500, 64, 128
+    rng = np.random.default_rng(6)
+    steps = []
+    for i in range(5):
+        trk, art, y = random_batch(rng, B, T, N - T, mean_len=15)
+        steps.append((y, np.ones(len(y), np.float32), _titles(rng, B, 25, 41)))
+    conf, dae_o, cnn_o, m, tm = _setup(N, T, H, B, 32, (3, 5, 7), lr=0.01)
+    sync_costs = [tm.train_step(m, y, yv, t, 0.8, 0.7, 0.3) for y, yv, t in steps]
+    p1 = tm.get_params(); tm.close(); m.close()
+    conf, dae_o, cnn_o, m, tm = _setup(N, T, H, B, 32, (3, 5, 7), lr=0.01)
+    got = [tm.train_step_async(m, y, yv, t, 0.8, 0.7, 0.3) for y, yv, t in steps]
+    assert got[0] is None
+    got = got[1:] + [tm.flush()]
+    assert tm.flush() is None
+    p2 = tm.get_params(); tm.close(); m.close()
+    assert got == sync_costs
+    for a, b in zip(p1, p2):
+        assert np.array_equal(a, b)
