@@ -712,6 +712,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     else build_ybits(m, slot, B, bpad);
     barrier(m);                                                               // B1
     CK(cudaEventRecord(s.consumed, m->st));                 // every rank has read this slot: it may be re-prepared
+    if (R > 1) { launch_transpose_hd(m->h_d, m->h_dT, R * bpad, H, m->st); m->launches += 1; }
 
     DecodeArgs d{};
     d.W = m->shadow; d.h_d = m->h_d; d.bias = m->b_dec; d.N = N; d.H = H; d.batch = B; d.bpad = bpad;

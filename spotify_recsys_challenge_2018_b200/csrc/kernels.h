@@ -89,6 +89,8 @@ struct EncodeArgs {
     PeerTable pt;
 };
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st);
+// several ranks: the encode does not store h_d^T remotely; every rank transposes its copy of the global h_d [K, H] after B1
+void launch_transpose_hd(const __nv_bfloat16* h_d, __nv_bfloat16* h_dT, int K, int H, cudaStream_t st);
 
 // y of the GLOBAL batch restricted to the item rows this rank owns, as a bitmask [local rows, K/32 words]:
 // bit (s * bpad + i) of row item_local(c) is set when row i of rank s's target CSR contains column c.

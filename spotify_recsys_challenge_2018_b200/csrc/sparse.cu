@@ -173,14 +173,18 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     const size_t hT_off = (size_t)k * K + row0 + r;
     const size_t h_off = (size_t)(row0 + r) * H + k;
     const int n_dst = bcast ? world : 1;
+    // h_d^T ([H, K], one 2-byte element per thread at a stride of K) is only written here on ONE GPU: with peers, 2-byte
+    // stores over NVLink are one packet each (the 8-GPU encode spent most of its 0.11 ms on them) -- every rank transposes
+    // its own copy of the global h_d after barrier B1 instead (k_transpose_hd)
+    const bool write_hT = !(bcast && world > 1);
     if (r >= B) {   // padding rows of the tensor-core operand
         if (k < H) {
             const __nv_bfloat16 z = __float2bfloat16(0.f);
             for (int s = 0; s < n_dst; ++s) {
                 (bcast ? peer_ptr(pt, s, h_d) : h_d)[h_off] = z;
-                (bcast ? peer_ptr(pt, s, h_dT) : h_dT)[hT_off] = z;
                 (bcast ? peer_ptr(pt, s, h) : h)[h_off] = 0.f;
             }
+            if (write_hT) h_dT[hT_off] = z;
         }
         return;
     }
@@ -272,8 +276,20 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     for (int s2 = 0; s2 < n_dst; ++s2) {
         (bcast ? peer_ptr(pt, s2, h) : h)[h_off] = hv;
         (bcast ? peer_ptr(pt, s2, h_d) : h_d)[h_off] = hb;
-        (bcast ? peer_ptr(pt, s2, h_dT) : h_dT)[hT_off] = hb;
     }
+    if (write_hT) h_dT[hT_off] = hb;
+}
+
+// h_d [K, H] -> h_d^T [H, K] (bf16), 32 x 32 tiles through shared memory: the local transpose of the gathered global batch
+__global__ void k_transpose_hd(const __nv_bfloat16* __restrict__ h_d, __nv_bfloat16* __restrict__ h_dT, int K, int H) {
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += 8) tile[y][threadIdx.x] = h_d[(size_t)(r0 + y) * H + c0 + threadIdx.x];
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += 8) h_dT[(size_t)(c0 + y) * K + r0 + threadIdx.x] = tile[threadIdx.x][y];
+}
+void launch_transpose_hd(const __nv_bfloat16* h_d, __nv_bfloat16* h_dT, int K, int H, cudaStream_t st) {
+    k_transpose_hd<<<dim3(K / 32, H / 32), dim3(32, 8), 0, st>>>(h_d, h_dT, K, H);
 }
 
 void launch_encode_fwd(const EncodeArgs& a, cudaStream_t st) {
@@ -373,17 +389,32 @@ void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, int
 __global__ void __launch_bounds__(256)
 k_da_all(const float* __restrict__ dh_sum, const float* __restrict__ h, float* __restrict__ da_out, int B, int bpad, int H,
          float kp, unsigned long long seed, unsigned long long step, int row_offset0, const __grid_constant__ PeerTable pt) {
-    const int i = blockIdx.x, s = blockIdx.y;
-    const int k = threadIdx.x;
-    if (k >= H) return;
-    const size_t o = ((size_t)s * bpad + i) * H + k;
-    if (i >= B) { da_out[o] = 0.f; return; }
-    float dh = 0.f;
-    for (int q = 0; q < pt.world; ++q) dh += (pt.world == 1 ? dh_sum : peer_ptr(pt, q, dh_sum))[o];
-    const float hv = h[o];
+    // 4 rows per block, thread = 4 consecutive hidden units of one row: every rank's share of the row is ONE 16-byte load per
+    // thread, all `world` of them in flight together (they are the NVLink round trips this kernel consists of)
+    const int H4 = H >> 2;
+    const int sub = threadIdx.x / H4, k4 = threadIdx.x - sub * H4;
+    const int i = blockIdx.x * (blockDim.x / H4) + sub, s = blockIdx.y;
+    if (i >= bpad) return;
+    const size_t o = (((size_t)s * bpad + i) * H >> 2) + k4;          // float4 index
+    if (i >= B) { reinterpret_cast<float4*>(da_out)[o] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    float4 part[kMaxWorld];
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+        if (q < pt.world) part[q] = reinterpret_cast<const float4*>(pt.world == 1 ? dh_sum : peer_ptr(pt, q, dh_sum))[o];
+    float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)                                // rank order: the same sum on every rank
+        if (q < pt.world) { dh.x += part[q].x; dh.y += part[q].y; dh.z += part[q].z; dh.w += part[q].w; }
+    const float4 hv = reinterpret_cast<const float4*>(h)[o];
     // the same key as the forward's mask (k_encode_fwd: local row + row_offset; rank s's offset is row_offset0 + s * B)
-    const bool keep = philox_keep(seed, kStreamHidden, step, static_cast<uint32_t>(row_offset0 + s * B + i), static_cast<uint32_t>(k), kp);
-    da_out[o] = keep ? dh * __fdiv_rn(1.f, kp) * (hv * (1.f - hv)) : 0.f;
+    const uint32_t grow = static_cast<uint32_t>(row_offset0 + s * B + i);
+    const float ikp = __fdiv_rn(1.f, kp);
+    float4 r;
+    r.x = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 0), kp) ? dh.x * ikp * (hv.x * (1.f - hv.x)) : 0.f;
+    r.y = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 1), kp) ? dh.y * ikp * (hv.y * (1.f - hv.y)) : 0.f;
+    r.z = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 2), kp) ? dh.z * ikp * (hv.z * (1.f - hv.z)) : 0.f;
+    r.w = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 3), kp) ? dh.w * ikp * (hv.w * (1.f - hv.w)) : 0.f;
+    reinterpret_cast<float4*>(da_out)[o] = r;
 }
 
 // db_enc[k] = sum_r da[r,k]: 8 row groups per block, combined in a fixed order
@@ -403,7 +434,9 @@ __global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __
 }
 
 void launch_da_all(const DaArgs& a, cudaStream_t st) {
-    k_da_all<<<dim3(a.bpad, a.pt.world), 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed, a.step, a.row_offset0, a.pt);
+    const int rows_per_block = 256 / (a.H / 4);
+    k_da_all<<<dim3((a.bpad + rows_per_block - 1) / rows_per_block, a.pt.world), 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H,
+                                                                                             a.kp, a.seed, a.step, a.row_offset0, a.pt);
     k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.bpad * a.pt.world, a.H, a.db_enc);
 }
 
@@ -626,6 +659,7 @@ void preload_sparse() {
     PRELOAD_KERNEL(k_gather_items_f32);
     PRELOAD_KERNEL(k_gather_rows_bf16);
     PRELOAD_KERNEL(k_encode_fwd);
+    PRELOAD_KERNEL(k_transpose_hd);
     PRELOAD_KERNEL(k_colsum);
     PRELOAD_KERNEL(k_scatter_shard);
     PRELOAD_KERNEL(k_scatter_det);
