@@ -244,7 +244,9 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
         if world > 1:
             from spotify_recsys_challenge_2018_b200.dp import ShardedRecommender
             rec = ShardedRecommender(m)
-        run = lambda i: rec.recommend(trk, tv, seeds, k=500)
+        # (reuse_output: the id matrix lands in page-locked memory owned by the model, as main_challenge.py's loop -- which
+        # maps a batch's ids to URIs before asking for the next batch -- allows)
+        run = lambda i: rec.recommend(trk, tv, seeds, k=500, reuse_output=True)
         if world > 1:
             # the merged per-shard lists must be the unsharded list (checked once, outside the timed region)
             got = rec.recommend(trk, tv, seeds, k=500, return_scores=True)

@@ -794,7 +794,10 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     ph_begin(m, PH_DA);
     launch_da_all(da, m->st);
     m->launches += 2;
-    if (R > 1) {   // db_dec rows from their owners; the cost is the rank-ordered sum of every rank's partial
+    // db_dec rows from their owners; the cost is the rank-ordered sum of every rank's partial.  Only the bias update and
+    // the cost read-back need them: a whole step defers both gathers to the bias stream (apply_adam), off the critical path
+    m->gather_deferred = R > 1 && m->par_step && !(m->debug & 256);
+    if (R > 1 && !m->gather_deferred) {
         launch_gather_items_f32(m->g_b_dec_sh, m->g_b_dec, N, m->pt, m->st);
         launch_sum_partials(m->cost_part, m->cost, 1, m->pt, m->st);
         m->launches += 2;
@@ -839,6 +842,12 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (fork_b) {                   // bias updates behind the decoder update on st3, next to the encoder's Adam
         sb = m->st3;
         CK(cudaStreamWaitEvent(sb, m->ev_da, 0));
+        if (m->gather_deferred) {
+            launch_gather_items_f32(m->g_b_dec_sh, m->g_b_dec, N, m->pt, sb);
+            launch_sum_partials(m->cost_part, m->cost, 1, m->pt, sb);
+            m->launches += 2;
+            m->gather_deferred = false;
+        }
     }
     ph_begin(m, PH_ADAM_BIAS, sb);
     a.row_touched = nullptr; a.w_bf16 = nullptr; a.row_len = 1;
@@ -1067,8 +1076,14 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
     run_encode(m, 0, bpad, rows, 1.0f, 1.0f, 0, false);
     CK(cudaEventRecord(s.consumed, m->st));
 
-    const int M1 = std::min(Tn, std::min(kCandCap - 128, std::max(round_up(Tn / 128, kTileItems), 2048)));
-    const int M2 = std::min(Tn, std::max(round_up(Tn / 8, kTileItems), M1));
+    // Pass A is dense and cheap: make its prefix as long as a candidate list (16 256 items), so that its thresholds are as
+    // tight as one pass can make them.  The expected list length of a pass over n items behind a prefix of M1 is
+    // kp x n / M1 (exchangeable scores; popularity-ranked ids only tighten it): when the WHOLE range fits 60 % of the list
+    // capacity -- item shards of <= ~260 k tracks, i.e. 8-way sharded challenge inference -- the middle pass and its
+    // select are skipped: two passes instead of three.
+    const int M1 = std::min(Tn, kCandCap - 128);
+    const bool two_pass = (double)kp * (double)Tn / (double)M1 <= 0.6 * kCandCap;
+    const int M2 = two_pass ? M1 : std::min(Tn, std::max(round_up(Tn / 8, kTileItems), M1));
     CK(cudaMemsetAsync(m->cand_cnt, 0, sizeof(int) * 3 * rows, m->st));
     launch_thr_from_topk(nullptr, nullptr, kp, B, rows, m->cand_thr, m->st);          // pass A keeps everything
     DecodeArgs d{};

@@ -170,24 +170,32 @@ class ShardedRecommender:
         """This rank's slice: lists stay on the device (model buffers "topk_idx" / "topk_score")."""
         self.model.recommend(x_positions, x_vals, seeds, k=k, item_range=self.range, on_device=True)
 
-    def merge(self, k=500, return_scores=False):
-        """Collective: store this rank's lists into every peer's merge buffer, barrier, merge locally -> host arrays."""
+    def merge(self, k=500, return_scores=False, reuse_output=False):
+        """Collective: store this rank's lists into every peer's merge buffer, barrier, merge locally -> host arrays
+        (`reuse_output=True`: page-locked arrays owned by this object, overwritten by the next call)."""
         import ctypes as C
         from . import _lib
+        from .models.DAEs import _PinnedPool
         B = self.model.n_batch
         pi, _, _ = self.model.buffer("topk_idx")
         ps, _, _ = self.model.buffer("topk_score")
-        out_i = np.empty((B, k), np.int32)
-        out_s = np.empty((B, k), np.float32) if return_scores else None
+        if reuse_output:
+            if not hasattr(self, "_pinned"):
+                self._pinned = _PinnedPool()
+            out_i = self._pinned.get((B, k), np.int32)
+            out_s = self._pinned.get((B, k), np.float32) if return_scores else None
+        else:
+            out_i = np.empty((B, k), np.int32)
+            out_s = np.empty((B, k), np.float32) if return_scores else None
         _lib.check(self._lib.dae_exchange_merge_topk(self._x, C.c_void_p(pi), C.c_void_p(ps), B, int(k),
                                                      out_i.ctypes.data_as(C.c_void_p),
                                                      out_s.ctypes.data_as(C.c_void_p) if out_s is not None else None,
                                                      C.c_void_p(self.model.stream) if self.model.stream else None))
         return (out_i, out_s) if return_scores else out_i
 
-    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False):
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, reuse_output=False):
         self.rank_shard(x_positions, x_vals, seeds, k)
-        return self.merge(k, return_scores)
+        return self.merge(k, return_scores, reuse_output)
 
     def launch_count(self):
         return int(self._lib.dae_exchange_launch_count(self._x))

@@ -59,7 +59,7 @@ def run(conf):
             cand = model_title.recommend(model, x_positions, x_ones, titles, seed,
                                          titles_use=[t[0] for t in titles_exist])
         else:
-            cand = model.recommend(x_positions, x_ones, seed, k=500)
+            cand = model.recommend(x_positions, x_ones, seed, k=500, reuse_output=True)
         for i in range(len(seed)):
             total_cands.append([pid[i]] + cand_to_uri(cand[i], reader.id2uri))  # main_challenge.py:89-90
         if reader.ch_idx == 0:

@@ -32,6 +32,23 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+class _PinnedPool:
+    """Page-locked host arrays for results that are consumed before the next call (`reuse_output=True`): a D2H copy into
+    pinned memory runs at PCIe speed, one into a fresh pageable NumPy array is staged by the driver at a fraction of it
+    (8 MB of ids per 4096-playlist challenge batch: ~1 ms vs ~0.2 ms).  torch is only the allocator here."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, shape, dtype):
+        import torch
+        key = (tuple(shape), np.dtype(dtype).str)
+        if key not in self._bufs:
+            tdt = {"<i4": torch.int32, "<f4": torch.float32, "<f8": torch.float64}[np.dtype(dtype).str]
+            self._bufs[key] = torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
+        return self._bufs[key].numpy()
+
+
 def _csr(lists, n_rows, pad_value=None):
     """Per-row id lists -> (ptr int32 [n_rows + 1], flat int32).  Rows past len(lists) (a short last batch) are empty, or hold
     the single id `pad_value` when one is given (the metrics kernel divides by the row length)."""
@@ -182,13 +199,15 @@ class DAE_tied:
                                                _ptr(out)))
         return out
 
-    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, item_range=None, on_device=False):
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, item_range=None, on_device=False,
+                  reuse_output=False):
         """Top-k track ids per playlist with the seeds removed (metrics.py:58-68, main_challenge.py:26-36),
         decode + ranking on the device.  `seeds`: list of per-row seed id lists, or the CSR pair (seed_ptr, seed_idx).
         -> int32 [batch, k].
         `item_range=(lo, hi)` ranks only that slice of the track catalogue (item-sharded inference; ids stay global).
         `on_device=True` skips the copy to the host: the lists stay in the device buffers "topk_idx" / "topk_score"
-        (self.buffer(name) -> pointer) and None is returned."""
+        (self.buffer(name) -> pointer) and None is returned.  `reuse_output=True` returns page-locked arrays owned by the
+        model that the NEXT call overwrites (the runners consume a batch's candidates before asking for the next)."""
         xp, xv = _coo(x_positions, x_vals)
         if isinstance(seeds, tuple):
             # already CSR: (seed_ptr int32 [batch + 1], seed_idx int32 [nnz]) -- large batches skip the Python list walk
@@ -204,8 +223,14 @@ class DAE_tied:
             flat = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int64).reshape(-1) for s in seeds])
                                         if lens and sum(lens) else np.zeros(0, np.int64))
             flat = np.clip(flat, -1, 2 ** 31 - 1).astype(np.int32)
-        idx = np.empty((self.n_batch, k), np.int32) if not on_device else None
-        sc = np.empty((self.n_batch, k), np.float32) if (return_scores and not on_device) else None
+        if reuse_output and not on_device:
+            if not hasattr(self, "_pinned"):
+                self._pinned = _PinnedPool()
+            idx = self._pinned.get((self.n_batch, k), np.int32)
+            sc = self._pinned.get((self.n_batch, k), np.float32) if return_scores else None
+        else:
+            idx = np.empty((self.n_batch, k), np.int32) if not on_device else None
+            sc = np.empty((self.n_batch, k), np.float32) if (return_scores and not on_device) else None
         lo, hi = item_range if item_range is not None else (0, self.n_tracks)
         _lib.check(self._lib.dae_model_recommend_range(self._h, _ptr(xp), _ptr(xv), xp.shape[0], self.n_batch,
                                                        _ptr(seed_ptr), _ptr(flat), int(k), int(lo), int(hi), _ptr(idx),
@@ -320,9 +345,9 @@ class DAE_title(DAE):
             return DAE.predict(self, x_positions, x_vals, tracks_only)
         return self.title_score.predict(self, x_positions, x_vals, titles, titles_use, tracks_only)
 
-    def recommend(self, x_positions, x_vals, seeds, titles=None, titles_use=1.0, k=500, return_scores=False):
+    def recommend(self, x_positions, x_vals, seeds, titles=None, titles_use=1.0, k=500, return_scores=False, **kw):
         if self.title_score is None or titles is None:
-            return DAE.recommend(self, x_positions, x_vals, seeds, k, return_scores)
+            return DAE.recommend(self, x_positions, x_vals, seeds, k, return_scores, **kw)
         return self.title_score.recommend(self, x_positions, x_vals, titles, seeds, titles_use, k, return_scores)
 
     def evaluate(self, x_positions, x_vals, seeds, answers, titles=None, titles_use=1.0, k=500):

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 IFS=';' read -ra V <<< "${VARIANTS:-;--no-overlap}"
 for rep in $(seq 1 ${REPS:-2}); do
   for i in "${!V[@]}"; do
-    timeout 300 python bench.py --no-cpu-baseline --steps ${STEPS:-100} --warmup 10 ${V[$i]} > gpurun_out/ab_${i}_${rep}.json 2> gpurun_out/ab_${i}_${rep}.err
+    timeout 300 python bench.py --no-cpu-baseline --no-aux --steps ${STEPS:-100} --warmup 10 ${V[$i]} > gpurun_out/ab_${i}_${rep}.json 2> gpurun_out/ab_${i}_${rep}.err
     python - "$i" "$rep" "${V[$i]}" <<'PY'
 import json, sys
 i, rep, v = sys.argv[1:4]
