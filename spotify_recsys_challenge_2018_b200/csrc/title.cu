@@ -89,12 +89,11 @@ k_charcnn_fwd(const long long* __restrict__ titles, const float* __restrict__ em
 // 256 titles of the shipped shape (the kernel is issue-bound).
 constexpr int kCnnG = 4;           // titles per CTA
 template <int NP>
-__global__ void __launch_bounds__(256)
-k_charcnn_fwd_tiled(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ conv_W,
-                    const float* __restrict__ conv_b, const CnnShape s, int wi, float* __restrict__ feat,
-                    unsigned char* __restrict__ argpos, __nv_bfloat16* __restrict__ feat_d, __nv_bfloat16* __restrict__ feat_dT,
-                    int B, int bpad, float kp_t, unsigned long long seed, unsigned long long step, int row_offset) {
-    extern __shared__ __align__(16) float s_x[];   // [kCnnG][L][Epad]: embedded titles, pad ids zero
+__device__ __forceinline__ void
+charcnn_fwd_body(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ conv_W,
+                 const float* __restrict__ conv_b, const CnnShape& s, int wi, float* __restrict__ feat,
+                 unsigned char* __restrict__ argpos, __nv_bfloat16* __restrict__ feat_d, __nv_bfloat16* __restrict__ feat_dT,
+                 int B, int bpad, float kp_t, unsigned long long seed, unsigned long long step, int row_offset, float* s_x) {
     const int Epad = (s.E + 3) & ~3;
     const int b0 = blockIdx.x * kCnnG;
     const int w = s.width[wi], P = s.L - w + 1, D = s.F * s.n_widths;
@@ -185,13 +184,23 @@ k_charcnn_fwd_tiled(const long long* __restrict__ titles, const float* __restric
     }
 }
 
-template <int NP>
-static void launch_fwd_tiled_np(const CnnFwdArgs& a, int wi, cudaStream_t st) {
-    const int Epad = (a.shape.E + 3) & ~3;
-    const size_t smem = sizeof(float) * (kCnnG * a.shape.L * Epad + kCnnG * a.shape.F) + sizeof(int) * kCnnG * a.shape.F;
-    k_charcnn_fwd_tiled<NP><<<(a.B + kCnnG - 1) / kCnnG, 256, smem, st>>>(
-        a.titles, a.emb, a.conv_W, a.conv_b, a.shape, wi, a.feat, a.argpos, a.feat_d, a.feat_dT, a.B, a.bpad, a.kp_t, a.seed,
-        a.step, a.row_offset);
+// ONE launch for all widths (blockIdx.y = width, widest first: its CTAs take longest): 4 x 64 CTAs fill the GPU, where one
+// launch per width left more than half of the SMs idle.  NP is dispatched per block (uniform) to the templated body.
+__global__ void __launch_bounds__(256)
+k_charcnn_fwd_tiled(const long long* __restrict__ titles, const float* __restrict__ emb, const float* __restrict__ conv_W,
+                    const float* __restrict__ conv_b, const CnnShape s, float* __restrict__ feat,
+                    unsigned char* __restrict__ argpos, __nv_bfloat16* __restrict__ feat_d, __nv_bfloat16* __restrict__ feat_dT,
+                    int B, int bpad, float kp_t, unsigned long long seed, unsigned long long step, int row_offset) {
+    extern __shared__ __align__(16) float s_x[];   // [kCnnG][L][Epad]: embedded titles, pad ids zero; then the halves' maxima
+    const int wi = s.n_widths - 1 - blockIdx.y;
+    const int np = (s.L - s.width[wi] + 2) / 2;
+#define CNN_CASE(n) case n: charcnn_fwd_body<n>(titles, emb, conv_W, conv_b, s, wi, feat, argpos, feat_d, feat_dT, B, bpad, kp_t, seed, step, row_offset, s_x); break;
+    switch (np) {
+        CNN_CASE(1) CNN_CASE(2) CNN_CASE(3) CNN_CASE(4) CNN_CASE(5) CNN_CASE(6) CNN_CASE(7) CNN_CASE(8) CNN_CASE(9)
+        CNN_CASE(10) CNN_CASE(11) CNN_CASE(12) CNN_CASE(13)
+        default: break;
+    }
+#undef CNN_CASE
 }
 
 void launch_charcnn_fwd(const CnnFwdArgs& a, cudaStream_t st) {
@@ -204,23 +213,11 @@ void launch_charcnn_fwd(const CnnFwdArgs& a, cudaStream_t st) {
     if (tiled) {
         // padding rows / columns of the operand copies are zero from allocation and never written (api_title.cu re-zeroes
         // them when the batch size changes); widest filters first: their CTAs take longest
-        for (int i = a.shape.n_widths - 1; i >= 0; --i) {
-            switch ((a.shape.L - a.shape.width[i] + 2) / 2) {
-                case 1: launch_fwd_tiled_np<1>(a, i, st); break;
-                case 2: launch_fwd_tiled_np<2>(a, i, st); break;
-                case 3: launch_fwd_tiled_np<3>(a, i, st); break;
-                case 4: launch_fwd_tiled_np<4>(a, i, st); break;
-                case 5: launch_fwd_tiled_np<5>(a, i, st); break;
-                case 6: launch_fwd_tiled_np<6>(a, i, st); break;
-                case 7: launch_fwd_tiled_np<7>(a, i, st); break;
-                case 8: launch_fwd_tiled_np<8>(a, i, st); break;
-                case 9: launch_fwd_tiled_np<9>(a, i, st); break;
-                case 10: launch_fwd_tiled_np<10>(a, i, st); break;
-                case 11: launch_fwd_tiled_np<11>(a, i, st); break;
-                case 12: launch_fwd_tiled_np<12>(a, i, st); break;
-                default: launch_fwd_tiled_np<13>(a, i, st); break;
-            }
-        }
+        const int Epad = (a.shape.E + 3) & ~3;
+        const size_t smem = sizeof(float) * (kCnnG * a.shape.L * Epad + kCnnG * a.shape.F) + sizeof(int) * kCnnG * a.shape.F;
+        k_charcnn_fwd_tiled<<<dim3((a.B + kCnnG - 1) / kCnnG, a.shape.n_widths), 256, smem, st>>>(
+            a.titles, a.emb, a.conv_W, a.conv_b, a.shape, a.feat, a.argpos, a.feat_d, a.feat_dT, a.B, a.bpad, a.kp_t, a.seed,
+            a.step, a.row_offset);
         return;
     }
     const int threads = ((D > kTitleFpad ? D : kTitleFpad) + 31) / 32 * 32;
@@ -501,10 +498,7 @@ void launch_transpose_pad(const float* src, float* dst, int D, int N, int ld, in
 void preload_title_cnn() {
     cudaFuncAttributes a;
     PRELOAD_KERNEL(k_charcnn_fwd);
-    PRELOAD_KERNEL(k_charcnn_fwd_tiled<9>);
-    PRELOAD_KERNEL(k_charcnn_fwd_tiled<10>);
-    PRELOAD_KERNEL(k_charcnn_fwd_tiled<11>);
-    PRELOAD_KERNEL(k_charcnn_fwd_tiled<12>);
+    PRELOAD_KERNEL(k_charcnn_fwd_tiled);
     PRELOAD_KERNEL(k_conv_transpose);
     cudaFuncSetAttribute(k_charcnn_bwd_emb, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     PRELOAD_KERNEL(k_mix_weights);
