@@ -1024,7 +1024,10 @@ static int ensure_buf(T** p, size_t* have, size_t need, cudaStream_t st) {
 // The [B, T] score matrix is never materialised.  Three filter passes over growing prefixes of the item range
 // ([lo, lo+M1) c [lo, lo+M2) c [lo, hi)): a pass appends every logit >= the playlist's threshold to its candidate list,
 // an exact top-(k + max #seeds) of the list gives the threshold of the next pass.  The kp-th largest logit of a SUBSET is
-// a lower bound of the kp-th largest of the whole range, so no member of the final top-k can be filtered out; with
+// a lower bound of the kp-th largest of the whole range, so no member of the final top-k can be filtered out.  (The final
+// order is on p = sigmoid(z) in fp32, where distinct logits can TIE -- near saturation, and all of z >= ~16.6 at exactly
+// 1.0f -- and the lower id wins a tie: k_thr_from_topk therefore lowers every threshold by the width of the sigmoid's
+// flat spot around it, and to 15 beyond that; tests/test_gpu_model.py has the saturated adversarial case.)  With
 // M2 / M1 = 16 and T / M2 = 8 the lists hold ~kp x 16 and ~kp x 8 entries for exchangeable scores (popularity-ranked ids
 // make the prefix bound tighter still).  A list that overflows its capacity is detected and the call falls back to the
 // tiled dense path, so the result is exact in every case.  Total decode work: (M1 + M2 + T) / T = 1.13x.

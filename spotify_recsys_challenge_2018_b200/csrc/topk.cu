@@ -133,6 +133,31 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     }
     const uint32_t thr = prefix;          // full 32-bit key of the want0-th largest element
     const uint32_t need_eq = want;        // how many elements equal to thr are needed (>= 1)
+    // Ties AT the cut go to the lowest item ids.  In a dense row the position is the id, and the ordered pick below does
+    // it.  In candidate-list mode the list order is arbitrary: when more entries tie with the threshold than are needed
+    // (scores near saturation), find the id cut-off X = the need_eq-th smallest id among them by bisection (31 counting
+    // sweeps over <= 16 K entries; only in that rare case) and accept exactly the ties with id <= X.
+    uint32_t id_cut = 0xFFFFFFFFu;
+    const uint32_t eq_total = s_hist[thr & 0xFFu];      // the last pass's histogram: entries whose full key == thr
+    if (rm != nullptr && eq_total > need_eq) {          // block-uniform
+        uint32_t lo = 0, hi = 0x7FFFFFFFu;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            __syncthreads();
+            if (t == 0) s_cnt[0] = 0;
+            __syncthreads();
+            uint32_t c = 0;
+            for (int i = t; i < T; i += kTopkThreads)
+                c += (score_key(load_score(x, i, sigmoid_out)) == thr && (uint32_t)rm[i] <= mid) ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if ((t & 31) == 0 && c) atomicAdd(&s_cnt[0], c);
+            __syncthreads();
+            if (s_cnt[0] >= need_eq) hi = mid; else lo = mid + 1;
+        }
+        id_cut = lo;
+        __syncthreads();
+    }
 
     // ---- collect: all keys > thr (any order) + the need_eq lowest-index keys == thr ---------
     if (t == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
@@ -149,7 +174,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
                 s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)(rm ? rm[i] : i));
         }
         if (eq_seen < need_eq) {          // ordered pick among ties: chunk-ordered block scan
-            const bool eq = in && key == thr;
+            const bool eq = in && key == thr && (rm == nullptr || (uint32_t)rm[i] <= id_cut);
             const uint32_t bal = __ballot_sync(0xffffffffu, eq);
             const uint32_t wrank = __popc(bal & ((1u << (t & 31)) - 1u));
             if ((t & 31) == 0) s_warp[t >> 5] = __popc(bal);
@@ -244,7 +269,16 @@ __global__ void k_thr_from_topk(const float* __restrict__ score, const int* __re
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     float t = CUDART_INF_F;
-    if (r < batch) t = (score != nullptr && idx[(size_t)r * kp + kp - 1] >= 0) ? score[(size_t)r * kp + kp - 1] : -CUDART_INF_F;
+    if (r < batch) {
+        t = (score != nullptr && idx[(size_t)r * kp + kp - 1] >= 0) ? score[(size_t)r * kp + kp - 1] : -CUDART_INF_F;
+        // The final list is ordered by p = sigmoid(z) in fp32 (ties: lower id first), the filter compares LOGITS: distinct
+        // logits collapse onto one p once 1 - p nears the fp32 resolution (and onto exactly 1.0f from z ~ 16.6 on), so an
+        // item just below the kp-th logit can tie in p with kept items and win on its id.  Keep everything whose p could
+        // equal the threshold item's: |dz| p (1 - p) < 2 ulp(p)  ->  dz < ~2.4e-7 (1 + e^z), 4x margin for the approximate
+        // exp / division; from z = 15 on simply everything >= 15 (a list that overflows falls back to the dense path).
+        if (t > 15.f) t = 15.f;
+        else if (t > -CUDART_INF_F) t -= 1e-6f * (1.f + __expf(t)) + 1e-6f * fabsf(t);
+    }
     thr[r] = t;
 }
 void launch_thr_from_topk(const float* score, const int* idx, int kp, int batch, int rows, float* thr, cudaStream_t st) {

@@ -407,6 +407,36 @@ def test_fused_decode_topk_equals_dense_ranking(N, T, H, B, k):
     m.close()
 
 
+@pytest.mark.parametrize("bias_hi", [9.0, 13.0, 30.0])
+def test_fused_decode_topk_with_saturated_scores(bias_hi):
+    """Adversarial for the fused decode + top-K: the filter compares logits, the final order is on fp32
+    sigmoid(z) with ties to the lower id.  A block of high-id items gets a large bias so that the top of every ranking
+    sits where distinct logits collapse onto one p (bias 13: 1 - p ~ 2e-6; bias 30: p == 1.0f exactly for thousands of
+    items, more than a candidate list holds -> the dense fallback).  The fused path must still equal the dense one."""
+    N, T, H, B, k = 200000, 180000, 64, 128, 500
+    conf = Conf(batch=B, n_input=N, n_tracks=T, hidden=H, lr=0.01, DAEval=None)
+    ora = O.DAEOracle(N, H, 0.01, tied=False, seed=5, mode="b200")
+    rng = np.random.default_rng(int(bias_hi))
+    ora.b_dec[:] = rng.normal(0, 0.5, N)
+    hot = rng.permutation(T)[:20000 if bias_hi >= 30 else 3000]
+    ora.b_dec[hot] = bias_hi + rng.normal(0, 0.3, len(hot))
+    m = DAE(conf)
+    m.trainable = False
+    m.fit()
+    m.set_params(ora.params())
+    trk, art, y = random_batch(rng, B, T, N - T, mean_len=30, empty_rows=(2,))
+    xv = np.ones(len(trk), np.float32)
+    seeds = [trk[trk[:, 0] == r, 1].tolist() for r in range(B)]
+    m.set_debug(32)
+    idx_d, sc_d = m.recommend(trk, xv, seeds, k=k, return_scores=True)
+    m.set_debug(16)
+    idx_f, sc_f = m.recommend(trk, xv, seeds, k=k, return_scores=True)
+    assert np.array_equal(sc_f, sc_d) and np.array_equal(idx_f, idx_d)
+    ties = (np.diff(sc_d, axis=1) == 0).mean()
+    assert ties > (0.5 if bias_hi >= 30 else 0.0)             # the case really exercises ties in p
+    m.close()
+
+
 def test_errors_are_loud():
     from spotify_recsys_challenge_2018_b200._lib import DaeError
     conf = Conf(batch=8, n_input=100, n_tracks=80, hidden=64, lr=0.01)
