@@ -1107,11 +1107,10 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         launch_decode_predict(da, m->st);
         TopkArgs ta{};
         ta.scores = m->scores; ta.ld = M1; ta.B = B; ta.T = M1; ta.k = kp; ta.idx_base = 0;
-        ta.out_idx = m->cand_tk_idx; ta.out_score = m->cand_tk_score;
+        ta.thr_out = m->cand_thr;                                     // threshold only: no collection, no sort
         launch_topk(ta, m->st);
-        launch_thr_from_topk(m->cand_tk_score, m->cand_tk_idx, kp, B, rows, m->cand_thr, m->st);
         ph_end(m, PH_REC_A);
-        m->launches += 3;
+        m->launches += 2;
         prev = M1;
     }
     for (int pass = 0; pass < 3; ++pass) {
@@ -1127,10 +1126,10 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         a.row_n = d.cand_cnt;
         if (stops[pass] < Tn) {                                    // threshold of the next pass: kp-th largest so far
             a.k = kp; a.seed_ptr = nullptr; a.seed_idx = nullptr; a.sigmoid_out = 0;
-            a.out_idx = m->cand_tk_idx; a.out_score = m->cand_tk_score;
+            a.thr_out = m->cand_thr;
             launch_topk(a, m->st);
-            launch_thr_from_topk(m->cand_tk_score, m->cand_tk_idx, kp, B, rows, m->cand_thr, m->st);
-            m->launches += 2;
+            a.thr_out = nullptr;
+            m->launches += 1;
         }
     }
     a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.sigmoid_out = 1;

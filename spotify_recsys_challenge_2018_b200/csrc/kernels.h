@@ -341,6 +341,8 @@ struct TopkArgs {
     const int* remap;         // [B, ld] or nullptr (entry i is item i)
     const int* row_n;         // [B] or nullptr (every row has T entries)
     int sigmoid_out;          // 1: scores are logits; out_score = sigmoid(logit)
+    float* thr_out;           // [B] or nullptr.  Not null: threshold-only mode -- thr_out[r] = the filter threshold derived
+                              // from the k-th largest score of row r (-inf when the row has fewer than k); nothing else is written
 };
 void launch_topk(const TopkArgs& a, cudaStream_t st);
 // thr[r] = score[r, kp-1] (r < batch, -inf when that slot is padding or score == nullptr), +inf for r in [batch, rows)

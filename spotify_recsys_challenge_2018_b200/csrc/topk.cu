@@ -34,6 +34,18 @@ __device__ __forceinline__ float load_score(const float* __restrict__ x, int i, 
     return sigmoid_out ? __fdividef(1.f, 1.f + __expf(-v)) : v;
 }
 
+// The final list of the fused decode + top-K is ordered by p = sigmoid(z) in fp32 (ties: lower id first), its filter
+// compares LOGITS: distinct logits collapse onto one p once 1 - p nears the fp32 resolution (and onto exactly 1.0f from
+// z ~ 16.6 on), so an item just below the K-th logit can tie in p with kept items and win on its id.  The filter threshold
+// derived from a K-th largest logit t therefore keeps everything whose p could equal the threshold item's:
+// |dz| p (1 - p) < 2 ulp(p)  ->  dz < ~2.4e-7 (1 + e^z), 4x margin for the approximate exp / division; from z = 15 on
+// simply everything >= 15 (a list that overflows falls back to the dense path).
+__device__ __forceinline__ float filter_threshold(float t) {
+    if (t > 15.f) return 15.f;
+    if (t > -CUDART_INF_F) return t - (1e-6f * (1.f + __expf(t)) + 1e-6f * fabsf(t));
+    return t;
+}
+
 // histogram increment with warp aggregation (scores cluster in a few bins -> avoid same-address atomics)
 __device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t digit, bool active) {
     const uint32_t amask = __ballot_sync(0xffffffffu, active);
@@ -79,7 +91,7 @@ __device__ void select_bin(const uint32_t* hist, int nbins, uint32_t want, uint3
 __global__ void __launch_bounds__(kTopkThreads, 2)     // 2 CTAs / SM: the kernel is latency-bound (block scans between passes)
 k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* __restrict__ seed_ptr,
        const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score,
-       const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out) {
+       const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out, float* __restrict__ thr_out) {
     __shared__ uint32_t s_hist[4096];
     __shared__ unsigned long long s_cand[kCandMax];
     __shared__ int s_seed[kCandMax];
@@ -133,6 +145,12 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     }
     const uint32_t thr = prefix;          // full 32-bit key of the want0-th largest element
     const uint32_t need_eq = want;        // how many elements equal to thr are needed (>= 1)
+    if (thr_out != nullptr) {
+        // threshold-only mode (the intermediate passes of the fused decode + top-K): the K-th largest logit is all that
+        // is needed -- no collection, no sort (half of this kernel's time).  Fewer than K entries: keep everything.
+        if (t == 0) thr_out[row] = filter_threshold(T >= K ? key_score(thr) : -CUDART_INF_F);
+        return;
+    }
     // Ties AT the cut go to the lowest item ids.  In a dense row the position is the id, and the ordered pick below does
     // it.  In candidate-list mode the list order is arbitrary: when more entries tie with the threshold than are needed
     // (scores near saturation), find the id cut-off X = the need_eq-th smallest id among them by bisection (31 counting
@@ -271,13 +289,7 @@ __global__ void k_thr_from_topk(const float* __restrict__ score, const int* __re
     float t = CUDART_INF_F;
     if (r < batch) {
         t = (score != nullptr && idx[(size_t)r * kp + kp - 1] >= 0) ? score[(size_t)r * kp + kp - 1] : -CUDART_INF_F;
-        // The final list is ordered by p = sigmoid(z) in fp32 (ties: lower id first), the filter compares LOGITS: distinct
-        // logits collapse onto one p once 1 - p nears the fp32 resolution (and onto exactly 1.0f from z ~ 16.6 on), so an
-        // item just below the kp-th logit can tie in p with kept items and win on its id.  Keep everything whose p could
-        // equal the threshold item's: |dz| p (1 - p) < 2 ulp(p)  ->  dz < ~2.4e-7 (1 + e^z), 4x margin for the approximate
-        // exp / division; from z = 15 on simply everything >= 15 (a list that overflows falls back to the dense path).
-        if (t > 15.f) t = 15.f;
-        else if (t > -CUDART_INF_F) t -= 1e-6f * (1.f + __expf(t)) + 1e-6f * fabsf(t);
+        t = filter_threshold(t);
     }
     thr[r] = t;
 }
@@ -352,7 +364,7 @@ void launch_metrics(const int* cand, long long ld, int B, int k, const int* ans_
 
 void launch_topk(const TopkArgs& a, cudaStream_t st) {
     k_topk<<<a.B, kTopkThreads, 0, st>>>(a.scores, a.ld, a.T, a.k, a.seed_ptr, a.seed_idx, a.idx_base, a.out_idx,
-                                         a.out_score, a.remap, a.row_n, a.sigmoid_out);
+                                         a.out_score, a.remap, a.row_n, a.sigmoid_out, a.thr_out);
 }
 
 // Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
