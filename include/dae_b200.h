@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DAE_B200_ABI_VERSION 2
+#define DAE_B200_ABI_VERSION 3
 
 typedef struct dae_model dae_model; /* opaque: parameters, Adam state, workspaces, stream */
 
@@ -136,14 +136,16 @@ int32_t dae_model_train_step_staged(dae_model* m, int32_t slot, float keep_prob,
 int32_t dae_model_sync_cost(dae_model* m, float* cost_out);
 
 /* ---- data parallelism over the GPUs of one box (the reference has none) --------------
- * One process (or model) per GPU, `world` of them.  The train step shards by playlist: every rank
- * runs encode / decode / loss / dh on its own batch rows, and the catalogue-sized state (W_enc,
- * W_dec, Adam moments) is row-sharded tile-cyclically, ZeRO style.  All exchange is plain loads /
- * stores into the peers' arenas over NVLink, fused into the producing kernels: the decode epilogue
- * stores each item tile's dz on the tile's owner, the owner's dW + Adam epilogue stores the new bf16
- * operand rows on every rank, encode gathers W_enc rows from their owners.  Two flag barriers per
- * step order it.  Every rank must stage batches of the same size and call the step functions in the
- * same order.  Attach once after dae_model_create on every rank:
+ * One process (or model) per GPU, `world` of them.  The split is hybrid.  Sparse side, by playlist: rank r stages,
+ * de-duplicates and encodes ITS rows of the global batch, gathering W_enc rows from the GPUs that own them, and stores
+ * its h / h_d rows and its normalised input into every rank's copy of the global batch.  Dense side, by item: the
+ * catalogue-sized state (W_enc, W_dec, Adam moments, the bf16 operand, dz, dW_dec) is row-sharded tile-cyclically, ZeRO
+ * style, and every rank decodes, differentiates and updates its OWN item rows against the whole global batch -- that
+ * state never crosses NVLink.  All exchange is plain loads / stores into the peers' arenas, issued by the kernels
+ * that produce or consume the data; three flag barriers per step order it (A: previous step over everywhere, B1: the
+ * global h_d has landed, B2: every rank's dh sums / db_dec rows / cost partial are complete).  Every rank must stage
+ * batches of the same size and call the step functions in the same order.  Attach once after dae_model_create on
+ * every rank:
  *   dae_model_ipc_handle  -> 64-byte cudaIpcMemHandle_t of this rank's arena (exchange them out of band)
  *   dae_model_attach_ipc  <- all `world` handles in rank order (own slot ignored)
  *   dae_model_attach_local: peers living in the SAME process (tests; several models on one or more GPUs) */
@@ -178,14 +180,20 @@ int64_t dae_exchange_launch_count(dae_exchange* x);
  * the decoder update on the main stream instead of overlapping it with the sparse / encoder tail of the step.
  * bit 4: dae_model_recommend[_range] always takes the fused decode + top-K path, bit 5: never.
  * bits 6 / 7 / 8: keep the target bitmask / the decoder update / the bias updates on the main stream (bisecting the
- * three forks of the whole-step call). */
+ * three forks of the whole-step call).  bit 10: stream the encoder Adam of the rows no playlist lists in the background,
+ * under the front of the step (k_adam_bg; bit-identical results, measured slower: off by default).  bit 11: dW_enc
+ * through fp32 red.add only (the multi-GPU default), bit 12: ordered gather for the rows listed by >= 3 playlists (the
+ * single-GPU default: bit-reproducible steps).  bit 13: %globaltimer stamps of the step's fork / join points into the
+ * buffer "trace" (tools/gpu_trace.py).  bit 14: the title branch forms dW_out in HBM ("g_W_out") and runs its Adam as a
+ * second kernel instead of the fused one. */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row
  * buffers hold the rows this rank owns in local-tile order (== global order when world == 1).  Names:
  * "g_dec" "g_enc" "g_b_enc" "g_b_dec" "g_b_enc_part" "g_b_dec_part" "touched" "cost" "W_enc" "W_dec"
  * "W_dec_bf16" "b_enc" "b_dec" "h" "h_d" "h_dT" "dzT" "dz_all" "dh_partial" "da" "x_row_ptr" "x_row_len"
- * "x_col" "x_val" "x_rowsum" "y_row_ptr" "y_row_len" "y_col" "ybits" "scores" "topk_idx" "topk_score" "mW_dec" "vW_dec" "mW_enc" "vW_enc". */
+ * "x_col" "x_val" "x_rowsum" "y_row_ptr" "y_row_len" "y_col" "ybits" "scores" "topk_idx" "topk_score" "mW_dec" "vW_dec" "mW_enc" "vW_enc"
+ * "bg_ctl" "trace".  "touched" = the rows of W_enc the batch lists in x (known before the backward), cleared at the end of the step. */
 int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_ptr, int64_t* n_elem, int32_t* elem_size);
 /* number of kernels launched by this model since creation (bench.py `gpu_launches`) */
 int64_t dae_model_launch_count(dae_model* m);
