@@ -214,6 +214,68 @@ def test_cli_host_side_reaches_the_device_boundary(tmp_path, monkeypatch, mode):
     assert "mode]" in (tmp_path / "run1" / "log.txt").read_text()
 
 
+def test_spotify_reader_matches_reference(tmp_path):
+    """MPD slices -> train / test-* / challenge_* files: the mirror of utils/spotify_reader.py must write the
+    CONTENT the reference's own classes wrote for the same synthetic slices (tests/golden/mpd_out, generated by
+    tests/golden/make_golden.py --mpd; Spotify_test upstream needs the SURVEY D11 shims to run at all)."""
+    import hashlib
+    import random
+    from spotify_recsys_challenge_2018_b200.utils import spotify_reader as sr
+    from tools.synth_mpd import write_mpd_slices
+    gold = os.path.join(GOLDEN, "mpd_out")
+    with open(os.path.join(gold, "MANIFEST.json")) as f:
+        man = json.load(f)
+    src = str(tmp_path / "mpd")
+    write_mpd_slices(src, seed=180610)
+    h = hashlib.sha256()
+    for root, _, files in sorted(os.walk(src)):
+        for fn in sorted(files):
+            with open(os.path.join(root, fn), "rb") as f:
+                h.update(f.read())
+    assert h.hexdigest() == man["input_sha256"], "the synthetic MPD generator drifted: regenerate the golden files"
+    out = str(tmp_path / "out")
+    paths = lambda d: [os.path.join(src, d, n) for n in sorted(os.listdir(os.path.join(src, d)))]
+    sr.Spotify_train(paths("train"), 3, 2, True, out)
+    train_json = os.path.join(out, "train")
+    for n, shuffle in ((0, False), (1, False), (5, False), (10, False), (25, False), (25, True)):
+        random.seed(180610 + n)
+        sr.Spotify_test(paths("test"), train_json, n, out, shuffle)
+    for seeds, in_order in (([0, 1], True), ([5], True), ([10, 25, 100], True), ([25, 100], False)):
+        sr.Spotify_challenge(paths("challenge"), train_json, out, seeds, in_order)
+    names = sorted(n for n in os.listdir(gold) if n != "MANIFEST.json")
+    assert sorted(os.listdir(out)) == names
+    for n in names:
+        with open(os.path.join(out, n)) as f:
+            got = json.load(f)
+        with open(os.path.join(gold, n)) as f:
+            want = json.load(f)
+        assert got.keys() == want.keys(), n
+        for k in want:
+            assert got[k] == want[k], (n, k)
+    # the readers consume the files as they are
+    r = rdr.data_reader(out, "train", 8)
+    assert r.num_tracks == len(want and json.load(open(train_json))["track_uri2id"])
+    r.next_batch()
+    # title helpers, directly
+    assert sr.normalize_name("  Road-Trip!! (2018)_mix ") == "road-trip 2018 mix"
+    assert sr.change_title2ixs("ab z") == [0, 1, 25] + [-1] * 22
+
+
+def test_data_generator_cli(tmp_path):
+    """The repaired data_generator writes every file the shipped configs name."""
+    from spotify_recsys_challenge_2018_b200 import data_generator as dg
+    from tools.synth_mpd import write_mpd_slices
+    src = str(tmp_path / "mpd")
+    write_mpd_slices(src, seed=3)
+    out = str(tmp_path / "data")
+    assert dg.main(["--datadir", out, "--mpd_tr", src + "/train", "--mpd_te", src + "/test", "--mpd_ch", src + "/challenge",
+                    "--mincount_trk", "3", "--mincount_art", "2"]) == 0
+    want = {"train", "test-0", "test-1", "test-5", "test-10", "test-25", "test-100", "test-25r", "test-100r",
+            "challenge_inorder_0to1", "challenge_inorder_5", "challenge_inorder_10to100", "challenge_random_25to100"}
+    assert want <= set(os.listdir(out))
+    assert dg.parse_divide("0-1,5,10-25,10-25r") == [([0, 1], True), ([5], True), ([10, 25], True), ([10, 25], False)]
+
+
 def test_merge_results_matches_reference(tmp_path):
     """results.csv written by the merger mirror == the file the reference's merge_results.py wrote for the same pickle
     (tests/golden/merge_results_golden.csv; one result file, so os.listdir order does not matter)."""

@@ -202,3 +202,54 @@ if __name__ == "__main__":
     ap.add_argument("--challenge", type=int, default=64)
     a = ap.parse_args()
     write_dataset(a.out, a.tracks, a.artists, a.train, a.test, a.challenge)
+
+
+def write_mpd_slices(out_dir, seed=180610, n_tracks=400, n_artists=150, train=(2, 60), test=(1, 70), n_challenge=48):
+    """Raw Million-Playlist-Dataset slices in Spotify's own JSON layout (what utils/spotify_reader.py consumes):
+    `<out>/train/mpd.slice.*.json`, `<out>/test/…` = {"playlists": [{"name", "pid", "tracks": [{"pos", "track_uri":
+    "spotify:track:<id>", "artist_uri": "spotify:artist:<id>", …}]}]} and `<out>/challenge/challenge_set.json` (playlists
+    with "num_samples", optionally without "name", in-order or randomly sampled seeds).  Small and adversarial: Zipf
+    popularity (so that minimum counts cut the vocabulary), the "various artists" id, punctuation / upper case / unknown
+    characters in titles, playlists longer than 250 tracks, tracks that only occur in the test slices."""
+    import json
+    rng = np.random.default_rng(seed)
+    words = ["chill", "WORKOUT!!", "Road-Trip", "90s (rock)", "study;time", "Party_2018", "sleep", "Jazz & Soul", "país",
+             "gym+run", "love <3", "summer.vibes", "#throwback", "Country", "k-pop", "lo/fi"]
+    artist_of = rng.integers(0, n_artists, n_tracks + 40)
+    def track(i, pos):
+        a = artist_of[i]
+        art = "0LyfQWJT6nXafLPZqxe9Of" if a == 0 else "A%05d" % a       # artist 0 = "various artists"
+        return {"pos": pos, "track_uri": "spotify:track:T%04d" % i, "artist_uri": "spotify:artist:" + art}   # (the fields read)
+    p = 1.0 / np.arange(1, n_tracks + 1)
+    p /= p.sum()
+    def playlist(pid, length, extra_unseen=0):
+        ids = rng.choice(n_tracks, size=length, p=p).tolist()
+        ids += (n_tracks + rng.integers(0, 40, extra_unseen)).tolist()     # tracks outside the training slices
+        rng.shuffle(ids)
+        name = " ".join(rng.choice(words, size=int(rng.integers(1, 4))).tolist())
+        return {"name": name, "pid": pid, "num_tracks": len(ids), "tracks": [track(i, k) for k, i in enumerate(ids)]}
+    pid = 0
+    for split, (n_files, per) in (("train", train), ("test", test)):
+        os.makedirs(os.path.join(out_dir, split), exist_ok=True)
+        for f in range(n_files):
+            pls = []
+            for _ in range(per):
+                length = int(np.clip(rng.lognormal(3.6, 0.8), 3, 300)) if split == "train" else int(rng.integers(8, 140))
+                pls.append(playlist(pid, length, extra_unseen=int(rng.integers(0, 3)) if split == "test" else 0))
+                pid += 1
+            with open(os.path.join(out_dir, split, "mpd.slice.%d-%d.json" % (f * per, f * per + per - 1)), "w") as fh:
+                json.dump({"info": {"slice": "%d-%d" % (f * per, f * per + per - 1)}, "playlists": pls}, fh, separators=(",", ":"))
+    os.makedirs(os.path.join(out_dir, "challenge"), exist_ok=True)
+    pls = []
+    for c in range(n_challenge):
+        n_seed = int(rng.choice([0, 1, 5, 10, 25, 100]))
+        full = playlist(1000000 + c, n_seed + int(rng.integers(5, 60)), extra_unseen=int(rng.integers(0, 2)))
+        in_order = bool(c % 3) or n_seed < 25
+        keep = list(range(n_seed)) if in_order else sorted(rng.choice(len(full["tracks"]), n_seed, replace=False).tolist())
+        pl = {"pid": full["pid"], "num_holdouts": len(full["tracks"]) - n_seed, "num_tracks": len(full["tracks"]),
+              "num_samples": n_seed, "tracks": [full["tracks"][k] for k in keep]}
+        if c % 5:
+            pl["name"] = full["name"]
+        pls.append(pl)
+    with open(os.path.join(out_dir, "challenge", "challenge_set.json"), "w") as fh:
+        json.dump({"playlists": pls}, fh, separators=(",", ":"))
