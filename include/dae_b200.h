@@ -180,7 +180,8 @@ int64_t dae_exchange_launch_count(dae_exchange* x);
  * the decoder update on the main stream instead of overlapping it with the sparse / encoder tail of the step.
  * bit 4: dae_model_recommend[_range] always takes the fused decode + top-K path, bit 5: never.
  * bits 6 / 7 / 8: keep the target bitmask / the decoder update / the bias updates on the main stream (bisecting the
- * three forks of the whole-step call).  bit 10: stream the encoder Adam of the rows no playlist lists in the background,
+ * three forks of the whole-step call).  bit 9: with >= 4 GPUs keep the encoder Adam of the unlisted rows behind the decoder
+ * update instead of next to the encode.  bit 10: stream the encoder Adam of the rows no playlist lists in the background,
  * under the front of the step (k_adam_bg; bit-identical results, measured slower: off by default).  bit 11: dW_enc
  * through fp32 red.add only (the multi-GPU default), bit 12: ordered gather for the rows listed by >= 3 playlists (the
  * single-GPU default: bit-reproducible steps).  bit 13: %globaltimer stamps of the step's fork / join points into the

@@ -673,6 +673,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     m->par_step = m->overlap_dec && !m->profiling && !(m->debug & (1 | 2 | 8));
     const bool fork_y = m->par_step && !(m->debug & 64);
     m->bg_inflight = false;
+    m->enc_early = false;
     if (fork_y) {
         CK(cudaEventRecord(m->ev_a, m->st));
         CK(cudaStreamWaitEvent(m->st3, m->ev_a, 0));
@@ -698,6 +699,21 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
             CK(cudaEventRecord(m->ev_bg, m->st4));
             m->bg_inflight = true;
             m->launches += 1;
+        }
+        // Four or more GPUs: a rank owns <= 1/4 of the rows, so the unlisted-row encoder pass (HBM-bound, 1/R of its
+        // single-GPU duration) is no longer than the encode (latency-bound over NVLink, growing with R): it runs NOW, next
+        // to the encode, instead of behind the decoder update on the critical path.  (One or two GPUs: it would only sit
+        // in front of G1's CTAs, which need whole SMs.)  Debug bit 9 keeps it behind the decoder update.
+        if (R >= 4 && !m->tied && m->cfg.reg_lambda == 0.f && !m->bg_inflight && !(m->debug & 512)) {
+            CK(cudaEventRecord(m->ev_touch, m->st3));
+            CK(cudaStreamWaitEvent(m->st4, m->ev_touch, 0));
+            AdamArgs a = adam_args(m);
+            a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
+            a.n = (long long)m->n_local * H; a.row_len = H; a.touch_mode = 1;
+            launch_adam_rows(a, nullptr, nullptr, m->st4, nullptr);
+            CK(cudaEventRecord(m->ev_bg, m->st4));
+            m->launches += 1;
+            m->enc_early = true;
         }
         build_ybits(m, slot, B, bpad, m->st3);
         stamp(m, m->st3, TR_YBITS);
@@ -764,7 +780,10 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
         // pass follows the decoder update directly on ITS stream (two HBM-bound kernels back to back), so the latency-
         // bound tail -- slow while it shares the SMs with them -- has both kernels' duration to finish; only the pass over
         // the listed rows (a few thousand) waits for it.
-        {
+        if (m->enc_early) {                     // already running since the start of the step (world >= 4): just join it
+            CK(cudaStreamWaitEvent(m->st3, m->ev_bg, 0));
+            m->enc_split = true;
+        } else {
             AdamArgs a = adam_args(m);
             a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
             a.n = (long long)m->n_local * H; a.row_len = H; a.touch_mode = 1;
@@ -863,6 +882,10 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (!m->tied) {   // encoder: gradient rows exist only where a batch touched them; all rows still update (dense TF1 Adam)
         a.w = m->W_enc; a.m = m->mW_enc; a.v = m->vW_enc; a.g = nullptr; a.row_touched = m->touched;
         a.n = (long long)m->n_local * H; a.row_len = H;
+        if (m->enc_early && !m->enc_split) {           // (decoder update not forked: join the early pass here)
+            CK(cudaStreamWaitEvent(m->st, m->ev_bg, 0));
+            m->enc_split = true;
+        }
         if (m->enc_split) {
             launch_adam_listed(a, m->g_enc, m->touched_list, m->st);   // the rows a playlist lists, with their gradient: all that is left
         } else {
@@ -870,7 +893,7 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
             if (m->bg_inflight) CK(cudaStreamWaitEvent(m->st, m->ev_bg, 0));
             launch_adam_rows(a, m->g_enc, nullptr, m->st, m->bg_inflight ? &m->bg : nullptr);
         }
-        m->bg_inflight = false; m->enc_split = false;
+        m->bg_inflight = false; m->enc_split = false; m->enc_early = false;
         m->launches += 1;
     }
     launch_clear_listed(H, m->g_enc, m->touched, m->touch_cnt, m->touched_list, m->st);

@@ -77,6 +77,7 @@ struct dae_model {
     BgAdam bg{};
     unsigned long long* trace = nullptr;   // debug bit 13: %globaltimer stamps of the step's fork / join points
     bool gather_deferred = false;   // world > 1: this step's db_dec / cost gathers run on the bias stream (apply_adam)
+    bool enc_early = false;         // world >= 4: the unlisted-row encoder pass was launched at the start of the step (st4)
     bool enc_split = false;         // this step's encoder Adam of the unlisted rows already follows the decoder update on st3
     bool bg_inflight = false;       // this step launched the background streamer (the dense encoder pass must account for it)
     int row_offset0 = 0;            // global row of rank 0's first playlist in the dropout keys of the step in flight

@@ -191,7 +191,12 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
             if (slot < (uint32_t)kCandMax)
                 s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)(rm ? rm[i] : i));
         }
-        if (eq_seen < need_eq) {          // ordered pick among ties: chunk-ordered block scan
+        if (eq_total == need_eq) {        // every entry equal to the threshold is needed (the common case: a unique K-th
+            if (in && key == thr) {       // score): no order to respect among them, no block scans
+                const uint32_t slot = (want0 - need_eq) + atomicAdd(&s_cnt[1], 1u);
+                s_cand[slot] = ((unsigned long long)key << 32) | (0xFFFFFFFFu - (uint32_t)(rm ? rm[i] : i));
+            }
+        } else if (eq_seen < need_eq) {   // ordered pick among ties: chunk-ordered block scan
             const bool eq = in && key == thr && (rm == nullptr || (uint32_t)rm[i] <= id_cut);
             const uint32_t bal = __ballot_sync(0xffffffffu, eq);
             const uint32_t wrank = __popc(bal & ((1u << (t & 31)) - 1u));
