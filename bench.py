@@ -248,9 +248,14 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
         # maps a batch's ids to URIs before asking for the next batch -- allows)
         run = lambda i: rec.recommend(trk, tv, seeds, k=500, reuse_output=True)
         if world > 1:
+            # every rank receives, merges and returns ITS 1 / world of the playlists (rows="own": a caller that writes its
+            # own part of the submission); --all-rows: every rank ends up with every list
+            rows = "all" if args.all_rows else "own"
+            run = lambda i: rec.recommend(trk, tv, seeds, k=500, reuse_output=True, rows=rows)
             # the merged per-shard lists must be the unsharded list (checked once, outside the timed region)
-            got = rec.recommend(trk, tv, seeds, k=500, return_scores=True)
+            got = rec.recommend(trk, tv, seeds, k=500, return_scores=True, rows=rows)
             want = m.recommend(trk, tv, seeds, k=500, return_scores=True)
+            want = tuple(w[rec.rows[0]:rec.rows[1]] for w in want)
             if not (np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])):
                 bad = np.nonzero((got[0] != want[0]).any(1))[0]
                 raise SystemExit("bench.py: item-sharded top-k differs from the unsharded list (rank %d, range %s): %d rows differ, "
@@ -260,8 +265,12 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
                                     want[0][bad[0]][:6] if len(bad) else "", want[1][bad[0]][:6] if len(bad) else ""))
         h2d = int(trk.nbytes + tv.nbytes + 4 * (B + 1) + 4 * len(trk))
         d2h, units, metric = B * 500 * 4, B, "dae_challenge_topk_playlists_per_sec"
+        if world > 1 and not args.all_rows:
+            d2h = (rec.rows[1] - rec.rows[0]) * 500 * 4
         desc = ("cfg5: challenge inference, top-500 over a %d-item decoder, batch %d in one call (fused decode + top-K, "
-                "16 batch tiles of 256 rows), latent %d, item axis sharded over %d GPU(s)" % (T, B, H, world))
+                "16 batch tiles of 256 rows), latent %d, item axis sharded over %d GPU(s)%s"
+                % (T, B, H, world, "" if world == 1 else (", merged lists on every rank" if args.all_rows else
+                                                          ", each rank merges and returns 1 / %d of the playlists" % world)))
         launches = m.launch_count
     for i in range(max(args.warmup, 3) if wl == "cfg3" else 2):
         run(i)
@@ -290,9 +299,11 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
         dt = float(t.item())
     # per-phase device times of a few profiled calls (not part of the timed region)
     phases = {}
-    if world == 1:
+    if world == 1 or wl == "cfg5":
         prof = tm if wl == "cfg3" else m
         prof.set_profiling(True)
+        if world > 1:
+            rec.set_profiling(True)
         for i in range(3):
             if wl == "cfg3":       # profiled steps are synchronous (the phase events are read at the end of each call)
                 tm.train_step(m, batches[i % 4][0], batches[i % 4][1], batches[i % 4][2], KP, 0.7, 0.01)
@@ -300,6 +311,9 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
                 run(i)
         torch.cuda.synchronize()
         phases = {k: (ms_ / max(n, 1)) for k, (ms_, n) in prof.phase_times().items() if n}
+        if world > 1:
+            phases.update(rec.phase_times())
+            rec.set_profiling(False)
         prof.set_profiling(False)
     if wl == "cfg3":
         tm.close()
@@ -325,7 +339,7 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
     else:
         # tensor-bound: 2 B T H flops of the decode; the fused path decodes 1.13x the catalogue (three growing prefixes)
         tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        alg = 2.0 * B * T * H
+        alg = 2.0 * B * T * H / world          # per rank: its slice of the item axis
         k_ms = phases.get("rec_filter_full")
         roof = None
         if k_ms:
@@ -333,7 +347,7 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
             roof = {"kernel": "k_itemtile<FILTER>, full-range pass of the fused decode + top-K (whole catalogue x whole batch)",
                     "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None,
                     "algorithmic_flops_per_launch": alg, "launch_ms": k_ms,
-                    "whole_call_tflops": alg / (ms_step / 1e3) / 1e12, "whole_call_frac": alg / (ms_step / 1e3) / 1e12 / tf,
+                    "whole_call_tflops_per_gpu": alg / (ms_step / 1e3) / 1e12, "whole_call_frac": alg / (ms_step / 1e3) / 1e12 / tf,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 TFLOP/s"}
     line = {"metric": metric, "value": units * steps / dt, "unit": "playlists/s", "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -412,6 +426,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="decoder update on the main stream (no overlap with the encoder tail)")
     ap.add_argument("--two-kernel", action="store_true", help="decoder dW and Adam as two kernels (gradient through HBM)")
     ap.add_argument("--no-dp-check", action="store_true", help="skip the N-rank == 1-rank self-check that precedes the timing at --gpus > 1")
+    ap.add_argument("--all-rows", action="store_true", help="cfg5 with --gpus N: every rank merges and returns every playlist's list")
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary cfg3 / cfg5 measurements appended to the default N=1 line")
     args = ap.parse_args()
     wl = args.workload

@@ -170,6 +170,22 @@ int32_t dae_exchange_attach_ipc(dae_exchange* x, const void* handles, int32_t n_
 int32_t dae_exchange_attach_local(dae_exchange* x, dae_exchange* const* peers, int32_t n_peers);
 int32_t dae_exchange_merge_topk(dae_exchange* x, const int32_t* idx_dev, const float* score_dev, int32_t batch, int32_t k,
                                 int32_t* out_idx, float* out_score, void* stream);
+/* the merge itself sharded by playlist: rank r receives, merges and returns rows [*row_begin, *row_end) = its 1 / world of
+ * the batch (ceil(batch / world) rows per rank); out_idx / out_score stay [batch, k] host arrays of which only those rows
+ * are written.  (world - 1) / world of ONE list set leaves each rank instead of world - 1 copies of it, and the merge and
+ * the read-back shrink by world: the call for a caller that writes its own rows of the submission. */
+int32_t dae_exchange_merge_topk_rows(dae_exchange* x, const int32_t* idx_dev, const float* score_dev, int32_t batch, int32_t k,
+                                     int32_t* row_begin, int32_t* row_end, int32_t* out_idx, float* out_score, void* stream);
+/* Filter thresholds of the fused decode + top-K shared across the item shards: while an exchange is set,
+ * dae_model_recommend_range on `m` is COLLECTIVE over the exchange's ranks (same batch, k and seeds everywhere; call it on
+ * the stream later handed to dae_exchange_merge_topk*).  Every shard selects its ceil((k + max seeds) / world)-th largest
+ * logit after a pass; the minimum over the shards (stored into every peer, one flag barrier) is exceeded by at least
+ * k + max seeds items of the whole catalogue, so no member of the global top-k is filtered out, and the candidate lists of
+ * the next pass are ~world times shorter than with per-shard thresholds.  x = NULL detaches. */
+int32_t dae_model_set_threshold_exchange(dae_model* m, dae_exchange* x);
+/* device times per call (ms, mean since switched on): out4 = stores, barrier, merge, read-back */
+int32_t dae_exchange_set_profiling(dae_exchange* x, int32_t on);
+int32_t dae_exchange_phase_ms(dae_exchange* x, float* out4);
 int64_t dae_exchange_launch_count(dae_exchange* x);
 
 /* debug / tuning flags.  bit 0: dae_model_backward_staged also forms dW_dec of the rows this rank owns

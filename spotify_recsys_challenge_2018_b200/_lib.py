@@ -86,6 +86,10 @@ SIGNATURES = {
     "dae_exchange_attach_ipc": (_I32, [_P, _P, _I32]),
     "dae_exchange_attach_local": (_I32, [_P, C.POINTER(_P), _I32]),
     "dae_exchange_merge_topk": (_I32, [_P, _P, _P, _I32, _I32, _P, _P, _P]),
+    "dae_exchange_merge_topk_rows": (_I32, [_P, _P, _P, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32), _P, _P, _P]),
+    "dae_model_set_threshold_exchange": (_I32, [_P, _P]),
+    "dae_exchange_set_profiling": (_I32, [_P, _I32]),
+    "dae_exchange_phase_ms": (_I32, [_P, C.POINTER(C.c_float)]),
     "dae_exchange_launch_count": (_I64, [_P]),
     "dae_topk_device": (_I32, [_P, _I64, _I32, _I32, _I32, _P, _P, _I32, _P, _P, _P]),
     "dae_metrics_device": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),

@@ -643,7 +643,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     // the loss is a mean over the GLOBAL batch (DAEs.py:100); dropout is keyed by the global row
     const int gb = global_batch > 0 ? global_batch : B * R;
     if (global_batch <= 0) row_offset = m->rank * B;
-    // the hidden-dropout mask of the backward (k_da_all) is keyed like the forward's: rank s's rows start at row_offset0 + s * B
+    // the hidden-dropout mask of the backward (k_da_own) is keyed like the forward's: rank s's rows start at row_offset0 + s * B
     if (R > 1 && row_offset != m->rank * B)
         return fail("world = %d: row_offset must be rank * batch = %d (got %d): the ranks' rows are consecutive blocks of the global batch",
                     R, m->rank * B, row_offset);
@@ -797,7 +797,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
         CK(cudaEventRecord(m->ev_dec, m->st3));
         m->dec_inflight = true;
     }
-    launch_reduce_splits(m->dh_partial, m->nsplit, bpad, H, R, m->dh_sum, m->st);
+    launch_reduce_splits(m->dh_partial, m->nsplit, bpad, H, m->pt, m->dh_sum, m->st);   // peer stores into the row owners' dh_sum
     ph_end(m, PH_DH);
     m->launches += 3 + 2;
 
@@ -811,7 +811,11 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
     da.dh_sum = m->dh_sum; da.h = m->h; da.da = m->da; da.db_enc = m->g_b_enc; da.B = B; da.bpad = bpad; da.H = H;
     da.kp = keep_prob; da.seed = m->cfg.seed; da.step = (unsigned long long)m->step; da.row_offset0 = m->row_offset0; da.pt = m->pt;
     ph_begin(m, PH_DA);
-    launch_da_all(da, m->st);
+    launch_da_own(da, m->st);                                                 // own rows, stored into every rank's da
+    barrier(m);                                                               // B3: every rank's da rows have arrived
+    // db_enc (column sums of da) feeds the bias update only: a whole step runs it on the bias stream (apply_adam)
+    m->colsum_deferred = m->par_step && !(m->debug & 256);
+    if (!m->colsum_deferred) launch_da_colsum(da, m->st);
     m->launches += 2;
     // db_dec rows from their owners; the cost is the rank-ordered sum of every rank's partial.  Only the bias update and
     // the cost read-back need them: a whole step defers both gathers to the bias stream (apply_adam), off the critical path
@@ -822,7 +826,7 @@ extern "C" int32_t dae_model_backward_staged(dae_model* m, int32_t slot, float k
         m->launches += 2;
     }
     ph_end(m, PH_DA);
-    if (m->par_step) CK(cudaEventRecord(m->ev_da, m->st));    // every bias gradient is final
+    if (m->par_step) CK(cudaEventRecord(m->ev_da, m->st));    // da and the decoder's bias gradient are final
 
     if (m->debug & 1) {    // parity tests: form dW_dec / dW_enc now, where they can be inspected before Adam consumes them
         DwArgs w = dw_args(m, bpad);
@@ -861,6 +865,12 @@ extern "C" int32_t dae_model_apply_adam(dae_model* m) {
     if (fork_b) {                   // bias updates behind the decoder update on st3, next to the encoder's Adam
         sb = m->st3;
         CK(cudaStreamWaitEvent(sb, m->ev_da, 0));
+        if (m->colsum_deferred) {
+            DaArgs da{};
+            da.da = m->da; da.db_enc = m->g_b_enc; da.bpad = bpad; da.H = H; da.pt = m->pt;
+            launch_da_colsum(da, sb);
+            m->colsum_deferred = false;
+        }
         if (m->gather_deferred) {
             launch_gather_items_f32(m->g_b_dec_sh, m->g_b_dec, N, m->pt, sb);
             launch_sum_partials(m->cost_part, m->cost, 1, m->pt, sb);
@@ -1097,6 +1107,11 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
     }
     m->full_stale = false;
     const int rows = bpad * nbt, Tn = hi - lo, kp = k + max_seeds;
+    // Item shards (m->thr_exchange): every shard's threshold select asks for its share kq = ceil(kp / world) and the minimum
+    // over the shards filters the next pass (exchange_min_thresholds: at least kp items of the catalogue exceed it)
+    const int xw = exchange_world(m->thr_exchange);
+    const int kq = (kp + xw - 1) / xw;
+    int n_thr_x = 0;
     TRY(ensure_cand(m, (size_t)rows, kp));
     CK(cudaStreamWaitEvent(m->st, s.prepared, 0));
     run_encode(m, 0, bpad, rows, 1.0f, 1.0f, 0, false);
@@ -1108,7 +1123,7 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
     // capacity -- item shards of <= ~260 k tracks, i.e. 8-way sharded challenge inference -- the middle pass and its
     // select are skipped: two passes instead of three.
     const int M1 = std::min(Tn, kCandCap - 128);
-    const bool two_pass = (double)kp * (double)Tn / (double)M1 <= 0.6 * kCandCap;
+    const bool two_pass = (double)kq * (double)Tn / (double)M1 <= 0.6 * kCandCap;
     const int M2 = two_pass ? M1 : std::min(Tn, std::max(round_up(Tn / 8, kTileItems), M1));
     CK(cudaMemsetAsync(m->cand_cnt, 0, sizeof(int) * 3 * rows, m->st));
     launch_thr_from_topk(nullptr, nullptr, kp, B, rows, m->cand_thr, m->st);          // pass A keeps everything
@@ -1129,9 +1144,10 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         da.n_out = M1; da.out = m->scores; da.ld_out = M1; da.raw_logits = 1;
         launch_decode_predict(da, m->st);
         TopkArgs ta{};
-        ta.scores = m->scores; ta.ld = M1; ta.B = B; ta.T = M1; ta.k = kp; ta.idx_base = 0;
+        ta.scores = m->scores; ta.ld = M1; ta.B = B; ta.T = M1; ta.k = kq; ta.idx_base = 0;
         ta.thr_out = m->cand_thr;                                     // threshold only: no collection, no sort
         launch_topk(ta, m->st);
+        if (xw > 1) { TRY(exchange_min_thresholds(m->thr_exchange, m->cand_thr, B, m->st)); ++n_thr_x; }
         ph_end(m, PH_REC_A);
         m->launches += 2;
         prev = M1;
@@ -1148,13 +1164,16 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         m->launches += 1;
         a.row_n = d.cand_cnt;
         if (stops[pass] < Tn) {                                    // threshold of the next pass: kp-th largest so far
-            a.k = kp; a.seed_ptr = nullptr; a.seed_idx = nullptr; a.sigmoid_out = 0;
+            a.k = kq; a.seed_ptr = nullptr; a.seed_idx = nullptr; a.sigmoid_out = 0;
             a.thr_out = m->cand_thr;
             launch_topk(a, m->st);
             a.thr_out = nullptr;
             m->launches += 1;
+            if (xw > 1) { TRY(exchange_min_thresholds(m->thr_exchange, m->cand_thr, B, m->st)); ++n_thr_x; }
         }
     }
+    if (n_thr_x > kThrExchangesPerCall) return fail("internal: %d threshold exchanges in one call", n_thr_x);
+    for (; xw > 1 && n_thr_x < kThrExchangesPerCall; ++n_thr_x) TRY(exchange_min_thresholds(m->thr_exchange, nullptr, 0, m->st));
     a.k = k; a.seed_ptr = sp; a.seed_idx = si; a.sigmoid_out = 1;
     a.out_idx = m->topk_idx; a.out_score = m->topk_score;
     ph_begin(m, PH_REC_SELECT);
@@ -1200,6 +1219,8 @@ extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos,
     const int Tn = item_hi - item_lo;
     // debug bit 4: always fused; bit 5: never
     bool fused = ((Tn >= kFusedMinItems) || (m->debug & 16)) && !(m->debug & 32) && k + max_seeds <= 1024 && Tn >= 2 * (k + max_seeds);
+    if (!fused)             // a shard on the dense path still takes part in its peers' threshold exchanges
+        for (int i = 0; m->thr_exchange && i < kThrExchangesPerCall; ++i) TRY(exchange_min_thresholds(m->thr_exchange, nullptr, 0, m->st));
     if (fused) {
         TRY(run_recommend_fused(m, k, item_lo, item_hi, sp, si, max_seeds));
         CK(cudaStreamSynchronize(m->st));
@@ -1223,6 +1244,14 @@ extern "C" int32_t dae_model_recommend_range(dae_model* m, const int64_t* x_pos,
     if (out_idx) CK(cudaMemcpyAsync(out_idx, m->topk_idx, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
     if (out_score) CK(cudaMemcpyAsync(out_score, m->topk_score, (size_t)batch * k * 4, cudaMemcpyDeviceToHost, m->st));
     return check_device_flag(m);
+}
+
+// Item-sharded inference: share the filter thresholds of the fused decode + top-K with the other shards through `x` (NULL
+// detaches).  From then on dae_model_recommend_range is COLLECTIVE over the exchange's ranks: same batch and k everywhere.
+extern "C" int32_t dae_model_set_threshold_exchange(dae_model* m, dae_exchange* x) {
+    if (!m) return fail("null argument");
+    m->thr_exchange = x;
+    return 0;
 }
 
 // answers CSR (host) -> device; metrics of the lists in `idx_dev` [batch, k] -> out_host [batch, 3] doubles
@@ -1292,6 +1321,7 @@ extern "C" int32_t dae_model_buffer(dae_model* m, const char* name, void** dev_p
         {"scores", m->scores, (int64_t)m->scores_elems, 4},
         {"topk_idx", m->topk_idx, (int64_t)m->topk_elems, 4}, {"topk_score", m->topk_score, (int64_t)m->topk_elems, 4},
         {"bg_ctl", m->bg.ctl, kBgCtlWords, 4}, {"trace", m->trace, 32, 8},
+        {"cand_cnt", m->cand_cnt, (int64_t)m->cand_rows * 3, 4},
         {"mW_dec", m->mW_dec, LH, 4}, {"vW_dec", m->vW_dec, LH, 4}, {"mW_enc", m->mW_enc, LH, 4}, {"vW_enc", m->vW_enc, LH, 4},
     };
     for (const E& e : table) {

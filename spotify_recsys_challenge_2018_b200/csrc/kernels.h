@@ -103,13 +103,14 @@ struct YbitsArgs {
 };
 void launch_ybits_shard(const YbitsArgs& a, cudaStream_t st);
 
-// dh of the global batch over this rank's item rows: fixed-order sum of the split-K partials -> dh_sum [K, H]
-void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, int n_batch_tiles, float* dh_sum, cudaStream_t st);
+// dh of the global batch over this rank's item rows: fixed-order sum of the split-K partials; the rows of rank s go into
+// slot [this rank] of rank s's dh_sum [world][bpad][H] (peer stores)
+void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, const PeerTable& pt, float* dh_sum, cudaStream_t st);
 
-struct DaArgs {               // da = dh * (keep/kp) * h(1-h) for EVERY row of the global batch (each rank computes all of it)
-    const float* dh_sum;      // [K, H] this rank's item-shard contribution; peers' through pt, summed in rank order
-    const float* h;           // [K, H] fp32 (rows written by their owners' encode)
-    float* da;                // [K, H]
+struct DaArgs {               // da = dh * (keep/kp) * h(1-h): each rank forms its own rows and stores them into every rank's da
+    const float* dh_sum;      // [world][bpad][H] every rank's item-shard contribution to THIS rank's rows, summed in rank order
+    const float* h;           // [K, H] fp32, only this rank's rows are filled
+    float* da;                // [K, H] of the global batch, complete after the barrier that follows launch_da_own
     float* db_enc;            // [H] column sums over the global batch
     int B, bpad, H;           // rows per rank, padded rows per rank
     float kp;
@@ -117,7 +118,8 @@ struct DaArgs {               // da = dh * (keep/kp) * h(1-h) for EVERY row of t
     int row_offset0;          // global row of rank 0's first playlist in the dropout keys (the forward uses row_offset0 + rank * B)
     PeerTable pt;
 };
-void launch_da_all(const DaArgs& a, cudaStream_t st);
+void launch_da_own(const DaArgs& a, cudaStream_t st);
+void launch_da_colsum(const DaArgs& a, cudaStream_t st);   // db_enc, once da is complete
 
 struct ScatterArgs {          // dW_enc rows owned by this rank, from the published input of the global batch and da (both local)
     PubInput pub;

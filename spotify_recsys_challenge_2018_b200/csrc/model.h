@@ -76,6 +76,7 @@ struct dae_model {
     cudaEvent_t ev_touch = nullptr, ev_bg = nullptr, ev_pre = nullptr;
     BgAdam bg{};
     unsigned long long* trace = nullptr;   // debug bit 13: %globaltimer stamps of the step's fork / join points
+    bool colsum_deferred = false;   // this step's db_enc column sums run on the bias stream (apply_adam)
     bool gather_deferred = false;   // world > 1: this step's db_dec / cost gathers run on the bias stream (apply_adam)
     bool enc_early = false;         // world >= 4: the unlisted-row encoder pass was launched at the start of the step (st4)
     bool enc_split = false;         // this step's encoder Adam of the unlisted rows already follows the decoder update on st3
@@ -141,6 +142,7 @@ struct dae_model {
     cudaEvent_t ev_cost[2] = {nullptr, nullptr};
     float* cost_ring = nullptr;      // pinned [2]
     int* err_ring = nullptr;         // pinned [2]
+    struct dae_exchange* thr_exchange = nullptr;   // item-sharded inference: filter thresholds are shared across the shards
     // optional per-phase device timing (bench.py roofline): events around each phase of a step
     bool profiling = false;
     cudaEvent_t ph_ev[2 * PH_COUNT] = {};
@@ -158,6 +160,12 @@ static int halloc(dae_model* m, T** p, size_t n) {
 }
 #define TRY(x) do { if (int rc_ = (x)) return rc_; } while (0)
 
+
+// api_dp.cu: filter thresholds shared across item shards (collective on `st`; thr == nullptr: barrier only)
+struct dae_exchange;
+int exchange_world(const dae_exchange* x);
+int exchange_min_thresholds(dae_exchange* x, float* thr, int n, cudaStream_t st);
+constexpr int kThrExchangesPerCall = 2;         // every rank runs exactly this many per recommend call, whatever its path
 
 // api.cu internals used by the title branch
 int stage_impl(dae_model* m, int32_t slot, const int64_t* x_pos, const float* x_val, int64_t nnz_x,

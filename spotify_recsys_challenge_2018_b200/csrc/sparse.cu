@@ -182,7 +182,6 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
             const __nv_bfloat16 z = __float2bfloat16(0.f);
             for (int s = 0; s < n_dst; ++s) {
                 (bcast ? peer_ptr(pt, s, h_d) : h_d)[h_off] = z;
-                (bcast ? peer_ptr(pt, s, h) : h)[h_off] = 0.f;
             }
             if (write_hT) h_dT[hT_off] = z;
         }
@@ -273,10 +272,8 @@ k_encode_fwd(const float* __restrict__ W, const float* __restrict__ b_enc, const
     const bool keep = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(k), kp);
     const float hd = keep ? __fdiv_rn(hv, kp) : 0.f;
     const __nv_bfloat16 hb = __float2bfloat16(hd);
-    for (int s2 = 0; s2 < n_dst; ++s2) {
-        (bcast ? peer_ptr(pt, s2, h) : h)[h_off] = hv;
-        (bcast ? peer_ptr(pt, s2, h_d) : h_d)[h_off] = hb;
-    }
+    h[h_off] = hv;                                 // fp32 h: only this rank's da needs it
+    for (int s2 = 0; s2 < n_dst; ++s2) (bcast ? peer_ptr(pt, s2, h_d) : h_d)[h_off] = hb;
     if (write_hT) h_dT[hT_off] = hb;
 }
 
@@ -363,8 +360,10 @@ void launch_touch_shard(const CsrWork& x, unsigned char* touched, int* touch_cnt
 // ------------------------------------------------------------------------------------------
 // encode backward, part 1: dh -> da for the whole global batch
 // ------------------------------------------------------------------------------------------
-// fixed-order sum of the split-K partials [bt][split][bpad][H] -> dh_sum [bt * bpad + row][H]
-__global__ void k_reduce_splits(const float* __restrict__ partial, int nsplit, int bpad, int H, float* __restrict__ out) {
+// fixed-order sum of the split-K partials [bt][split][bpad][H] of batch tile bt (= the rows of rank bt) -> straight into
+// rank bt's dh_sum, slot [this rank][row][H]: the reduce-scatter half of the dh all-reduce, as 1 KB peer stores
+__global__ void k_reduce_splits(const float* __restrict__ partial, int nsplit, int bpad, int H, float* __restrict__ out,
+                                const __grid_constant__ PeerTable pt) {
     const int bt = blockIdx.y, r = blockIdx.x, k = threadIdx.x;
     if (k >= H) return;
     const size_t stride = (size_t)bpad * H;
@@ -378,43 +377,48 @@ __global__ void k_reduce_splits(const float* __restrict__ partial, int nsplit, i
         d3 += p[(size_t)(s + 3) * stride];
     }
     for (; s < nsplit; ++s) d0 += p[(size_t)s * stride];
-    out[((size_t)bt * bpad + r) * H + k] = (d0 + d1) + (d2 + d3);
+    float* dst = pt.world == 1 ? out : peer_ptr(pt, bt, out);
+    dst[((size_t)pt.rank * bpad + r) * H + k] = (d0 + d1) + (d2 + d3);
 }
-void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, int n_batch_tiles, float* dh_sum, cudaStream_t st) {
-    k_reduce_splits<<<dim3(bpad, n_batch_tiles), 256, 0, st>>>(partial, nsplit, bpad, H, dh_sum);
+void launch_reduce_splits(const float* partial, int nsplit, int bpad, int H, const PeerTable& pt, float* dh_sum, cudaStream_t st) {
+    k_reduce_splits<<<dim3(bpad, pt.world), 256, 0, st>>>(partial, nsplit, bpad, H, dh_sum, pt);
 }
 
-// Row g = s * bpad + i of the global batch: dh = sum over ranks (fixed order) of their item-shard sums,
-// da = dh * (keep / kp) * h (1 - h).  Every rank computes every row (K x H values), so da itself never crosses NVLink.
+// Row i of THIS rank's playlists: dh = sum over ranks q (fixed order) of the item-shard sums they stored into slot q of
+// the local dh_sum, da = dh * (keep / kp) * h (1 - h), stored into every rank's da [K, H] at row rank * bpad + i: the
+// all-gather half.  Per rank and step 2 * (world - 1) * bpad * H * 4 bytes cross NVLink as stores, none as loads.
 __global__ void __launch_bounds__(256)
-k_da_all(const float* __restrict__ dh_sum, const float* __restrict__ h, float* __restrict__ da_out, int B, int bpad, int H,
+k_da_own(const float* __restrict__ dh_sum, const float* __restrict__ h, float* __restrict__ da_out, int B, int bpad, int H,
          float kp, unsigned long long seed, unsigned long long step, int row_offset0, const __grid_constant__ PeerTable pt) {
-    // 4 rows per block, thread = 4 consecutive hidden units of one row: every rank's share of the row is ONE 16-byte load per
-    // thread, all `world` of them in flight together (they are the NVLink round trips this kernel consists of)
+    // 4 rows per block, thread = 4 consecutive hidden units of one row
     const int H4 = H >> 2;
     const int sub = threadIdx.x / H4, k4 = threadIdx.x - sub * H4;
-    const int i = blockIdx.x * (blockDim.x / H4) + sub, s = blockIdx.y;
+    const int i = blockIdx.x * (blockDim.x / H4) + sub;
     if (i >= bpad) return;
-    const size_t o = (((size_t)s * bpad + i) * H >> 2) + k4;          // float4 index
-    if (i >= B) { reinterpret_cast<float4*>(da_out)[o] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
-    float4 part[kMaxWorld];
+    const size_t o = (((size_t)pt.rank * bpad + i) * H >> 2) + k4;    // float4 index of the row in h and da
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < B) {
+        float4 part[kMaxWorld];
 #pragma unroll
-    for (int q = 0; q < kMaxWorld; ++q)
-        if (q < pt.world) part[q] = reinterpret_cast<const float4*>(pt.world == 1 ? dh_sum : peer_ptr(pt, q, dh_sum))[o];
-    float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < kMaxWorld; ++q)
+            if (q < pt.world) part[q] = reinterpret_cast<const float4*>(dh_sum)[(((size_t)q * bpad + i) * H >> 2) + k4];
+        float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < kMaxWorld; ++q)                                // rank order: the same sum on every rank
-        if (q < pt.world) { dh.x += part[q].x; dh.y += part[q].y; dh.z += part[q].z; dh.w += part[q].w; }
-    const float4 hv = reinterpret_cast<const float4*>(h)[o];
-    // the same key as the forward's mask (k_encode_fwd: local row + row_offset; rank s's offset is row_offset0 + s * B)
-    const uint32_t grow = static_cast<uint32_t>(row_offset0 + s * B + i);
-    const float ikp = __fdiv_rn(1.f, kp);
-    float4 r;
-    r.x = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 0), kp) ? dh.x * ikp * (hv.x * (1.f - hv.x)) : 0.f;
-    r.y = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 1), kp) ? dh.y * ikp * (hv.y * (1.f - hv.y)) : 0.f;
-    r.z = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 2), kp) ? dh.z * ikp * (hv.z * (1.f - hv.z)) : 0.f;
-    r.w = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 3), kp) ? dh.w * ikp * (hv.w * (1.f - hv.w)) : 0.f;
-    reinterpret_cast<float4*>(da_out)[o] = r;
+        for (int q = 0; q < kMaxWorld; ++q)                            // rank order
+            if (q < pt.world) { dh.x += part[q].x; dh.y += part[q].y; dh.z += part[q].z; dh.w += part[q].w; }
+        const float4 hv = reinterpret_cast<const float4*>(h)[o];
+        // the same key as the forward's mask (k_encode_fwd: local row + row_offset = row_offset0 + rank * B)
+        const uint32_t grow = static_cast<uint32_t>(row_offset0 + pt.rank * B + i);
+        const float ikp = __fdiv_rn(1.f, kp);
+        r.x = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 0), kp) ? dh.x * ikp * (hv.x * (1.f - hv.x)) : 0.f;
+        r.y = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 1), kp) ? dh.y * ikp * (hv.y * (1.f - hv.y)) : 0.f;
+        r.z = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 2), kp) ? dh.z * ikp * (hv.z * (1.f - hv.z)) : 0.f;
+        r.w = philox_keep(seed, kStreamHidden, step, grow, static_cast<uint32_t>(4 * k4 + 3), kp) ? dh.w * ikp * (hv.w * (1.f - hv.w)) : 0.f;
+    }
+    if (pt.world == 1) { reinterpret_cast<float4*>(da_out)[o] = r; return; }
+#pragma unroll
+    for (int d = 0; d < kMaxWorld; ++d)
+        if (d < pt.world) reinterpret_cast<float4*>(peer_ptr(pt, d, da_out))[o] = r;
 }
 
 // db_enc[k] = sum_r da[r,k]: 8 row groups per block, combined in a fixed order
@@ -433,10 +437,12 @@ __global__ void k_colsum(const float* __restrict__ x, int rows, int H, float* __
     }
 }
 
-void launch_da_all(const DaArgs& a, cudaStream_t st) {
+void launch_da_own(const DaArgs& a, cudaStream_t st) {
     const int rows_per_block = 256 / (a.H / 4);
-    k_da_all<<<dim3((a.bpad + rows_per_block - 1) / rows_per_block, a.pt.world), 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H,
-                                                                                             a.kp, a.seed, a.step, a.row_offset0, a.pt);
+    k_da_own<<<(a.bpad + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(a.dh_sum, a.h, a.da, a.B, a.bpad, a.H, a.kp, a.seed,
+                                                                            a.step, a.row_offset0, a.pt);
+}
+void launch_da_colsum(const DaArgs& a, cudaStream_t st) {
     k_colsum<<<(a.H + 31) / 32, dim3(32, 8), 0, st>>>(a.da, a.bpad * a.pt.world, a.H, a.db_enc);
 }
 
@@ -655,7 +661,7 @@ void preload_sparse() {
     PRELOAD_KERNEL(k_row_sort_dedup);
     PRELOAD_KERNEL(k_ybits_shard);
     PRELOAD_KERNEL(k_reduce_splits);
-    PRELOAD_KERNEL(k_da_all);
+    PRELOAD_KERNEL(k_da_own);
     PRELOAD_KERNEL(k_gather_items_f32);
     PRELOAD_KERNEL(k_gather_rows_bf16);
     PRELOAD_KERNEL(k_encode_fwd);

@@ -88,12 +88,94 @@ __device__ void select_bin(const uint32_t* hist, int nbins, uint32_t want, uint3
     __syncthreads();
 }
 
+// Whole block: the want-th largest of n <= 2 * kTopkThreads keys held in shared memory at keys[i * stride] (radix passes of
+// 12 + 12 + 8 bits); 0 when want > n.  passes == 2 stops after 24 bits and returns them with the low 8 bits clear: a lower
+// bound of the want-th largest (within 2^-15 relative), which is all a pre-threshold needs.
+__device__ uint32_t select_kth_smem(const uint32_t* keys, int stride, int n, uint32_t want, int passes, uint32_t* s_hist,
+                                    uint32_t* s_warp, uint32_t* s_out) {
+    const int t = threadIdx.x;
+    if (want > (uint32_t)n) return 0u;
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < passes; ++pass) {
+        const int sh = pass == 0 ? 20 : (pass == 1 ? 8 : 0);
+        const int nb = pass == 2 ? 256 : 4096;
+        for (int i = t; i < nb; i += kTopkThreads) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = t; i < 2 * kTopkThreads; i += kTopkThreads) {
+            bool act = i < n;
+            const uint32_t key = act ? keys[(size_t)i * stride] : 0u;
+            if (pass == 1) act = act && ((key >> 20) == prefix);
+            if (pass == 2) act = act && ((key >> 8) == prefix);
+            hist_add(s_hist, (key >> sh) & (uint32_t)(nb - 1), act);
+        }
+        __syncthreads();
+        select_bin(s_hist, nb, want, s_warp, s_out);
+        want -= s_out[1];
+        prefix = (pass == 0) ? s_out[0] : ((prefix << (pass == 1 ? 12 : 8)) | s_out[0]);
+        __syncthreads();
+    }
+    return passes == 2 ? prefix << 8 : prefix;
+}
+
+// Descending bitonic sort of s[0..npow) (npow a power of two, 32 <= npow <= 2 * kTopkThreads), whole block.  Thread t keeps
+// elements t (and t + 1024: TWO) in registers: compare-exchange distances below 32 are warp shuffles, the distance 1024 is
+// inside the thread, the others go through shared memory with ONE barrier each (two buffers alternate; s2: npow entries of
+// scratch).  The network is fully unrolled: directions and distances are immediates, ~9 instructions per step.
+template <bool TWO>
+__device__ __forceinline__ void bitonic_desc_t(unsigned long long* s, unsigned long long* s2, int npow) {
+    const int t = threadIdx.x;
+    unsigned long long v0 = s[t], v1 = TWO ? s[t + kTopkThreads] : 0ull;
+    auto pick = [](unsigned long long a, unsigned long long b, bool take_max) { return ((a < b) == take_max) ? b : a; };
+    int cur = 1;
+#pragma unroll
+    for (int lk = 1; lk <= (TWO ? 11 : 10); ++lk) {
+        const int k = 1 << lk;
+        if (k > npow) break;                              // block-uniform
+#pragma unroll
+        for (int lj = lk - 1; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            if (TWO && j == kTopkThreads) {               // elements t and t + 1024 of the same thread (k == 2048: descending)
+                const unsigned long long a = v0, b = v1;
+                v0 = pick(a, b, true);
+                v1 = pick(b, a, false);
+                continue;
+            }
+            unsigned long long p0, p1 = 0ull;
+            if (j >= 32) {
+                unsigned long long* buf = cur ? s2 : s;
+                cur ^= 1;
+                buf[t] = v0;
+                if (TWO) buf[t + kTopkThreads] = v1;
+                __syncthreads();
+                p0 = buf[t ^ j];
+                if (TWO) p1 = buf[(t ^ j) + kTopkThreads];
+            } else {
+                p0 = __shfl_xor_sync(0xffffffffu, v0, j);
+                if (TWO) p1 = __shfl_xor_sync(0xffffffffu, v1, j);
+            }
+            // element i: descending block when (i & k) == 0, lower partner when (i & j) == 0; it keeps the max iff both agree
+            const bool max0 = (((t >> lk) ^ (t >> lj)) & 1) == 0;
+            v0 = pick(v0, p0, max0);
+            if (TWO) v1 = pick(v1, p1, lk == 10 ? !max0 : max0);      // i = t + 1024: only bit 10 differs (k == 1024 flips)
+        }
+    }
+    __syncthreads();                                      // the last shared-memory step may still be read by slower warps
+    s[t] = v0;
+    if (TWO) s[t + kTopkThreads] = v1;
+    __syncthreads();
+}
+__device__ __noinline__ void bitonic_desc(unsigned long long* s, unsigned long long* s2, int npow) {
+    if (npow > kTopkThreads) bitonic_desc_t<true>(s, s2, npow);
+    else bitonic_desc_t<false>(s, s2, npow);
+}
+
 __global__ void __launch_bounds__(kTopkThreads, 2)     // 2 CTAs / SM: the kernel is latency-bound (block scans between passes)
 k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* __restrict__ seed_ptr,
        const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score,
        const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out, float* __restrict__ thr_out) {
-    __shared__ uint32_t s_hist[4096];
-    __shared__ unsigned long long s_cand[kCandMax];
+    __shared__ __align__(16) uint32_t s_hist[4096];
+    __shared__ __align__(16) unsigned long long s_cand[kCandMax];
     __shared__ int s_seed[kCandMax];
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_out[2];
@@ -105,15 +187,94 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     const int* rm = remap != nullptr ? remap + (size_t)row * ld : nullptr;
     if (row_n != nullptr) T = min(row_n[row], (int)ld);
 
-    int nseed = 0;
+    int nseed = 0, sb = 0;
     if (seed_ptr != nullptr) {
-        const int sb = seed_ptr[row];
+        sb = seed_ptr[row];
         nseed = min(seed_ptr[row + 1] - sb, kCandMax - K > 0 ? kCandMax - K : 0);
-        for (int i = t; i < nseed; i += kTopkThreads) s_seed[i] = seed_idx[sb + i] - idx_base;
     }
     uint32_t want = (uint32_t)min(K + nseed, T);
     if (want > (uint32_t)kCandMax) want = kCandMax;
     const uint32_t want0 = want;
+    const int ncand = (int)want0;
+
+    // ---- fast path: ONE scan for a pre-threshold, one to gather what passes it, then a sort of that small set ----------
+    // The row is cut into 2048 groups (thread t: elements t + 1024 j, even j -> group t, odd j -> group t + 1024).  The
+    // want-th largest of the group MAXIMA is a lower bound of the want-th largest element (each of those want groups holds
+    // an element >= it), and close to it while want << 2048: everything >= it (typically 1.0-1.4 x want entries) is
+    // gathered into shared memory and sorted by (score desc, id asc) -- the first `want` entries are exactly what the three
+    // radix passes + ordered tie collection below produce.  More than 2048 gathered entries (heavy ties, want near 2048):
+    // the general path below redoes the row.
+    bool sorted = false;
+    if (want0 > 0 && want0 <= (uint32_t)kTopkThreads) {
+        uint32_t t0 = 0u;                                   // pre-threshold key; 0 = keep everything (T <= 2048)
+        if (T > kCandMax) {
+            uint32_t m0 = 0u, m1 = 0u;
+            int i = t;
+            for (; i + 7 * kTopkThreads < T; i += 8 * kTopkThreads) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = x[i + u * kTopkThreads];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t key = score_key(sigmoid_out ? __fdividef(1.f, 1.f + __expf(-v[u])) : v[u]);
+                    if (u & 1) m1 = max(m1, key); else m0 = max(m0, key);
+                }
+            }
+            for (int u = 0; i < T; i += kTopkThreads, ++u) {
+                const uint32_t key = score_key(load_score(x, i, sigmoid_out));
+                if (u & 1) m1 = max(m1, key); else m0 = max(m0, key);
+            }
+            uint32_t* s_max = reinterpret_cast<uint32_t*>(s_seed);      // the seeds are loaded after the select
+            s_max[t] = m0;
+            s_max[t + kTopkThreads] = m1;
+            __syncthreads();
+            t0 = select_kth_smem(s_max, 1, 2 * kTopkThreads, want0, 2, s_hist, s_warp, s_out);
+        }
+        if (t == 0) s_cnt[0] = 0;
+        __syncthreads();
+        const int Tround4 = (T + 4 * kTopkThreads - 1) / (4 * kTopkThreads) * (4 * kTopkThreads);
+        for (int i0 = t; i0 < Tround4; i0 += 4 * kTopkThreads) {
+            uint32_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kTopkThreads;
+                key[u] = i < T ? score_key(load_score(x, i, sigmoid_out)) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kTopkThreads;
+                const bool hit = i < T && key[u] >= t0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (bal) {
+                    const int lane = t & 31, leader = __ffs(bal) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&s_cnt[0], (uint32_t)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+                    if (hit && slot < (uint32_t)kCandMax)
+                        s_cand[slot] = ((unsigned long long)key[u] << 32) | (0xFFFFFFFFu - (uint32_t)(rm ? rm[i] : i));
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t c = s_cnt[0];
+        if (c <= (uint32_t)kCandMax) {
+            if (thr_out != nullptr) {      // threshold only: the K-th largest of the gathered keys (the high words), no sort
+                const uint32_t kth = T >= K ? select_kth_smem(reinterpret_cast<const uint32_t*>(s_cand) + 1, 2, (int)c, (uint32_t)K, 3,
+                                                              s_hist, s_warp, s_out) : 0u;
+                if (t == 0) thr_out[row] = filter_threshold(T >= K ? key_score(kth) : -CUDART_INF_F);
+                return;
+            }
+            int npow = 32;
+            while (npow < (int)c) npow <<= 1;
+            for (int i = (int)c + t; i < npow; i += kTopkThreads) s_cand[i] = 0ull;
+            __syncthreads();
+            bitonic_desc(s_cand, reinterpret_cast<unsigned long long*>(s_hist), npow);
+            sorted = true;
+        }
+        __syncthreads();
+    }
+    if (!sorted) {
 
     // ---- pass 1..3: radix select of the want-th largest key -------------------------------
     uint32_t prefix = 0;      // selected high bits so far
@@ -220,25 +381,14 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     __syncthreads();
     // slots [0, want0-need_eq) hold keys > thr (count == above_total == want0-need_eq), then the ties
     (void)above_total;
-    const int ncand = (int)want0;
-    int npow = 1;
+    int npow = 32;
     while (npow < ncand) npow <<= 1;
     for (int i = ncand + t; i < npow; i += kTopkThreads) s_cand[i] = 0ull;
     __syncthreads();
-    // ---- bitonic sort, descending on (key, ~idx) => score desc, index asc ----------------------
-    for (int k = 2; k <= npow; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = t; i < npow; i += kTopkThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = s_cand[i], b = s_cand[ixj];
-                    const bool desc = (i & k) == 0;
-                    if ((a < b) == desc) { s_cand[i] = b; s_cand[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    bitonic_desc(s_cand, reinterpret_cast<unsigned long long*>(s_hist), npow);   // on (key, ~idx): score desc, index asc
+    }   // !sorted
+    for (int i = t; i < nseed; i += kTopkThreads) s_seed[i] = seed_idx[sb + i] - idx_base;
+    __syncthreads();
     // ---- drop seeds, ordered compaction, first K --------------------------------------------------
     // each thread owns 2 consecutive candidates (kCandMax / kTopkThreads)
     uint32_t keepf[2] = {0, 0};

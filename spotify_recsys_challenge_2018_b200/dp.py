@@ -143,6 +143,7 @@ class ShardedRecommender:
         self._x = C.c_void_p()
         _lib.check(self._lib.dae_exchange_create(model.device, world, rank, model.n_batch, int(max_k), C.byref(self._x)))
         self.max_k = int(max_k)
+        self.share_thresholds = True
         if not explicit and world > 1:
             self.attach_ipc(group)
 
@@ -167,12 +168,26 @@ class ShardedRecommender:
         _lib.check(self._lib.dae_exchange_attach_local(self._x, arr, len(recommenders)))
 
     def rank_shard(self, x_positions, x_vals, seeds, k=500):
-        """This rank's slice: lists stay on the device (model buffers "topk_idx" / "topk_score")."""
-        self.model.recommend(x_positions, x_vals, seeds, k=k, item_range=self.range, on_device=True)
+        """This rank's slice: lists stay on the device (model buffers "topk_idx" / "topk_score").  Collective when
+        `share_thresholds` (default): the shards agree on the filter thresholds of the fused decode + top-K (the minimum
+        over the shards of each one's ceil(kp / world)-th largest logit), which shortens every shard's candidate lists by
+        ~world; the lists returned are the same either way."""
+        from . import _lib
+        share = self.share_thresholds and self.world > 1
+        if share:
+            _lib.check(self._lib.dae_model_set_threshold_exchange(self.model._h, self._x))
+        try:
+            self.model.recommend(x_positions, x_vals, seeds, k=k, item_range=self.range, on_device=True)
+        finally:
+            if share:
+                _lib.check(self._lib.dae_model_set_threshold_exchange(self.model._h, None))
 
-    def merge(self, k=500, return_scores=False, reuse_output=False):
+    def merge(self, k=500, return_scores=False, reuse_output=False, rows="all"):
         """Collective: store this rank's lists into every peer's merge buffer, barrier, merge locally -> host arrays
-        (`reuse_output=True`: page-locked arrays owned by this object, overwritten by the next call)."""
+        (`reuse_output=True`: page-locked arrays owned by this object, overwritten by the next call).
+        rows="own": the merge is sharded by playlist -- this rank receives, merges and returns only ITS rows
+        [r0, r1) of the batch (`self.rows` after the call; the returned arrays are those rows): 1 / world of the stores,
+        the merge and the read-back, for callers that write their own part of the submission."""
         import ctypes as C
         from . import _lib
         from .models.DAEs import _PinnedPool
@@ -187,15 +202,38 @@ class ShardedRecommender:
         else:
             out_i = np.empty((B, k), np.int32)
             out_s = np.empty((B, k), np.float32) if return_scores else None
-        _lib.check(self._lib.dae_exchange_merge_topk(self._x, C.c_void_p(pi), C.c_void_p(ps), B, int(k),
-                                                     out_i.ctypes.data_as(C.c_void_p),
-                                                     out_s.ctypes.data_as(C.c_void_p) if out_s is not None else None,
-                                                     C.c_void_p(self.model.stream) if self.model.stream else None))
+        st = C.c_void_p(self.model.stream) if self.model.stream else None
+        po_i = out_i.ctypes.data_as(C.c_void_p)
+        po_s = out_s.ctypes.data_as(C.c_void_p) if out_s is not None else None
+        if rows == "own":
+            r0, r1 = C.c_int32(), C.c_int32()
+            _lib.check(self._lib.dae_exchange_merge_topk_rows(self._x, C.c_void_p(pi), C.c_void_p(ps), B, int(k),
+                                                              C.byref(r0), C.byref(r1), po_i, po_s, st))
+            self.rows = (r0.value, r1.value)
+            out_i = out_i[r0.value:r1.value]
+            out_s = out_s[r0.value:r1.value] if out_s is not None else None
+        elif rows == "all":
+            _lib.check(self._lib.dae_exchange_merge_topk(self._x, C.c_void_p(pi), C.c_void_p(ps), B, int(k), po_i, po_s, st))
+            self.rows = (0, B)
+        else:
+            raise ValueError("rows must be 'all' or 'own'")
         return (out_i, out_s) if return_scores else out_i
 
-    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, reuse_output=False):
+    def recommend(self, x_positions, x_vals, seeds, k=500, return_scores=False, reuse_output=False, rows="all"):
         self.rank_shard(x_positions, x_vals, seeds, k)
-        return self.merge(k, return_scores, reuse_output)
+        return self.merge(k, return_scores, reuse_output, rows)
+
+    def set_profiling(self, on):
+        from . import _lib
+        _lib.check(self._lib.dae_exchange_set_profiling(self._x, 1 if on else 0))
+
+    def phase_times(self):
+        """ms per call: stores, barrier, merge, read-back (device times, mean over the profiled calls)."""
+        import ctypes as C
+        from . import _lib
+        out = (C.c_float * 4)()
+        _lib.check(self._lib.dae_exchange_phase_ms(self._x, out))
+        return dict(zip(("exchange_store", "exchange_barrier", "exchange_merge", "exchange_d2h"), [float(v) for v in out]))
 
     def launch_count(self):
         return int(self._lib.dae_exchange_launch_count(self._x))

@@ -273,10 +273,13 @@ def test_sharded_recommender_peer_store_merge_local(world, N, T, H, B, k):
     import threading
     res = [None] * world
     for rc in recs:                      # first call allocates the models' list buffers: cudaMalloc synchronises the DEVICE,
-        rc.rank_shard(trk, xv, seeds, k)  # which ranks sharing one GPU must not do while a peer's barrier kernel is spinning
+        # which ranks sharing one GPU must not do while a peer's barrier kernel is spinning (rank_shard itself is
+        # collective -- the shards exchange their filter thresholds -- so the warm-up goes through the model)
+        rc.model.recommend(trk, xv, seeds, k=k, item_range=rc.range, on_device=True)
 
     def run(r):
         for call in range(3):
+            recs[r].share_thresholds = call != 1          # per-shard thresholds (call 1) and shared ones: the same lists
             recs[r].rank_shard(trk, xv, seeds, k)
             res[r] = recs[r].merge(k, return_scores=True)
     ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
@@ -287,6 +290,27 @@ def test_sharded_recommender_peer_store_merge_local(world, N, T, H, B, k):
     for r in range(world):
         got_i, got_s = res[r]
         assert np.array_equal(got_i, want_i) and np.array_equal(got_s, want_s), r
+
+    # the merge sharded by playlist (rows="own"): every rank returns exactly its rows of the unsharded ranking, the rows
+    # of all ranks tile the batch, and the calls keep alternating the merge buffers with the "all" calls before them
+    def run_own(r):
+        for call in range(3):
+            recs[r].rank_shard(trk, xv, seeds, k)
+            res[r] = recs[r].merge(k, return_scores=True, rows="own")
+    ts = [threading.Thread(target=run_own, args=(r,)) for r in range(world)]
+    for t_ in ts:
+        t_.start()
+    for t_ in ts:
+        t_.join(timeout=300)
+    nxt = 0
+    for r in range(world):
+        r0, r1 = recs[r].rows
+        assert r0 == nxt and r1 >= r0
+        nxt = r1
+        got_i, got_s = res[r]
+        assert got_i.shape == (r1 - r0, k)
+        assert np.array_equal(got_i, want_i[r0:r1]) and np.array_equal(got_s, want_s[r0:r1]), r
+    assert nxt == B
     for rc in recs:
         rc.close()
     for m in ms:

@@ -29,7 +29,7 @@ if [ -z "$SKIP_NCU" ]; then
   B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-aux"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launch.log 2>&1; echo "launch list rc=$?"
   # hot kernels of one step, in launch order; skip the first 4 steps' worth of matches, capture one step's worth (+ slack)
-  KRE='k_adam_rows_vec4|k_adam_listed|k_itemtile|k_dw_adam|k_dh|k_encode_fwd|k_scatter_shard|k_scatter_det|k_da_all'
+  KRE='k_adam_rows_vec4|k_adam_listed|k_itemtile|k_dw_adam|k_dh|k_encode_fwd|k_scatter_shard|k_scatter_det|k_da_own'
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s ${NCU_SKIP:-36} -c ${NCU_COUNT:-9} -f -o gpurun_out/prof_hot $B > gpurun_out/ncu_hot.log 2>&1; echo "full capture rc=$?"
   ncu -i gpurun_out/prof_hot.ncu-rep --page raw --csv > gpurun_out/prof_hot.raw.csv 2>/dev/null
   ncu -i gpurun_out/prof_hot.ncu-rep --page details --csv > gpurun_out/prof_hot.details.csv 2>/dev/null
