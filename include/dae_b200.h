@@ -202,7 +202,9 @@ int64_t dae_exchange_launch_count(dae_exchange* x);
  * through fp32 red.add only (the multi-GPU default), bit 12: ordered gather for the rows listed by >= 3 playlists (the
  * single-GPU default: bit-reproducible steps).  bit 13: %globaltimer stamps of the step's fork / join points into the
  * buffer "trace" (tools/gpu_trace.py).  bit 14: the title branch forms dW_out in HBM ("g_W_out") and runs its Adam as a
- * second kernel instead of the fused one. */
+ * second kernel instead of the fused one.  bit 15 (process-wide, experiment): inference batches of more than 256 rows
+ * decode in 128-row tiles, clusters of two tiles sharing every W chunk through TMA multicast (measured slower than the
+ * default 256-row tiles; kept for A/B). */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row

@@ -47,7 +47,8 @@ constexpr int kABytes = kTileItems * 128;           // one K-chunk of the stream
 constexpr int kBChunkBytes = 256 * 128;             // one K-chunk of the resident operand: <=256 rows x 128 B
 constexpr int kSmemB = 4 * kBChunkBytes;            // 131072
 constexpr int kSmemA = kStages * kABytes;           // 98304
-constexpr int kSmemBars = 256;
+constexpr int kSmemBars = 512;
+constexpr int kMaxRing = 12;                          // barrier slots of the streamed-operand ring (inference modes size it at run time)
 constexpr int kSmemThr = kMaxBpad * 4;              // FILTER: per-playlist thresholds of the CTA's batch tile
 constexpr int kWStg = kABytes / 8 / 16;             // FILTER: candidates staged per epilogue warp (128) in one ring stage's worth of smem
 constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + kSmemThr + 1024;  // + alignment slack
@@ -87,6 +88,8 @@ struct ItemTileDev {
     int item0;               // catalogue id of row 0 of the streamed operand
     int raw_logits;          // PREDICT: write z instead of sigmoid(z)
     unsigned long long* trace;   // debug: %globaltimer when the first / last CTA of the grid started
+    int pair;                // PREDICT / FILTER: launched as clusters of two batch tiles (grid.y) that share every W chunk
+    int ring;                // PREDICT / FILTER: 16 KB stages behind the resident operand (FILTER gives the last one to staging)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -198,13 +201,26 @@ struct CandOut {
 // atomics of 32 entries are in flight together, instead of one per hit stalling the scan.
 __device__ __noinline__ void flush_candidates(const uint2* seg, int n, const CandOut o) {
     const int lane = threadIdx.x & 31;
-    for (int i = lane; i < n; i += 32) {
-        const uint2 e = seg[i];
-        const int b = o.b0 + (int)(e.x & 255u);
-        const int gp = atomicAdd(o.cnt + b, 1);
-        if (gp < o.cap) {
-            o.val[(size_t)b * o.cap + gp] = __uint_as_float(e.y);
-            o.idx[(size_t)b * o.cap + gp] = o.item0 + (int)(e.x >> 8);
+    // four rounds of 32 entries at a time: all their returned atomics are issued before the first dependent store, so a
+    // whole staging segment (128 entries) costs ONE round trip to L2, not four
+    for (int i0 = 0; i0 < n; i0 += 128) {
+        uint2 e[4];
+        int gp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32 + lane;
+            e[u] = i < n ? seg[i] : make_uint2(0xFFFFFFFFu, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            gp[u] = e[u].x != 0xFFFFFFFFu ? atomicAdd(o.cnt + o.b0 + (int)(e[u].x & 255u), 1) : o.cap;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (gp[u] < o.cap) {
+                const int b = o.b0 + (int)(e[u].x & 255u);
+                o.val[(size_t)b * o.cap + gp[u]] = __uint_as_float(e[u].y);
+                o.idx[(size_t)b * o.cap + gp[u]] = o.item0 + (int)(e[u].x >> 8);
+            }
         }
     }
     __syncwarp();
@@ -218,26 +234,37 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
-    // ring stages that exist in shared memory (TRAIN: 4, see kStagesTrain) and that carry W chunks (FILTER gives the
-    // last one, 16 KB, to the candidate staging buffer)
-    constexpr int RING = MODE == MODE_TRAIN ? kStagesTrain : kStages;
-    constexpr int NST = MODE == MODE_FILTER ? kStages - 1 : RING;
+    // Shared memory: the resident operand (h_d of the batch tile: kchunks x [n_cols rows x 128 B]), then the ring of W
+    // chunks, then barriers at a fixed offset.  TRAIN: 4 stages behind a 128 KB resident area (kStagesTrain).  Inference:
+    // the ring takes ALL the space the resident operand leaves -- the decode is paced by bytes in flight (TMA latency x
+    // rate), and a 128-row batch tile (64 KB resident) leaves 10 stages where a 256-row one leaves 6; FILTER gives the last
+    // stage, 16 KB, to the candidate staging buffer.
+    const int bchunk = MODE == MODE_TRAIN ? kBChunkBytes : p.n_cols * 128;
+    const int RING = MODE == MODE_TRAIN ? kStagesTrain : p.ring;
+    const int NST = MODE == MODE_FILTER ? RING - 1 : RING;
+    constexpr int kRingBytes = (MODE == MODE_TRAIN ? kStagesTrain : kStages) * kABytes;
     uint8_t* sB = smem;
-    uint8_t* sA = smem + kSmemB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemB + RING * kABytes);
-    uint64_t* full = bars;                 // [kStages]
-    uint64_t* empty = bars + kStages;      // [kStages]
-    uint64_t* bfull = bars + 2 * kStages;  // [1]
+    uint8_t* sA = smem + (MODE == MODE_TRAIN ? kSmemB : ((p.kchunks * bchunk + 1023) & ~1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemB + kRingBytes);
+    uint64_t* full = bars;                 // [kMaxRing]
+    uint64_t* empty = bars + kMaxRing;     // [kMaxRing]
+    uint64_t* bfull = bars + 2 * kMaxRing; // [1]
     uint64_t* tfull = bfull + 1;           // [2]
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
-    float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + RING * kABytes + kSmemBars);   // [n_cols] (FILTER)
+    float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + kRingBytes + kSmemBars);   // [n_cols] (FILTER)
     uint2* stg = reinterpret_cast<uint2*>(sA + NST * kABytes);                       // [kEpiWarps][kWStg] (column | item << 8, logit)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int bt = blockIdx.y;
+    // Pair mode (cluster dims (1, 2, 1)): the two CTAs hold different batch tiles and walk the same item tiles in lock
+    // step.  Each W chunk is read from L2 ONCE -- by the CTA whose rank equals the chunk's parity -- and multicast into both
+    // CTAs' rings; every MMA commit releases the stage in both.  The decode is L2 -> SM bandwidth bound otherwise (16 batch
+    // tiles x 1 GB of W through L2 per pass: ncu 2.6 TB/s, tensor pipe 33 % busy).
+    const bool pair = MODE != MODE_TRAIN && p.pair != 0;
+    const int crank = bt & 1;
     if (MODE == MODE_TRAIN && p.trace != nullptr && threadIdx.x == 0) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -251,9 +278,9 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kMaxRing; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], pair ? 2 : 1);      // a stage is free once BOTH CTAs of the pair have consumed it
         }
         mbar_init(bfull, 1);
         for (int a = 0; a < 2; ++a) {
@@ -265,6 +292,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();                    // the peer's barriers exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -275,7 +303,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const uint64_t pol_keep = policy_evict_last();
             mbar_expect_tx(bfull, static_cast<uint32_t>(p.kchunks * p.n_cols * 128));
             for (int kc = 0; kc < p.kchunks; ++kc)
-                tma_load_2d_hint(sB + kc * kBChunkBytes, &tmB, bfull, kc * 64, bt * p.n_cols, pol_keep);
+                tma_load_2d_hint(sB + kc * bchunk, &tmB, bfull, kc * 64, bt * p.n_cols, pol_keep);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
@@ -283,8 +311,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_expect_tx(&full[stage], kABytes);
                     // several batch tiles re-read the same item tile: keep it in L2 then, stream it otherwise
-                    tma_load_2d_hint(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
-                                     gridDim.y > 1 ? pol_keep : pol_stream);
+                    if (!pair)
+                        tma_load_2d_hint(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems,
+                                         gridDim.y > 1 ? pol_keep : pol_stream);
+                    else if ((kc & 1) == crank)
+                        tma_load_2d_mcast(sA + stage * kABytes, &tmA, &full[stage], kc * 64, tile * kTileItems, 0x3, pol_keep);
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -307,14 +338,15 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-                    const uint32_t b_addr = smem_u32(sB + kc * kBChunkBytes);
+                    const uint32_t b_addr = smem_u32(sB + kc * bchunk);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t ad = umma_smem_desc(a_addr + ks * 32, 16, 1024);
                         const uint64_t bd = umma_smem_desc(b_addr + ks * 32, 16, 1024);
                         umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);
+                    if (pair) umma_commit_mcast(&empty[stage], 0x3);
+                    else umma_commit(&empty[stage]);
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tfull[acc]);
@@ -497,6 +529,12 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (lane == 0) mbar_arrive(&tempty[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
+            if (MODE == MODE_FILTER) {
+                // staged hits leave for the global lists AFTER the accumulator is released: the flush is a round trip to L2
+                // (returned atomics), and the MMA of the tile after next must not wait for it.  (A flush in the middle of
+                // the scan above only happens when one tile yields more hits than the segment holds.)
+                if (wn > kWStg / 2) { flush_candidates(seg, wn, cout); wn = 0; }
+            }
         }
         if (MODE == MODE_FILTER) {
             if (wn > 0) flush_candidates(seg, wn, cout);
@@ -510,6 +548,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();      // no CTA leaves while its peer may still signal its barriers
     tc_fence_after();
     if (MODE == MODE_TRAIN) {
         if (threadIdx.x == 0) {
@@ -549,10 +588,27 @@ int decode_grid(int N, int n_batch_tiles) {
     return tiles < gx ? tiles : gx;
 }
 
+static int g_itemtile_pair = 0;       // dae_model_set_debug bit 15 sets it (multicast batch-tile pairs: measured, no gain)
+void set_itemtile_pair(int on) { g_itemtile_pair = on; }
+
 template <int MODE>
-static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, const ItemTileDev& p, dim3 grid,
-                            cudaStream_t st) {
-    k_itemtile<MODE><<<grid, kItemThreads, MODE == MODE_TRAIN ? kSmemItemTileTrain : kSmemItemTile, st>>>(tmA, tmB, p);
+static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, ItemTileDev p, dim3 grid, cudaStream_t st) {
+    const size_t smem = MODE == MODE_TRAIN ? kSmemItemTileTrain : kSmemItemTile;
+    // an even number of batch tiles (PREDICT / FILTER over a large batch): clusters of two batch tiles share the W stream
+    p.pair = (MODE != MODE_TRAIN && g_itemtile_pair && grid.y >= 2 && grid.y % 2 == 0) ? 1 : 0;
+    p.ring = (kSmemB + kSmemA - ((p.kchunks * p.n_cols * 128 + 1023) & ~1023)) / kABytes;
+    if (p.ring > kMaxRing) p.ring = kMaxRing;
+    if (!p.pair) {
+        k_itemtile<MODE><<<grid, kItemThreads, smem, st>>>(tmA, tmB, p);
+        return;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kItemThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_itemtile<MODE>, tmA, tmB, p);
 }
 
 void launch_decode_train(const DecodeArgs& a, cudaStream_t st) {

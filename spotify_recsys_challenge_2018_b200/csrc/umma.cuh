@@ -95,6 +95,20 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         "l"(policy)
         : "memory");
 }
+// The same load delivered to the same shared-memory offset (and signalled on the mbarrier at the same offset) of every CTA
+// of the cluster whose bit is set in cta_mask: one L2 read feeds several SMs.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                                  int32_t c1, uint16_t cta_mask, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5, %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "h"(cta_mask), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // 1-D bulk copies (no tensor map): contiguous global <-> shared, 16-byte aligned, size % 16 == 0.
 // Load completion is signalled on an mbarrier (complete_tx::bytes); stores are tracked per issuing thread
 // in bulk async-groups (commit_group / wait_group[.read]).
@@ -185,6 +199,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// The same arrival on the mbarrier at this offset in every CTA of the cluster named by cta_mask.
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
 // TMEM -> registers: each lane of the warp reads 32 consecutive fp32 columns of its own TMEM lane

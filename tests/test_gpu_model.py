@@ -381,6 +381,13 @@ def test_fused_decode_topk_equals_dense_ranking(N, T, H, B, k):
     assert np.array_equal(idx_f, idx_d)
     for r in range(B):
         assert not (set(idx_f[r].tolist()) & set(seeds[r]))
+    # bit 15: 128-row batch tiles decoded in multicast pairs (clusters of two batch tiles share every W chunk) instead of
+    # 256-row tiles: the same scores, bit for bit, on both paths
+    for flags in (32 | 32768, 16 | 32768):
+        m.set_debug(flags)
+        idx_u, sc_u = m.recommend(trk, xv, seeds, k=k, return_scores=True)
+        assert np.array_equal(sc_u, sc_d) and np.array_equal(idx_u, idx_d), flags
+    m.set_debug(16)
     # item-sharded (dp.ShardedRecommender's data path): per-range lists merged on the device by (score desc, id asc)
     # == the host statement of the rule == the whole-catalogue list
     import ctypes as C
