@@ -1131,7 +1131,11 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
     // select are skipped: two passes instead of three.
     const int M1 = std::min(Tn, kCandCap - 128);
     const bool two_pass = (double)kq * (double)Tn / (double)M1 <= 0.6 * kCandCap;
-    const int M2 = two_pass ? M1 : std::min(Tn, std::max(round_up(Tn / 8, kTileItems), M1));
+    // middle prefix: as short as the candidate lists of the full-range pass allow (expected length kq x Tn / M2 <= 60 % of
+    // the capacity), but not below Tn / 16 -- a pass costs ~0.2 ms + 2.6 ms per million items + ~0.05 us per candidate
+    // and playlist (4096 playlists), which puts the optimum near Tn / 16 for 2 M items
+    const int M2min = (int)std::min((double)Tn, (double)kq * (double)Tn / (0.6 * kCandCap));
+    const int M2 = two_pass ? M1 : std::min(Tn, std::max(std::max(round_up(Tn / 16, kTileItems), round_up(M2min, kTileItems)), M1));
     CK(cudaMemsetAsync(m->cand_cnt, 0, sizeof(int) * 3 * rows, m->st));
     launch_thr_from_topk(nullptr, nullptr, kp, B, rows, m->cand_thr, m->st);          // pass A keeps everything
     DecodeArgs d{};
@@ -1151,7 +1155,8 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         da.n_out = M1; da.out = m->scores; da.ld_out = M1; da.raw_logits = 1;
         launch_decode_predict(da, m->st);
         TopkArgs ta{};
-        ta.scores = m->scores; ta.ld = M1; ta.B = B; ta.T = M1; ta.k = kq; ta.idx_base = 0;
+        ta.scores = m->scores; ta.ld = M1; ta.B = B; ta.T = M1; ta.k = k; ta.idx_base = 0;
+        ta.seed_ptr = sp; ta.thr_div = xw;                            // per row: its share of k + its own number of seeds
         ta.thr_out = m->cand_thr;                                     // threshold only: no collection, no sort
         launch_topk(ta, m->st);
         if (xw > 1) { TRY(exchange_min_thresholds(m->thr_exchange, m->cand_thr, B, m->st)); ++n_thr_x; }
@@ -1171,7 +1176,7 @@ static int run_recommend_fused(dae_model* m, int k, int lo, int hi, const int* s
         m->launches += 1;
         a.row_n = d.cand_cnt;
         if (stops[pass] < Tn) {                                    // threshold of the next pass: kp-th largest so far
-            a.k = kq; a.seed_ptr = nullptr; a.seed_idx = nullptr; a.sigmoid_out = 0;
+            a.k = k; a.seed_ptr = sp; a.seed_idx = nullptr; a.sigmoid_out = 0; a.thr_div = xw;
             a.thr_out = m->cand_thr;
             launch_topk(a, m->st);
             a.thr_out = nullptr;

@@ -345,7 +345,9 @@ struct TopkArgs {
     const int* row_n;         // [B] or nullptr (every row has T entries)
     int sigmoid_out;          // 1: scores are logits; out_score = sigmoid(logit)
     float* thr_out;           // [B] or nullptr.  Not null: threshold-only mode -- thr_out[r] = the filter threshold derived
-                              // from the k-th largest score of row r (-inf when the row has fewer than k); nothing else is written
+                              // from the kreq-th largest score of row r (-inf when the row has fewer), where
+                              // kreq = ceil((k + #seeds of row r) / thr_div); nothing else is written (seed_idx is not read)
+    int thr_div;              // threshold-only mode: number of item shards that share the thresholds (0 / 1: none)
 };
 void launch_topk(const TopkArgs& a, cudaStream_t st);
 // thr[r] = score[r, kp-1] (r < batch, -inf when that slot is padding or score == nullptr), +inf for r in [batch, rows)

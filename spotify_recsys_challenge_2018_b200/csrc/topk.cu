@@ -173,7 +173,7 @@ __device__ __noinline__ void bitonic_desc(unsigned long long* s, unsigned long l
 __global__ void __launch_bounds__(kTopkThreads, 2)     // 2 CTAs / SM: the kernel is latency-bound (block scans between passes)
 k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* __restrict__ seed_ptr,
        const int* __restrict__ seed_idx, int idx_base, int* __restrict__ out_idx, float* __restrict__ out_score,
-       const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out, float* __restrict__ thr_out) {
+       const int* __restrict__ remap, const int* __restrict__ row_n, int sigmoid_out, float* __restrict__ thr_out, int thr_div) {
     __shared__ __align__(16) uint32_t s_hist[4096];
     __shared__ __align__(16) unsigned long long s_cand[kCandMax];
     __shared__ int s_seed[kCandMax];
@@ -192,7 +192,10 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
         sb = seed_ptr[row];
         nseed = min(seed_ptr[row + 1] - sb, kCandMax - K > 0 ? kCandMax - K : 0);
     }
-    uint32_t want = (uint32_t)min(K + nseed, T);
+    // threshold-only mode: this shard's share of the row's k + #seeds (every shard finds that many above ITS threshold, so
+    // at least k + #seeds items of the catalogue exceed the minimum of the shards' thresholds)
+    const int Kreq = thr_out != nullptr ? (K + nseed + thr_div - 1) / thr_div : K + nseed;
+    uint32_t want = (uint32_t)min(Kreq, T);
     if (want > (uint32_t)kCandMax) want = kCandMax;
     const uint32_t want0 = want;
     const int ncand = (int)want0;
@@ -260,9 +263,9 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
         const uint32_t c = s_cnt[0];
         if (c <= (uint32_t)kCandMax) {
             if (thr_out != nullptr) {      // threshold only: the K-th largest of the gathered keys (the high words), no sort
-                const uint32_t kth = T >= K ? select_kth_smem(reinterpret_cast<const uint32_t*>(s_cand) + 1, 2, (int)c, (uint32_t)K, 3,
-                                                              s_hist, s_warp, s_out) : 0u;
-                if (t == 0) thr_out[row] = filter_threshold(T >= K ? key_score(kth) : -CUDART_INF_F);
+                const uint32_t kth = T >= Kreq ? select_kth_smem(reinterpret_cast<const uint32_t*>(s_cand) + 1, 2, (int)c, want0, 3,
+                                                                 s_hist, s_warp, s_out) : 0u;
+                if (t == 0) thr_out[row] = filter_threshold(T >= Kreq ? key_score(kth) : -CUDART_INF_F);
                 return;
             }
             int npow = 32;
@@ -309,7 +312,7 @@ k_topk(const float* __restrict__ scores, long long ld, int T, int K, const int* 
     if (thr_out != nullptr) {
         // threshold-only mode (the intermediate passes of the fused decode + top-K): the K-th largest logit is all that
         // is needed -- no collection, no sort (half of this kernel's time).  Fewer than K entries: keep everything.
-        if (t == 0) thr_out[row] = filter_threshold(T >= K ? key_score(thr) : -CUDART_INF_F);
+        if (t == 0) thr_out[row] = filter_threshold(T >= Kreq ? key_score(thr) : -CUDART_INF_F);
         return;
     }
     // Ties AT the cut go to the lowest item ids.  In a dense row the position is the id, and the ordered pick below does
@@ -519,7 +522,7 @@ void launch_metrics(const int* cand, long long ld, int B, int k, const int* ans_
 
 void launch_topk(const TopkArgs& a, cudaStream_t st) {
     k_topk<<<a.B, kTopkThreads, 0, st>>>(a.scores, a.ld, a.T, a.k, a.seed_ptr, a.seed_idx, a.idx_base, a.out_idx,
-                                         a.out_score, a.remap, a.row_n, a.sigmoid_out, a.thr_out);
+                                         a.out_score, a.remap, a.row_n, a.sigmoid_out, a.thr_out, a.thr_div > 0 ? a.thr_div : 1);
 }
 
 // Force the module / functions to load now: with CUDA's lazy loading the FIRST launch of a kernel may
