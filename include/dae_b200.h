@@ -142,8 +142,10 @@ int32_t dae_model_sync_cost(dae_model* m, float* cost_out);
  * catalogue-sized state (W_enc, W_dec, Adam moments, the bf16 operand, dz, dW_dec) is row-sharded tile-cyclically, ZeRO
  * style, and every rank decodes, differentiates and updates its OWN item rows against the whole global batch -- that
  * state never crosses NVLink.  All exchange is plain loads / stores into the peers' arenas, issued by the kernels
- * that produce or consume the data; three flag barriers per step order it (A: previous step over everywhere, B1: the
- * global h_d has landed, B2: every rank's dh sums / db_dec rows / cost partial are complete).  Every rank must stage
+ * that produce or consume the data; four flag barriers per step order it (A: previous step over everywhere, B1: the
+ * global h_d has landed, B2: the split-K sums of dh have been stored into their row owners (a reduce-scatter by peer
+ * stores) and every rank's db_dec rows / cost partial are complete, B3: every rank's da rows -- formed by the row owner
+ * only and stored into every rank's copy, an all-gather by peer stores -- have arrived).  Every rank must stage
  * batches of the same size and call the step functions in the same order.  Attach once after dae_model_create on
  * every rank:
  *   dae_model_ipc_handle  -> 64-byte cudaIpcMemHandle_t of this rank's arena (exchange them out of band)

@@ -62,7 +62,7 @@ def attach_peers(model, group=None):
 class DataParallelDAE:
     """A models.DAEs model created with conf.world / conf.rank on this rank's GPU, attached to its peers.
 
-    train_step_staged is the single-GPU call: the library enqueues the three cross-GPU flag barriers
+    train_step_staged is the single-GPU call: the library enqueues the four cross-GPU flag barriers
     of the step itself (include/dae_b200.h, "data parallelism").  Every rank must stage batches of the same size and call in the same order."""
 
     def __init__(self, model, group=None):
