@@ -235,6 +235,8 @@ def aux_workload(args, wl, rank=0, world=1, steps=None):
         m = DAE(conf)
         m.trainable = False
         m.fit()
+        if args.debug_flags:
+            m.set_debug(args.debug_flags)
         trk, art, y, titles, tv, av = g.coo_batch(B, rng)
         trk = np.ascontiguousarray(trk); tv = tv.astype(np.float32)
         order = np.argsort(trk[:, 0], kind="stable")

@@ -997,6 +997,7 @@ extern "C" int32_t dae_model_set_debug(dae_model* m, int32_t flags) {
     if (!m) return fail("null model");
     m->debug = flags;
     set_itemtile_pair((flags & 32768) ? 1 : 0);      // process-wide: multicast batch-tile pairs + 128-row tiles (A/B)
+    set_itemtile_tune((flags >> 16) & 0xff);         // process-wide: A/B switches of the FILTER epilogue
     return 0;
 }
 

@@ -25,6 +25,7 @@
 // consecutive phases of every barrier it waits on.  tests/test_sync_protocol.py models it.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -90,6 +91,7 @@ struct ItemTileDev {
     unsigned long long* trace;   // debug: %globaltimer when the first / last CTA of the grid started
     int pair;                // PREDICT / FILTER: launched as clusters of two batch tiles (grid.y) that share every W chunk
     int ring;                // PREDICT / FILTER: 16 KB stages behind the resident operand (FILTER gives the last one to staging)
+    int tune;                // FILTER A/B switches (dae_model_set_debug bits 16..): bit 0 = no flush in the idle time before a tile
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -160,6 +162,17 @@ __device__ __forceinline__ void train_chunk_exact(const uint32_t (&r)[kCw], uint
 
 // min of three (sm_100 FMNMX3)
 __device__ __forceinline__ float min3(float a, float b, float c) { float y; asm("min.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
+// max of three (FMNMX3) and the packed two-lane fp32 add of sm_100 (FADD2: one issue slot for two accumulator columns)
+__device__ __forceinline__ float max3(float a, float b, float c) { float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
+__device__ __forceinline__ float2 add2(uint32_t a0, uint32_t a1, float b0, float b1) {
+    unsigned long long a, b, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d));
+    return r;
+}
 
 // G1 TRAIN epilogue, the common case: 16 full columns treated as y = 0 (targets are ~5e-4 dense; the few y = 1
 // cells are patched afterwards from tensor memory).  Per element: t = -z log2e (bias folded, FFMA), e = 2^t (MUFU),
@@ -194,13 +207,13 @@ __device__ __forceinline__ void train_chunk_y0(const uint32_t (&r)[kCw], float c
     lg_sum = ls; dz_sum = sd; minden = md;
 }
 
-struct CandOut {
-    float* val; int* idx; int* cnt; int cap; int item0; int b0;    // b0: first playlist of the CTA's batch tile
-};
 // One warp moves its staged candidates (column | item << 8, logit) to the playlists' global lists: the returned global
 // atomics of 32 entries are in flight together, instead of one per hit stalling the scan.
-__device__ __noinline__ void flush_candidates(const uint2* seg, int n, const CandOut o) {
+// (`o` = the kernel's parameter block: it lives in the constant bank, so the scan keeps no output pointers in registers.)
+__device__ __noinline__ void flush_candidates(const uint2* seg, int n, const ItemTileDev& o) {
     const int lane = threadIdx.x & 31;
+    const int b0 = blockIdx.y * o.n_cols;          // first playlist of the CTA's batch tile
+    __syncwarp();                                  // the segment was written by other lanes
     // four rounds of 32 entries at a time: all their returned atomics are issued before the first dependent store, so a
     // whole staging segment (128 entries) costs ONE round trip to L2, not four
     for (int i0 = 0; i0 < n; i0 += 128) {
@@ -213,17 +226,79 @@ __device__ __noinline__ void flush_candidates(const uint2* seg, int n, const Can
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            gp[u] = e[u].x != 0xFFFFFFFFu ? atomicAdd(o.cnt + o.b0 + (int)(e[u].x & 255u), 1) : o.cap;
+            gp[u] = e[u].x != 0xFFFFFFFFu ? atomicAdd(o.cand_cnt + b0 + (int)(e[u].x & 255u), 1) : o.cand_cap;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (gp[u] < o.cap) {
-                const int b = o.b0 + (int)(e[u].x & 255u);
-                o.val[(size_t)b * o.cap + gp[u]] = __uint_as_float(e[u].y);
-                o.idx[(size_t)b * o.cap + gp[u]] = o.item0 + (int)(e[u].x >> 8);
+            if (gp[u] < o.cand_cap) {
+                const int b = b0 + (int)(e[u].x & 255u);
+                o.cand_val[(size_t)b * o.cand_cap + gp[u]] = __uint_as_float(e[u].y);
+                o.cand_idx[(size_t)b * o.cand_cap + gp[u]] = o.item0 + (int)(e[u].x >> 8);
             }
         }
     }
     __syncwarp();
+}
+
+// The rare half chunks of the FILTER scan that hold a hit (the scan's pre-test passed for some lane): the exact per-cell
+// test z_k = acc_k + bias >= thr_k into a per-lane hit mask, then the hits go to the warp's PRIVATE staging segment at
+// positions from a warp scan of the lanes' hit counts (no atomics, no block barriers; list order is irrelevant to the
+// select) and from there to the playlists' global lists 100+ at a time.  Re-reads the 16 accumulator columns at `taddr`
+// (the caller's copy would have to live across the call).  thr0 = index of the first column's threshold; tag = column |
+// item << 8 of column 0; returns the new number of staged entries.
+__device__ __noinline__ int filter_hits(uint32_t taddr, int thr0, float bzf, uint32_t tag, uint2* seg, int wn, const ItemTileDev& p) {
+    const int lane = threadIdx.x & 31;
+    uint32_t r[kCw];
+    tmem_ld16(taddr, r);
+    tmem_ld_wait();
+    const float4* th4 = reinterpret_cast<const float4*>(p.thr + thr0);
+    uint32_t hit = 0;                                // bit k: this lane's cell of column k passes
+#pragma unroll
+    for (int j4 = 0; j4 < kCw / 4; ++j4) {
+        const float4 th = __ldg(th4 + j4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float z = __uint_as_float(r[4 * j4 + u]) + bzf;
+            r[4 * j4 + u] = __float_as_uint(z);
+            const float t = u == 0 ? th.x : (u == 1 ? th.y : (u == 2 ? th.z : th.w));
+            if (z >= t) hit |= 1u << (4 * j4 + u);
+        }
+    }
+    if (!__any_sync(0xffffffffu, hit != 0)) return wn;
+    const int mine = __popc(hit);
+    int pos = mine;                                  // inclusive scan of the lanes' hit counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += up;
+    }
+    const int tot = __shfl_sync(0xffffffffu, pos, 31);
+    if (wn + tot > kWStg) { flush_candidates(seg, wn, p); wn = 0; }
+    if (tot <= kWStg) {
+        uint2* dst = seg + wn + (pos - mine);
+#pragma unroll
+        for (int k = 0; k < kCw; ++k) {
+            if ((hit >> k) & 1u) {
+                *dst = make_uint2(tag + k, r[k]);
+                ++dst;
+            }
+        }
+        return wn + tot;
+    }
+    // more hits in one half chunk than a segment holds (a playlist whose threshold is still -inf): column by column,
+    // flushing as the segment fills
+#pragma unroll 1
+    for (int k = 0; k < kCw; ++k) {
+        const unsigned am = __ballot_sync(0xffffffffu, (hit >> k) & 1u);
+        if (am == 0) continue;
+        if (wn + 32 > kWStg) { flush_candidates(seg, wn, p); wn = 0; }
+        uint32_t zk = 0;
+#pragma unroll
+        for (int kk = 0; kk < kCw; ++kk) zk = kk == k ? r[kk] : zk;
+        if ((am >> lane) & 1u) seg[wn + __popc(am & ((1u << lane) - 1u))] = make_uint2(tag + k, zk);
+        wn += __popc(am);
+        __syncwarp();
+    }
+    return wn;
 }
 
 // blockIdx.y = batch tile: TRAIN decodes this rank's item rows against every rank's rows of the global batch
@@ -272,7 +347,13 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         atomicMax(p.trace + 1, now);
     }
     if (MODE == MODE_FILTER) {
-        for (int i = threadIdx.x; i < p.n_cols; i += blockDim.x) thr_smem[i] = p.thr[bt * p.n_cols + i];
+        // the scan's pre-test works on max_k(z_k - thr_k): shared memory holds MINUS the threshold, loosened by more than the
+        // rounding of either form of the comparison (the exact test z_k >= thr_k of the rare chunks that pass the pre-test
+        // reads the thresholds themselves, from L1 / L2)
+        for (int i = threadIdx.x; i < p.n_cols; i += blockDim.x) {
+            const float t = p.thr[bt * p.n_cols + i];
+            thr_smem[i] = fabsf(t) <= 3.0e38f ? -(t - (1e-3f + 4e-7f * fabsf(t))) : -t;
+        }
     }
 
     if (threadIdx.x == 0) {
@@ -373,8 +454,6 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         // FILTER: this warp's staging segment, entries staged (warp-uniform), where they go
         uint2* seg = stg + (warp - 2) * kWStg;
         int wn = 0;
-        const unsigned ltmask = (1u << lane) - 1u;
-        const CandOut cout{p.cand_val, p.cand_idx, p.cand_cnt, p.cand_cap, p.item0, bt * p.n_cols};
         // per-tile scalars of this lane's item row (bias, target words of the warp's two chunks) are fetched ONE TILE
         // AHEAD: they come from HBM (~1 us) and would otherwise stall the warp at the top of every tile
         float bz_nx = 0.f;
@@ -403,6 +482,13 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             float db = 0.f, lt = 0.f;
             const float c2 = bz * c1;
             const float bzf = item_ok ? bz : __int_as_float(0x7fc00000);   // FILTER: rows past the range compare false (NaN)
+            if (MODE == MODE_FILTER) {
+                // A flush is a round trip to L2 (returned atomics): a warp that is AHEAD of the tensor core -- its next
+                // accumulator is not ready -- flushes now, for free; a warp that is behind keeps scanning and flushes only
+                // when its segment is nearly full (below).  Every tile needs all 16 warps, so a flush on the critical warp
+                // would delay the whole CTA.
+                if (wn >= 32 && !(p.tune & 1) && !mbar_test(&tfull[acc], acc_phase)) { flush_candidates(seg, wn, p); wn = 0; }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
@@ -458,42 +544,31 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     }
                 } else if (MODE == MODE_FILTER) {
                     // fused decode + top-K, filter stage: keep the logits >= the playlist's threshold (a lower bound of
-                    // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.3 % of the cells pass in
-                    // the full-range pass.  Per cell: FADD, FSETP, ballot, uniform branch.  Hits go to the warp's PRIVATE
-                    // staging segment (position from the ballot, count in a warp-uniform register: no atomics, no block
-                    // barriers) and from there to the global lists 100+ at a time.
+                    // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.03 % of the cells pass in
+                    // the full-range pass, ~4 % in the middle one.  The scan is a PRE-TEST on the lane's 16 cells at once:
+                    // m = max_k (acc_k - thr'_k) (one FADD2 + one FMNMX3 per two cells, thr' = the threshold loosened beyond
+                    // the rounding of both forms), then (m + bias) >= -tol and ONE vote per half chunk.  Only half chunks
+                    // that pass (14 % in the full-range pass) go through filter_hits (out of line: it re-reads its 16
+                    // columns from tensor memory, so the scan keeps a small register set and nothing of the tile loop
+                    // spills).
 #pragma unroll 1
                     for (int hh = 0; hh < 2; ++hh) {
                         const int col0 = c * 32 + hh * kCw;
                         uint32_t r[kCw];
                         tmem_ld16(t_addr + col0, r);
                         tmem_ld_wait();
-                        const float4* th4 = reinterpret_cast<const float4*>(thr_smem + col0);
-                        // all 16 ballots first (independent: they pipeline), then the rare hits column by column
-                        unsigned am[kCw];
+                        const float4* nth4 = reinterpret_cast<const float4*>(thr_smem + col0);
+                        float mx = -CUDART_INF_F;
 #pragma unroll
                         for (int j4 = 0; j4 < kCw / 4; ++j4) {
-                            const float4 th = th4[j4];                       // same address for every lane: broadcast
-                            am[4 * j4 + 0] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 0]) + bzf >= th.x);
-                            am[4 * j4 + 1] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 1]) + bzf >= th.y);
-                            am[4 * j4 + 2] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 2]) + bzf >= th.z);
-                            am[4 * j4 + 3] = __ballot_sync(0xffffffffu, __uint_as_float(r[4 * j4 + 3]) + bzf >= th.w);
+                            const float4 nt = nth4[j4];                      // same address for every lane: broadcast
+                            const float2 d0 = add2(r[4 * j4 + 0], r[4 * j4 + 1], nt.x, nt.y);
+                            const float2 d1 = add2(r[4 * j4 + 2], r[4 * j4 + 3], nt.z, nt.w);
+                            mx = max3(mx, d0.x, d0.y);
+                            mx = max3(mx, d1.x, d1.y);
                         }
-                        unsigned any = 0;
-#pragma unroll
-                        for (int k = 0; k < kCw; ++k) any |= am[k];
-                        if (any != 0) {
-#pragma unroll
-                            for (int k = 0; k < kCw; ++k) {
-                                if (am[k] != 0) {
-                                    if (wn + 32 > kWStg) { flush_candidates(seg, wn, cout); wn = 0; }
-                                    if ((am[k] >> lane) & 1u)
-                                        seg[wn + __popc(am[k] & ltmask)] = make_uint2((uint32_t)(col0 + k) | ((uint32_t)item << 8),
-                                                                                      __float_as_uint(__uint_as_float(r[k]) + bzf));
-                                    wn += __popc(am[k]);
-                                }
-                            }
-                        }
+                        if (__any_sync(0xffffffffu, mx + bzf >= -4e-7f * fabsf(bzf)))        // tolerance: rounding of (acc - thr) ~ ulp(bias)
+                            wn = filter_hits(t_addr + col0, bt * p.n_cols + col0, bzf, (uint32_t)col0 | ((uint32_t)item << 8), seg, wn, p);
                     }
                 } else {
                     uint32_t r[32];
@@ -533,11 +608,11 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 // staged hits leave for the global lists AFTER the accumulator is released: the flush is a round trip to L2
                 // (returned atomics), and the MMA of the tile after next must not wait for it.  (A flush in the middle of
                 // the scan above only happens when one tile yields more hits than the segment holds.)
-                if (wn > kWStg / 2) { flush_candidates(seg, wn, cout); wn = 0; }
+                if (wn > ((p.tune & 1) ? kWStg / 2 : kWStg - 40)) { flush_candidates(seg, wn, p); wn = 0; }
             }
         }
         if (MODE == MODE_FILTER) {
-            if (wn > 0) flush_candidates(seg, wn, cout);
+            if (wn > 0) flush_candidates(seg, wn, p);
         }
         if (MODE == MODE_TRAIN) {
 #pragma unroll
@@ -590,6 +665,8 @@ int decode_grid(int N, int n_batch_tiles) {
 
 static int g_itemtile_pair = 0;       // dae_model_set_debug bit 15 sets it (multicast batch-tile pairs: measured, no gain)
 void set_itemtile_pair(int on) { g_itemtile_pair = on; }
+static int g_itemtile_tune = 0;       // dae_model_set_debug bits 16.. (A/B switches of the FILTER epilogue)
+void set_itemtile_tune(int bits) { g_itemtile_tune = bits; }
 
 template <int MODE>
 static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, ItemTileDev p, dim3 grid, cudaStream_t st) {
@@ -597,6 +674,7 @@ static void launch_itemtile(const CUtensorMap& tmA, const CUtensorMap& tmB, Item
     // an even number of batch tiles (PREDICT / FILTER over a large batch): clusters of two batch tiles share the W stream
     p.pair = (MODE != MODE_TRAIN && g_itemtile_pair && grid.y >= 2 && grid.y % 2 == 0) ? 1 : 0;
     p.ring = (kSmemB + kSmemA - ((p.kchunks * p.n_cols * 128 + 1023) & ~1023)) / kABytes;
+    p.tune = g_itemtile_tune;
     if (p.ring > kMaxRing) p.ring = kMaxRing;
     if (!p.pair) {
         k_itemtile<MODE><<<grid, kItemThreads, smem, st>>>(tmA, tmB, p);

@@ -185,6 +185,7 @@ struct DecodeArgs {
 };
 int decode_grid(int N, int n_batch_tiles);
 void launch_decode_train(const DecodeArgs& a, cudaStream_t st);    // G1: z, loss, dz, db_dec
+void set_itemtile_tune(int bits); // A/B switches of the FILTER epilogue (dae_model_set_debug bits 16..)
 void set_itemtile_pair(int on);   // PREDICT / FILTER: clusters of two batch tiles share each W chunk (TMA multicast)
 void launch_decode_predict(const DecodeArgs& a, cudaStream_t st);  // G1: z, sigmoid, scores
 void launch_decode_filter(const DecodeArgs& a, cudaStream_t st);   // G1f: z > threshold -> candidate lists

@@ -56,6 +56,13 @@ static __device__ __noinline__ void trap_report(uint32_t a, uint32_t b, const ui
     }
     __trap();
 }
+// Non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 // Bounded spin: a protocol bug traps (-> launch error on the host) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const uint64_t* dump = nullptr, int ndump = 0) {
     const uint32_t addr = smem_u32(bar);
