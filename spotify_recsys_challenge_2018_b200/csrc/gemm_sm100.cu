@@ -51,7 +51,16 @@ constexpr int kSmemA = kStages * kABytes;           // 98304
 constexpr int kSmemBars = 512;
 constexpr int kMaxRing = 12;                          // barrier slots of the streamed-operand ring (inference modes size it at run time)
 constexpr int kSmemThr = kMaxBpad * 4;              // FILTER: per-playlist thresholds of the CTA's batch tile
-constexpr int kWStg = kABytes / 8 / 16;             // FILTER: candidates staged per epilogue warp (128) in one ring stage's worth of smem
+// FILTER gives the last TWO ring stages (32 KB) to its epilogue warps, 2 KB each: a queue of accumulator rows that passed the
+// scan's pre-test (kQRec records of 16 logits-to-be + bias + tag, 80 B apart) and two staging halves of kWHalf candidates
+// (one fills while the other one's list appends are in flight)
+constexpr int kFilterStgStages = 2;
+constexpr int kWarpStgBytes = kFilterStgStages * kABytes / 16;       // 2048
+constexpr int kQRec = 12;
+constexpr int kQWords = 20;
+constexpr int kWHalf = 64;
+constexpr int kStgOff = 1024;                       // staging halves at +1024 / +1536 of the warp's 2 KB block (queue: 960 B at +0)
+static_assert(kQRec * kQWords * 4 <= kStgOff && kStgOff + 2 * kWHalf * 8 <= kWarpStgBytes, "per-warp FILTER buffers");
 constexpr int kSmemItemTile = kSmemB + kSmemA + kSmemBars + kSmemThr + 1024;  // + alignment slack
 // TRAIN runs a 4-stage ring: the epilogue paces the kernel (one tile = 4 chunks is ahead of the MMA at any time), and
 // the 32 KB it gives up is what lets the background optimizer streamer (optim.cu: k_adam_bg, 31 KB) share the SM
@@ -90,8 +99,9 @@ struct ItemTileDev {
     int raw_logits;          // PREDICT: write z instead of sigmoid(z)
     unsigned long long* trace;   // debug: %globaltimer when the first / last CTA of the grid started
     int pair;                // PREDICT / FILTER: launched as clusters of two batch tiles (grid.y) that share every W chunk
-    int ring;                // PREDICT / FILTER: 16 KB stages behind the resident operand (FILTER gives the last one to staging)
-    int tune;                // FILTER A/B switches (dae_model_set_debug bits 16..): bit 0 = no flush in the idle time before a tile
+    int ring;                // PREDICT / FILTER: 16 KB stages behind the resident operand (FILTER gives the last two to its epilogue)
+    int tune;                // FILTER switches (dae_model_set_debug bits 16..), TIMING EXPERIMENTS ONLY (wrong results):
+                             // bit 1 = the epilogue releases every accumulator unread, bit 2 = the scan never queues a row
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -207,98 +217,67 @@ __device__ __forceinline__ void train_chunk_y0(const uint32_t (&r)[kCw], float c
     lg_sum = ls; dz_sum = sd; minden = md;
 }
 
-// One warp moves its staged candidates (column | item << 8, logit) to the playlists' global lists: the returned global
-// atomics of 32 entries are in flight together, instead of one per hit stalling the scan.
+// ---- FILTER epilogue helpers (fused decode + top-K) --------------------------------------------------------------
+// The list appends of one staging half (n <= 64 entries of (column | item << 8, logit)) in two steps: flush_begin issues
+// the returned atomics that reserve the entries' positions in their playlists' lists and does NOT wait for them;
+// flush_end, at the next swap of the halves, stores the entries (re-read from the half, which nobody touches in between)
+// at those positions.  A flush is a round trip to L2 (1-2 us): nothing waits it out.
 // (`o` = the kernel's parameter block: it lives in the constant bank, so the scan keeps no output pointers in registers.)
-__device__ __noinline__ void flush_candidates(const uint2* seg, int n, const ItemTileDev& o) {
+__device__ __forceinline__ void flush_begin(const uint2* half, int n, const ItemTileDev& o, int& g0, int& g1) {
     const int lane = threadIdx.x & 31;
     const int b0 = blockIdx.y * o.n_cols;          // first playlist of the CTA's batch tile
-    __syncwarp();                                  // the segment was written by other lanes
-    // four rounds of 32 entries at a time: all their returned atomics are issued before the first dependent store, so a
-    // whole staging segment (128 entries) costs ONE round trip to L2, not four
-    for (int i0 = 0; i0 < n; i0 += 128) {
-        uint2 e[4];
-        int gp[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 32 + lane;
-            e[u] = i < n ? seg[i] : make_uint2(0xFFFFFFFFu, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            gp[u] = e[u].x != 0xFFFFFFFFu ? atomicAdd(o.cand_cnt + b0 + (int)(e[u].x & 255u), 1) : o.cand_cap;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (gp[u] < o.cand_cap) {
-                const int b = b0 + (int)(e[u].x & 255u);
-                o.cand_val[(size_t)b * o.cand_cap + gp[u]] = __uint_as_float(e[u].y);
-                o.cand_idx[(size_t)b * o.cand_cap + gp[u]] = o.item0 + (int)(e[u].x >> 8);
-            }
-        }
+    __syncwarp();                                  // the half was written by other lanes
+    g0 = o.cand_cap; g1 = o.cand_cap;
+    if (lane < n) g0 = atomicAdd(o.cand_cnt + b0 + (int)(half[lane].x & 255u), 1);
+    if (lane + 32 < n) g1 = atomicAdd(o.cand_cnt + b0 + (int)(half[lane + 32].x & 255u), 1);
+}
+__device__ __noinline__ void flush_end(const uint2* half, int n, const ItemTileDev& o, int g0, int g1) {
+    const int lane = threadIdx.x & 31;
+    const int b0 = blockIdx.y * o.n_cols;
+    if (lane < n && g0 < o.cand_cap) {
+        const uint2 e = half[lane];
+        const size_t at = (size_t)(b0 + (int)(e.x & 255u)) * o.cand_cap + g0;
+        o.cand_val[at] = __uint_as_float(e.y);
+        o.cand_idx[at] = o.item0 + (int)(e.x >> 8);
+    }
+    if (lane + 32 < n && g1 < o.cand_cap) {
+        const uint2 e = half[lane + 32];
+        const size_t at = (size_t)(b0 + (int)(e.x & 255u)) * o.cand_cap + g1;
+        o.cand_val[at] = __uint_as_float(e.y);
+        o.cand_idx[at] = o.item0 + (int)(e.x >> 8);
     }
     __syncwarp();
 }
 
-// The rare half chunks of the FILTER scan that hold a hit (the scan's pre-test passed for some lane): the exact per-cell
-// test z_k = acc_k + bias >= thr_k into a per-lane hit mask, then the hits go to the warp's PRIVATE staging segment at
-// positions from a warp scan of the lanes' hit counts (no atomics, no block barriers; list order is irrelevant to the
-// select) and from there to the playlists' global lists 100+ at a time.  Re-reads the 16 accumulator columns at `taddr`
-// (the caller's copy would have to live across the call).  thr0 = index of the first column's threshold; tag = column |
-// item << 8 of column 0; returns the new number of staged entries.
-__device__ __noinline__ int filter_hits(uint32_t taddr, int thr0, float bzf, uint32_t tag, uint2* seg, int wn, const ItemTileDev& p) {
-    const int lane = threadIdx.x & 31;
-    uint32_t r[kCw];
-    tmem_ld16(taddr, r);
-    tmem_ld_wait();
-    const float4* th4 = reinterpret_cast<const float4*>(p.thr + thr0);
-    uint32_t hit = 0;                                // bit k: this lane's cell of column k passes
-#pragma unroll
-    for (int j4 = 0; j4 < kCw / 4; ++j4) {
-        const float4 th = __ldg(th4 + j4);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float z = __uint_as_float(r[4 * j4 + u]) + bzf;
-            r[4 * j4 + u] = __float_as_uint(z);
-            const float t = u == 0 ? th.x : (u == 1 ? th.y : (u == 2 ? th.z : th.w));
-            if (z >= t) hit |= 1u << (4 * j4 + u);
-        }
-    }
-    if (!__any_sync(0xffffffffu, hit != 0)) return wn;
-    const int mine = __popc(hit);
-    int pos = mine;                                  // inclusive scan of the lanes' hit counts
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, pos, o);
-        if (lane >= o) pos += up;
-    }
-    const int tot = __shfl_sync(0xffffffffu, pos, 31);
-    if (wn + tot > kWStg) { flush_candidates(seg, wn, p); wn = 0; }
-    if (tot <= kWStg) {
-        uint2* dst = seg + wn + (pos - mine);
-#pragma unroll
-        for (int k = 0; k < kCw; ++k) {
-            if ((hit >> k) & 1u) {
-                *dst = make_uint2(tag + k, r[k]);
-                ++dst;
-            }
-        }
-        return wn + tot;
-    }
-    // more hits in one half chunk than a segment holds (a playlist whose threshold is still -inf): column by column,
-    // flushing as the segment fills
+// Queued accumulator rows -> staged candidates, the whole warp on two records at a time (lane = cell k of record
+// lane >> 4): the scan's own test per cell, (acc_k - thr'_k) + bias >= -tol with the same rounding (thr' = the loosened
+// threshold in shared memory: whatever passes z_k >= thr_k passes this, and the few extra candidates just below a
+// threshold are harmless -- the select is exact on whatever the lists hold), hits appended to the staging half at
+// positions from the ballot.  Stops when the half cannot take a pair's hits: returns entries staged | records done << 16.
+__device__ __noinline__ uint32_t process_queue(const float* qb, int qi, int qn, const float* nthr, uint2* seg, int wn) {
+    const int lane = threadIdx.x & 31, k = lane & 15, sub = lane >> 4;
+    const unsigned ltmask = (1u << lane) - 1u;
 #pragma unroll 1
-    for (int k = 0; k < kCw; ++k) {
-        const unsigned am = __ballot_sync(0xffffffffu, (hit >> k) & 1u);
-        if (am == 0) continue;
-        if (wn + 32 > kWStg) { flush_candidates(seg, wn, p); wn = 0; }
-        uint32_t zk = 0;
-#pragma unroll
-        for (int kk = 0; kk < kCw; ++kk) zk = kk == k ? r[kk] : zk;
-        if ((am >> lane) & 1u) seg[wn + __popc(am & ((1u << lane) - 1u))] = make_uint2(tag + k, zk);
-        wn += __popc(am);
-        __syncwarp();
+    for (; qi < qn; qi += 2) {
+        const int rec = qi + sub;
+        bool pass = false;
+        uint32_t tag = 0;
+        float z = 0.f;
+        if (rec < qn) {
+            const float* R = qb + rec * kQWords;
+            const float a = R[k], bz = R[16];
+            tag = __float_as_uint(R[17]);
+            const float nt = nthr[(tag & 255u) + k];
+            pass = __fadd_rn(__fadd_rn(a, nt), bz) >= -4e-7f * fabsf(bz);
+            z = a + bz;                                          // the logit, as the dense path forms it
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        const int n = __popc(bal);
+        if (wn + n > kWHalf) break;                              // warp-uniform: the caller swaps halves and comes back
+        if (pass) seg[wn + __popc(bal & ltmask)] = make_uint2(tag + k, __float_as_uint(z));
+        wn += n;
     }
-    return wn;
+    return (uint32_t)wn | ((uint32_t)(qi < qn ? qi : qn) << 16);
 }
 
 // blockIdx.y = batch tile: TRAIN decodes this rank's item rows against every rank's rows of the global batch
@@ -316,7 +295,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // stage, 16 KB, to the candidate staging buffer.
     const int bchunk = MODE == MODE_TRAIN ? kBChunkBytes : p.n_cols * 128;
     const int RING = MODE == MODE_TRAIN ? kStagesTrain : p.ring;
-    const int NST = MODE == MODE_FILTER ? RING - 1 : RING;
+    const int NST = MODE == MODE_FILTER ? RING - kFilterStgStages : RING;
     constexpr int kRingBytes = (MODE == MODE_TRAIN ? kStagesTrain : kStages) * kABytes;
     uint8_t* sB = smem;
     uint8_t* sA = smem + (MODE == MODE_TRAIN ? kSmemB : ((p.kchunks * bchunk + 1023) & ~1023));
@@ -329,7 +308,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* loss_smem = reinterpret_cast<float*>(tmem_slot + 1);  // [kEpiWarps]
     float* thr_smem = reinterpret_cast<float*>(smem + kSmemB + kRingBytes + kSmemBars);   // [n_cols] (FILTER)
-    uint2* stg = reinterpret_cast<uint2*>(sA + NST * kABytes);                       // [kEpiWarps][kWStg] (column | item << 8, logit)
+    uint8_t* stg = sA + NST * kABytes;                                            // FILTER: [kEpiWarps][kWarpStgBytes]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -403,8 +382,17 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The WHOLE warp walks the loop (converged) and one elected lane issues: inside an `if (lane == 0)` region the
+        // compiler wraps every tcgen05 instruction in an elect / branch loop and rebuilds both descriptors from their byte
+        // addresses, ~110 instructions per K chunk on one dependent chain -- the issue loop then took LONGER than the MMAs
+        // it feeds (ncu: half of this warp's samples).  Descriptors advance by adding to their low word (start address
+        // >> 4: no carry out of the 14-bit field below 256 KB).
+        {
             const uint32_t idesc = umma_idesc_bf16(kTileItems, static_cast<uint32_t>(p.n_cols), 0, 0);
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, version 1, SWIZZLE_128B
+            const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);      // LBO field = 1 (unused for K-major)
+            const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_step = static_cast<uint32_t>(bchunk) >> 4;
             mbar_wait(bfull, 0);
             tc_fence_after();
             int stage = 0;
@@ -418,19 +406,20 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-                    const uint32_t b_addr = smem_u32(sB + kc * bchunk);
+                    const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * (kABytes >> 4);
+                    const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(kc) * b_step;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = umma_smem_desc(a_addr + ks * 32, 16, 1024);
-                        const uint64_t bd = umma_smem_desc(b_addr + ks * 32, 16, 1024);
-                        umma_bf16(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16(d_tmem, umma_desc_pack(a_lo + 2 * ks, kDescHi), umma_desc_pack(b_lo + 2 * ks, kDescHi), idesc,
+                                      (kc | ks) != 0 ? 1u : 0u);
+                        if (pair) umma_commit_mcast(&empty[stage], 0x3);
+                        else umma_commit(&empty[stage]);
+                        if (kc == p.kchunks - 1) umma_commit(&tfull[acc]);      // same thread as the MMAs it tracks
                     }
-                    if (pair) umma_commit_mcast(&empty[stage], 0x3);
-                    else umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tfull[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -452,8 +441,29 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const float c_pos = -p.inv_batch, c_neg = kNegWeight * p.inv_batch;
         const float ic = 1.f / c_neg;
         // FILTER: this warp's staging segment, entries staged (warp-uniform), where they go
-        uint2* seg = stg + (warp - 2) * kWStg;
-        int wn = 0;
+        // FILTER: the warp's queue of accumulator rows (qn records) and its staging halves: `seg` is being filled (wn
+        // entries), the other one (address ^ 512) holds the pn entries whose list appends are in flight (positions g0 / g1)
+        float* const qb = reinterpret_cast<float*>(stg + (warp - 2) * kWarpStgBytes);
+        uint2* seg = reinterpret_cast<uint2*>(stg + (warp - 2) * kWarpStgBytes + kStgOff);
+        auto other_half = [](uint2* h) { return reinterpret_cast<uint2*>(reinterpret_cast<uintptr_t>(h) ^ (uintptr_t)(kWHalf * 8)); };
+        int wn = 0, pn = 0, g0 = 0, g1 = 0, qn = 0;
+        // every queued row through the cell test into the staging half; a full half is handed to the L2 (appends begun, not
+        // awaited) and the other one -- its appends of the previous swap long done -- takes over
+        auto drain = [&]() {
+            __syncwarp();                                   // the queue was written by other lanes
+            int qi = 0;
+            while (qi < qn) {
+                const uint32_t rv = process_queue(qb, qi, qn, thr_smem, seg, wn);
+                wn = (int)(rv & 0xffffu); qi = (int)(rv >> 16);
+                if (qi < qn) {
+                    if (pn > 0) flush_end(other_half(seg), pn, p, g0, g1);
+                    flush_begin(seg, wn, p, g0, g1);
+                    pn = wn; wn = 0;
+                    seg = other_half(seg);
+                }
+            }
+            qn = 0;
+        };
         // per-tile scalars of this lane's item row (bias, target words of the warp's two chunks) are fetched ONE TILE
         // AHEAD: they come from HBM (~1 us) and would otherwise stall the warp at the top of every tile
         float bz_nx = 0.f;
@@ -482,16 +492,72 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             float db = 0.f, lt = 0.f;
             const float c2 = bz * c1;
             const float bzf = item_ok ? bz : __int_as_float(0x7fc00000);   // FILTER: rows past the range compare false (NaN)
-            if (MODE == MODE_FILTER) {
-                // A flush is a round trip to L2 (returned atomics): a warp that is AHEAD of the tensor core -- its next
-                // accumulator is not ready -- flushes now, for free; a warp that is behind keeps scanning and flushes only
-                // when its segment is nearly full (below).  Every tile needs all 16 warps, so a flush on the critical warp
-                // would delay the whole CTA.
-                if (wn >= 32 && !(p.tune & 1) && !mbar_test(&tfull[acc], acc_phase)) { flush_candidates(seg, wn, p); wn = 0; }
-            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + lane_addr + static_cast<uint32_t>(acc * 256);
+            if (MODE == MODE_FILTER) {
+            // fused decode + top-K, filter stage: keep the logits >= the playlist's threshold (a lower bound of
+            // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.03 % of the cells pass in
+            // the full-range pass, ~4 % in the middle one -- and they cluster on ROWS: a popular item passes for
+            // most playlists of the tile, so one lane quadrant's four warps find hits in every half chunk of a
+            // tile while the other twelve find none, on nearly every tile.  Every tile needs all 16 warps before
+            // the tensor core may reuse the accumulator, so the scan does the minimum while it holds it: a PRE-TEST
+            // on the lane's 16 cells at once, m = max_k (acc_k - thr'_k) (one FADD2 + one FMNMX3 per two cells,
+            // thr' = the threshold loosened beyond the rounding of both forms), (m + bias) >= -tol, one vote per
+            // half chunk; a lane that passes copies its 16 accumulator values to the warp's queue (5 stores).  The
+            // per-cell test, the staging and the list appends happen AFTER the accumulator is released (`drain`),
+            // where a hot warp's extra work is absorbed by the slack of the two-accumulator pipeline instead of
+            // stalling the CTA (ncu + timing experiments: 4.4 ms with the hit path inside the scan, 2.4 without any).
+            // The accumulator columns of the NEXT half chunk are requested before the current one is examined (two register
+            // sets): the tensor-memory read latency (~100 cycles with 16 warps reading) is off the warp's serial path.
+            const int nh = (p.tune & 2) ? 0 : (part < nchunks ? 2 * ((nchunks - part + 3) >> 2) : 0);   // this warp's half chunks
+            auto col_of = [&](int j) { return (part + 4 * (j >> 1)) * 32 + (j & 1) * kCw; };
+            auto examine = [&](const uint32_t (&r)[kCw], int col0) {
+                const float4* nth4 = reinterpret_cast<const float4*>(thr_smem + col0);
+                float mxa = -CUDART_INF_F, mxb = -CUDART_INF_F;
+#pragma unroll
+                for (int j4 = 0; j4 < kCw / 4; ++j4) {
+                    const float4 nt = nth4[j4];                      // same address for every lane: broadcast
+                    const float2 d0 = add2(r[4 * j4 + 0], r[4 * j4 + 1], nt.x, nt.y);
+                    const float2 d1 = add2(r[4 * j4 + 2], r[4 * j4 + 3], nt.z, nt.w);
+                    mxa = max3(mxa, d0.x, d0.y);
+                    mxb = max3(mxb, d1.x, d1.y);
+                }
+                bool mine = fmaxf(mxa, mxb) + bzf >= -4e-7f * fabsf(bzf);   // tolerance: rounding of (acc - thr) ~ ulp(bias)
+                unsigned rem = __ballot_sync(0xffffffffu, mine);
+                if (p.tune & 4) rem = 0;
+#pragma unroll 1
+                while (rem != 0) {                                   // (one round unless the queue fills up)
+                    if (qn == kQRec) drain();
+                    const int room = kQRec - qn;
+                    const int rank = __popc(rem & ((1u << lane) - 1u));
+                    if (mine && rank < room) {
+                        float* R = qb + (qn + rank) * kQWords;
+#pragma unroll
+                        for (int j4 = 0; j4 < kCw / 4; ++j4)
+                            *reinterpret_cast<uint4*>(R + 4 * j4) = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                        *reinterpret_cast<float2*>(R + 16) = make_float2(bzf, __uint_as_float((uint32_t)col0 | ((uint32_t)item << 8)));
+                        mine = false;
+                    }
+                    const int cnt = __popc(rem);
+                    qn += cnt < room ? cnt : room;
+                    rem = __ballot_sync(0xffffffffu, mine);
+                }
+            };
+            uint32_t ra[kCw], rb[kCw];
+            if (nh > 0) tmem_ld16(t_addr + col_of(0), ra);
+#pragma unroll 1
+            for (int j = 0; j < nh; j += 2) {
+                tmem_ld_wait();
+                if (j + 1 < nh) tmem_ld16(t_addr + col_of(j + 1), rb);
+                examine(ra, col_of(j));
+                if (j + 1 < nh) {
+                    tmem_ld_wait();
+                    if (j + 2 < nh) tmem_ld16(t_addr + col_of(j + 2), ra);
+                    examine(rb, col_of(j + 1));
+                }
+            }
+            } else
 #pragma unroll 1
             for (int c = part; c < nchunks; c += 4) {
                 if (MODE == MODE_TRAIN) {
@@ -542,34 +608,6 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                             }
                         }
                     }
-                } else if (MODE == MODE_FILTER) {
-                    // fused decode + top-K, filter stage: keep the logits >= the playlist's threshold (a lower bound of
-                    // its (K + #seeds)-th largest logit, so no member of the top-K can be lost); ~0.03 % of the cells pass in
-                    // the full-range pass, ~4 % in the middle one.  The scan is a PRE-TEST on the lane's 16 cells at once:
-                    // m = max_k (acc_k - thr'_k) (one FADD2 + one FMNMX3 per two cells, thr' = the threshold loosened beyond
-                    // the rounding of both forms), then (m + bias) >= -tol and ONE vote per half chunk.  Only half chunks
-                    // that pass (14 % in the full-range pass) go through filter_hits (out of line: it re-reads its 16
-                    // columns from tensor memory, so the scan keeps a small register set and nothing of the tile loop
-                    // spills).
-#pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int col0 = c * 32 + hh * kCw;
-                        uint32_t r[kCw];
-                        tmem_ld16(t_addr + col0, r);
-                        tmem_ld_wait();
-                        const float4* nth4 = reinterpret_cast<const float4*>(thr_smem + col0);
-                        float mx = -CUDART_INF_F;
-#pragma unroll
-                        for (int j4 = 0; j4 < kCw / 4; ++j4) {
-                            const float4 nt = nth4[j4];                      // same address for every lane: broadcast
-                            const float2 d0 = add2(r[4 * j4 + 0], r[4 * j4 + 1], nt.x, nt.y);
-                            const float2 d1 = add2(r[4 * j4 + 2], r[4 * j4 + 3], nt.z, nt.w);
-                            mx = max3(mx, d0.x, d0.y);
-                            mx = max3(mx, d1.x, d1.y);
-                        }
-                        if (__any_sync(0xffffffffu, mx + bzf >= -4e-7f * fabsf(bzf)))        // tolerance: rounding of (acc - thr) ~ ulp(bias)
-                            wn = filter_hits(t_addr + col0, bt * p.n_cols + col0, bzf, (uint32_t)col0 | ((uint32_t)item << 8), seg, wn, p);
-                    }
                 } else {
                     uint32_t r[32];
                     tmem_ld32(t_addr + c * 32, r);
@@ -605,14 +643,15 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
             if (MODE == MODE_FILTER) {
-                // staged hits leave for the global lists AFTER the accumulator is released: the flush is a round trip to L2
-                // (returned atomics), and the MMA of the tile after next must not wait for it.  (A flush in the middle of
-                // the scan above only happens when one tile yields more hits than the segment holds.)
-                if (wn > ((p.tune & 1) ? kWStg / 2 : kWStg - 40)) { flush_candidates(seg, wn, p); wn = 0; }
+                if (qn > 0) drain();
             }
         }
         if (MODE == MODE_FILTER) {
-            if (wn > 0) flush_candidates(seg, wn, p);
+            if (pn > 0) flush_end(other_half(seg), pn, p, g0, g1);
+            if (wn > 0) {
+                flush_begin(seg, wn, p, g0, g1);
+                flush_end(seg, wn, p, g0, g1);
+            }
         }
         if (MODE == MODE_TRAIN) {
 #pragma unroll

@@ -191,6 +191,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// low word (start address >> 4 | LBO field << 16) + high word (SBO field | version | layout) -> descriptor
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+// One lane of a converged warp (the same one on every call): the issuer of tcgen05.mma / tcgen05.commit.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A[smem] . B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
