@@ -326,12 +326,13 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         atomicMax(p.trace + 1, now);
     }
     if (MODE == MODE_FILTER) {
-        // the scan's pre-test works on max_k(z_k - thr_k): shared memory holds MINUS the threshold, loosened by more than the
-        // rounding of either form of the comparison (the exact test z_k >= thr_k of the rare chunks that pass the pre-test
-        // reads the thresholds themselves, from L1 / L2)
+        // the scan works on max_k(acc_k - thr_k) + bias: shared memory holds MINUS the threshold, loosened by more than the
+        // rounding of either form of the comparison -- (acc - thr) + bias against fl(acc + bias) >= thr: half an ulp of
+        // |thr| and of |bias| (the scan adds 4e-7 |bias|), ~6e-8 relative each -- so that nothing with z >= thr is dropped;
+        // what passes in addition (a few items within ~1e-6 below a threshold) only makes a list longer
         for (int i = threadIdx.x; i < p.n_cols; i += blockDim.x) {
             const float t = p.thr[bt * p.n_cols + i];
-            thr_smem[i] = fabsf(t) <= 3.0e38f ? -(t - (1e-3f + 4e-7f * fabsf(t))) : -t;
+            thr_smem[i] = fabsf(t) <= 3.0e38f ? -(t - (2e-6f + 4e-7f * fabsf(t))) : -t;
         }
     }
 
