@@ -206,7 +206,9 @@ int64_t dae_exchange_launch_count(dae_exchange* x);
  * buffer "trace" (tools/gpu_trace.py).  bit 14: the title branch forms dW_out in HBM ("g_W_out") and runs its Adam as a
  * second kernel instead of the fused one.  bit 15 (process-wide, experiment): inference batches of more than 256 rows
  * decode in 128-row tiles, clusters of two tiles sharing every W chunk through TMA multicast (measured slower than the
- * default 256-row tiles; kept for A/B). */
+ * default 256-row tiles; kept for A/B).  bits 17 / 18 (process-wide, TIMING EXPERIMENTS ONLY -- the rankings are wrong):
+ * the filter pass of the fused decode + top-K releases every accumulator unread / scans but never queues a row (the
+ * floors quoted in DESIGN.md section 4, "FILTER epilogue"). */
 int32_t dae_model_set_debug(dae_model* m, int32_t flags);
 
 /* Named device buffers (pointer, element count, element size) for parity tests.  Catalogue-row
