@@ -464,6 +464,7 @@ k_itemtile(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 }
             }
             qn = 0;
+            __syncwarp();                                   // every lane has read its records before any lane queues new ones
         };
         // per-tile scalars of this lane's item row (bias, target words of the warp's two chunks) are fetched ONE TILE
         // AHEAD: they come from HBM (~1 us) and would otherwise stall the warp at the top of every tile
